@@ -1,0 +1,235 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into or called by the product path.
+//
+// C-ABI shim around the *unmodified* reference CPU implementation (nanoporetech/dorado),
+// compiled in place from /root/reference by oracle/Makefile into oracle/_ref/libdorado_ref.so.
+// It exposes the reference's own functions so the C restatement (oracle/crf_oracle.c) and the
+// CUDA engine can be checked against the real thing:
+//   * model forward      dorado/basecall/model/{CRFModel,TxModel}.cpp  (libtorch CPU, fp32)
+//   * CRF scans          dorado/basecall/decode/CPUDecoder.cpp:43-92   (inner::forward/backward_scores)
+//   * beam search        dorado/basecall/decode/beam_search.cpp:522    (beam_search_decode)
+//   * whole decode       dorado/basecall/decode/CPUDecoder.cpp:100     (CPUDecoder::beam_search_part_2)
+// Everything here is glue written for this repo; no reference source is copied.
+#include "basecall/decode/CPUDecoder.h"
+#include "basecall/decode/beam_search.h"
+#include "basecall/model/CRFModel.h"
+#include "basecall/model/TxModel.h"
+#include "config/BasecallModelConfig.h"
+
+#include <ATen/ATen.h>
+#include <torch/torch.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct RefModel {
+    dorado::config::BasecallModelConfig config;
+    torch::nn::ModuleHolder<torch::nn::AnyModule> module{nullptr};
+};
+
+// "B2W1" flat weight container: see dorado_b200/weights.py
+std::vector<at::Tensor> read_b2w(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) {
+        throw std::runtime_error("cannot open weights file " + path);
+    }
+    char magic[4];
+    f.read(magic, 4);
+    if (std::memcmp(magic, "B2W1", 4) != 0) {
+        throw std::runtime_error("bad magic in " + path);
+    }
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), 4);
+    std::vector<at::Tensor> out;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t name_len = 0, ndim = 0;
+        f.read(reinterpret_cast<char*>(&name_len), 4);
+        std::string name(name_len, '\0');
+        f.read(name.data(), name_len);
+        f.read(reinterpret_cast<char*>(&ndim), 4);
+        std::vector<int64_t> dims(ndim);
+        int64_t numel = 1;
+        for (uint32_t d = 0; d < ndim; ++d) {
+            uint32_t v = 0;
+            f.read(reinterpret_cast<char*>(&v), 4);
+            dims[d] = v;
+            numel *= v;
+        }
+        at::Tensor t = at::empty(dims, at::kFloat);
+        f.read(reinterpret_cast<char*>(t.data_ptr<float>()), numel * 4);
+        if (!f) {
+            throw std::runtime_error("truncated weights file " + path);
+        }
+        out.push_back(t);
+    }
+    return out;
+}
+
+template <typename F>
+int guarded(F&& fn) {
+    try {
+        at::InferenceMode guard;
+        fn();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void ref_set_num_threads(int n) { at::set_num_threads(n); }
+
+// config_dir: directory holding config.toml (directory name must be a non-deprecated model name).
+// weights:    B2W1 file with tensors in the order of dorado/basecall/crf_utils.cpp:26-150.
+void* ref_model_create(const char* config_dir, const char* weights) {
+    RefModel* m = nullptr;
+    int rc = guarded([&] {
+        auto owned = std::make_unique<RefModel>();
+        owned->config = dorado::config::load_model_config(config_dir);
+        auto state = read_b2w(weights);
+        const auto opts = at::TensorOptions().dtype(at::kFloat).device(at::kCPU);
+        if (owned->config.is_tx_model()) {
+            auto model = dorado::basecall::model::TxModel(owned->config, opts);
+            dorado::utils::load_state_dict(*model, state);
+            model->eval();
+            owned->module = torch::nn::ModuleHolder<torch::nn::AnyModule>(torch::nn::AnyModule(model));
+        } else {
+            auto model = dorado::basecall::model::CRFModel(owned->config);
+            model->load_state_dict(state);
+            model->eval();
+            owned->module = torch::nn::ModuleHolder<torch::nn::AnyModule>(torch::nn::AnyModule(model));
+        }
+        m = owned.release();
+    });
+    return rc == 0 ? m : nullptr;
+}
+
+void ref_model_destroy(void* h) { delete static_cast<RefModel*>(h); }
+
+// info[0..5] = stride, outsize, state_len, is_tx, clamp, num_features ; qinfo = qscale, qbias
+int ref_model_info(void* h, int* info, float* qinfo) {
+    auto* m = static_cast<RefModel*>(h);
+    info[0] = m->config.stride;
+    info[1] = m->config.outsize;
+    info[2] = m->config.state_len;
+    info[3] = m->config.is_tx_model() ? 1 : 0;
+    info[4] = m->config.clamp ? 1 : 0;
+    info[5] = m->config.num_features;
+    qinfo[0] = m->config.qscale;
+    qinfo[1] = m->config.qbias;
+    return 0;
+}
+
+// signal [N,1,T] fp32 -> scores [N,T_out,C] fp32 ; what ModelRunner::call_chunks runs first
+// (dorado/basecall/ModelRunner.cpp:35).
+int ref_forward(void* h, const float* signal, int N, int T, float* scores, int* t_out, int* c_out) {
+    auto* m = static_cast<RefModel*>(h);
+    return guarded([&] {
+        at::Tensor x = at::from_blob(const_cast<float*>(signal), {N, 1, T}, at::kFloat).clone();
+        at::Tensor y = m->module->forward(x).contiguous();
+        *t_out = int(y.size(1));
+        *c_out = int(y.size(2));
+        if (scores) {
+            std::memcpy(scores, y.data_ptr<float>(), size_t(y.numel()) * 4);
+        }
+    });
+}
+
+// One chunk: scores [T,C] fp32 -> fwd, bwd, posts [T+1, C/4] fp32 using the reference's scans
+// (CPUDecoder.cpp:43-92) and softmax (CPUDecoder.cpp:130).
+int ref_scans(const float* scores, int T, int C, float blank, float* fwd, float* bwd, float* posts) {
+    return guarded([&] {
+        namespace inner = dorado::basecall::decode::inner;
+        at::Tensor s = at::from_blob(const_cast<float*>(scores), {T, 1, C}, at::kFloat).clone();
+        at::Tensor f = inner::forward_scores(s, blank);
+        at::Tensor b = inner::backward_scores(s, blank);
+        at::Tensor p = at::softmax(f + b, -1);
+        const size_t bytes = size_t(T + 1) * size_t(C / 4) * 4;
+        std::memcpy(fwd, f.contiguous().data_ptr<float>(), bytes);
+        std::memcpy(bwd, b.contiguous().data_ptr<float>(), bytes);
+        std::memcpy(posts, p.contiguous().data_ptr<float>(), bytes);
+    });
+}
+
+// Reference beam search on caller-provided guides/posts (beam_search.cpp:522-606).
+// scores: [T,C] fp32 (is_half=0) or IEEE half bits (is_half=1). seq/qstr/moves sized T.
+int ref_beam_search_decode(const void* scores,
+                           int is_half,
+                           int T,
+                           int C,
+                           const float* bwd,
+                           const float* posts,
+                           int beam_width,
+                           float beam_cut,
+                           float blank,
+                           float q_shift,
+                           float q_scale,
+                           char* seq,
+                           char* qstr,
+                           uint8_t* moves,
+                           int* n_bases) {
+    return guarded([&] {
+        at::Tensor s = at::from_blob(const_cast<void*>(scores), {T, C}, is_half ? at::kHalf : at::kFloat);
+        at::Tensor b = at::from_blob(const_cast<float*>(bwd), {T + 1, C / 4}, at::kFloat);
+        at::Tensor p = at::from_blob(const_cast<float*>(posts), {T + 1, C / 4}, at::kFloat);
+        auto [sequence, qstring, mv] = dorado::basecall::decode::beam_search_decode(
+                s, b, p, size_t(beam_width), beam_cut, blank, q_shift, q_scale, 1.0f);
+        *n_bases = int(sequence.size());
+        std::memcpy(seq, sequence.data(), sequence.size());
+        std::memcpy(qstr, qstring.data(), qstring.size());
+        std::memcpy(moves, mv.data(), mv.size());
+    });
+}
+
+// Whole reference decode on a batch: scores [N,T,C] fp32 -> per chunk seq/qstr/moves (row pitch T).
+// Follows ModelRunner::call_chunks (ModelRunner.cpp:35-39): transpose to TNC then
+// CPUDecoder::beam_search_part_2.
+int ref_decode_chunks(const float* scores,
+                      int N,
+                      int T,
+                      int C,
+                      int beam_width,
+                      float beam_cut,
+                      float blank,
+                      float q_shift,
+                      float q_scale,
+                      char* seq,
+                      char* qstr,
+                      uint8_t* moves,
+                      int* n_bases) {
+    return guarded([&] {
+        using namespace dorado::basecall::decode;
+        at::Tensor s = at::from_blob(const_cast<float*>(scores), {N, T, C}, at::kFloat);
+        at::Tensor tnc = s.transpose(0, 1).contiguous();
+        DecoderOptions opts;
+        opts.beam_width = size_t(beam_width);
+        opts.beam_cut = beam_cut;
+        opts.blank_score = blank;
+        opts.q_shift = q_shift;
+        opts.q_scale = q_scale;
+        CPUDecoder dec;
+        auto res = dec.beam_search_part_2(dec.beam_search_part_1({tnc, N, opts}));
+        for (int i = 0; i < N; ++i) {
+            n_bases[i] = int(res[i].sequence.size());
+            std::memcpy(seq + size_t(i) * T, res[i].sequence.data(), res[i].sequence.size());
+            std::memcpy(qstr + size_t(i) * T, res[i].qstring.data(), res[i].qstring.size());
+            std::memcpy(moves + size_t(i) * T, res[i].moves.data(), res[i].moves.size());
+        }
+    });
+}
+
+}  // extern "C"
