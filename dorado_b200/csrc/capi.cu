@@ -1,0 +1,169 @@
+// C ABI of libb200call.so (declared in include/b200call.h): status codes instead of exceptions,
+// plain pointers and sizes, no torch types.
+#include "b200call.h"
+
+#include "common.cuh"
+#include "decode.h"
+#include "engine.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& fn) {
+    try {
+        fn();
+        return B200_OK;
+    } catch (const std::invalid_argument& e) {
+        g_last_error = e.what();
+        return B200_ERR_INVALID;
+    } catch (const b200::CudaError& e) {
+        g_last_error = e.what();
+        return B200_ERR_CUDA;
+    } catch (const b200::Unsupported& e) {
+        g_last_error = e.what();
+        return B200_ERR_UNSUPPORTED;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return B200_ERR_INTERNAL;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_last_error.c_str(); }
+const char* b200_version(void) { return "b200call 0.1 (sm_100a)"; }
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void b200_default_decoder_options(b200_decoder_options* o) {
+    // decode::DecoderOptions defaults (dorado/basecall/include/basecall/DecodedChunk.h:15-23)
+    o->beam_width = 32;
+    o->beam_cut = 100.0f;
+    o->blank_score = 2.0f;
+    o->q_shift = 0.0f;
+    o->q_scale = 1.0f;
+    o->move_pad = 0;
+}
+
+int b200_engine_create(const b200_model_desc* desc, const b200_tensor* tensors, int32_t num_tensors, int32_t device,
+                       b200_engine** out) {
+    return guarded([&] {
+        if (!desc || !tensors || !out) throw std::invalid_argument("b200_engine_create: null argument");
+        *out = reinterpret_cast<b200_engine*>(new b200::Engine(*desc, tensors, num_tensors, device));
+    });
+}
+
+int b200_engine_destroy(b200_engine* e) {
+    return guarded([&] { delete reinterpret_cast<b200::Engine*>(e); });
+}
+
+int b200_engine_get_stats(const b200_engine* e, b200_stats* out) {
+    return guarded([&] {
+        if (!e || !out) throw std::invalid_argument("b200_engine_get_stats: null argument");
+        *out = reinterpret_cast<const b200::Engine*>(e)->stats();
+    });
+}
+
+int b200_runner_create(b200_engine* e, int32_t batch_size, int32_t chunk_size, b200_runner** out) {
+    return guarded([&] {
+        if (!e || !out) throw std::invalid_argument("b200_runner_create: null argument");
+        *out = reinterpret_cast<b200_runner*>(new b200::Runner(*reinterpret_cast<b200::Engine*>(e), batch_size, chunk_size));
+    });
+}
+
+int b200_runner_destroy(b200_runner* r) {
+    return guarded([&] { delete reinterpret_cast<b200::Runner*>(r); });
+}
+
+int b200_runner_set_decoder_options(b200_runner* r, const b200_decoder_options* o) {
+    return guarded([&] {
+        if (!r || !o) throw std::invalid_argument("b200_runner_set_decoder_options: null argument");
+        reinterpret_cast<b200::Runner*>(r)->set_decoder_options(*o);
+    });
+}
+
+int32_t b200_runner_batch_size(const b200_runner* r) { return r ? reinterpret_cast<const b200::Runner*>(r)->batch_size() : 0; }
+int32_t b200_runner_chunk_size(const b200_runner* r) { return r ? reinterpret_cast<const b200::Runner*>(r)->chunk_size() : 0; }
+int32_t b200_runner_out_len(const b200_runner* r) { return r ? reinterpret_cast<const b200::Runner*>(r)->out_len() : 0; }
+
+int b200_runner_accept_chunk_f16(b200_runner* r, int32_t idx, const uint16_t* samples, int64_t len) {
+    return guarded([&] {
+        if (!r || !samples) throw std::invalid_argument("b200_runner_accept_chunk_f16: null argument");
+        reinterpret_cast<b200::Runner*>(r)->accept_chunk_f16(idx, samples, len);
+    });
+}
+
+int b200_runner_accept_chunk_f32(b200_runner* r, int32_t idx, const float* samples, int64_t len) {
+    return guarded([&] {
+        if (!r || !samples) throw std::invalid_argument("b200_runner_accept_chunk_f32: null argument");
+        reinterpret_cast<b200::Runner*>(r)->accept_chunk_f32(idx, samples, len);
+    });
+}
+
+uint16_t* b200_runner_input(b200_runner* r) { return r ? reinterpret_cast<b200::Runner*>(r)->input() : nullptr; }
+
+int b200_runner_call_chunks(b200_runner* r, int32_t num_chunks, b200_result* out) {
+    return guarded([&] {
+        if (!r || !out) throw std::invalid_argument("b200_runner_call_chunks: null argument");
+        *out = reinterpret_cast<b200::Runner*>(r)->call_chunks(num_chunks);
+    });
+}
+
+int b200_runner_upload(b200_runner* r) {
+    return guarded([&] {
+        if (!r) throw std::invalid_argument("b200_runner_upload: null argument");
+        reinterpret_cast<b200::Runner*>(r)->upload();
+    });
+}
+
+int b200_runner_step_device(b200_runner* r, int32_t num_chunks, int32_t iters, float* total_ms, float* forward_ms,
+                            float* decode_ms) {
+    return guarded([&] {
+        if (!r || !total_ms) throw std::invalid_argument("b200_runner_step_device: null argument");
+        reinterpret_cast<b200::Runner*>(r)->step_device(num_chunks, iters, total_ms, forward_ms, decode_ms);
+    });
+}
+
+int b200_runner_forward_scores(b200_runner* r, int32_t num_chunks, uint16_t* scores_out) {
+    return guarded([&] {
+        if (!r || !scores_out) throw std::invalid_argument("b200_runner_forward_scores: null argument");
+        reinterpret_cast<b200::Runner*>(r)->forward_scores_to_host(num_chunks, scores_out);
+    });
+}
+
+int b200_decode_scores(int32_t device, const uint16_t* scores, int32_t N, int32_t T, int32_t C, float clamp_val,
+                       const b200_decoder_options* opts, uint8_t* moves, char* sequence, char* qstring,
+                       int32_t* n_bases) {
+    return guarded([&] {
+        if (!scores || !opts || !moves || !sequence || !qstring || !n_bases) {
+            throw std::invalid_argument("b200_decode_scores: null argument");
+        }
+        b200::decode_host_scores(device, scores, N, T, C, clamp_val, *opts, moves, sequence, qstring, n_bases);
+    });
+}
+
+int b200_test_gemm(int32_t device, const uint16_t* a, const uint16_t* b, const float* bias, int32_t M, int32_t N,
+                   int32_t K, int32_t activation, uint16_t* c) {
+    return guarded([&] {
+        if (!a || !b || !c) throw std::invalid_argument("b200_test_gemm: null argument");
+        b200::test_gemm_host(device, a, b, bias, M, N, K, activation, c);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// CRF decode entry points (device pointers). See decode.cu.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct DecodeArgs {
+    const __half* scores;  // [N][T][4^(state_len+1)] fp16
+    int N;
+    int T;
+    int state_len;
+    float clamp_val;  // > 0: clamp scores to +-clamp_val on read (dorado/basecall/decode/Decoder.cpp:19)
+    // DecoderOptions (dorado/basecall/include/basecall/DecodedChunk.h:15-23)
+    int beam_width;
+    float log_beam_cut;  // logf(beam_cut) or FLT_MAX when beam_cut <= 0 (beam_search.cpp:147-148)
+    float blank;
+    float q_shift;
+    float q_scale;
+    // scratch
+    float* bwd;   // decode_scratch_bytes() -> bwd_bytes
+    uint2* beam;  //                        -> beam_bytes
+    // outputs (device), rows of T
+    uint8_t* moves;
+    char* sequence;
+    char* qstring;
+    int32_t* n_bases;
+};
+
+size_t decode_scratch_bytes(int N, int T, int state_len, size_t* bwd_bytes, size_t* beam_bytes);
+void decode_scores(const DecodeArgs& args, cudaStream_t stream);
+
+}  // namespace b200

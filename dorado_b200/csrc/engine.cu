@@ -1,0 +1,316 @@
+// Engine / Runner: see engine.h.  Mirrors the control flow of the reference's CudaCaller::call_chunks
+// (dorado/basecall/CudaCaller.cpp:224-271): H2D copy, forward, decode part 1 on the GPU, D2H of the
+// 3 x N x T byte result -- here without libtorch, Koi or a separate GPU worker thread (the per-device
+// mutex gives the same one-batch-in-flight FIFO behaviour as the reference's task queue).
+#include "engine.h"
+
+#include "decode.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace b200 {
+
+Arena::~Arena() {
+    if (m_base) cudaFree(m_base);
+}
+
+void Arena::reserve(size_t bytes) {
+    if (m_base) throw std::logic_error("Arena::reserve called twice");
+    B200_CUDA(cudaMalloc(&m_base, bytes));
+    m_cap = bytes;
+    m_off = 0;
+}
+
+void* Arena::take(size_t bytes) {
+    const size_t aligned = (bytes + 255) & ~size_t(255);
+    if (m_off + aligned > m_cap) throw std::logic_error("Arena overflow");
+    void* p = m_base + m_off;
+    m_off += aligned;
+    return p;
+}
+
+// byte offset of the int32 n_bases array behind the three [N][T] byte planes
+static size_t nb_offset(int N, int T) { return ((size_t)3 * N * T + 15) & ~size_t(15); }
+
+float log_beam_cut_of(float beam_cut) {
+    // beam_search.cpp:147-148
+    return beam_cut > 0.0f ? logf(beam_cut) : std::numeric_limits<float>::max();
+}
+
+void require_sm100(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw CudaError("b200call: no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) throw std::invalid_argument("b200call: bad device index");
+    cudaDeviceProp prop{};
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        throw CudaError(std::string("b200call: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor) + "; this build contains sm_100a code only");
+    }
+    B200_CUDA(cudaSetDevice(device));
+}
+
+Engine::Engine(const b200_model_desc& desc, const b200_tensor* tensors, int num_tensors, int device)
+        : m_desc(desc), m_device(device) {
+    if (desc.state_len < 3 || desc.state_len > 5) throw std::invalid_argument("state_len must be 3..5");
+    if (desc.outsize != (1 << (2 * (desc.state_len + 1)))) throw std::invalid_argument("outsize != 4^(state_len+1)");
+    require_sm100(device);
+    B200_CUDA(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+    if (desc.model_type == B200_MODEL_LSTM) {
+        m_model = make_lstm_model(desc, tensors, num_tensors);
+    } else if (desc.model_type == B200_MODEL_TX) {
+        m_model = make_tx_model(desc, tensors, num_tensors);
+    } else {
+        throw std::invalid_argument("unknown model_type");
+    }
+}
+
+Engine::~Engine() {
+    cudaSetDevice(m_device);
+    m_model.reset();
+    if (m_stream) cudaStreamDestroy(m_stream);
+}
+
+b200_stats Engine::stats() const {
+    b200_stats s{};
+    s.batches_called = batches_called.load();
+    s.model_decode_ms = model_decode_ms;
+    s.h2d_ms = h2d_ms;
+    s.d2h_ms = d2h_ms;
+    s.gpu_launches = gpu_launches.load();
+    s.arena_bytes = arena_bytes.load();
+    return s;
+}
+
+Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine), m_N(batch_size), m_T_in(chunk_size) {
+    const auto& d = engine.desc();
+    if (batch_size < 1) throw std::invalid_argument("batch_size must be >= 1");
+    const int stride_inner = d.model_type == B200_MODEL_TX ? d.stride * d.upsample_scale : d.stride;
+    const int gran = d.model_type == B200_MODEL_TX ? stride_inner * 16 : d.stride;
+    if (chunk_size < gran || chunk_size % gran != 0) {
+        // BatchParams::normalise (dorado/config/BatchParams.cpp:89-105) is the caller's job
+        throw std::invalid_argument("chunk_size must be a positive multiple of " + std::to_string(gran));
+    }
+    m_T_out = chunk_size / d.stride;
+    m_C = d.outsize;
+    b200_default_decoder_options(&m_opts);
+    m_opts.q_scale = d.qscale;
+    m_opts.q_shift = d.qbias;
+
+    B200_CUDA(cudaSetDevice(engine.device()));
+    const size_t in_bytes = (size_t)m_N * m_T_in * sizeof(uint16_t);
+    m_out_bytes = nb_offset(m_N, m_T_out) + (size_t)m_N * sizeof(int32_t);
+    B200_CUDA(cudaHostAlloc(&m_h_input, in_bytes, cudaHostAllocDefault));
+    std::memset(m_h_input, 0, in_bytes);
+    B200_CUDA(cudaHostAlloc(&m_h_out, m_out_bytes, cudaHostAllocDefault));
+
+    size_t bwd_b = 0, beam_b = 0;
+    decode_scratch_bytes(m_N, m_T_out, d.state_len, &bwd_b, &beam_b);
+    const size_t scores_b = (size_t)m_N * m_T_out * m_C * sizeof(__half);
+    const size_t ws_b = engine.model().workspace_bytes(m_N, m_T_in);
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    m_arena.reserve(al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(m_out_bytes) + 4096);
+    m_d_input = static_cast<__half*>(m_arena.take(in_bytes));
+    m_d_scores = static_cast<__half*>(m_arena.take(scores_b));
+    m_d_ws = m_arena.take(ws_b);
+    m_d_bwd = static_cast<float*>(m_arena.take(bwd_b));
+    m_d_beam = static_cast<uint2*>(m_arena.take(beam_b));
+    m_d_out = static_cast<unsigned char*>(m_arena.take(m_out_bytes));
+    engine.arena_bytes += (int64_t)m_arena.capacity();
+    for (auto& e : m_ev) B200_CUDA(cudaEventCreate(&e));
+}
+
+Runner::~Runner() {
+    cudaSetDevice(m_engine.device());
+    for (auto& e : m_ev) {
+        if (e) cudaEventDestroy(e);
+    }
+    if (m_h_input) cudaFreeHost(m_h_input);
+    if (m_h_out) cudaFreeHost(m_h_out);
+}
+
+void Runner::set_decoder_options(const b200_decoder_options& o) {
+    if (o.beam_width < 1 || o.beam_width > 32) throw std::invalid_argument("beam_width must be in [1, 32]");
+    if (o.move_pad != 0) throw Unsupported("move_pad is not implemented");
+    m_opts = o;
+}
+
+void Runner::accept_chunk_f16(int idx, const uint16_t* samples, int64_t len) {
+    if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
+    if (len != m_T_in) throw std::invalid_argument("accept_chunk: chunk length != chunk_size");
+    std::memcpy(m_h_input + (size_t)idx * m_T_in, samples, (size_t)len * sizeof(uint16_t));
+}
+
+void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
+    if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
+    if (len != m_T_in) throw std::invalid_argument("accept_chunk: chunk length != chunk_size");
+    __half* dst = reinterpret_cast<__half*>(m_h_input + (size_t)idx * m_T_in);
+    for (int64_t i = 0; i < len; ++i) dst[i] = __float2half_rn(samples[i]);
+}
+
+void Runner::run_forward(int n) {
+    m_engine.model().forward(m_d_input, n, m_T_in, m_d_scores, m_d_ws, m_engine.stream());
+    m_engine.gpu_launches += m_engine.model().launches_per_forward();
+}
+
+void Runner::run_decode(int n) {
+    const auto& d = m_engine.desc();
+    DecodeArgs a{};
+    a.scores = m_d_scores;
+    a.N = n;
+    a.T = m_T_out;
+    a.state_len = d.state_len;
+    a.clamp_val = d.clamp ? 5.0f : 0.0f;  // decode/Decoder.cpp:19
+    a.beam_width = m_opts.beam_width;
+    a.log_beam_cut = log_beam_cut_of(m_opts.beam_cut);
+    a.blank = m_opts.blank_score;
+    a.q_shift = m_opts.q_shift;
+    a.q_scale = m_opts.q_scale;
+    a.bwd = m_d_bwd;
+    a.beam = m_d_beam;
+    // output rows are packed for the n chunks actually called
+    a.moves = m_d_out;
+    a.sequence = reinterpret_cast<char*>(m_d_out + (size_t)m_N * m_T_out);
+    a.qstring = reinterpret_cast<char*>(m_d_out + (size_t)2 * m_N * m_T_out);
+    a.n_bases = reinterpret_cast<int32_t*>(m_d_out + nb_offset(m_N, m_T_out));
+    decode_scores(a, m_engine.stream());
+    m_engine.gpu_launches += 3;
+}
+
+void Runner::upload() {
+    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)m_N * m_T_in * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                              m_engine.stream()));
+    B200_CUDA(cudaStreamSynchronize(m_engine.stream()));
+}
+
+b200_result Runner::call_chunks(int num_chunks) {
+    if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("call_chunks: num_chunks out of range");
+    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    cudaStream_t s = m_engine.stream();
+    B200_CUDA(cudaEventRecord(m_ev[0], s));
+    B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t),
+                              cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaEventRecord(m_ev[1], s));
+    run_forward(num_chunks);
+    run_decode(num_chunks);
+    B200_CUDA(cudaEventRecord(m_ev[2], s));
+    B200_CUDA(cudaMemcpyAsync(m_h_out, m_d_out, m_out_bytes, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaEventRecord(m_ev[3], s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    B200_CUDA(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
+    m_engine.h2d_ms += ms;
+    B200_CUDA(cudaEventElapsedTime(&ms, m_ev[1], m_ev[2]));
+    m_engine.model_decode_ms += ms;
+    B200_CUDA(cudaEventElapsedTime(&ms, m_ev[2], m_ev[3]));
+    m_engine.d2h_ms += ms;
+    ++m_engine.batches_called;
+
+    b200_result r{};
+    r.moves = m_h_out;
+    r.sequence = reinterpret_cast<const char*>(m_h_out + (size_t)m_N * m_T_out);
+    r.qstring = reinterpret_cast<const char*>(m_h_out + (size_t)2 * m_N * m_T_out);
+    r.n_bases = reinterpret_cast<const int32_t*>(m_h_out + nb_offset(m_N, m_T_out));
+    r.t_out = m_T_out;
+    r.num_chunks = num_chunks;
+    return r;
+}
+
+void Runner::step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms) {
+    if (num_chunks < 1 || num_chunks > m_N || iters < 1) throw std::invalid_argument("step_device: bad arguments");
+    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    cudaStream_t s = m_engine.stream();
+    float fwd = 0, dec = 0;
+    for (int i = 0; i < iters; ++i) {
+        B200_CUDA(cudaEventRecord(m_ev[0], s));
+        run_forward(num_chunks);
+        B200_CUDA(cudaEventRecord(m_ev[1], s));
+        run_decode(num_chunks);
+        B200_CUDA(cudaEventRecord(m_ev[2], s));
+        B200_CUDA(cudaStreamSynchronize(s));
+        float ms = 0;
+        B200_CUDA(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
+        fwd += ms;
+        B200_CUDA(cudaEventElapsedTime(&ms, m_ev[1], m_ev[2]));
+        dec += ms;
+    }
+    *total_ms = fwd + dec;
+    if (forward_ms) *forward_ms = fwd;
+    if (decode_ms) *decode_ms = dec;
+}
+
+void Runner::forward_scores_to_host(int num_chunks, uint16_t* scores_out) {
+    if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("forward_scores: num_chunks out of range");
+    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    cudaStream_t s = m_engine.stream();
+    B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t),
+                              cudaMemcpyHostToDevice, s));
+    run_forward(num_chunks);
+    B200_CUDA(cudaMemcpyAsync(scores_out, m_d_scores, (size_t)num_chunks * m_T_out * m_C * sizeof(__half),
+                              cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+}
+
+void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C, float clamp_val,
+                        const b200_decoder_options& opts, uint8_t* moves, char* sequence, char* qstring,
+                        int32_t* n_bases) {
+    int state_len = 0;
+    for (int sl = 3; sl <= 5; ++sl) {
+        if (C == (1 << (2 * (sl + 1)))) state_len = sl;
+    }
+    if (!state_len) throw std::invalid_argument("decode: C must be 4^(state_len+1) with state_len 3..5");
+    if (opts.move_pad != 0) throw Unsupported("move_pad is not implemented");
+    require_sm100(device);
+    cudaStream_t s;
+    B200_CUDA(cudaStreamCreate(&s));
+    size_t bwd_b = 0, beam_b = 0;
+    decode_scratch_bytes(N, T, state_len, &bwd_b, &beam_b);
+    const size_t sc_b = (size_t)N * T * C * sizeof(__half);
+    const size_t out_b = nb_offset(N, T) + (size_t)N * 4;
+    Arena arena;
+    arena.reserve(sc_b + bwd_b + beam_b + out_b + 4096);
+    auto* d_sc = static_cast<__half*>(arena.take(sc_b));
+    DecodeArgs a{};
+    a.scores = d_sc;
+    a.N = N;
+    a.T = T;
+    a.state_len = state_len;
+    a.clamp_val = clamp_val;
+    a.beam_width = opts.beam_width;
+    a.log_beam_cut = log_beam_cut_of(opts.beam_cut);
+    a.blank = opts.blank_score;
+    a.q_shift = opts.q_shift;
+    a.q_scale = opts.q_scale;
+    a.bwd = static_cast<float*>(arena.take(bwd_b));
+    a.beam = static_cast<uint2*>(arena.take(beam_b));
+    auto* d_out = static_cast<unsigned char*>(arena.take(out_b));
+    a.moves = d_out;
+    a.sequence = reinterpret_cast<char*>(d_out + (size_t)N * T);
+    a.qstring = reinterpret_cast<char*>(d_out + (size_t)2 * N * T);
+    a.n_bases = reinterpret_cast<int32_t*>(d_out + nb_offset(N, T));
+    try {
+        B200_CUDA(cudaMemcpyAsync(d_sc, scores, sc_b, cudaMemcpyHostToDevice, s));
+        decode_scores(a, s);
+        B200_CUDA(cudaMemcpyAsync(moves, a.moves, (size_t)N * T, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(sequence, a.sequence, (size_t)N * T, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(qstring, a.qstring, (size_t)N * T, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(n_bases, a.n_bases, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+        cudaStreamDestroy(s);
+        throw;
+    }
+    cudaStreamDestroy(s);
+}
+
+}  // namespace b200

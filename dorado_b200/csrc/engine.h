@@ -1,0 +1,123 @@
+// Host side of libb200call.so: Engine (one model replica per device, the reference's CudaCaller) and
+// Runner (pinned batch slots + device arena, the reference's CudaModelRunner).
+#pragma once
+
+#include "b200call.h"
+#include "common.cuh"
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+struct Unsupported : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// Simple bump arena over one cudaMalloc (the reference plans its working memory the same way:
+// dorado/nn/WorkingMemory.cpp:27-112). 256-byte aligned slices.
+class Arena {
+public:
+    Arena() = default;
+    ~Arena();
+    Arena(const Arena&) = delete;
+    Arena& operator=(const Arena&) = delete;
+    void reserve(size_t bytes);
+    void* take(size_t bytes);
+    void reset() { m_off = 0; }
+    size_t capacity() const { return m_cap; }
+
+private:
+    unsigned char* m_base = nullptr;
+    size_t m_cap = 0, m_off = 0;
+};
+
+// Network forward: fp16 signal [N][T_in] on device -> fp16 scores [N][T_out][outsize] on device.
+class Model {
+public:
+    virtual ~Model() = default;
+    virtual size_t workspace_bytes(int N, int T_in) const = 0;
+    virtual void forward(const __half* signal, int N, int T_in, __half* scores, void* workspace,
+                         cudaStream_t stream) = 0;
+    virtual int launches_per_forward() const = 0;
+};
+
+std::unique_ptr<Model> make_lstm_model(const b200_model_desc& desc, const b200_tensor* tensors, int n);
+std::unique_ptr<Model> make_tx_model(const b200_model_desc& desc, const b200_tensor* tensors, int n);
+
+class Engine {
+public:
+    Engine(const b200_model_desc& desc, const b200_tensor* tensors, int num_tensors, int device);
+    ~Engine();
+    const b200_model_desc& desc() const { return m_desc; }
+    int device() const { return m_device; }
+    cudaStream_t stream() const { return m_stream; }
+    Model& model() { return *m_model; }
+    std::mutex& gpu_mutex() { return m_gpu_mutex; }  // one batch in flight per device (CudaCaller.cpp:204-214)
+    b200_stats stats() const;
+
+    std::atomic<int64_t> batches_called{0};
+    std::atomic<int64_t> gpu_launches{0};
+    std::atomic<int64_t> arena_bytes{0};
+    double model_decode_ms = 0, h2d_ms = 0, d2h_ms = 0;  // guarded by gpu_mutex
+
+private:
+    b200_model_desc m_desc;
+    int m_device;
+    cudaStream_t m_stream = nullptr;
+    std::unique_ptr<Model> m_model;
+    std::mutex m_gpu_mutex;
+};
+
+class Runner {
+public:
+    Runner(Engine& engine, int batch_size, int chunk_size);
+    ~Runner();
+    int batch_size() const { return m_N; }
+    int chunk_size() const { return m_T_in; }
+    int out_len() const { return m_T_out; }
+    uint16_t* input() { return m_h_input; }
+    void set_decoder_options(const b200_decoder_options& o);
+    void accept_chunk_f16(int idx, const uint16_t* samples, int64_t len);
+    void accept_chunk_f32(int idx, const float* samples, int64_t len);
+    b200_result call_chunks(int num_chunks);
+    void upload();
+    void step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms);
+    void forward_scores_to_host(int num_chunks, uint16_t* scores_out);
+
+private:
+    void run_forward(int n);
+    void run_decode(int n);
+
+    Engine& m_engine;
+    int m_N, m_T_in, m_T_out, m_C;
+    b200_decoder_options m_opts;
+    // pinned host (input and output are separate allocations; the reference aliases them)
+    uint16_t* m_h_input = nullptr;
+    unsigned char* m_h_out = nullptr;  // moves | sequence | qstring | n_bases
+    // device
+    Arena m_arena;
+    __half* m_d_input = nullptr;
+    __half* m_d_scores = nullptr;
+    void* m_d_ws = nullptr;
+    float* m_d_bwd = nullptr;
+    uint2* m_d_beam = nullptr;
+    unsigned char* m_d_out = nullptr;
+    size_t m_out_bytes = 0;
+    cudaEvent_t m_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C, float clamp_val,
+                        const b200_decoder_options& opts, uint8_t* moves, char* sequence, char* qstring,
+                        int32_t* n_bases);
+void test_gemm_host(int device, const uint16_t* a, const uint16_t* b, const float* bias, int M, int N, int K,
+                    int activation, uint16_t* c);
+
+float log_beam_cut_of(float beam_cut);
+void require_sm100(int device);
+
+}  // namespace b200

@@ -1,0 +1,177 @@
+"""Python mirror of the reference runner interface on top of the C ABI.
+
+``B200ModelRunner`` has the methods of ``dorado::basecall::ModelRunnerBase``
+(dorado/basecall/include/basecall/ModelRunnerBase.h:20-38) with numpy arrays where the reference takes
+``at::Tensor``: ``accept_chunk(idx, chunk)``, ``call_chunks(n) -> [DecodedChunk]``, ``config()``,
+``chunk_size()``, ``batch_size()``, ``batch_timeouts_ms()``, ``terminate()``, ``restart()``,
+``get_name()``, ``sample_stats()``.  ``B200Caller`` is the per-device engine (the reference's
+``CudaCaller``); several runners may share one caller and are serialised per GPU like
+``CudaCaller::call_chunks`` (dorado/basecall/CudaCaller.cpp:224-271).
+
+The C++ adapter a dorado maintainer would use is include/B200ModelRunner.h; this module is the same
+thing for the Python tests and bench.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import itertools
+from typing import List
+
+import numpy as np
+
+from . import lib as L
+from .config import BasecallModelConfig
+
+
+@dataclasses.dataclass
+class DecodedChunk:
+    """decode::DecodedChunk (dorado/basecall/include/basecall/DecodedChunk.h:9-13)."""
+    sequence: str
+    qstring: str
+    moves: np.ndarray
+
+
+class B200Caller:
+    """One model replica on one GPU (CudaCaller, dorado/basecall/CudaCaller.cpp:149-202)."""
+
+    def __init__(self, cfg: BasecallModelConfig, weights: dict, device: int = 0):
+        self.cfg = cfg
+        self.device = device
+        lib = L.load_library()
+        desc = L.model_desc_from_config(cfg)
+        self._keep = []
+        arr = (L.Tensor * len(weights))()
+        for i, (name, w) in enumerate(weights.items()):
+            w = np.ascontiguousarray(w, np.float32)
+            self._keep.append(w)
+            arr[i].name = name.encode()
+            arr[i].data = w.ctypes.data_as(C.POINTER(C.c_float))
+            arr[i].ndim = w.ndim
+            for k, dim in enumerate(w.shape):
+                arr[i].dims[k] = dim
+        self.handle = C.c_void_p()
+        L.check(lib.b200_engine_create(C.byref(desc), arr, len(weights), device, C.byref(self.handle)))
+        self._keep = None  # the engine copied everything to the device
+        self._terminated = False
+
+    def stats(self) -> dict:
+        s = L.Stats()
+        L.check(L.load_library().b200_engine_get_stats(self.handle, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+
+    def close(self):
+        if self.handle:
+            L.load_library().b200_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class B200ModelRunner:
+    _ids = itertools.count()
+
+    def __init__(self, caller: B200Caller, batch_size: int, chunk_size: int):
+        self.caller = caller
+        self._lib = L.load_library()
+        self.handle = C.c_void_p()
+        chunk_size = caller.cfg.normalise_chunk_size(chunk_size)
+        L.check(self._lib.b200_runner_create(caller.handle, batch_size, chunk_size, C.byref(self.handle)))
+        self._name = f"B200ModelRunner_{caller.device}_{next(self._ids)}"
+        self._N, self._T = batch_size, chunk_size
+        self._t_out = self._lib.b200_runner_out_len(self.handle)
+        buf = self._lib.b200_runner_input(self.handle)
+        self._input = np.ctypeslib.as_array(buf, shape=(batch_size, chunk_size)).view(np.float16)
+
+    # --- ModelRunnerBase ---------------------------------------------------------------------
+    def accept_chunk(self, chunk_idx: int, chunk: np.ndarray) -> None:
+        """chunk: [1, chunk_size] or [chunk_size], float16 (CUDA dtype) or float32."""
+        c = np.ascontiguousarray(chunk).reshape(-1)
+        if c.dtype == np.float16:
+            L.check(self._lib.b200_runner_accept_chunk_f16(self.handle, chunk_idx, c.ctypes.data, c.size))
+        else:
+            c = c.astype(np.float32, copy=False)
+            L.check(self._lib.b200_runner_accept_chunk_f32(self.handle, chunk_idx, c.ctypes.data, c.size))
+
+    def call_chunks(self, num_chunks: int) -> List[DecodedChunk]:
+        r = L.Result()
+        L.check(self._lib.b200_runner_call_chunks(self.handle, num_chunks, C.byref(r)))
+        T = r.t_out
+        moves = np.ctypeslib.as_array(r.moves, shape=(self._N, T))
+        seq = np.ctypeslib.as_array(C.cast(r.sequence, C.POINTER(C.c_uint8)), shape=(self._N, T))
+        qs = np.ctypeslib.as_array(C.cast(r.qstring, C.POINTER(C.c_uint8)), shape=(self._N, T))
+        nb = np.ctypeslib.as_array(r.n_bases, shape=(self._N,))
+        out = []
+        for i in range(num_chunks):
+            n = int(nb[i])
+            out.append(DecodedChunk(bytes(seq[i, :n]).decode("ascii"), bytes(qs[i, :n]).decode("ascii"),
+                                    moves[i].copy()))
+        return out
+
+    def config(self) -> BasecallModelConfig:
+        return self.caller.cfg
+
+    def chunk_size(self) -> int:
+        return self._T
+
+    def batch_size(self) -> int:
+        return self._N
+
+    def variable_chunk_sizes(self) -> bool:
+        return False
+
+    def batch_timeouts_ms(self):
+        return (300000, 30000)  # CudaCaller.cpp:126-138, non low-latency
+
+    def is_low_latency(self) -> bool:
+        return False
+
+    def terminate(self) -> None:
+        pass
+
+    def restart(self) -> None:
+        pass
+
+    def get_name(self) -> str:
+        return self._name
+
+    def sample_stats(self) -> dict:
+        s = self.caller.stats()
+        return {"batches_called": float(s["batches_called"]), "model_decode_ms": float(s["model_decode_ms"])}
+
+    # --- stage-level / measurement hooks -------------------------------------------------------
+    def input_view(self) -> np.ndarray:
+        """Pinned fp16 [batch, chunk_size] input buffer."""
+        return self._input
+
+    def forward_scores(self, num_chunks: int) -> np.ndarray:
+        out = np.empty((num_chunks, self._t_out, self.caller.cfg.outsize), np.float16)
+        L.check(self._lib.b200_runner_forward_scores(self.handle, num_chunks, out.ctypes.data))
+        return out
+
+    def upload(self) -> None:
+        L.check(self._lib.b200_runner_upload(self.handle))
+
+    def step_device(self, num_chunks: int, iters: int = 1):
+        tot, fwd, dec = C.c_float(), C.c_float(), C.c_float()
+        L.check(self._lib.b200_runner_step_device(self.handle, num_chunks, iters, C.byref(tot), C.byref(fwd),
+                                                  C.byref(dec)))
+        return tot.value, fwd.value, dec.value
+
+    def out_len(self) -> int:
+        return self._t_out
+
+    def close(self):
+        if self.handle:
+            self._lib.b200_runner_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

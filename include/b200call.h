@@ -1,0 +1,175 @@
+/* b200call.h -- C ABI of the B200-native batched basecalling engine (libb200call.so).
+ *
+ * Drop-in boundary: dorado::basecall::ModelRunnerBase
+ * (dorado/basecall/include/basecall/ModelRunnerBase.h:20-38).  The C++ adapter
+ * include/B200ModelRunner.h implements that interface on top of the entry points below, replacing
+ *   CudaModelRunner            dorado/basecall/CudaModelRunner.cpp:13-77
+ *   CudaCaller                 dorado/basecall/CudaCaller.cpp:149-720
+ *   CRFModel / TxModel (CUDA)  dorado/basecall/model/CRFModel.cpp:69-115, dorado/nn/*.cpp run_koi paths
+ *   CUDADecoder                dorado/basecall/decode/CUDADecoder.cpp:17-173
+ *   Koi                        cmake/Koi.cmake (closed libkoi.a)
+ * No C++ types, exceptions or torch types cross this boundary: plain pointers and sizes only.
+ * Every function returns B200_OK (0) or a negative b200_status; b200_last_error() gives the message
+ * for the calling thread.  The library fails loudly (B200_ERR_CUDA) when no sm_100 device is usable;
+ * there is no CPU fallback.
+ */
+#ifndef B200CALL_H
+#define B200CALL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+typedef enum b200_status {
+    B200_OK = 0,
+    B200_ERR_INVALID = -1,     /* bad argument / unsupported model shape (std::invalid_argument in the adapter) */
+    B200_ERR_CUDA = -2,        /* CUDA runtime / launch failure, no usable device */
+    B200_ERR_UNSUPPORTED = -3, /* valid request outside what this build implements */
+    B200_ERR_INTERNAL = -4
+} b200_status;
+
+/* config::Activation (dorado/config/include/config/common.h) */
+enum { B200_ACT_SWISH = 0, B200_ACT_SWISH_CLAMP = 1, B200_ACT_TANH = 2 };
+/* model family */
+enum { B200_MODEL_LSTM = 0, B200_MODEL_TX = 1 };
+
+/* config::ConvParams (dorado/config/include/config/common.h) */
+typedef struct b200_conv_desc {
+    int32_t insize, size, winlen, stride, activation;
+} b200_conv_desc;
+
+/* The fields of config::BasecallModelConfig that the hot path reads
+ * (dorado/config/include/config/BasecallModelConfig.h). */
+typedef struct b200_model_desc {
+    int32_t model_type; /* B200_MODEL_LSTM | B200_MODEL_TX */
+    int32_t num_convs;
+    b200_conv_desc convs[8];
+    int32_t state_len;
+    int32_t outsize; /* 4^(state_len+1) */
+    int32_t stride;  /* samples per output block */
+    int32_t clamp;   /* config.clamp: scores clamped to +-5 (applied on decoder read) */
+    float qscale, qbias;
+    /* LSTM models (dorado/basecall/model/CRFModel.cpp:29-62) */
+    int32_t lstm_size, lstm_layers;
+    int32_t linear_bias;  /* config.bias */
+    int32_t out_features; /* 0 = no linear decomposition */
+    float crf_scale;      /* 5.0 => tanh(x)*5 on the last linear (pre-v4.x models) */
+    /* transformer models (dorado/nn/TxModules.cpp, dorado/basecall/model/TxModel.cpp) */
+    int32_t d_model, nhead, dim_feedforward, depth;
+    int32_t attn_window_upper, attn_window_lower;
+    int32_t upsample_scale, max_seq_len;
+    float deepnorm_alpha, theta, tx_crf_scale;
+} b200_model_desc;
+
+/* Host fp32 tensors, named and ordered as the reference's *.tensor files
+ * (dorado/basecall/crf_utils.cpp:26-150); torch layouts ([out,in], conv [C_out,C_in,W]). */
+typedef struct b200_tensor {
+    const char* name;
+    const float* data;
+    int32_t ndim;
+    int64_t dims[4];
+} b200_tensor;
+
+/* decode::DecoderOptions (dorado/basecall/include/basecall/DecodedChunk.h:15-23) */
+typedef struct b200_decoder_options {
+    int32_t beam_width; /* <= 32 */
+    float beam_cut;
+    float blank_score;
+    float q_shift;
+    float q_scale;
+    int32_t move_pad; /* accepted for ABI parity; must be 0 */
+} b200_decoder_options;
+
+/* Result of one call_chunks(): pinned host arrays owned by the runner, rows of t_out bytes.
+ * Chunk i of the batch: moves[i*t_out .. +t_out), sequence/qstring[i*t_out .. +n_bases[i]).
+ * == decode::DecodedChunk {sequence, qstring, moves} (DecodedChunk.h:9-13). */
+typedef struct b200_result {
+    const uint8_t* moves;
+    const char* sequence;
+    const char* qstring;
+    const int32_t* n_bases;
+    int32_t t_out;
+    int32_t num_chunks;
+} b200_result;
+
+typedef struct b200_stats {
+    int64_t batches_called;
+    double model_decode_ms; /* GPU time forward+decode, CudaCaller.cpp:316-321 */
+    double h2d_ms, d2h_ms;
+    int64_t gpu_launches; /* kernels launched by this engine since creation */
+    int64_t arena_bytes;
+} b200_stats;
+
+typedef struct b200_engine b200_engine; /* per-device model replica  (CudaCaller) */
+typedef struct b200_runner b200_runner; /* per-thread batch slot set (CudaModelRunner) */
+
+B200_API const char* b200_last_error(void);
+B200_API const char* b200_version(void);
+B200_API int b200_device_count(void);
+
+B200_API void b200_default_decoder_options(b200_decoder_options* opts);
+
+/* CudaCaller::CudaCaller (CudaCaller.cpp:149-202): upload + re-lay-out weights on `device`. */
+B200_API int b200_engine_create(const b200_model_desc* desc,
+                                const b200_tensor* tensors,
+                                int32_t num_tensors,
+                                int32_t device,
+                                b200_engine** out);
+B200_API int b200_engine_destroy(b200_engine* engine);
+B200_API int b200_engine_get_stats(const b200_engine* engine, b200_stats* out);
+
+/* CudaModelRunner::CudaModelRunner (CudaModelRunner.cpp:13-19) + CudaCaller::create_input/output_tensor
+ * (CudaCaller.cpp:289-314): pinned fp16 input [batch, 1, chunk_size], pinned output, device arena. */
+B200_API int b200_runner_create(b200_engine* engine, int32_t batch_size, int32_t chunk_size, b200_runner** out);
+B200_API int b200_runner_destroy(b200_runner* runner);
+B200_API int b200_runner_set_decoder_options(b200_runner* runner, const b200_decoder_options* opts);
+B200_API int32_t b200_runner_batch_size(const b200_runner* runner);
+B200_API int32_t b200_runner_chunk_size(const b200_runner* runner);
+B200_API int32_t b200_runner_out_len(const b200_runner* runner); /* chunk_size / stride */
+
+/* ModelRunnerBase::accept_chunk (CudaModelRunner.cpp:21-31): copy one chunk (fp16 bits, `len` samples,
+ * len == chunk_size) into batch slot chunk_idx. */
+B200_API int b200_runner_accept_chunk_f16(b200_runner* runner, int32_t chunk_idx, const uint16_t* samples, int64_t len);
+/* Same, converting from fp32 on the way in (CPU ModelRunner's dtype, ModelRunner.cpp:47-49). */
+B200_API int b200_runner_accept_chunk_f32(b200_runner* runner, int32_t chunk_idx, const float* samples, int64_t len);
+/* Direct access to the pinned input (what the reference's accept_chunk writes through index_put_). */
+B200_API uint16_t* b200_runner_input(b200_runner* runner);
+
+/* ModelRunnerBase::call_chunks (CudaCaller.cpp:224-271): H2D, forward, decode, D2H; blocking. */
+B200_API int b200_runner_call_chunks(b200_runner* runner, int32_t num_chunks, b200_result* out);
+
+/* Measurement hooks (bench.py): run `iters` forward+decode passes over the batch already resident on
+ * the device (uploaded by the last call_chunks / upload) and report device time from CUDA events on the
+ * engine's stream; decode_ms/forward_ms may be NULL. */
+B200_API int b200_runner_upload(b200_runner* runner);
+B200_API int b200_runner_step_device(b200_runner* runner, int32_t num_chunks, int32_t iters, float* total_ms,
+                                     float* forward_ms, float* decode_ms);
+
+/* Stage-level entry points so scores and decode can be parity-checked independently (host buffers). */
+B200_API int b200_runner_forward_scores(b200_runner* runner, int32_t num_chunks, uint16_t* scores_out /* [n,t_out,outsize] fp16 */);
+B200_API int b200_decode_scores(int32_t device,
+                                const uint16_t* scores /* [N,T,C] fp16 bits, host */,
+                                int32_t N,
+                                int32_t T,
+                                int32_t C,
+                                float clamp_val,
+                                const b200_decoder_options* opts,
+                                uint8_t* moves,
+                                char* sequence,
+                                char* qstring,
+                                int32_t* n_bases);
+
+/* Kernel-level test hooks (host buffers; used by tests/ only). */
+B200_API int b200_test_gemm(int32_t device, const uint16_t* a /* [M,K] fp16 */, const uint16_t* b /* [N,K] fp16 */,
+                            const float* bias /* [N] or NULL */, int32_t M, int32_t N, int32_t K, int32_t activation,
+                            uint16_t* c /* [M,N] fp16 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CALL_H */
