@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <vector>
 
 namespace b200 {
 
@@ -33,6 +34,29 @@ void* Arena::take(size_t bytes) {
 
 // byte offset of the int32 n_bases array behind the three [N][T] byte planes
 static size_t nb_offset(int N, int T) { return ((size_t)3 * N * T + 15) & ~size_t(15); }
+
+const b200_tensor& find_tensor(const b200_tensor* tensors, int n, const std::string& name) {
+    for (int i = 0; i < n; ++i) {
+        if (tensors[i].name && name == tensors[i].name) return tensors[i];
+    }
+    throw std::invalid_argument("missing weight tensor '" + name + "'");
+}
+
+__half* upload_f16(const std::vector<float>& v) {
+    std::vector<__half> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2half_rn(v[i]);
+    __half* d = nullptr;
+    B200_CUDA(cudaMalloc(&d, h.size() * sizeof(__half) + 16));
+    B200_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return d;
+}
+
+float* upload_f32(const std::vector<float>& v) {
+    float* d = nullptr;
+    B200_CUDA(cudaMalloc(&d, v.size() * sizeof(float) + 16));
+    B200_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+}
 
 float log_beam_cut_of(float beam_cut) {
     // beam_search.cpp:147-148
@@ -122,6 +146,9 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     m_d_beam = static_cast<uint2*>(m_arena.take(beam_b));
     m_d_out = static_cast<unsigned char*>(m_arena.take(m_out_bytes));
     engine.arena_bytes += (int64_t)m_arena.capacity();
+    B200_CUDA(cudaMemset(m_d_input, 0, in_bytes));
+    B200_CUDA(cudaMemset(m_d_ws, 0, ws_b));
+    m_plan = engine.model().make_plan(m_N, m_T_in, m_d_input, m_d_scores, m_d_ws, ws_b);
     for (auto& e : m_ev) B200_CUDA(cudaEventCreate(&e));
 }
 
@@ -154,8 +181,9 @@ void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
 }
 
 void Runner::run_forward(int n) {
-    m_engine.model().forward(m_d_input, n, m_T_in, m_d_scores, m_d_ws, m_engine.stream());
-    m_engine.gpu_launches += m_engine.model().launches_per_forward();
+    (void)n;  // the whole batch is computed; only the first n chunks are decoded and returned
+    m_plan->run(m_engine.stream());
+    m_engine.gpu_launches += m_plan->launches();
 }
 
 void Runner::run_decode(int n) {

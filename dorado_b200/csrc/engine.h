@@ -36,18 +36,33 @@ private:
     size_t m_cap = 0, m_off = 0;
 };
 
-// Network forward: fp16 signal [N][T_in] on device -> fp16 scores [N][T_out][outsize] on device.
+// Network forward for one fixed batch shape: fp16 signal [N][T_in] on device -> fp16 scores
+// [N][T_out][outsize] on device.  A plan owns its tensor maps and launch parameters (all pointers are
+// fixed slices of the runner's arena), so a forward is just a sequence of launches.  The whole batch
+// is always computed (slots beyond num_chunks hold stale data and are ignored, as in the reference).
+class ForwardPlan {
+public:
+    virtual ~ForwardPlan() = default;
+    virtual void run(cudaStream_t stream) = 0;
+    virtual int launches() const = 0;
+};
+
 class Model {
 public:
     virtual ~Model() = default;
     virtual size_t workspace_bytes(int N, int T_in) const = 0;
-    virtual void forward(const __half* signal, int N, int T_in, __half* scores, void* workspace,
-                         cudaStream_t stream) = 0;
-    virtual int launches_per_forward() const = 0;
+    virtual std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores,
+                                                   void* workspace, size_t workspace_bytes) = 0;
 };
 
 std::unique_ptr<Model> make_lstm_model(const b200_model_desc& desc, const b200_tensor* tensors, int n);
 std::unique_ptr<Model> make_tx_model(const b200_model_desc& desc, const b200_tensor* tensors, int n);
+
+// weight lookup helpers shared by the model builders
+const b200_tensor& find_tensor(const b200_tensor* tensors, int n, const std::string& name);
+// upload fp32 host data as fp16 / fp32 device arrays (freed with cudaFree by the owner)
+__half* upload_f16(const std::vector<float>& v);
+float* upload_f32(const std::vector<float>& v);
 
 class Engine {
 public:
@@ -104,6 +119,7 @@ private:
     __half* m_d_input = nullptr;
     __half* m_d_scores = nullptr;
     void* m_d_ws = nullptr;
+    std::unique_ptr<ForwardPlan> m_plan;
     float* m_d_bwd = nullptr;
     uint2* m_d_beam = nullptr;
     unsigned char* m_d_out = nullptr;

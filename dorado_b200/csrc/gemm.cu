@@ -1,6 +1,336 @@
+// tcgen05 GEMM for the dense layers of the basecaller (last conv as a strided GEMM, CRF linear, and every
+// transformer projection).  Successor of the reference's cuBLAS/Koi call sites:
+//   matmul_f16 (cublasGemmEx)      dorado/torch_utils/cuda_utils.cpp:386-403
+//   host_linear / cutlass conv     dorado/nn/ConvStack.cpp:257, dorado/nn/CRFModules.cpp:112
+//   koi_linear / koi_mm_swiglu     dorado/nn/TxModules.cpp:653-697
+//
+// One 128 x BN output tile per CTA.  Warp roles: warp 0 = TMA producer (A and W tiles, 128-byte swizzle,
+// 4-stage mbarrier ring), warp 1 = single-thread tcgen05.mma issuer (accumulator in TMEM), warps 2-5 =
+// epilogue (tcgen05.ld -> bias / activation / residual -> fp16 -> 16-byte global stores).
+// A is addressed through a 3-D tensor map (k, row, batch) so that overlapping-row views work: the last
+// conv of the LSTM models reads its im2col rows straight from the NTC activation buffer with row stride
+// = stride * C_in (the reference's "cutlass_conv" trick, ConvStack.cpp:236-275).
+#include "gemm.h"
+
+#include "common.cuh"
 #include "engine.h"
+
+#include <cstring>
+#include <vector>
+
 namespace b200 {
-void test_gemm_host(int, const uint16_t*, const uint16_t*, const float*, int, int, int, int, uint16_t*) {
-    throw Unsupported("gemm: not built yet");
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmKernelParams {
+    int rows_per_batch, tiles_per_batch, N, num_k_blocks, bn, act;
+    const float* bias;
+    __half* out;
+    long long out_m1, out_s0, out_s1;
+    const __half* residual;
+    float alpha;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    switch (act) {
+        case GEMM_ACT_SWISH: return v / (1.0f + __expf(-v));
+        case GEMM_ACT_SWISH_CLAMP: return fminf(v / (1.0f + __expf(-v)), 3.5f);
+        case GEMM_ACT_TANH: return 1.0f - 2.0f / (__expf(2.0f * v) + 1.0f);
+        case GEMM_ACT_TANH_X5: return 5.0f * (1.0f - 2.0f / (__expf(2.0f * v) + 1.0f));
+        default: return v;
+    }
 }
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                           const __grid_constant__ CUtensorMap tma_w,
+                                                                           const GemmKernelParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: stages x (A 16 KB | W bn*128 B), then barriers
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = BM * BK * 2;
+    const uint32_t w_bytes = (uint32_t)p.bn * BK * 2;
+    const uint32_t stage_bytes = a_bytes + w_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_a);
+        tc::prefetch_tmap(&tma_w);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, p.tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int batch = blockIdx.x / p.tiles_per_batch;
+    const int r0 = (blockIdx.x % p.tiles_per_batch) * BM;
+    const int n0 = blockIdx.y * p.bn;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
+                uint8_t* a_s = smem + s * stage_bytes;
+                tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
+                tc::tma_load_2d(a_s + a_bytes, &tma_w, &full[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            const uint32_t idesc = tc::umma_idesc_f16(BM, p.bn);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                tc::mbar_wait(&full[s], (kb / STAGES) & 1);
+                tc::tc_fence_after();
+                const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
+                const uint64_t adesc = tc::umma_desc_sw128(a_addr);
+                const uint64_t bdesc = tc::umma_desc_sw128(a_addr + a_bytes);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                    tc::umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                tc::umma_commit(&empty[s]);
+            }
+            tc::umma_commit(tmem_full);
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
+        const int lg = warp & 3;
+        const int row = r0 + lg * 32 + lane;
+        const bool valid = row < p.rows_per_batch;
+        const long long g = (long long)batch * p.rows_per_batch + row;
+        const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
+        const int n_out_total = p.act == GEMM_ACT_SWIGLU ? p.N / 2 : p.N;
+        tc::mbar_wait(tmem_full, 0);
+        tc::tc_fence_after();
+        for (int c = 0; c < p.bn / 32; ++c) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
+            tc::tmem_ld_wait();
+            const int nc = n0 + c * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                v[j] = __uint_as_float(r[j]);
+                if (p.bias) v[j] += __ldg(p.bias + nc + j);
+            }
+            if (p.act == GEMM_ACT_SWIGLU) {
+                if (valid) {
+                    __half2 h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float y0 = v[4 * j], g0 = v[4 * j + 1], y1 = v[4 * j + 2], g1 = v[4 * j + 3];
+                        h[j] = __floats2half2_rn(y0 * (g0 / (1.0f + __expf(-g0))), y1 * (g1 / (1.0f + __expf(-g1))));
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc / 2);
+                    dst[0] = *reinterpret_cast<uint4*>(&h[0]);
+                    dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+                }
+            } else {
+                if (p.residual && valid) {
+                    const uint4* res = reinterpret_cast<const uint4*>(p.residual + g * (long long)n_out_total + nc);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 rv = __ldg(res + q);
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(rh[j]);
+                            v[q * 8 + 2 * j] += p.alpha * f.x;
+                            v[q * 8 + 2 * j + 1] += p.alpha * f.y;
+                        }
+                    }
+                }
+                if (valid) {
+                    __half2 h[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        h[j] = __floats2half2_rn(act_apply(v[2 * j], p.act), act_apply(v[2 * j + 1], p.act));
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = *reinterpret_cast<uint4*>(&h[4 * q]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) throw CudaError("cuTensorMapEncodeTiled entry point not available");
+        fn = reinterpret_cast<EncodeFn>(p);
+    }
+    return fn;
+}
+
+CUtensorMap encode(const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    CUtensorMap m;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                                       strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    }
+    return m;
+}
+
+}  // namespace
+
+CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes, uint32_t box_inner,
+                         uint32_t box_outer) {
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {outer_stride_bytes};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const CUtensorMapSwizzle swz = box_inner * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : box_inner * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                         : CU_TENSOR_MAP_SWIZZLE_NONE;
+    return encode(base, 2, dims, strides, box, swz);
+}
+
+CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
+                         uint32_t b0, uint32_t b1, uint32_t b2) {
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+    const cuuint32_t box[3] = {b0, b1, b2};
+    const CUtensorMapSwizzle swz = b0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : b0 * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+    return encode(base, 3, dims, strides, box, swz);
+}
+
+static int pick_bn(int N) {
+    // largest tile width <= 256 that divides N and is a multiple of 32
+    for (int bn = 256; bn >= 32; bn -= 32) {
+        if (N % bn == 0) return bn;
+    }
+    return 0;
+}
+
+GemmPlan make_gemm_plan(const GemmDesc& d) {
+    if (d.K % BK != 0 || d.K <= 0) throw std::invalid_argument("gemm: K must be a positive multiple of 64");
+    if (d.N % 32 != 0) throw std::invalid_argument("gemm: N must be a multiple of 32");
+    if (d.batches < 1 || d.rows_per_batch < 1) throw std::invalid_argument("gemm: empty A");
+    if ((d.a_row_stride * 2) % 16 != 0 || (d.a_batch_stride * 2) % 16 != 0) {
+        throw std::invalid_argument("gemm: A strides must be multiples of 16 bytes");
+    }
+    GemmPlan p{};
+    p.d = d;
+    p.bn = pick_bn(d.N);
+    if (d.N / p.bn < 2 && d.N >= 128 && (long long)d.batches * ((d.rows_per_batch + BM - 1) / BM) < 96) {
+        p.bn = pick_bn(d.N / 2);  // few row tiles: split N further to fill more SMs
+    }
+    if (p.bn == 0) throw std::invalid_argument("gemm: no valid tile width");
+    if (d.act == GEMM_ACT_SWIGLU && (p.bn % 64) != 0) throw std::invalid_argument("gemm: swiglu needs BN % 64 == 0");
+    p.tiles_per_batch = (d.rows_per_batch + BM - 1) / BM;
+    p.grid = dim3((unsigned)(p.tiles_per_batch * d.batches), (unsigned)(d.N / p.bn), 1);
+    p.smem = (size_t)STAGES * (BM * BK * 2 + (size_t)p.bn * BK * 2) + 256 + 1024;
+    const uint64_t batch_stride = d.batches > 1 ? (uint64_t)d.a_batch_stride * 2 : (uint64_t)d.a_row_stride * 2 * d.rows_per_batch;
+    p.tma_a = make_tmap_3d(d.a, (uint64_t)(d.a_inner > 0 ? d.a_inner : d.K), (uint64_t)d.rows_per_batch, (uint64_t)d.batches, (uint64_t)d.a_row_stride * 2,
+                           batch_stride, BK, BM, 1);
+    p.tma_w = make_tmap_2d(d.w, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)d.K * 2, BK, (uint32_t)p.bn);
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    return p;
+}
+
+void run_gemm(const GemmPlan& p, cudaStream_t stream) {
+    GemmKernelParams k{};
+    k.rows_per_batch = p.d.rows_per_batch;
+    k.tiles_per_batch = p.tiles_per_batch;
+    k.N = p.d.N;
+    k.num_k_blocks = p.d.K / BK;
+    k.bn = p.bn;
+    k.act = p.d.act;
+    k.bias = p.d.bias;
+    k.out = p.d.out;
+    k.out_m1 = p.d.out_m1;
+    k.out_s0 = p.d.out_s0;
+    k.out_s1 = p.d.out_s1;
+    k.residual = p.d.residual;
+    k.alpha = p.d.alpha;
+    uint32_t cols = 32;
+    while ((int)cols < p.bn) cols <<= 1;
+    k.tmem_cols = cols;
+    gemm_f16_tcgen05_kernel<<<p.grid, GEMM_THREADS, p.smem, stream>>>(p.tma_a, p.tma_w, k);
+    B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hook: host buffers in, host buffer out
+// ------------------------------------------------------------------------------------------------
+void test_gemm_host(int device, const uint16_t* a, const uint16_t* b, const float* bias, int M, int N, int K, int activation,
+                    uint16_t* c) {
+    require_sm100(device);
+    const int Kp = (K + BK - 1) / BK * BK;
+    const int n_out = activation == GEMM_ACT_SWIGLU ? N / 2 : N;
+    Arena arena;
+    arena.reserve((size_t)M * Kp * 2 + (size_t)N * Kp * 2 + (size_t)N * 4 + (size_t)M * n_out * 2 + 4096);
+    auto* d_a = static_cast<__half*>(arena.take((size_t)M * Kp * 2));
+    auto* d_w = static_cast<__half*>(arena.take((size_t)N * Kp * 2));
+    auto* d_bias = static_cast<float*>(arena.take((size_t)N * 4));
+    auto* d_c = static_cast<__half*>(arena.take((size_t)M * n_out * 2));
+    B200_CUDA(cudaMemset(d_a, 0, (size_t)M * Kp * 2));
+    B200_CUDA(cudaMemset(d_w, 0, (size_t)N * Kp * 2));
+    B200_CUDA(cudaMemcpy2D(d_a, (size_t)Kp * 2, a, (size_t)K * 2, (size_t)K * 2, M, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy2D(d_w, (size_t)Kp * 2, b, (size_t)K * 2, (size_t)K * 2, N, cudaMemcpyHostToDevice));
+    if (bias) B200_CUDA(cudaMemcpy(d_bias, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+    GemmDesc d{};
+    d.a = d_a;
+    d.batches = 1;
+    d.rows_per_batch = M;
+    d.a_row_stride = Kp;
+    d.a_batch_stride = (int64_t)M * Kp;
+    d.w = d_w;
+    d.N = N;
+    d.K = Kp;
+    d.bias = bias ? d_bias : nullptr;
+    d.act = activation;
+    d.out = d_c;
+    d.out_m1 = 1;
+    d.out_s0 = n_out;
+    d.out_s1 = 0;
+    const GemmPlan plan = make_gemm_plan(d);
+    run_gemm(plan, nullptr);
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(c, d_c, (size_t)M * n_out * 2, cudaMemcpyDeviceToHost));
+}
+
 }  // namespace b200

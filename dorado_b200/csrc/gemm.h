@@ -1,0 +1,54 @@
+// tcgen05 GEMM with fused epilogue:  out[row(g)][n] = act( sum_k A[g][k] * W[n][k] + bias[n] ), fp16 in/out,
+// fp32 accumulation in TMEM.  See gemm.cu.
+#pragma once
+
+#include "tc.cuh"
+
+namespace b200 {
+
+enum GemmAct : int {
+    GEMM_ACT_NONE = -1,
+    GEMM_ACT_SWISH = 0,        // config::Activation::SWISH
+    GEMM_ACT_SWISH_CLAMP = 1,  // SWISH_CLAMP (3.5)
+    GEMM_ACT_TANH = 2,         // TANH
+    GEMM_ACT_TANH_X5 = 3,      // tanh(x) * 5 (pre-v4.x CRF linear, dorado/nn/CRFModules.cpp:27-31)
+    GEMM_ACT_SWIGLU = 4,       // columns (2j, 2j+1) = (y, gate) -> silu(gate) * y, N/2 outputs (TxModules.cpp:170-176)
+};
+
+struct GemmDesc {
+    // A: logical [batches][rows_per_batch][K] fp16, K contiguous; row/batch strides in elements
+    const __half* a = nullptr;
+    int batches = 1;
+    int rows_per_batch = 0;
+    int64_t a_row_stride = 0;
+    int64_t a_batch_stride = 0;
+    // W: [N][K] fp16 (K contiguous, row stride = K_pad)
+    const __half* w = nullptr;
+    int N = 0;
+    int K = 0;  // multiple of 64 (pad weights with zeros)
+    int a_inner = 0;  // extent of A's K dimension in the tensor map (0 = K); elements beyond read as zero
+    const float* bias = nullptr;
+    int act = GEMM_ACT_NONE;
+    // output: global row g = batch * rows_per_batch + row  ->  out + (g / out_m1) * out_s0 + (g % out_m1) * out_s1
+    __half* out = nullptr;
+    int64_t out_m1 = 1;
+    int64_t out_s0 = 0;
+    int64_t out_s1 = 0;
+    // optional fused residual epilogue (deepnorm): v = v + alpha * residual[g][n]; requires act == NONE
+    const __half* residual = nullptr;
+    float alpha = 0.0f;
+};
+
+struct GemmPlan {
+    CUtensorMap tma_a, tma_w;
+    GemmDesc d;
+    int bn = 128;
+    int tiles_per_batch = 0;
+    dim3 grid;
+    size_t smem = 0;
+};
+
+GemmPlan make_gemm_plan(const GemmDesc& d);
+void run_gemm(const GemmPlan& p, cudaStream_t stream);
+
+}  // namespace b200

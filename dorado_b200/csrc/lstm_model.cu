@@ -1,6 +1,655 @@
+// Conv -> LSTM -> linear CRF forward (fast / hac models) for sm_100a.
+//
+// Replaces, for the CUDA path of dorado/basecall/model/CRFModel.cpp:69-115:
+//   ConvStack layers 1,2   host_convolution_f16              dorado/nn/ConvStack.cpp:216-232
+//   ConvStack layer 3      host_linear "cutlass conv"        dorado/nn/ConvStack.cpp:236-275  -> gemm.cu
+//   LSTMStack              host_cutlass_lstm/host_small_lstm dorado/nn/LSTMStack.cpp:127-238 -> lstm_layer_kernel
+//   LinearCRF              host_linear                       dorado/nn/CRFModules.cpp:49-122   -> gemm.cu
+// Semantics are those of the CPU modules (ConvStack.cpp:146-163, LSTMStack.cpp:29-41, CRFModules.cpp:24-34).
+//
+// Activation layouts in HBM (fp16):
+//   signal  [N][T_in]
+//   x2      [N][T_in + 2*pad3 + 8][16]      conv2 output, NTC, zero rows = conv3's padding (+ K padding)
+//   seq     [T_out][N][C]                   time-major LSTM buffer, updated in place by every layer
+//   scores  [N][T_out][outsize]
 #include "engine.h"
+#include "gemm.h"
+#include "tc.cuh"
+
+#include <cstring>
+#include <vector>
+
 namespace b200 {
-std::unique_ptr<Model> make_lstm_model(const b200_model_desc&, const b200_tensor*, int) {
-    throw Unsupported("LSTM model forward: not built yet");
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// conv1 (1 -> C1, w1) + conv2 (C1 -> 16, w2), both stride 1, fused; fp32 math, fp16 NTC output.
+// ------------------------------------------------------------------------------------------------
+constexpr int CONV_TT = 256;  // output samples per CTA
+constexpr int MAXW = 9;
+
+struct Conv12Params {
+    const __half* x;  // [N][T]
+    __half* out;      // [N][T_pad][16], row r <-> sample r - front_pad
+    const float* w;   // packed: w1 [c1][w1] | b1 [16] | w2 [k][ci][co] (16x16 per tap) | b2 [16]
+    int N, T, T_pad, front_pad;
+    int c1, w1, w2, act1, act2;
+};
+
+constexpr int CONV_W_FLOATS = 16 * MAXW + 16 + MAXW * 16 * 16 + 16;
+
+__device__ __forceinline__ float conv_act(float v, int act) {
+    switch (act) {
+        case B200_ACT_SWISH: return v / (1.0f + __expf(-v));
+        case B200_ACT_SWISH_CLAMP: return fminf(v / (1.0f + __expf(-v)), 3.5f);
+        default: return 1.0f - 2.0f / (__expf(2.0f * v) + 1.0f);
+    }
 }
+
+__global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
+    const int n = blockIdx.y;
+    const int t0 = blockIdx.x * CONV_TT;
+    const int p1 = p.w1 / 2, p2 = p.w2 / 2;
+    constexpr int Y1P = CONV_TT + 2 * MAXW;  // channel-major pitch: consecutive threads -> consecutive banks
+    __shared__ float xs[CONV_TT + 4 * MAXW];
+    __shared__ float y1[16 * Y1P];
+    __shared__ __align__(16) float ws[CONV_W_FLOATS];
+    const float* s_w1 = ws;
+    const float* s_b1 = ws + 16 * MAXW;
+    const float* s_w2 = s_b1 + 16;
+    const float* s_b2 = s_w2 + MAXW * 16 * 16;
+    for (int i = threadIdx.x; i < CONV_W_FLOATS; i += CONV_TT) ws[i] = __ldg(p.w + i);
+    const int nx = CONV_TT + 2 * (p1 + p2);
+    for (int i = threadIdx.x; i < nx; i += CONV_TT) {
+        const int t = t0 - p1 - p2 + i;
+        xs[i] = (t >= 0 && t < p.T) ? __half2float(p.x[(size_t)n * p.T + t]) : 0.0f;
+    }
+    __syncthreads();
+    const int n1 = CONV_TT + 2 * p2;
+    for (int i = threadIdx.x; i < n1; i += CONV_TT) {
+        const int t = t0 - p2 + i;  // conv1 output position
+        const bool inside = t >= 0 && t < p.T;
+        for (int c = 0; c < p.c1; ++c) {
+            float acc = s_b1[c];
+            for (int k = 0; k < p.w1; ++k) acc += s_w1[c * p.w1 + k] * xs[i + k];
+            y1[c * Y1P + i] = inside ? conv_act(acc, p.act1) : 0.0f;  // conv2 zero-pads conv1's *output*
+        }
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t < p.T) {
+        float acc[16];
+#pragma unroll
+        for (int co = 0; co < 16; ++co) acc[co] = s_b2[co];
+        for (int k = 0; k < p.w2; ++k) {
+            for (int ci = 0; ci < p.c1; ++ci) {
+                const float v = y1[ci * Y1P + threadIdx.x + k];
+                const float4* w = reinterpret_cast<const float4*>(&s_w2[(k * 16 + ci) * 16]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = w[q];
+                    acc[4 * q + 0] += v * wv.x;
+                    acc[4 * q + 1] += v * wv.y;
+                    acc[4 * q + 2] += v * wv.z;
+                    acc[4 * q + 3] += v * wv.w;
+                }
+            }
+        }
+        __half2 h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(conv_act(acc[2 * j], p.act2), conv_act(acc[2 * j + 1], p.act2));
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T_pad + p.front_pad + t) * 16);
+        dst[0] = *reinterpret_cast<uint4*>(&h[0]);
+        dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM layer: all T steps of one layer in one persistent launch.
+//
+// Orientation is "weights as the M operand": per step, for each tile m of 32 hidden units,
+//     D_m[128 gate rows][NB chunks] = Wp_m[128][2C] * Z_t[NB][2C]^T ,  Z_t = [x_t ; h_{t-1}]
+// where the 128 rows of Wp_m are (i | f | g | o) x 32 units, so one epilogue warp handles one gate type and
+// a CTA owns NB chunks for the whole sequence (no inter-CTA traffic).  MMA operands live in shared memory as
+// K-major tiles of 32 fp16 (64-byte swizzle): weights are TMA-loaded (resident when they fit, else streamed
+// from L2 every step through a ring), x_t arrives by TMA, h_t is written by the epilogue.
+// Accumulators are double-buffered in TMEM so the epilogue of tile m overlaps the MMAs of tile m+1.
+// ------------------------------------------------------------------------------------------------
+constexpr int LSTM_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int KBLK = 32;           // K elements per smem block (64 B rows, SWIZZLE_64B)
+constexpr int WBLK_BYTES = 128 * KBLK * 2;
+
+struct LstmParams {
+    __half* seq;        // [T][N][C] in place
+    const float* bias;  // [4C] permuted like the weight rows (b_ih + b_hh)
+    int T, N, C, reverse;
+    int nb;         // chunks per CTA (16 or 32)
+    int w_stages;   // 0 => weights resident
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    // K-major, rows of 64 B, 8-row groups 512 B apart, SWIZZLE_64B (layout type 4)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
+    // byte offset of fp16 element (row, col<32) in a [rows x 32] SWIZZLE_64B tile
+    return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3))) << 4) + ((col & 7) << 1));
+}
+
+__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_f(float v) { return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f); }
+
+template <int NB>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_kernel(const __grid_constant__ CUtensorMap tma_x,
+                                                                    const __grid_constant__ CUtensorMap tma_w,
+                                                                    const LstmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int C = p.C;
+    const int MT = C / 32;        // gate tiles per step
+    const int KB = 2 * C / KBLK;  // K blocks per tile
+    const int KBX = C / KBLK;     // of which x
+    const bool resident = p.w_stages == 0;
+    const int w_blocks = resident ? MT * KB : p.w_stages;
+    constexpr int ZBLK = NB * KBLK * 2;  // bytes of one Z block
+    uint8_t* w_s = smem;
+    uint8_t* z_s = w_s + (size_t)w_blocks * WBLK_BYTES;  // [2][KB][ZBLK]
+    float* g_s = reinterpret_cast<float*>(z_s + (size_t)2 * KB * ZBLK);  // [4][NB][32]
+    float* c_s = g_s + 4 * NB * 32;                                       // [MT][NB][32] cell state
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c_s + (size_t)MT * NB * 32);
+    uint64_t* x_full = bars;            // [2]
+    uint64_t* z_free = bars + 2;        // [2]
+    uint64_t* h_ready = bars + 4;       // [2]
+    uint64_t* acc_full = bars + 6;      // [2]
+    uint64_t* acc_empty = bars + 8;     // [2]
+    uint64_t* w_full = bars + 10;       // [w_stages] or [1]
+    uint64_t* w_empty = w_full + (resident ? 1 : p.w_stages);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_empty + (resident ? 1 : p.w_stages));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * NB;
+    constexpr uint32_t TMEM_COLS = 2 * NB < 32 ? 32 : 2 * NB;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&x_full[i], 1);
+            tc::mbar_init(&z_free[i], 1);
+            tc::mbar_init(&h_ready[i], 128);
+            tc::mbar_init(&acc_full[i], 1);
+            tc::mbar_init(&acc_empty[i], 128);
+        }
+        const int nwb = resident ? 1 : p.w_stages;
+        for (int i = 0; i < nwb; ++i) {
+            tc::mbar_init(&w_full[i], 1);
+            tc::mbar_init(&w_empty[i], 1);
+        }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_x);
+        tc::prefetch_tmap(&tma_w);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (tc::elect_one()) {
+            if (resident) {
+                tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)(MT * KB * WBLK_BYTES));
+                for (int m = 0; m < MT; ++m) {
+                    for (int kb = 0; kb < KB; ++kb) {
+                        tc::tma_load_2d(w_s + (size_t)(m * KB + kb) * WBLK_BYTES, &tma_w, &w_full[0], kb * KBLK, m * 128);
+                    }
+                }
+            }
+            long long wj = 0;  // streamed weight block counter
+            for (int s = 0; s < p.T; ++s) {
+                const int t = p.reverse ? p.T - 1 - s : s;
+                const int buf = s & 1;
+                tc::mbar_wait(&z_free[buf], ((s >> 1) & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&x_full[buf], (uint32_t)(KBX * ZBLK));
+                for (int kb = 0; kb < KBX; ++kb) {
+                    tc::tma_load_2d(z_s + (size_t)(buf * KB + kb) * ZBLK, &tma_x, &x_full[buf], kb * KBLK, t * p.N + n0);
+                }
+                if (!resident) {
+                    for (int m = 0; m < MT; ++m) {
+                        for (int kb = 0; kb < KB; ++kb, ++wj) {
+                            const int st = (int)(wj % p.w_stages);
+                            tc::mbar_wait(&w_empty[st], (uint32_t)(((wj / p.w_stages) & 1) ^ 1));
+                            tc::mbar_arrive_expect_tx(&w_full[st], WBLK_BYTES);
+                            tc::tma_load_2d(w_s + (size_t)st * WBLK_BYTES, &tma_w, &w_full[st], kb * KBLK, m * 128);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (tc::elect_one()) {
+            const uint32_t idesc = tc::umma_idesc_f16(128, NB);
+            if (resident) {
+                tc::mbar_wait(&w_full[0], 0);
+            }
+            long long wj = 0, j = 0;  // weight block counter, tile counter
+            for (int s = 0; s < p.T; ++s) {
+                const int buf = s & 1;
+                tc::mbar_wait(&x_full[buf], (s >> 1) & 1);
+                tc::mbar_wait(&h_ready[buf], (s >> 1) & 1);
+                tc::tc_fence_after();
+                const uint32_t z_addr = tc::smem_u32(z_s + (size_t)buf * KB * ZBLK);
+                for (int m = 0; m < MT; ++m, ++j) {
+                    const int ab = (int)(j & 1);
+                    tc::mbar_wait(&acc_empty[ab], (uint32_t)(((j >> 1) & 1) ^ 1));
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ab * NB);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        uint32_t w_addr;
+                        int st = 0;
+                        if (resident) {
+                            w_addr = tc::smem_u32(w_s + (size_t)(m * KB + kb) * WBLK_BYTES);
+                        } else {
+                            st = (int)(wj % p.w_stages);
+                            tc::mbar_wait(&w_full[st], (uint32_t)((wj / p.w_stages) & 1));
+                            tc::tc_fence_after();
+                            w_addr = tc::smem_u32(w_s + (size_t)st * WBLK_BYTES);
+                            ++wj;
+                        }
+                        const uint64_t adesc = umma_desc_sw64(w_addr);
+                        const uint64_t bdesc = umma_desc_sw64(z_addr + (uint32_t)(kb * ZBLK));
+                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                        tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                        if (!resident) tc::umma_commit(&w_empty[st]);
+                    }
+                    tc::umma_commit(&acc_full[ab]);
+                }
+                tc::umma_commit(&z_free[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue: gates, cell update, h_t ----------------
+        const int ew = warp - 2;      // 0..3
+        const int gate = warp & 3;    // TMEM lane quarter this warp may read == gate type (i,f,g,o)
+        const int tid = ew * 32 + lane;
+        // cell-update role: unit = lane, chunks n = ew, ew + 4, ...
+        constexpr int CPT = NB / 4;
+        for (int i = tid; i < MT * NB * 32; i += 128) c_s[i] = 0.0f;
+        // h_{-1} = 0 in Z[0]'s h blocks
+        for (int i = tid; i < KBX * ZBLK / 16; i += 128) {
+            reinterpret_cast<uint4*>(z_s + (size_t)KBX * ZBLK)[i] = make_uint4(0, 0, 0, 0);
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&h_ready[0]);
+
+        long long j = 0;
+        for (int s = 0; s < p.T; ++s) {
+            const int t = p.reverse ? p.T - 1 - s : s;
+            const int nbuf = (s + 1) & 1;
+            uint8_t* zh_next = z_s + (size_t)(nbuf * KB + KBX) * ZBLK;
+            __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
+#pragma unroll 1
+            for (int m = 0; m < MT; ++m, ++j) {
+                const int ab = (int)(j & 1);
+                tc::mbar_wait(&acc_full[ab], (uint32_t)((j >> 1) & 1));
+                tc::tc_fence_after();
+                uint32_t r[NB];
+                const uint32_t taddr = tmem_base + ((uint32_t)(gate * 32) << 16) + (uint32_t)(ab * NB);
+                if constexpr (NB == 16) {
+                    tc::tmem_ld_32x16(taddr, r);
+                } else {
+                    tc::tmem_ld_32x32(taddr, r);
+                }
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                tc::mbar_arrive(&acc_empty[ab]);
+                const float b = __ldg(p.bias + m * 128 + gate * 32 + lane);
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    const float v = __uint_as_float(r[n]) + b;
+                    g_s[(gate * NB + n) * 32 + lane] = gate == 2 ? tanh_f(v) : sigmoid_f(v);
+                }
+                named_bar_sync(1, 128);
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    const int n = ew + 4 * i;
+                    const float ig = g_s[(0 * NB + n) * 32 + lane];
+                    const float fg = g_s[(1 * NB + n) * 32 + lane];
+                    const float gg = g_s[(2 * NB + n) * 32 + lane];
+                    const float og = g_s[(3 * NB + n) * 32 + lane];
+                    float* cp = &c_s[((size_t)m * NB + n) * 32 + lane];  // owned by this thread for all steps
+                    const float cs = fg * (*cp) + ig * gg;
+                    *cp = cs;
+                    const __half h = __float2half_rn(og * tanh_f(cs));
+                    *reinterpret_cast<__half*>(zh_next + (size_t)m * ZBLK + sw64_offset(n, lane)) = h;
+                    if (n0 + n < p.N) y_t[(size_t)n * C + m * 32 + lane] = h;
+                }
+                named_bar_sync(1, 128);  // g_s reuse
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&h_ready[nbuf]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct LstmLayerWeights {
+    __half* w = nullptr;   // [4C][2C] permuted rows, [W_ih | W_hh]
+    float* bias = nullptr; // [4C] permuted
+};
+
+class LstmModel;
+
+class LstmPlan final : public ForwardPlan {
+public:
+    void run(cudaStream_t stream) override;
+    int launches() const override { return 1 + 1 + num_layers + num_linear; }
+
+    Conv12Params conv12{};
+    dim3 conv12_grid;
+    GemmPlan conv3;
+    std::vector<CUtensorMap> lstm_x, lstm_w;
+    std::vector<LstmParams> lstm_p;
+    int lstm_grid = 0, lstm_nb = 16;
+    size_t lstm_smem = 0;
+    GemmPlan linear1, linear2;
+    int num_layers = 0, num_linear = 1;
+    const LstmModel* model = nullptr;
+};
+
+class LstmModel final : public Model {
+public:
+    LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n);
+    ~LstmModel() override;
+    size_t workspace_bytes(int N, int T_in) const override;
+    std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
+                                           size_t ws_bytes) override;
+
+    b200_model_desc desc;
+    float* conv_w = nullptr;  // packed conv1 / conv2 weights (see Conv12Params::w)
+    __half* w3 = nullptr;               // [C][K3p]
+    float* b3 = nullptr;
+    int K3 = 0, K3p = 0;
+    std::vector<LstmLayerWeights> layers;
+    __half* wl1 = nullptr;  // [out1][Cp]
+    float* bl1 = nullptr;
+    __half* wl2 = nullptr;  // decomposition: [outsize][out_features_p]
+    int Cp = 0, out1 = 0, out1p = 0;
+
+private:
+    int pad3() const { return desc.convs[2].winlen / 2; }
+    int t_pad(int T_in) const { return T_in + 2 * pad3() + 8; }
+    int n_pad(int N) const { return (N + 15) / 16 * 16; }
+};
+
+LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : desc(d) {
+    if (d.num_convs != 3) throw std::invalid_argument("Expected 3 convolution layers but found: " + std::to_string(d.num_convs));
+    const auto &c1 = d.convs[0], &c2 = d.convs[1], &c3 = d.convs[2];
+    if (c1.insize != 1 || c1.stride != 1 || c2.stride != 1 || c2.size != 16 || c1.size > 16 || c1.winlen > MAXW ||
+        c2.winlen > MAXW || c2.insize != c1.size || c3.insize != 16) {
+        throw Unsupported("conv stack shape outside what conv12_kernel implements");
+    }
+    const int C = d.lstm_size;
+    if (C != c3.size || C % 32 != 0 || C > 384) throw Unsupported("lstm_size must be a multiple of 32, <= 384");
+    if (d.lstm_layers < 1 || d.lstm_layers > 8) throw std::invalid_argument("bad lstm_layers");
+
+    // conv1: torch [c1][1][w] -> [c1][w]; conv2: torch [co][ci][k] -> [k][ci][co]
+    {
+        const auto& tw = find_tensor(tensors, n, "0.conv.weight.tensor");
+        const auto& tb = find_tensor(tensors, n, "0.conv.bias.tensor");
+        const auto& tw2 = find_tensor(tensors, n, "1.conv.weight.tensor");
+        const auto& tb2 = find_tensor(tensors, n, "1.conv.bias.tensor");
+        std::vector<float> pk(CONV_W_FLOATS, 0.0f);
+        float* w1 = pk.data();
+        float* b1 = w1 + 16 * MAXW;
+        float* w2 = b1 + 16;
+        float* b2 = w2 + MAXW * 16 * 16;
+        std::memcpy(w1, tw.data, sizeof(float) * (size_t)c1.size * c1.winlen);
+        std::memcpy(b1, tb.data, sizeof(float) * c1.size);
+        for (int co = 0; co < 16; ++co)
+            for (int ci = 0; ci < c2.insize; ++ci)
+                for (int k = 0; k < c2.winlen; ++k)
+                    w2[((size_t)k * 16 + ci) * 16 + co] = tw2.data[((size_t)co * c2.insize + ci) * c2.winlen + k];
+        std::memcpy(b2, tb2.data, sizeof(float) * 16);
+        conv_w = upload_f32(pk);
+    }
+    // conv3 as GEMM weights: [C][k*16 + ci], K padded to a multiple of 64
+    {
+        const auto& tw = find_tensor(tensors, n, "2.conv.weight.tensor");
+        const auto& tb = find_tensor(tensors, n, "2.conv.bias.tensor");
+        K3 = c3.winlen * 16;
+        K3p = (K3 + 63) / 64 * 64;
+        std::vector<float> w((size_t)C * K3p, 0.0f);
+        for (int co = 0; co < C; ++co)
+            for (int ci = 0; ci < 16; ++ci)
+                for (int k = 0; k < c3.winlen; ++k)
+                    w[(size_t)co * K3p + k * 16 + ci] = tw.data[((size_t)co * 16 + ci) * c3.winlen + k];
+        w3 = upload_f16(w);
+        b3 = upload_f32(std::vector<float>(tb.data, tb.data + C));
+    }
+    // LSTM layers: permute gate rows into tiles of (i|f|g|o) x 32 units, concatenate [W_ih | W_hh]
+    for (int l = 0; l < d.lstm_layers; ++l) {
+        const std::string pfx = std::to_string(d.num_convs + l + 1) + ".rnn.";
+        const auto& wih = find_tensor(tensors, n, pfx + "weight_ih_l0.tensor");
+        const auto& whh = find_tensor(tensors, n, pfx + "weight_hh_l0.tensor");
+        const auto& bih = find_tensor(tensors, n, pfx + "bias_ih_l0.tensor");
+        const auto& bhh = find_tensor(tensors, n, pfx + "bias_hh_l0.tensor");
+        std::vector<float> w((size_t)4 * C * 2 * C), b((size_t)4 * C);
+        for (int m = 0; m < C / 32; ++m)
+            for (int g = 0; g < 4; ++g)
+                for (int u = 0; u < 32; ++u) {
+                    const int dst = m * 128 + g * 32 + u;
+                    const int src = g * C + m * 32 + u;
+                    std::memcpy(&w[(size_t)dst * 2 * C], &wih.data[(size_t)src * C], sizeof(float) * C);
+                    std::memcpy(&w[(size_t)dst * 2 * C + C], &whh.data[(size_t)src * C], sizeof(float) * C);
+                    b[dst] = bih.data[src] + bhh.data[src];
+                }
+        LstmLayerWeights lw;
+        lw.w = upload_f16(w);
+        lw.bias = upload_f32(b);
+        layers.push_back(lw);
+    }
+    // linear(s)
+    {
+        const int layer = d.num_convs + d.lstm_layers + 1;
+        const auto& tw = find_tensor(tensors, n, std::to_string(layer) + ".linear.weight.tensor");
+        out1 = d.out_features > 0 ? d.out_features : d.outsize;
+        Cp = (C + 63) / 64 * 64;
+        std::vector<float> w((size_t)out1 * Cp, 0.0f);
+        for (int o = 0; o < out1; ++o) std::memcpy(&w[(size_t)o * Cp], &tw.data[(size_t)o * C], sizeof(float) * C);
+        wl1 = upload_f16(w);
+        if (d.linear_bias || (d.out_features == 0 && false)) {
+            const auto& tb = find_tensor(tensors, n, std::to_string(layer) + ".linear.bias.tensor");
+            bl1 = upload_f32(std::vector<float>(tb.data, tb.data + out1));
+        }
+        if (d.out_features > 0) {
+            if (out1 % 64 != 0) throw Unsupported("out_features must be a multiple of 64");
+            const auto& tw2 = find_tensor(tensors, n, std::to_string(layer + 1) + ".linear.weight.tensor");
+            wl2 = upload_f16(std::vector<float>(tw2.data, tw2.data + (size_t)d.outsize * out1));
+        }
+    }
+}
+
+LstmModel::~LstmModel() {
+    cudaFree(conv_w);
+    cudaFree(w3);
+    cudaFree(b3);
+    for (auto& l : layers) {
+        cudaFree(l.w);
+        cudaFree(l.bias);
+    }
+    cudaFree(wl1);
+    cudaFree(bl1);
+    cudaFree(wl2);
+}
+
+size_t LstmModel::workspace_bytes(int N, int T_in) const {
+    const int T_out = T_in / desc.stride;
+    const size_t x2 = (size_t)N * t_pad(T_in) * 16 * 2 + 4096;
+    const size_t seq = (size_t)(T_out + 1) * n_pad(N) * desc.lstm_size * 2 + 4096;
+    const size_t mid = desc.out_features > 0 ? (size_t)T_out * n_pad(N) * desc.out_features * 2 + 4096 : 0;
+    return x2 + seq + mid;
+}
+
+std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
+                                                  size_t ws_bytes) {
+    const int C = desc.lstm_size;
+    const int T_out = T_in / desc.stride;
+    const int Np = n_pad(N);
+    if (Np != N) {
+        // the reference's tensor-core LSTM has the same kind of constraint (multiples of 64, CudaCaller.h:60-63)
+        throw std::invalid_argument("batch_size must be a multiple of 16 for LSTM models");
+    }
+    auto plan = std::make_unique<LstmPlan>();
+    plan->model = this;
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base;
+        base += (bytes + 255) & ~size_t(255);
+        if ((size_t)(base - static_cast<uint8_t*>(ws)) > ws_bytes) throw std::logic_error("LSTM workspace overflow");
+        return p;
+    };
+    const int Tp = t_pad(T_in);
+    __half* x2 = reinterpret_cast<__half*>(take((size_t)N * Tp * 16 * 2));
+    __half* seq = reinterpret_cast<__half*>(take((size_t)(T_out + 1) * Np * C * 2));
+    __half* mid = desc.out_features > 0 ? reinterpret_cast<__half*>(take((size_t)T_out * Np * desc.out_features * 2)) : nullptr;
+
+    // conv1 + conv2
+    plan->conv12 = Conv12Params{signal, x2, conv_w, N, T_in, Tp, pad3(), desc.convs[0].size, desc.convs[0].winlen,
+                                desc.convs[1].winlen, desc.convs[0].activation, desc.convs[1].activation};
+    plan->conv12_grid = dim3((T_in + CONV_TT - 1) / CONV_TT, N, 1);
+
+    // conv3: rows (n, t) read K3p contiguous halfs starting at x2[n][stride * t]
+    {
+        if (T_in % desc.stride != 0) throw std::invalid_argument("chunk size must be a multiple of the model stride");
+        GemmDesc g{};
+        g.a = x2;
+        g.batches = N;
+        g.rows_per_batch = T_out;
+        g.a_row_stride = (int64_t)desc.convs[2].stride * 16;
+        g.a_batch_stride = (int64_t)Tp * 16;
+        g.w = w3;
+        g.N = C;
+        g.K = K3p;
+        g.bias = b3;
+        g.act = desc.convs[2].activation;
+        g.out = seq;
+        g.out_m1 = T_out;        // g = n * T_out + t
+        g.out_s0 = C;            // n
+        g.out_s1 = (int64_t)Np * C;  // t
+        plan->conv3 = make_gemm_plan(g);
+    }
+    // LSTM layers
+    {
+        plan->num_layers = desc.lstm_layers;
+        const int nb = 16;
+        plan->lstm_nb = nb;
+        plan->lstm_grid = Np / nb;
+        const size_t w_bytes = (size_t)4 * C * 2 * C * 2;
+        const bool resident = w_bytes <= 150 * 1024;
+        const int KB = 2 * C / KBLK;
+        const int w_stages = resident ? 0 : 12;
+        const size_t wsm = resident ? w_bytes : (size_t)w_stages * WBLK_BYTES;
+        plan->lstm_smem = 1024 + wsm + (size_t)2 * KB * nb * KBLK * 2 + (size_t)4 * nb * 32 * 4 + (size_t)(C / 32) * nb * 32 * 4 +
+                          8 * (10 + 2 * 16) + 64;
+        for (int l = 0; l < desc.lstm_layers; ++l) {
+            plan->lstm_x.push_back(make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, KBLK, nb));
+            plan->lstm_w.push_back(make_tmap_2d(layers[l].w, (uint64_t)2 * C, (uint64_t)4 * C, (uint64_t)2 * C * 2, KBLK, 128));
+            LstmParams lp{};
+            lp.seq = seq;
+            lp.bias = layers[l].bias;
+            lp.T = T_out;
+            lp.N = Np;
+            lp.C = C;
+            lp.reverse = (l % 2 == 0) ? 1 : 0;  // reverse_first = true (CRFModel.cpp:40, LSTMStack.cpp:31-41)
+            lp.nb = nb;
+            lp.w_stages = w_stages;
+            plan->lstm_p.push_back(lp);
+        }
+        static bool attr = false;
+        if (!attr) {
+            B200_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        if (plan->lstm_smem > 227 * 1024) throw Unsupported("LSTM shared-memory plan does not fit");
+    }
+    // linear CRF (+ optional decomposition); rows g = t * Np + n  ->  scores[n][t][:]
+    {
+        GemmDesc g{};
+        g.a = seq;
+        g.batches = 1;
+        g.rows_per_batch = T_out * Np;
+        g.a_row_stride = C;
+        g.a_batch_stride = (int64_t)T_out * Np * C;
+        g.w = wl1;
+        g.N = out1;
+        g.K = Cp;
+        g.a_inner = C;
+        g.bias = bl1;
+        if (desc.out_features > 0) {
+            g.act = GEMM_ACT_NONE;
+            g.out = mid;
+            g.out_m1 = 1;
+            g.out_s0 = out1;
+            g.out_s1 = 0;
+            plan->linear1 = make_gemm_plan(g);
+            GemmDesc g2{};
+            g2.a = mid;
+            g2.batches = 1;
+            g2.rows_per_batch = T_out * Np;
+            g2.a_row_stride = out1;
+            g2.a_batch_stride = (int64_t)T_out * Np * out1;
+            g2.w = wl2;
+            g2.N = desc.outsize;
+            g2.K = out1;
+            g2.act = desc.crf_scale == 5.0f ? GEMM_ACT_TANH_X5 : GEMM_ACT_NONE;
+            g2.out = scores;
+            g2.out_m1 = Np;
+            g2.out_s0 = desc.outsize;
+            g2.out_s1 = (int64_t)T_out * desc.outsize;
+            plan->linear2 = make_gemm_plan(g2);
+            plan->num_linear = 2;
+        } else {
+            g.act = desc.crf_scale == 5.0f ? GEMM_ACT_TANH_X5 : GEMM_ACT_NONE;
+            g.out = scores;
+            g.out_m1 = Np;                                  // g = t * Np + n
+            g.out_s0 = desc.outsize;                        // t
+            g.out_s1 = (int64_t)T_out * desc.outsize;       // n
+            plan->linear1 = make_gemm_plan(g);
+            plan->num_linear = 1;
+        }
+    }
+    return plan;
+}
+
+void LstmPlan::run(cudaStream_t stream) {
+    conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
+    run_gemm(conv3, stream);
+    for (int l = 0; l < num_layers; ++l) {
+        lstm_layer_kernel<16><<<lstm_grid, LSTM_THREADS, lstm_smem, stream>>>(lstm_x[l], lstm_w[l], lstm_p[l]);
+    }
+    run_gemm(linear1, stream);
+    if (num_linear == 2) run_gemm(linear2, stream);
+    B200_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+std::unique_ptr<Model> make_lstm_model(const b200_model_desc& desc, const b200_tensor* tensors, int n) {
+    return std::make_unique<LstmModel>(desc, tensors, n);
+}
+
 }  // namespace b200

@@ -1,0 +1,90 @@
+"""GPU parity of the network forward + the whole call_chunks path through the C ABI.
+
+Scores: engine fp16 scores vs the fp32 numpy oracle (oracle/nn_oracle.py, itself pinned against the compiled
+reference in tests/test_oracle_vs_reference.py).  north_star tolerance: 1e-3 relative for fp16 scores; scores
+live in [-5, 5] so the check is |d| <= 1e-3 * max|ref| (= 5e-3 absolute at the clamp) for >= 99.9 % of
+elements and 4x that for every element (fp16 activations between layers: ulp(1.0) = 9.8e-4).
+Decode: the engine's sequence / qstring / moves must be bit-identical to the CPU oracle decoding the engine's
+own fp16 scores.
+"""
+import numpy as np
+import pytest
+
+from conftest import model_dir
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(kind, N, T, seed=1234):
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir(kind))
+    w = synthetic_weights(cfg, 42)
+    caller = B200Caller(cfg, w)
+    runner = B200ModelRunner(caller, N, T)
+    rng = np.random.default_rng(seed)
+    sig = rng.standard_normal((N, runner.chunk_size())).astype(np.float16)
+    for i in range(N):
+        runner.accept_chunk(i, sig[i])
+    return cfg, w, caller, runner, sig
+
+
+def _check_scores(got, ref):
+    got = got.astype(np.float32)
+    scale = max(1.0, float(np.abs(ref).max()))
+    err = np.abs(got - ref)
+    frac_bad = float((err > 1e-3 * scale).mean())
+    assert frac_bad <= 1e-3, f"{frac_bad:.2e} of scores off by more than 1e-3 relative (max err {err.max():.4f})"
+    assert err.max() <= 4e-3 * scale, f"max score error {err.max():.4f}"
+
+
+@pytest.mark.parametrize("kind,N,T", [("fast", 16, 1200), ("fast", 48, 3000), ("hac", 16, 1200), ("hac", 32, 1998)])
+def test_lstm_model_scores(kind, N, T):
+    from oracle import nn_oracle
+    cfg, w, caller, runner, sig = _setup(kind, N, T)
+    got = runner.forward_scores(N)
+    ref = nn_oracle.forward(cfg, w, sig.astype(np.float32))
+    assert got.shape == ref.shape
+    _check_scores(got, ref)
+
+
+@pytest.mark.parametrize("kind,N,T", [("fast", 32, 3000), ("hac", 16, 1998)])
+def test_call_chunks_end_to_end(crf_oracle, kind, N, T):
+    cfg, w, caller, runner, sig = _setup(kind, N, T)
+    scores = runner.forward_scores(N)
+    chunks = runner.call_chunks(N)
+    assert len(chunks) == N
+    ref = crf_oracle.decode(scores, clamp_val=5.0 if cfg.clamp else 0.0, q_shift=cfg.qbias, q_scale=cfg.qscale)
+    for i, c in enumerate(chunks):
+        assert c.sequence == ref.sequences[i]
+        assert c.qstring == ref.qstrings[i]
+        np.testing.assert_array_equal(c.moves, ref.moves[i])
+        assert len(c.moves) == runner.chunk_size() // cfg.stride
+        assert len(c.sequence) == len(c.qstring) == int(c.moves.sum())
+    # partial batch: the first k results do not depend on what the other slots hold
+    k = 5
+    part = runner.call_chunks(k)
+    assert [p.sequence for p in part] == [c.sequence for c in chunks[:k]]
+    stats = runner.sample_stats()
+    assert stats["batches_called"] == 2 and stats["model_decode_ms"] > 0
+    assert caller.stats()["gpu_launches"] > 0
+
+
+def test_runner_rejects_bad_shapes():
+    from dorado_b200 import lib as L
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir("fast"))
+    caller = B200Caller(cfg, synthetic_weights(cfg, 1))
+    with pytest.raises(L.B200Error):
+        B200ModelRunner(caller, 7, 1200)  # LSTM batch must be a multiple of 16
+    r = B200ModelRunner(caller, 16, 1203)  # normalised down to a multiple of the stride (BatchParams::normalise)
+    assert r.chunk_size() == 1200
+    with pytest.raises(L.B200Error):
+        r.accept_chunk(16, np.zeros(1200, np.float16))
+    with pytest.raises(L.B200Error):
+        r.accept_chunk(0, np.zeros(1199, np.float16))
+    with pytest.raises(L.B200Error):
+        r.call_chunks(17)
