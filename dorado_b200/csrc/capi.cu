@@ -147,6 +147,13 @@ int b200_runner_forward_scores(b200_runner* r, int32_t num_chunks, uint16_t* sco
     });
 }
 
+int b200_runner_debug_read_workspace(b200_runner* r, uint64_t offset, uint64_t bytes, void* dst) {
+    return guarded([&] {
+        if (!r || !dst) throw std::invalid_argument("debug_read_workspace: null argument");
+        reinterpret_cast<b200::Runner*>(r)->debug_read_workspace(offset, bytes, dst);
+    });
+}
+
 int b200_decode_scores(int32_t device, const uint16_t* scores, int32_t N, int32_t T, int32_t C, float clamp_val,
                        const b200_decoder_options* opts, uint8_t* moves, char* sequence, char* qstring,
                        int32_t* n_bases) {

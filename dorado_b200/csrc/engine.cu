@@ -142,12 +142,16 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     m_d_input = static_cast<__half*>(m_arena.take(in_bytes));
     m_d_scores = static_cast<__half*>(m_arena.take(scores_b));
     m_d_ws = m_arena.take(ws_b);
+    m_ws_bytes = ws_b;
     m_d_bwd = static_cast<float*>(m_arena.take(bwd_b));
     m_d_beam = static_cast<uint2*>(m_arena.take(beam_b));
     m_d_out = static_cast<unsigned char*>(m_arena.take(m_out_bytes));
     engine.arena_bytes += (int64_t)m_arena.capacity();
-    B200_CUDA(cudaMemset(m_d_input, 0, in_bytes));
-    B200_CUDA(cudaMemset(m_d_ws, 0, ws_b));
+    // zero padding rows / unused slots once, on the engine's own (non-blocking) stream so it is ordered
+    // before the first forward
+    B200_CUDA(cudaMemsetAsync(m_d_input, 0, in_bytes, engine.stream()));
+    B200_CUDA(cudaMemsetAsync(m_d_ws, 0, ws_b, engine.stream()));
+    B200_CUDA(cudaStreamSynchronize(engine.stream()));
     m_plan = engine.model().make_plan(m_N, m_T_in, m_d_input, m_d_scores, m_d_ws, ws_b);
     for (auto& e : m_ev) B200_CUDA(cudaEventCreate(&e));
 }
@@ -287,6 +291,14 @@ void Runner::forward_scores_to_host(int num_chunks, uint16_t* scores_out) {
     B200_CUDA(cudaMemcpyAsync(scores_out, m_d_scores, (size_t)num_chunks * m_T_out * m_C * sizeof(__half),
                               cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));
+}
+
+void Runner::debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst) {
+    if (offset + bytes > m_ws_bytes) throw std::invalid_argument("debug_read_workspace: out of range");
+    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    B200_CUDA(cudaStreamSynchronize(m_engine.stream()));
+    B200_CUDA(cudaMemcpy(dst, static_cast<unsigned char*>(m_d_ws) + offset, bytes, cudaMemcpyDeviceToHost));
 }
 
 void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C, float clamp_val,

@@ -103,6 +103,7 @@ public:
     void upload();
     void step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms);
     void forward_scores_to_host(int num_chunks, uint16_t* scores_out);
+    void debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst);
 
 private:
     void run_forward(int n);
@@ -119,6 +120,7 @@ private:
     __half* m_d_input = nullptr;
     __half* m_d_scores = nullptr;
     void* m_d_ws = nullptr;
+    size_t m_ws_bytes = 0;
     std::unique_ptr<ForwardPlan> m_plan;
     float* m_d_bwd = nullptr;
     uint2* m_d_beam = nullptr;

@@ -16,6 +16,7 @@
 #include "gemm.h"
 #include "tc.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -638,6 +639,17 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
 void LstmPlan::run(cudaStream_t stream) {
     conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
     run_gemm(conv3, stream);
+    int nl = num_layers;
+    if (const char* dbg = getenv("B200_DEBUG_LSTM_LAYERS")) {  // debug: stop after k LSTM layers (tools/debug_forward.py)
+        nl = atoi(dbg);
+        if (nl < num_layers) {
+            for (int l = 0; l < nl; ++l) {
+                lstm_layer_kernel<16><<<lstm_grid, LSTM_THREADS, lstm_smem, stream>>>(lstm_x[l], lstm_w[l], lstm_p[l]);
+            }
+            B200_CUDA(cudaGetLastError());
+            return;
+        }
+    }
     for (int l = 0; l < num_layers; ++l) {
         lstm_layer_kernel<16><<<lstm_grid, LSTM_THREADS, lstm_smem, stream>>>(lstm_x[l], lstm_w[l], lstm_p[l]);
     }

@@ -153,6 +153,11 @@ class B200ModelRunner:
         L.check(self._lib.b200_runner_forward_scores(self.handle, num_chunks, out.ctypes.data))
         return out
 
+    def debug_read_workspace(self, offset: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        L.check(self._lib.b200_runner_debug_read_workspace(self.handle, offset, nbytes, out.ctypes.data))
+        return out
+
     def upload(self) -> None:
         L.check(self._lib.b200_runner_upload(self.handle))
 

@@ -164,6 +164,9 @@ B200_API int b200_decode_scores(int32_t device,
                                 char* qstring,
                                 int32_t* n_bases);
 
+/* Debug: copy `bytes` of the runner's forward workspace (device) starting at `offset` to `dst` (host). */
+B200_API int b200_runner_debug_read_workspace(b200_runner* runner, uint64_t offset, uint64_t bytes, void* dst);
+
 /* Kernel-level test hooks (host buffers; used by tests/ only). */
 B200_API int b200_test_gemm(int32_t device, const uint16_t* a /* [M,K] fp16 */, const uint16_t* b /* [N,K] fp16 */,
                             const float* bias /* [N] or NULL */, int32_t M, int32_t N, int32_t K, int32_t activation,

@@ -43,7 +43,7 @@ def conv1d(x, w, b, stride, act):
     return y.reshape(N, T_out, Cout).transpose(0, 2, 1).astype(np.float32)
 
 
-def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse):
+def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse, quant=lambda a: a):
     """x [N,T,C] -> [N,T,C]; reverse runs the recurrence from the last timestep."""
     N, T, C = x.shape
     if reverse:
@@ -57,7 +57,7 @@ def lstm_layer(x, w_ih, w_hh, b_ih, b_hh, reverse):
         g = gx[:, t] + h @ whh_t
         i, f, gg, o = g[:, :C], g[:, C:2 * C], g[:, 2 * C:3 * C], g[:, 3 * C:]
         c = _sigmoid(f) * c + _sigmoid(i) * np.tanh(gg)
-        h = (_sigmoid(o) * np.tanh(c)).astype(np.float32)
+        h = quant((_sigmoid(o) * np.tanh(c)).astype(np.float32))
         out[:, t] = h
     return out[:, ::-1] if reverse else out
 
@@ -111,12 +111,23 @@ def windowed_attention(q, k, v, win, cpu_split_quirk=False, num_splits=12):
     return out
 
 
+def _q16(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
 def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_quirk: bool = False,
-            return_intermediates: bool = False):
-    """signal [N,T] (or [N,1,T]) fp32 -> scores [N,T_out,C] fp32 (clamped when cfg.clamp)."""
+            return_intermediates: bool = False, emulate_fp16: bool = False):
+    """signal [N,T] (or [N,1,T]) fp32 -> scores [N,T_out,C] fp32 (clamped when cfg.clamp).
+
+    emulate_fp16=True models the storage precision of a CUDA half-precision path (the reference's own
+    CUDA path, and this engine): matrix weights and every activation tensor that reaches HBM are rounded
+    to fp16, arithmetic stays fp32."""
     x = np.ascontiguousarray(signal, np.float32).reshape(signal.shape[0], 1, -1)
     inter = {}
-    names = list(w.keys())
+    q = _q16 if emulate_fp16 else (lambda a: a)
+    if emulate_fp16:
+        w = {k: (_q16(v) if v.ndim >= 2 and not (k.startswith("0.conv") or k.startswith("1.conv")) else v)
+             for k, v in w.items()}
     if cfg.is_tx_model:
         tx = cfg.tx
         for i, c in enumerate(cfg.convs):
@@ -148,22 +159,25 @@ def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_qui
 
     for i, c in enumerate(cfg.convs):
         x = conv1d(x, w[f"{i}.conv.weight.tensor"], w[f"{i}.conv.bias.tensor"], c.stride, c.activation)
+        if i >= 1:
+            x = q(x)  # conv1 output stays on chip (fused conv1+conv2 kernel)
         inter[f"conv{i}"] = x
     x = np.ascontiguousarray(x.transpose(0, 2, 1))
     nconv = len(cfg.convs)
     for l in range(cfg.lstm_layers):
         p = f"{nconv + l + 1}.rnn."
         x = lstm_layer(x, w[p + "weight_ih_l0.tensor"], w[p + "weight_hh_l0.tensor"], w[p + "bias_ih_l0.tensor"],
-                       w[p + "bias_hh_l0.tensor"], reverse=(l % 2 == 0))
+                       w[p + "bias_hh_l0.tensor"], reverse=(l % 2 == 0), quant=q)
         inter[f"lstm{l}"] = x
     layer = nconv + cfg.lstm_layers + 1
     scores = x @ w[f"{layer}.linear.weight.tensor"].T
     if f"{layer}.linear.bias.tensor" in w:
         scores = scores + w[f"{layer}.linear.bias.tensor"]
     if cfg.out_features is not None:
-        scores = scores @ w[f"{layer + 1}.linear.weight.tensor"].T
+        scores = q(scores) @ w[f"{layer + 1}.linear.weight.tensor"].T
     if cfg.scale == 5.0:
         scores = np.tanh(scores) * np.float32(5.0)
+    scores = q(scores)
     if cfg.clamp:
         scores = np.clip(scores, -5.0, 5.0)
     scores = scores.astype(np.float32)
