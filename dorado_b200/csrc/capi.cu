@@ -147,6 +147,15 @@ int b200_runner_forward_scores(b200_runner* r, int32_t num_chunks, uint16_t* sco
     });
 }
 
+int b200_runner_profile(b200_runner* r, int32_t num_chunks, char* buf, uint64_t buf_len) {
+    return guarded([&] {
+        if (!r || !buf || buf_len == 0) throw std::invalid_argument("b200_runner_profile: null argument");
+        const std::string s = reinterpret_cast<b200::Runner*>(r)->profile(num_chunks);
+        std::strncpy(buf, s.c_str(), buf_len - 1);
+        buf[buf_len - 1] = 0;
+    });
+}
+
 int b200_runner_debug_read_workspace(b200_runner* r, uint64_t offset, uint64_t bytes, void* dst) {
     return guarded([&] {
         if (!r || !dst) throw std::invalid_argument("debug_read_workspace: null argument");

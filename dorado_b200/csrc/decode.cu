@@ -21,6 +21,7 @@
 
 #include "b200_crf_math.h"
 #include "common.cuh"
+#include "engine.h"
 
 namespace b200 {
 
@@ -711,12 +712,13 @@ size_t traceback_smem_bytes(int T) {
 }
 
 template <int SL>
-void launch_decode(const DecodeArgs& a, cudaStream_t stream) {
+void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) {
     constexpr int P = Dims<SL>::P;
     {
         constexpr int GROUPS = (256 / P) > 0 ? (256 / P) : 1;
         const int grid = (a.N + GROUPS - 1) / GROUPS;
         crf_bwd_scan_kernel<SL><<<grid, P * GROUPS, 0, stream>>>(a.scores, a.bwd, a.N, a.T, a.clamp_val, a.blank);
+        if (prof) prof->mark("crf_bwd_scan", stream);
     }
     {
         constexpr int GT = P < 32 ? 32 : P;
@@ -725,6 +727,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream) {
         const int grid = (a.N + GROUPS - 1) / GROUPS;
         crf_fwd_beam_kernel<SL><<<grid, THREADS, 0, stream>>>(a.scores, a.bwd, a.beam, a.N, a.T, a.clamp_val,
                                                                 a.blank, a.beam_width, a.log_beam_cut);
+        if (prof) prof->mark("crf_fwd_beam", stream);
     }
     {
         const size_t smem = traceback_smem_bytes(a.T);
@@ -737,6 +740,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream) {
         const int grid = (a.N + kTbWarps - 1) / kTbWarps;
         crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.q_scale, a.q_shift, a.moves,
                                                                     a.sequence, a.qstring, a.n_bases);
+        if (prof) prof->mark("crf_traceback", stream);
     }
     B200_CUDA(cudaGetLastError());
 }
@@ -752,7 +756,7 @@ size_t decode_scratch_bytes(int N, int T, int state_len, size_t* bwd_bytes, size
     return b1 + b2;
 }
 
-void decode_scores(const DecodeArgs& a, cudaStream_t stream) {
+void decode_scores(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) {
     if (a.beam_width < 1 || a.beam_width > kBeamW) {
         throw std::invalid_argument("b200 decode: beam_width must be in [1, 32]");
     }
@@ -760,9 +764,9 @@ void decode_scores(const DecodeArgs& a, cudaStream_t stream) {
         throw std::invalid_argument("b200 decode: need 1 <= T <= 65535 and N >= 1");
     }
     switch (a.state_len) {
-        case 3: launch_decode<3>(a, stream); break;
-        case 4: launch_decode<4>(a, stream); break;
-        case 5: launch_decode<5>(a, stream); break;
+        case 3: launch_decode<3>(a, stream, prof); break;
+        case 4: launch_decode<4>(a, stream, prof); break;
+        case 5: launch_decode<5>(a, stream, prof); break;
         default: throw std::invalid_argument("b200 decode: state_len must be 3, 4 or 5");
     }
 }

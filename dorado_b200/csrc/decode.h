@@ -31,6 +31,7 @@ struct DecodeArgs {
 };
 
 size_t decode_scratch_bytes(int N, int T, int state_len, size_t* bwd_bytes, size_t* beam_bytes);
-void decode_scores(const DecodeArgs& args, cudaStream_t stream);
+struct ProfileSink;
+void decode_scores(const DecodeArgs& args, cudaStream_t stream, ProfileSink* prof = nullptr);
 
 }  // namespace b200

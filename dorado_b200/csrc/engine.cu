@@ -190,7 +190,7 @@ void Runner::run_forward(int n) {
     m_engine.gpu_launches += m_plan->launches();
 }
 
-void Runner::run_decode(int n) {
+void Runner::run_decode(int n, ProfileSink* prof) {
     const auto& d = m_engine.desc();
     DecodeArgs a{};
     a.scores = m_d_scores;
@@ -210,7 +210,7 @@ void Runner::run_decode(int n) {
     a.sequence = reinterpret_cast<char*>(m_d_out + (size_t)m_N * m_T_out);
     a.qstring = reinterpret_cast<char*>(m_d_out + (size_t)2 * m_N * m_T_out);
     a.n_bases = reinterpret_cast<int32_t*>(m_d_out + nb_offset(m_N, m_T_out));
-    decode_scores(a, m_engine.stream());
+    decode_scores(a, m_engine.stream(), prof);
     m_engine.gpu_launches += 3;
 }
 
@@ -291,6 +291,46 @@ void Runner::forward_scores_to_host(int num_chunks, uint16_t* scores_out) {
     B200_CUDA(cudaMemcpyAsync(scores_out, m_d_scores, (size_t)num_chunks * m_T_out * m_C * sizeof(__half),
                               cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));
+}
+
+void ProfileSink::begin(cudaStream_t s) { mark("begin", s); }
+
+void ProfileSink::mark(const char* name, cudaStream_t s) {
+    cudaEvent_t e;
+    B200_CUDA(cudaEventCreate(&e));
+    B200_CUDA(cudaEventRecord(e, s));
+    events.push_back(e);
+    names.emplace_back(name);
+}
+
+std::vector<std::pair<std::string, float>> ProfileSink::report() {
+    std::vector<std::pair<std::string, float>> out;
+    for (size_t i = 1; i < events.size(); ++i) {
+        float ms = 0;
+        B200_CUDA(cudaEventElapsedTime(&ms, events[i - 1], events[i]));
+        out.emplace_back(names[i], ms);
+    }
+    return out;
+}
+
+ProfileSink::~ProfileSink() {
+    for (auto e : events) cudaEventDestroy(e);
+}
+
+std::string Runner::profile(int num_chunks) {
+    if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("profile: num_chunks out of range");
+    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    cudaStream_t s = m_engine.stream();
+    ProfileSink sink;
+    sink.begin(s);
+    m_plan->run(s, &sink);
+    m_engine.gpu_launches += m_plan->launches();
+    run_decode(num_chunks, &sink);
+    B200_CUDA(cudaStreamSynchronize(s));
+    std::string out;
+    for (auto& kv : sink.report()) out += kv.first + "=" + std::to_string(kv.second) + ";";
+    return out;
 }
 
 void Runner::debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst) {

@@ -40,10 +40,21 @@ private:
 // [N][T_out][outsize] on device.  A plan owns its tensor maps and launch parameters (all pointers are
 // fixed slices of the runner's arena), so a forward is just a sequence of launches.  The whole batch
 // is always computed (slots beyond num_chunks hold stale data and are ignored, as in the reference).
+// Optional per-kernel timing: mark() records an event after each launch; report() turns them into
+// (kernel name, milliseconds) pairs once the stream has drained.  Used by bench.py for the roofline line.
+struct ProfileSink {
+    std::vector<cudaEvent_t> events;
+    std::vector<std::string> names;
+    void begin(cudaStream_t s);
+    void mark(const char* name, cudaStream_t s);
+    std::vector<std::pair<std::string, float>> report();
+    ~ProfileSink();
+};
+
 class ForwardPlan {
 public:
     virtual ~ForwardPlan() = default;
-    virtual void run(cudaStream_t stream) = 0;
+    virtual void run(cudaStream_t stream, ProfileSink* prof = nullptr) = 0;
     virtual int launches() const = 0;
 };
 
@@ -104,10 +115,12 @@ public:
     void step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms);
     void forward_scores_to_host(int num_chunks, uint16_t* scores_out);
     void debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst);
+    // one forward+decode pass with an event after every launch; returns "name=ms;name=ms;..."
+    std::string profile(int num_chunks);
 
 private:
     void run_forward(int n);
-    void run_decode(int n);
+    void run_decode(int n, ProfileSink* prof = nullptr);
 
     Engine& m_engine;
     int m_N, m_T_in, m_T_out, m_C;

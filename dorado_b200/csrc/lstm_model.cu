@@ -356,7 +356,7 @@ class LstmModel;
 
 class LstmPlan final : public ForwardPlan {
 public:
-    void run(cudaStream_t stream) override;
+    void run(cudaStream_t stream, ProfileSink* prof) override;
     int launches() const override { return 1 + 1 + num_layers + num_linear; }
 
     Conv12Params conv12{};
@@ -636,9 +636,11 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     return plan;
 }
 
-void LstmPlan::run(cudaStream_t stream) {
+void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
     conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
+    if (prof) prof->mark("conv12", stream);
     run_gemm(conv3, stream);
+    if (prof) prof->mark("conv3_gemm", stream);
     int nl = num_layers;
     if (const char* dbg = getenv("B200_DEBUG_LSTM_LAYERS")) {  // debug: stop after k LSTM layers (tools/debug_forward.py)
         nl = atoi(dbg);
@@ -652,9 +654,14 @@ void LstmPlan::run(cudaStream_t stream) {
     }
     for (int l = 0; l < num_layers; ++l) {
         lstm_layer_kernel<16><<<lstm_grid, LSTM_THREADS, lstm_smem, stream>>>(lstm_x[l], lstm_w[l], lstm_p[l]);
+        if (prof) prof->mark("lstm_layer", stream);
     }
     run_gemm(linear1, stream);
-    if (num_linear == 2) run_gemm(linear2, stream);
+    if (prof) prof->mark("linear_gemm", stream);
+    if (num_linear == 2) {
+        run_gemm(linear2, stream);
+        if (prof) prof->mark("linear2_gemm", stream);
+    }
     B200_CUDA(cudaGetLastError());
 }
 

@@ -153,6 +153,17 @@ class B200ModelRunner:
         L.check(self._lib.b200_runner_forward_scores(self.handle, num_chunks, out.ctypes.data))
         return out
 
+    def profile(self, num_chunks: int):
+        """One forward+decode pass timed per launch: [(kernel name, ms), ...] in launch order."""
+        buf = C.create_string_buffer(8192)
+        L.check(self._lib.b200_runner_profile(self.handle, num_chunks, buf, len(buf)))
+        out = []
+        for item in buf.value.decode().split(";"):
+            if item:
+                k, v = item.split("=")
+                out.append((k, float(v)))
+        return out
+
     def debug_read_workspace(self, offset: int, nbytes: int) -> np.ndarray:
         out = np.empty(nbytes, np.uint8)
         L.check(self._lib.b200_runner_debug_read_workspace(self.handle, offset, nbytes, out.ctypes.data))

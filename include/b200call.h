@@ -164,6 +164,10 @@ B200_API int b200_decode_scores(int32_t device,
                                 char* qstring,
                                 int32_t* n_bases);
 
+/* One forward+decode pass with a CUDA event after every kernel launch.  Writes "name=ms;name=ms;..." (launch order,
+ * device milliseconds) into buf. */
+B200_API int b200_runner_profile(b200_runner* runner, int32_t num_chunks, char* buf, uint64_t buf_len);
+
 /* Debug: copy `bytes` of the runner's forward workspace (device) starting at `offset` to `dst` (host). */
 B200_API int b200_runner_debug_read_workspace(b200_runner* runner, uint64_t offset, uint64_t bytes, void* dst);
 
