@@ -117,16 +117,16 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
 // from L2 every step through a ring), x_t arrives by TMA, h_t is written by the epilogue.
 // Accumulators are double-buffered in TMEM so the epilogue of tile m overlaps the MMAs of tile m+1.
 // ------------------------------------------------------------------------------------------------
-constexpr int LSTM_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int KBLK = 32;           // K elements per smem block (64 B rows, SWIZZLE_64B)
 constexpr int WBLK_BYTES = 128 * KBLK * 2;
+constexpr int UN = 16;             // UMMA N: rows of a Z block (chunks, zero-padded when a CTA owns fewer)
+constexpr int ZBLK = UN * KBLK * 2;
 
 struct LstmParams {
     __half* seq;        // [T][N][C] in place
     const float* bias;  // [4C] permuted like the weight rows (b_ih + b_hh)
     int T, N, C, reverse;
-    int nb;         // chunks per CTA (16 or 32)
-    int w_stages;   // 0 => weights resident
+    int w_stages;  // 0 => weights resident in shared memory
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -148,45 +148,65 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
 __device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float tanh_f(float v) { return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f); }
 
-template <int NB>
-__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_kernel(const __grid_constant__ CUtensorMap tma_x,
-                                                                    const __grid_constant__ CUtensorMap tma_w,
-                                                                    const LstmParams p) {
+// C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).
+// NBR = chunks owned by this CTA (4, 8 or 16: small values spread a small batch over more SMs; the MMA is
+//       always N = 16 wide, padded rows are zero).
+// G   = C/32 tiles are spread over G epilogue groups of 4 warps (tile m -> group m % G) and, when the weights
+//       are resident, over G MMA-issuing warps, so the gate math and the MMA issue of the tiles of one step
+//       run concurrently.
+// Per step the x_t half of the product is issued as soon as x_t has landed (it does not depend on the
+// recurrence) and only the h_{t-1} half sits on the critical path.
+template <int C>
+struct LstmCfg {
+    static constexpr int MT = C / 32;
+    static constexpr int G = (MT % 6 == 0) ? 6 : (MT % 4 == 0) ? 4 : 3;
+    static constexpr int KB = 2 * C / KBLK;
+    static constexpr int KBX = C / KBLK;
+    static constexpr int THREADS = 32 * (1 + G) + 128 * G;
+    static constexpr uint32_t TMEM_COLS = 2 * MT * UN <= 32 ? 32 : 2 * MT * UN <= 64 ? 64 : 2 * MT * UN <= 128 ? 128 : 2 * MT * UN <= 256 ? 256 : 512;
+    static_assert(MT % G == 0 && 2 * MT * UN <= 512, "unsupported LSTM size");
+};
+
+template <int C, int NBR>
+__global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(const __grid_constant__ CUtensorMap tma_x,
+                                                                           const __grid_constant__ CUtensorMap tma_w,
+                                                                           const LstmParams p) {
+    using Cfg = LstmCfg<C>;
+    constexpr int MT = Cfg::MT, G = Cfg::G, KB = Cfg::KB, KBX = Cfg::KBX;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int C = p.C;
-    const int MT = C / 32;        // gate tiles per step
-    const int KB = 2 * C / KBLK;  // K blocks per tile
-    const int KBX = C / KBLK;     // of which x
     const bool resident = p.w_stages == 0;
     const int w_blocks = resident ? MT * KB : p.w_stages;
-    constexpr int ZBLK = NB * KBLK * 2;  // bytes of one Z block
     uint8_t* w_s = smem;
-    uint8_t* z_s = w_s + (size_t)w_blocks * WBLK_BYTES;  // [2][KB][ZBLK]
-    float* g_s = reinterpret_cast<float*>(z_s + (size_t)2 * KB * ZBLK);  // [4][NB][32]
-    float* c_s = g_s + 4 * NB * 32;                                       // [MT][NB][32] cell state
-    uint64_t* bars = reinterpret_cast<uint64_t*>(c_s + (size_t)MT * NB * 32);
-    uint64_t* x_full = bars;            // [2]
-    uint64_t* z_free = bars + 2;        // [2]
-    uint64_t* h_ready = bars + 4;       // [2]
-    uint64_t* acc_full = bars + 6;      // [2]
-    uint64_t* acc_empty = bars + 8;     // [2]
-    uint64_t* w_full = bars + 10;       // [w_stages] or [1]
+    uint8_t* z_s = w_s + (size_t)w_blocks * WBLK_BYTES;                   // [2][KB][ZBLK]
+    float* g_s = reinterpret_cast<float*>(z_s + (size_t)2 * KB * ZBLK);   // [G][4][NBR][32]
+    float* c_s = g_s + (size_t)G * 4 * NBR * 32;                          // [MT][NBR][32] cell state
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c_s + (size_t)MT * NBR * 32);
+    uint64_t* x_full = bars;          // [2]  TMA -> MMA
+    uint64_t* z_free = bars + 2;      // [2]  MMA done with Z[buf] -> TMA
+    uint64_t* h_ready = bars + 4;     // [2]  epilogue wrote h into Z[buf] -> MMA
+    uint64_t* acc_free = bars + 6;    // [2]  epilogue done reading accumulator set -> MMA
+    uint64_t* acc_full = bars + 8;    // [2][MT] MMA -> epilogue
+    uint64_t* w_full = acc_full + 2 * MT;
     uint64_t* w_empty = w_full + (resident ? 1 : p.w_stages);
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_empty + (resident ? 1 : p.w_stages));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * NB;
-    constexpr uint32_t TMEM_COLS = 2 * NB < 32 ? 32 : 2 * NB;
+    const int n0 = blockIdx.x * NBR;
+    const int mma_warps = resident ? G : 1;
 
+    // zero Z (padding rows, h_{-1}) and the cell state before anything asynchronous starts
+    for (int i = threadIdx.x; i < 2 * KB * ZBLK / 16; i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < MT * NBR * 32; i += blockDim.x) c_s[i] = 0.0f;
+    tc::fence_proxy_async_smem();
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&x_full[i], 1);
-            tc::mbar_init(&z_free[i], 1);
-            tc::mbar_init(&h_ready[i], 128);
-            tc::mbar_init(&acc_full[i], 1);
-            tc::mbar_init(&acc_empty[i], 128);
+            tc::mbar_init(&z_free[i], (uint32_t)mma_warps);
+            tc::mbar_init(&h_ready[i], G * 128);
+            tc::mbar_init(&acc_free[i], G * 128);
         }
+        for (int i = 0; i < 2 * MT; ++i) tc::mbar_init(&acc_full[i], 1);
         const int nwb = resident ? 1 : p.w_stages;
         for (int i = 0; i < nwb; ++i) {
             tc::mbar_init(&w_full[i], 1);
@@ -196,7 +216,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_kernel(const __gri
         tc::prefetch_tmap(&tma_x);
         tc::prefetch_tmap(&tma_w);
     }
-    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -218,130 +238,162 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_layer_kernel(const __gri
                 const int t = p.reverse ? p.T - 1 - s : s;
                 const int buf = s & 1;
                 tc::mbar_wait(&z_free[buf], ((s >> 1) & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&x_full[buf], (uint32_t)(KBX * ZBLK));
+                tc::mbar_arrive_expect_tx(&x_full[buf], (uint32_t)(KBX * NBR * KBLK * 2));
                 for (int kb = 0; kb < KBX; ++kb) {
                     tc::tma_load_2d(z_s + (size_t)(buf * KB + kb) * ZBLK, &tma_x, &x_full[buf], kb * KBLK, t * p.N + n0);
                 }
                 if (!resident) {
-                    for (int m = 0; m < MT; ++m) {
-                        for (int kb = 0; kb < KB; ++kb, ++wj) {
-                            const int st = (int)(wj % p.w_stages);
-                            tc::mbar_wait(&w_empty[st], (uint32_t)(((wj / p.w_stages) & 1) ^ 1));
-                            tc::mbar_arrive_expect_tx(&w_full[st], WBLK_BYTES);
-                            tc::tma_load_2d(w_s + (size_t)st * WBLK_BYTES, &tma_w, &w_full[st], kb * KBLK, m * 128);
+                    // same order as the MMA issue: x blocks of every tile, then h blocks of every tile
+                    for (int half = 0; half < 2; ++half) {
+                        for (int m = 0; m < MT; ++m) {
+                            for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb, ++wj) {
+                                const int st = (int)(wj % p.w_stages);
+                                tc::mbar_wait(&w_empty[st], (uint32_t)(((wj / p.w_stages) & 1) ^ 1));
+                                tc::mbar_arrive_expect_tx(&w_full[st], WBLK_BYTES);
+                                tc::tma_load_2d(w_s + (size_t)st * WBLK_BYTES, &tma_w, &w_full[st], kb * KBLK, m * 128);
+                            }
                         }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (tc::elect_one()) {
-            const uint32_t idesc = tc::umma_idesc_f16(128, NB);
+    } else if (warp <= G) {
+        // ---------------- MMA issuers ----------------
+        const int mw = warp - 1;
+        if (mw < mma_warps && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
+            const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
+            const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
             if (resident) {
                 tc::mbar_wait(&w_full[0], 0);
-            }
-            long long wj = 0, j = 0;  // weight block counter, tile counter
-            for (int s = 0; s < p.T; ++s) {
-                const int buf = s & 1;
-                tc::mbar_wait(&x_full[buf], (s >> 1) & 1);
-                tc::mbar_wait(&h_ready[buf], (s >> 1) & 1);
-                tc::tc_fence_after();
-                const uint32_t z_addr = tc::smem_u32(z_s + (size_t)buf * KB * ZBLK);
-                for (int m = 0; m < MT; ++m, ++j) {
-                    const int ab = (int)(j & 1);
-                    tc::mbar_wait(&acc_empty[ab], (uint32_t)(((j >> 1) & 1) ^ 1));
+                // this warp owns tiles mw, mw + G, ...; descriptors are base + compile-time offsets
+                for (int s = 0; s < p.T; ++s) {
+                    const int buf = s & 1;
+                    const uint32_t par = (uint32_t)((s >> 1) & 1);
+                    const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
+                    tc::mbar_wait(&x_full[buf], par);
+                    tc::mbar_wait(&acc_free[buf], par ^ 1);
                     tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(ab * NB);
-                    for (int kb = 0; kb < KB; ++kb) {
-                        uint32_t w_addr;
-                        int st = 0;
-                        if (resident) {
-                            w_addr = tc::smem_u32(w_s + (size_t)(m * KB + kb) * WBLK_BYTES);
-                        } else {
-                            st = (int)(wj % p.w_stages);
-                            tc::mbar_wait(&w_full[st], (uint32_t)((wj / p.w_stages) & 1));
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (half == 1) {
+                            tc::mbar_wait(&h_ready[buf], par);
                             tc::tc_fence_after();
-                            w_addr = tc::smem_u32(w_s + (size_t)st * WBLK_BYTES);
-                            ++wj;
                         }
-                        const uint64_t adesc = umma_desc_sw64(w_addr);
-                        const uint64_t bdesc = umma_desc_sw64(z_addr + (uint32_t)(kb * ZBLK));
-                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
-                        tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
-                        if (!resident) tc::umma_commit(&w_empty[st]);
+#pragma unroll
+                        for (int i = 0; i < MT / G; ++i) {
+                            const int m = mw + i * G;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * MT + m) * UN);
+                            const uint64_t wd = wdesc0 + (uint64_t)((m * KB * WBLK_BYTES) >> 4);
+#pragma unroll
+                            for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb) {
+                                const uint64_t adesc = wd + (uint64_t)((kb * WBLK_BYTES) >> 4);
+                                const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
+                                tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                                tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                            }
+                            if (half == 1) tc::umma_commit(&acc_full[buf * MT + m]);
+                        }
                     }
-                    tc::umma_commit(&acc_full[ab]);
+                    tc::umma_commit(&z_free[buf]);
                 }
-                tc::umma_commit(&z_free[buf]);
+            } else {
+                long long wj = 0;
+                for (int s = 0; s < p.T; ++s) {
+                    const int buf = s & 1;
+                    const uint32_t par = (uint32_t)((s >> 1) & 1);
+                    const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
+                    tc::mbar_wait(&x_full[buf], par);
+                    tc::mbar_wait(&acc_free[buf], par ^ 1);
+                    tc::tc_fence_after();
+                    for (int half = 0; half < 2; ++half) {
+                        if (half == 1) {
+                            tc::mbar_wait(&h_ready[buf], par);
+                            tc::tc_fence_after();
+                        }
+                        for (int m = 0; m < MT; ++m) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * MT + m) * UN);
+                            for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb, ++wj) {
+                                const int st = (int)(wj % p.w_stages);
+                                tc::mbar_wait(&w_full[st], (uint32_t)((wj / p.w_stages) & 1));
+                                tc::tc_fence_after();
+                                const uint64_t adesc = wdesc0 + (uint64_t)((st * WBLK_BYTES) >> 4);
+                                const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
+                                tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                                tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                                tc::umma_commit(&w_empty[st]);
+                            }
+                            if (half == 1) tc::umma_commit(&acc_full[buf * MT + m]);
+                        }
+                    }
+                    tc::umma_commit(&z_free[buf]);
+                }
             }
         }
     } else {
-        // ---------------- epilogue: gates, cell update, h_t ----------------
-        const int ew = warp - 2;      // 0..3
-        const int gate = warp & 3;    // TMEM lane quarter this warp may read == gate type (i,f,g,o)
-        const int tid = ew * 32 + lane;
-        // cell-update role: unit = lane, chunks n = ew, ew + 4, ...
-        constexpr int CPT = NB / 4;
-        for (int i = tid; i < MT * NB * 32; i += 128) c_s[i] = 0.0f;
-        // h_{-1} = 0 in Z[0]'s h blocks
-        for (int i = tid; i < KBX * ZBLK / 16; i += 128) {
-            reinterpret_cast<uint4*>(z_s + (size_t)KBX * ZBLK)[i] = make_uint4(0, 0, 0, 0);
-        }
-        tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&h_ready[0]);
+        // ---------------- epilogue groups: gates, cell update, h_t ----------------
+        const int ewarp = warp - (1 + G);
+        const int g = ewarp >> 2;    // group
+        const int ew = ewarp & 3;    // warp within group -> chunks ew, ew + 4, ...
+        const int gate = warp & 3;   // TMEM lane quarter this warp may read == gate type (i,f,g,o)
+        float* gs = g_s + (size_t)g * 4 * NBR * 32;
+        constexpr int CPT = NBR / 4;
+        tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0 is in place (zeroed before the CTA-wide sync)
 
-        long long j = 0;
         for (int s = 0; s < p.T; ++s) {
             const int t = p.reverse ? p.T - 1 - s : s;
-            const int nbuf = (s + 1) & 1;
+            const int buf = s & 1, nbuf = buf ^ 1;
+            const uint32_t par = (uint32_t)((s >> 1) & 1);
             uint8_t* zh_next = z_s + (size_t)(nbuf * KB + KBX) * ZBLK;
             __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
-#pragma unroll 1
-            for (int m = 0; m < MT; ++m, ++j) {
-                const int ab = (int)(j & 1);
-                tc::mbar_wait(&acc_full[ab], (uint32_t)((j >> 1) & 1));
+#pragma unroll
+            for (int i = 0; i < MT / G; ++i) {
+                const int m = g + i * G;
+                tc::mbar_wait(&acc_full[buf * MT + m], par);
                 tc::tc_fence_after();
-                uint32_t r[NB];
-                const uint32_t taddr = tmem_base + ((uint32_t)(gate * 32) << 16) + (uint32_t)(ab * NB);
-                if constexpr (NB == 16) {
+                uint32_t r[NBR];
+                const uint32_t taddr = tmem_base + ((uint32_t)(gate * 32) << 16) + (uint32_t)((buf * MT + m) * UN);
+                if constexpr (NBR == 16) {
                     tc::tmem_ld_32x16(taddr, r);
+                } else if constexpr (NBR == 8) {
+                    tc::tmem_ld_32x8(taddr, r);
                 } else {
-                    tc::tmem_ld_32x32(taddr, r);
+                    tc::tmem_ld_32x4(taddr, r);
                 }
                 tc::tmem_ld_wait();
-                tc::tc_fence_before();
-                tc::mbar_arrive(&acc_empty[ab]);
                 const float b = __ldg(p.bias + m * 128 + gate * 32 + lane);
 #pragma unroll
-                for (int n = 0; n < NB; ++n) {
+                for (int n = 0; n < NBR; ++n) {
                     const float v = __uint_as_float(r[n]) + b;
-                    g_s[(gate * NB + n) * 32 + lane] = gate == 2 ? tanh_f(v) : sigmoid_f(v);
+                    gs[(gate * NBR + n) * 32 + lane] = gate == 2 ? tanh_f(v) : sigmoid_f(v);
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + g, 128);
 #pragma unroll
-                for (int i = 0; i < CPT; ++i) {
-                    const int n = ew + 4 * i;
-                    const float ig = g_s[(0 * NB + n) * 32 + lane];
-                    const float fg = g_s[(1 * NB + n) * 32 + lane];
-                    const float gg = g_s[(2 * NB + n) * 32 + lane];
-                    const float og = g_s[(3 * NB + n) * 32 + lane];
-                    float* cp = &c_s[((size_t)m * NB + n) * 32 + lane];  // owned by this thread for all steps
+                for (int j = 0; j < CPT; ++j) {
+                    const int n = ew + 4 * j;
+                    const float ig = gs[(0 * NBR + n) * 32 + lane];
+                    const float fg = gs[(1 * NBR + n) * 32 + lane];
+                    const float gg = gs[(2 * NBR + n) * 32 + lane];
+                    const float og = gs[(3 * NBR + n) * 32 + lane];
+                    float* cp = &c_s[((size_t)m * NBR + n) * 32 + lane];  // owned by this thread for all steps
                     const float cs = fg * (*cp) + ig * gg;
                     *cp = cs;
                     const __half h = __float2half_rn(og * tanh_f(cs));
                     *reinterpret_cast<__half*>(zh_next + (size_t)m * ZBLK + sw64_offset(n, lane)) = h;
-                    if (n0 + n < p.N) y_t[(size_t)n * C + m * 32 + lane] = h;
+                    y_t[(size_t)n * C + m * 32 + lane] = h;
                 }
-                named_bar_sync(1, 128);  // g_s reuse
+                if (i + 1 < MT / G) named_bar_sync(1 + g, 128);  // gs reuse within the step
             }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_free[buf]);
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&h_ready[nbuf]);
+            named_bar_sync(1 + g, 128);  // gs reuse across steps
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,8 +416,9 @@ public:
     GemmPlan conv3;
     std::vector<CUtensorMap> lstm_x, lstm_w;
     std::vector<LstmParams> lstm_p;
-    int lstm_grid = 0, lstm_nb = 16;
+    int lstm_grid = 0, lstm_nbr = 16, lstm_groups = 3, lstm_threads = 0;
     size_t lstm_smem = 0;
+    void launch_lstm(int l, cudaStream_t stream) const;
     GemmPlan linear1, linear2;
     int num_layers = 0, num_linear = 1;
     const LstmModel* model = nullptr;
@@ -404,7 +457,7 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
         throw Unsupported("conv stack shape outside what conv12_kernel implements");
     }
     const int C = d.lstm_size;
-    if (C != c3.size || C % 32 != 0 || C > 384) throw Unsupported("lstm_size must be a multiple of 32, <= 384");
+    if (C != c3.size || C % 32 != 0 || C > 512) throw Unsupported("lstm_size must be a multiple of 32, <= 512");
     if (d.lstm_layers < 1 || d.lstm_layers > 8) throw std::invalid_argument("bad lstm_layers");
 
     // conv1: torch [c1][1][w] -> [c1][w]; conv2: torch [co][ci][k] -> [k][ci][co]
@@ -556,18 +609,31 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     // LSTM layers
     {
         plan->num_layers = desc.lstm_layers;
-        const int nb = 16;
-        plan->lstm_nb = nb;
-        plan->lstm_grid = Np / nb;
+        const int MT = C / 32;
         const size_t w_bytes = (size_t)4 * C * 2 * C * 2;
         const bool resident = w_bytes <= 150 * 1024;
+        // chunks per CTA: spread small batches over more SMs when the weights are resident; when they are
+        // streamed from L2 every step, fewer and fatter CTAs keep that traffic down
+        int nbr = 16;
+        if (resident) {
+            if (Np / 16 < 100 && Np % 8 == 0) nbr = 8;
+            if (Np / 8 < 100 && Np % 4 == 0) nbr = 4;
+        }
+        if (C != 96 && C != 128 && C != 192 && C != 256 && C != 384 && C != 512) {
+            throw Unsupported("lstm_size must be one of 96, 128, 192, 256, 384, 512");
+        }
+        const int G = (MT % 6 == 0) ? 6 : (MT % 4 == 0) ? 4 : 3;
+        plan->lstm_nbr = nbr;
+        plan->lstm_groups = G;
+        plan->lstm_threads = 64 + 128 * G;
+        plan->lstm_grid = Np / nbr;
         const int KB = 2 * C / KBLK;
         const int w_stages = resident ? 0 : 12;
         const size_t wsm = resident ? w_bytes : (size_t)w_stages * WBLK_BYTES;
-        plan->lstm_smem = 1024 + wsm + (size_t)2 * KB * nb * KBLK * 2 + (size_t)4 * nb * 32 * 4 + (size_t)(C / 32) * nb * 32 * 4 +
-                          8 * (10 + 2 * 16) + 64;
+        plan->lstm_smem = 1024 + wsm + (size_t)2 * KB * ZBLK + (size_t)G * 4 * nbr * 32 * 4 + (size_t)MT * nbr * 32 * 4 +
+                          8 * (8 + 2 * MT + 2 * 16) + 64;
         for (int l = 0; l < desc.lstm_layers; ++l) {
-            plan->lstm_x.push_back(make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, KBLK, nb));
+            plan->lstm_x.push_back(make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, KBLK, nbr));
             plan->lstm_w.push_back(make_tmap_2d(layers[l].w, (uint64_t)2 * C, (uint64_t)4 * C, (uint64_t)2 * C * 2, KBLK, 128));
             LstmParams lp{};
             lp.seq = seq;
@@ -576,14 +642,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             lp.N = Np;
             lp.C = C;
             lp.reverse = (l % 2 == 0) ? 1 : 0;  // reverse_first = true (CRFModel.cpp:40, LSTMStack.cpp:31-41)
-            lp.nb = nb;
             lp.w_stages = w_stages;
             plan->lstm_p.push_back(lp);
-        }
-        static bool attr = false;
-        if (!attr) {
-            B200_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
         }
         if (plan->lstm_smem > 227 * 1024) throw Unsupported("LSTM shared-memory plan does not fit");
     }
@@ -636,6 +696,38 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     return plan;
 }
 
+template <int C, int NBR>
+static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<C, NBR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
+                                                                                        pl.lstm_p[l]);
+}
+
+template <int C>
+static void launch_lstm_c(const LstmPlan& pl, int l, cudaStream_t stream) {
+    switch (pl.lstm_nbr) {
+        case 4: launch_lstm_t<C, 4>(pl, l, stream); break;
+        case 8: launch_lstm_t<C, 8>(pl, l, stream); break;
+        default: launch_lstm_t<C, 16>(pl, l, stream); break;
+    }
+}
+
+void LstmPlan::launch_lstm(int l, cudaStream_t stream) const {
+    switch (lstm_p[l].C) {
+        case 96: launch_lstm_c<96>(*this, l, stream); break;
+        case 128: launch_lstm_c<128>(*this, l, stream); break;
+        case 192: launch_lstm_c<192>(*this, l, stream); break;
+        case 256: launch_lstm_c<256>(*this, l, stream); break;
+        case 384: launch_lstm_c<384>(*this, l, stream); break;
+        case 512: launch_lstm_c<512>(*this, l, stream); break;
+        default: throw Unsupported("no LSTM kernel instantiation for this lstm_size");
+    }
+}
+
 void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
     conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
     if (prof) prof->mark("conv12", stream);
@@ -646,14 +738,14 @@ void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
         nl = atoi(dbg);
         if (nl < num_layers) {
             for (int l = 0; l < nl; ++l) {
-                lstm_layer_kernel<16><<<lstm_grid, LSTM_THREADS, lstm_smem, stream>>>(lstm_x[l], lstm_w[l], lstm_p[l]);
+                launch_lstm(l, stream);
             }
             B200_CUDA(cudaGetLastError());
             return;
         }
     }
     for (int l = 0; l < num_layers; ++l) {
-        lstm_layer_kernel<16><<<lstm_grid, LSTM_THREADS, lstm_smem, stream>>>(lstm_x[l], lstm_w[l], lstm_p[l]);
+        launch_lstm(l, stream);
         if (prof) prof->mark("lstm_layer", stream);
     }
     run_gemm(linear1, stream);

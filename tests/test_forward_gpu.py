@@ -47,7 +47,7 @@ def _check_scores(got, ref16, ref32, clamp):
     assert np.abs(got - ref32).max() <= 2e-2 * scale
 
 
-@pytest.mark.parametrize("kind,N,T", [("fast", 16, 1200), ("fast", 48, 3000), ("hac", 16, 1200), ("hac", 32, 1998)])
+@pytest.mark.parametrize("kind,N,T", [("fast", 16, 1200), ("fast", 48, 3000), ("fast", 800, 600), ("fast", 1664, 300), ("hac", 16, 1200), ("hac", 32, 1998)])
 def test_lstm_model_scores(kind, N, T):
     from oracle import nn_oracle
     cfg, w, caller, runner, sig = _setup(kind, N, T)
