@@ -1,6 +1,621 @@
+// Conv -> Transformer encoder -> upsample -> scaled CRF linear forward (sup models) for sm_100a.
+//
+// Replaces the CUDA path of dorado/basecall/model/TxModel.cpp:20-41 and dorado/nn/TxModules.cpp:
+//   conv stack (torch conv1d on the reference's CUDA path)   ConvStack.cpp:146-163    -> conv1 kernel + gemm.cu
+//   koi_qkv_rotary / koi_masked_attention                    TxModules.cpp:642-648    -> gemm.cu + tx_attention_kernel
+//   koi_linear (out_proj, fc2) + koi_rmsnorm_residual        TxModules.cpp:653-712    -> gemm.cu (fused residual) + rmsnorm
+//   koi_mm_swiglu                                            TxModules.cpp:683        -> gemm.cu (SwiGLU epilogue)
+//   LinearUpsample, LinearScaledCRF                          LinearUpsample.cpp:17-23, TxModules.cpp:1010-1016 -> gemm.cu
+// Semantics follow the CPU modules: TxEncoderImpl::forward (TxModules.cpp:859-906), MultiHeadAttentionImpl
+// (:346-426, true window -win_upper <= j - i <= win_lower, see DESIGN.md on the CPU split quirk), RotaryEmbedding
+// (:220-250, half-split rotation), GatedMLP (:170-176), RMSNorm (RMSNorm.cpp:14-18).
+//
+// Activations are NTC fp16.  Every conv after the first is a strided GEMM over the zero-padded NTC buffer of
+// the previous layer (row stride = stride * C_in), all projections are tcgen05 GEMMs; the residual stream is
+// x <- RMSNorm(sublayer(x) + alpha * x) with the "+ alpha * x" fused into the GEMM epilogue.
 #include "engine.h"
+#include "gemm.h"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 namespace b200 {
-std::unique_ptr<Model> make_tx_model(const b200_model_desc&, const b200_tensor*, int) {
-    throw Unsupported("transformer model forward: not built yet");
+
+namespace {
+
+__device__ __forceinline__ float swish_f(float v) { return v / (1.0f + __expf(-v)); }
+
+// ------------------------------------------------------------------------------------------------
+// conv1: 1 -> C1 channels, stride 1.  out[n][pad_out + t][c] = swish(b[c] + sum_k w[c][k] x[n][t + k - W/2])
+// ------------------------------------------------------------------------------------------------
+struct Conv1Params {
+    const __half* x;   // [N][T]
+    __half* out;       // [N][T_pad][C1]
+    const float* w;    // [C1][W] then bias [C1]
+    int N, T, T_pad, pad_out, C1, W, act;
+};
+
+__global__ void __launch_bounds__(256) tx_conv1_kernel(const Conv1Params p) {
+    // thread = (t, group of 8 channels)
+    const int groups = p.C1 / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.N * p.T * groups;
+    if (idx >= total) return;
+    const int cg = (int)(idx % groups);
+    const long long nt = idx / groups;
+    const int t = (int)(nt % p.T);
+    const int n = (int)(nt / p.T);
+    float xs[9];
+    const int half_w = p.W / 2;
+    for (int k = 0; k < p.W; ++k) {
+        const int tt = t + k - half_w;
+        xs[k] = (tt >= 0 && tt < p.T) ? __half2float(p.x[(size_t)n * p.T + tt]) : 0.0f;
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = cg * 8 + 2 * j + e;
+            float acc = __ldg(p.w + p.C1 * p.W + c);
+            for (int k = 0; k < p.W; ++k) acc += __ldg(p.w + c * p.W + k) * xs[k];
+            v[e] = p.act == B200_ACT_TANH ? (1.0f - 2.0f / (__expf(2.0f * acc) + 1.0f))
+                                          : (p.act == B200_ACT_SWISH_CLAMP ? fminf(swish_f(acc), 3.5f) : swish_f(acc));
+        }
+        h[j] = __floats2half2_rn(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T_pad + p.pad_out + t) * p.C1 + cg * 8) = *reinterpret_cast<uint4*>(h);
 }
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm over rows of 512 (RMSNorm.cpp:14-18): x * rsqrt(mean(x^2) + eps) * w ; one warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm512_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                                         const float* __restrict__ w, long long rows) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const uint4* src = reinterpret_cast<const uint4*>(in + row * 512) + lane * 2;
+    uint4 v[2] = {src[0], src[1]};
+    float f[16];
+    float ss = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = __half22float2(h[j]);
+            f[q * 8 + 2 * j] = a.x;
+            f[q * 8 + 2 * j + 1] = a.y;
+            ss += a.x * a.x + a.y * a.y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.0f / 512.0f) + 1e-5f);
+    __half2 o2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane * 16 + 2 * j;
+        o2[j] = __floats2half2_rn(f[2 * j] * rstd * __ldg(w + c), f[2 * j + 1] * rstd * __ldg(w + c + 1));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + row * 512) + lane * 2;
+    dst[0] = *reinterpret_cast<uint4*>(&o2[0]);
+    dst[1] = *reinterpret_cast<uint4*>(&o2[4]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sliding-window attention with rotary embedding, head_dim 64.
+// One CTA = 64 queries of one (chunk, head); 4 warps x 16 query rows; keys in blocks of 64.
+// qkv: [N*T][3][H][64] fp16 (output of the Wqkv GEMM); out: [N*T][H*64] fp16.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_D = 64;
+constexpr int ATT_PITCH = 72;  // halfs per smem row (padding kills the 128-byte-stride bank conflicts)
+
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnParams {
+    const __half* qkv;
+    __half* out;
+    const float* rope;  // [T_max][32][2] (cos, sin)
+    int N, T, H;
+    int win_upper, win_lower;  // keys j with -win_upper <= j - i <= win_lower
+};
+
+// load 64 rows x 64 dims of q or k (which = 0 / 1) for tokens [t0, t0+64) with rotary embedding into smem [64][PITCH]
+__device__ __forceinline__ void load_rope_tile(const AttnParams& p, int n, int h, int which, int t0, __half* dst) {
+    // thread handles (row, 8-dim group j in 0..3) pairs: needs dims [8j, 8j+8) and [32+8j, 32+8j+8)
+    for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
+        const int r = i >> 2, j = i & 3;
+        const int t = t0 + r;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && t < p.T) {
+            const __half* src = p.qkv + (((size_t)n * p.T + t) * 3 + which) * p.H * ATT_D + (size_t)h * ATT_D;
+            const uint4 a = *reinterpret_cast<const uint4*>(src + 8 * j);
+            const uint4 b = *reinterpret_cast<const uint4*>(src + 32 + 8 * j);
+            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+            const __half2* bh = reinterpret_cast<const __half2*>(&b);
+            const float2* cs = reinterpret_cast<const float2*>(p.rope + ((size_t)t * 32 + 8 * j) * 2);
+            __half2 ol[4], oh[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 x1 = __half22float2(ah[e]), x2 = __half22float2(bh[e]);
+                const float2 c0 = cs[2 * e], c1 = cs[2 * e + 1];  // (cos, sin) for dims 8j+2e, 8j+2e+1
+                ol[e] = __floats2half2_rn(c0.x * x1.x - c0.y * x2.x, c1.x * x1.y - c1.y * x2.y);
+                oh[e] = __floats2half2_rn(c0.y * x1.x + c0.x * x2.x, c1.y * x1.y + c1.x * x2.y);
+            }
+            lo = *reinterpret_cast<uint4*>(ol);
+            hi = *reinterpret_cast<uint4*>(oh);
+        }
+        *reinterpret_cast<uint4*>(dst + r * ATT_PITCH + 8 * j) = lo;
+        *reinterpret_cast<uint4*>(dst + r * ATT_PITCH + 32 + 8 * j) = hi;
+    }
+}
+
+__global__ void __launch_bounds__(128) tx_attention_kernel(const AttnParams p) {
+    __shared__ __align__(16) __half q_s[64 * ATT_PITCH];
+    __shared__ __align__(16) __half k_s[64 * ATT_PITCH];
+    __shared__ __align__(16) __half vt_s[64 * ATT_PITCH];  // transposed: [d][key]
+    const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+    const int q0 = qt * 64;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+
+    load_rope_tile(p, n, h, 0, q0, q_s);
+    __syncthreads();
+    // Q fragments for this warp's 16 rows: 4 k-steps
+    uint32_t qa[4][4];
+    {
+        const __half* qb = q_s + (warp * 16) * ATT_PITCH;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(qb + g * ATT_PITCH + ks * 16 + 2 * tig);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qb + (g + 8) * ATT_PITCH + ks * 16 + 2 * tig);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(qb + g * ATT_PITCH + ks * 16 + 8 + 2 * tig);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(qb + (g + 8) * ATT_PITCH + ks * 16 + 8 + 2 * tig);
+        }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.0f;
+    float row_max[2] = {-INFINITY, -INFINITY}, row_sum[2] = {0.0f, 0.0f};
+    const int qi[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+
+    int kstart = q0 - p.win_upper;
+    if (kstart < 0) kstart = 0;
+    kstart &= ~63;
+    int kend = q0 + 63 + p.win_lower + 1;
+    if (kend > p.T) kend = p.T;
+
+    for (int kb = kstart; kb < kend; kb += 64) {
+        __syncthreads();  // previous block's smem reads done
+        load_rope_tile(p, n, h, 1, kb, k_s);
+        // V transposed: thread handles (key r, 8-dim group j)
+        for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+            const int r = i >> 3, j = i & 7;
+            const int t = kb + r;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (t < p.T) {
+                v = *reinterpret_cast<const uint4*>(p.qkv + (((size_t)n * p.T + t) * 3 + 2) * p.H * ATT_D + (size_t)h * ATT_D + 8 * j);
+            }
+            const __half* vh = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vt_s[(8 * j + e) * ATT_PITCH + r] = vh[e];
+        }
+        __syncthreads();
+
+        // S = Q K^T : 8 key tiles of 8
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const __half* kp = k_s + (nt * 8 + g) * ATT_PITCH + ks * 16 + 2 * tig;
+                mma_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+            }
+        }
+        // scale, mask, online softmax
+        float blk_max[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = e >> 1;
+                const int j = kb + nt * 8 + 2 * tig + (e & 1);
+                const int d = j - qi[r];
+                const bool ok = j < p.T && d >= -p.win_upper && d <= p.win_lower && qi[r] < p.T;
+                s[nt][e] = ok ? s[nt][e] * 0.125f : -INFINITY;
+                blk_max[r] = fmaxf(blk_max[r], s[nt][e]);
+            }
+        }
+        float scale_old[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            blk_max[r] = fmaxf(blk_max[r], __shfl_xor_sync(0xffffffffu, blk_max[r], 1));
+            blk_max[r] = fmaxf(blk_max[r], __shfl_xor_sync(0xffffffffu, blk_max[r], 2));
+            const float nm = fmaxf(row_max[r], blk_max[r]);
+            scale_old[r] = nm == -INFINITY ? 1.0f : __expf(row_max[r] - nm);
+            row_max[r] = nm;
+            row_sum[r] *= scale_old[r];
+        }
+        uint32_t pa[4][4];  // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float pv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = e >> 1;
+                pv[e] = row_max[r] == -INFINITY ? 0.0f : __expf(s[nt][e] - row_max[r]);
+                row_sum[r] += pv[e];
+            }
+            const __half2 lo = __floats2half2_rn(pv[0], pv[1]), hi = __floats2half2_rn(pv[2], pv[3]);
+            pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&lo);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+        // O = O * scale + P V
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            o[dt][0] *= scale_old[0];
+            o[dt][1] *= scale_old[0];
+            o[dt][2] *= scale_old[1];
+            o[dt][3] *= scale_old[1];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const __half* vp = vt_s + (dt * 8 + g) * ATT_PITCH + ks * 16 + 2 * tig;
+                mma_16816(o[dt], pa[ks], *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+            }
+        }
+    }
+    // finalise: divide by the row sums (quad-reduced) and store
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        row_sum[r] += __shfl_xor_sync(0xffffffffu, row_sum[r], 1);
+        row_sum[r] += __shfl_xor_sync(0xffffffffu, row_sum[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (qi[r] < p.T) {
+            const float inv = row_sum[r] > 0.0f ? 1.0f / row_sum[r] : 0.0f;
+            __half* dst = p.out + ((size_t)n * p.T + qi[r]) * p.H * ATT_D + (size_t)h * ATT_D;
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) {
+                *reinterpret_cast<__half2*>(dst + dt * 8 + 2 * tig) = __floats2half2_rn(o[dt][2 * r] * inv, o[dt][2 * r + 1] * inv);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TxLayerWeights {
+    __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    float *bo = nullptr, *n1 = nullptr, *n2 = nullptr;
+};
+
+class TxModel;
+
+class TxPlan final : public ForwardPlan {
+public:
+    void run(cudaStream_t stream, ProfileSink* prof) override;
+    int launches() const override { return n_launches; }
+    Conv1Params conv1{};
+    std::vector<GemmPlan> convs;  // conv 2..n
+    struct Layer {
+        GemmPlan qkv, out_proj, fc1, fc2;
+        AttnParams attn;
+        const float *n1, *n2;
+    };
+    std::vector<Layer> layers;
+    GemmPlan upsample, crf;
+    __half *x = nullptr, *y = nullptr;
+    long long rows = 0;
+    int N = 0, T = 0, H = 0;
+    int n_launches = 0;
+};
+
+class TxModel final : public Model {
+public:
+    TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n);
+    ~TxModel() override;
+    size_t workspace_bytes(int N, int T_in) const override;
+    std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
+                                           size_t ws_bytes) override;
+    b200_model_desc desc;
+    float* conv1_w = nullptr;
+    std::vector<__half*> conv_w;  // conv 2..n  [C_out][W*C_in]
+    std::vector<float*> conv_b;
+    std::vector<TxLayerWeights> layers;
+    __half *wu = nullptr, *wc = nullptr;
+    float* bu = nullptr;
+    float* rope = nullptr;
+    std::vector<void*> owned;
+
+private:
+    struct Shapes {
+        std::vector<int> t;      // time length after conv i
+        std::vector<int> t_pad;  // padded rows of the buffer holding conv i's output
+        std::vector<int> pad;    // front padding of that buffer (= next conv's winlen/2)
+    };
+    Shapes shapes(int T_in) const;
+};
+
+TxModel::Shapes TxModel::shapes(int T_in) const {
+    Shapes s;
+    int t = T_in;
+    for (int i = 0; i < desc.num_convs; ++i) {
+        const auto& c = desc.convs[i];
+        t = (t + 2 * (c.winlen / 2) - c.winlen) / c.stride + 1;
+        const int next_pad = i + 1 < desc.num_convs ? desc.convs[i + 1].winlen / 2 : 0;
+        s.t.push_back(t);
+        s.pad.push_back(next_pad);
+        s.t_pad.push_back(t + 2 * next_pad + 16);
+    }
+    return s;
+}
+
+TxModel::TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : desc(d) {
+    if (d.d_model != 512 || d.nhead != 8) throw Unsupported("transformer path implements d_model 512, 8 heads (sup)");
+    if (d.num_convs < 2 || d.convs[0].insize != 1 || d.convs[0].stride != 1 || d.convs[0].winlen > 9 || d.convs[0].size % 8) {
+        throw Unsupported("transformer conv stack shape not supported");
+    }
+    if (d.convs[d.num_convs - 1].size != d.d_model) throw std::invalid_argument("last conv size != d_model");
+    auto up16 = [&](const std::vector<float>& v) {
+        __half* p = upload_f16(v);
+        owned.push_back(p);
+        return p;
+    };
+    auto up32 = [&](const float* data, size_t cnt) {
+        float* p = upload_f32(std::vector<float>(data, data + cnt));
+        owned.push_back(p);
+        return p;
+    };
+    {
+        const auto& tw = find_tensor(tensors, n, "conv.0.conv.weight.tensor");
+        const auto& tb = find_tensor(tensors, n, "conv.0.conv.bias.tensor");
+        const int c1 = d.convs[0].size, w = d.convs[0].winlen;
+        std::vector<float> pk((size_t)c1 * w + c1);
+        std::memcpy(pk.data(), tw.data, sizeof(float) * (size_t)c1 * w);
+        std::memcpy(pk.data() + (size_t)c1 * w, tb.data, sizeof(float) * c1);
+        conv1_w = up32(pk.data(), pk.size());
+    }
+    for (int i = 1; i < d.num_convs; ++i) {
+        const auto& c = d.convs[i];
+        const std::string pfx = "conv." + std::to_string(i) + ".conv.";
+        const auto& tw = find_tensor(tensors, n, pfx + "weight.tensor");
+        const auto& tb = find_tensor(tensors, n, pfx + "bias.tensor");
+        const int K = c.winlen * c.insize;
+        if (K % 64 != 0 || c.size % 32 != 0) throw Unsupported("conv K = winlen * insize must be a multiple of 64");
+        std::vector<float> w((size_t)c.size * K);
+        for (int co = 0; co < c.size; ++co)
+            for (int ci = 0; ci < c.insize; ++ci)
+                for (int k = 0; k < c.winlen; ++k)
+                    w[(size_t)co * K + (size_t)k * c.insize + ci] = tw.data[((size_t)co * c.insize + ci) * c.winlen + k];
+        conv_w.push_back(up16(w));
+        conv_b.push_back(up32(tb.data, c.size));
+    }
+    const int dm = d.d_model, ff = d.dim_feedforward;
+    for (int l = 0; l < d.depth; ++l) {
+        const std::string pfx = "transformer_encoder." + std::to_string(l) + ".";
+        TxLayerWeights lw;
+        const auto& wqkv = find_tensor(tensors, n, pfx + "self_attn.Wqkv.weight.tensor");
+        lw.wqkv = up16(std::vector<float>(wqkv.data, wqkv.data + (size_t)3 * dm * dm));
+        const auto& wo = find_tensor(tensors, n, pfx + "self_attn.out_proj.weight.tensor");
+        lw.wo = up16(std::vector<float>(wo.data, wo.data + (size_t)dm * dm));
+        lw.bo = up32(find_tensor(tensors, n, pfx + "self_attn.out_proj.bias.tensor").data, dm);
+        // fc1 rows [y(0..ff) | gate(0..ff)] (TxModules.cpp:170-176) interleaved to (y_j, gate_j) pairs
+        const auto& w1 = find_tensor(tensors, n, pfx + "ff.fc1.weight.tensor");
+        std::vector<float> w1i((size_t)2 * ff * dm);
+        for (int j = 0; j < ff; ++j) {
+            std::memcpy(&w1i[(size_t)(2 * j) * dm], &w1.data[(size_t)j * dm], sizeof(float) * dm);
+            std::memcpy(&w1i[(size_t)(2 * j + 1) * dm], &w1.data[(size_t)(ff + j) * dm], sizeof(float) * dm);
+        }
+        lw.w1 = up16(w1i);
+        const auto& w2 = find_tensor(tensors, n, pfx + "ff.fc2.weight.tensor");
+        lw.w2 = up16(std::vector<float>(w2.data, w2.data + (size_t)dm * ff));
+        lw.n1 = up32(find_tensor(tensors, n, pfx + "norm1.weight.tensor").data, dm);
+        lw.n2 = up32(find_tensor(tensors, n, pfx + "norm2.weight.tensor").data, dm);
+        layers.push_back(lw);
+    }
+    {
+        const auto& tw = find_tensor(tensors, n, "upsample.linear.weight.tensor");
+        wu = up16(std::vector<float>(tw.data, tw.data + (size_t)d.upsample_scale * dm * dm));
+        bu = up32(find_tensor(tensors, n, "upsample.linear.bias.tensor").data, (size_t)d.upsample_scale * dm);
+        const auto& tc_ = find_tensor(tensors, n, "crf.linear.weight.tensor");
+        std::vector<float> w((size_t)d.outsize * dm);
+        for (size_t i = 0; i < w.size(); ++i) w[i] = tc_.data[i] * d.tx_crf_scale;  // TxModules.cpp:1011-1014
+        wc = up16(w);
+    }
+    {
+        // RotaryEmbeddingImpl (TxModules.cpp:184-218): inv_freq via pow in double, angles/cos/sin in fp32
+        const int half = 32, tmax = d.max_seq_len > 0 ? d.max_seq_len : 2048;
+        std::vector<float> tab((size_t)tmax * half * 2);
+        for (int i = 0; i < half; ++i) {
+            const float fi = (float)(2 * i) / 64.0f;
+            const float inv = (float)(1.0 / std::pow((double)d.theta, (double)fi));
+            for (int t = 0; t < tmax; ++t) {
+                const float ang = (float)t * inv;
+                tab[((size_t)t * half + i) * 2] = std::cos(ang);
+                tab[((size_t)t * half + i) * 2 + 1] = std::sin(ang);
+            }
+        }
+        rope = up32(tab.data(), tab.size());
+    }
+}
+
+TxModel::~TxModel() {
+    for (void* p : owned) cudaFree(p);
+}
+
+size_t TxModel::workspace_bytes(int N, int T_in) const {
+    const Shapes s = shapes(T_in);
+    size_t total = 0;
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    for (int i = 0; i + 1 < desc.num_convs; ++i) total += al((size_t)N * s.t_pad[i] * desc.convs[i].size * 2);
+    const size_t rows = (size_t)N * s.t.back();
+    total += al(rows * 512 * 2) * 3;                               // x, y, attn out
+    total += al(rows * 1536 * 2);                                  // qkv
+    total += al(rows * (size_t)desc.dim_feedforward * 2);          // ff hidden
+    total += al(rows * (size_t)desc.upsample_scale * 512 * 2);     // upsampled
+    return total + 4096;
+}
+
+std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
+                                                size_t ws_bytes) {
+    const Shapes s = shapes(T_in);
+    const int T = s.t.back();
+    if (T > (desc.max_seq_len > 0 ? desc.max_seq_len : 2048)) {
+        throw std::invalid_argument("RotE - maximum sequence length exceeded - your chunksize may be too large");
+    }
+    auto plan = std::make_unique<TxPlan>();
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    auto take = [&](size_t bytes) {
+        uint8_t* p = base;
+        base += (bytes + 255) & ~size_t(255);
+        if ((size_t)(base - static_cast<uint8_t*>(ws)) > ws_bytes) throw std::logic_error("tx workspace overflow");
+        return reinterpret_cast<__half*>(p);
+    };
+    std::vector<__half*> cbuf;
+    for (int i = 0; i + 1 < desc.num_convs; ++i) cbuf.push_back(take((size_t)N * s.t_pad[i] * desc.convs[i].size * 2));
+    const long long rows = (long long)N * T;
+    __half* x = take((size_t)rows * 512 * 2);
+    __half* y = take((size_t)rows * 512 * 2);
+    __half* att = take((size_t)rows * 512 * 2);
+    __half* qkv = take((size_t)rows * 1536 * 2);
+    __half* hid = take((size_t)rows * desc.dim_feedforward * 2);
+    __half* ups = take((size_t)rows * desc.upsample_scale * 512 * 2);
+
+    plan->conv1 = Conv1Params{signal, cbuf[0], conv1_w, N, T_in, s.t_pad[0], s.pad[0], desc.convs[0].size, desc.convs[0].winlen,
+                              desc.convs[0].activation};
+    for (int i = 1; i < desc.num_convs; ++i) {
+        const auto& c = desc.convs[i];
+        GemmDesc g{};
+        g.a = cbuf[i - 1];  // row r <-> time r - pad; output t starts at row stride * t
+        g.batches = N;
+        g.rows_per_batch = s.t[i];
+        g.a_row_stride = (int64_t)c.stride * c.insize;
+        g.a_batch_stride = (int64_t)s.t_pad[i - 1] * c.insize;
+        g.w = conv_w[i - 1];
+        g.N = c.size;
+        g.K = c.winlen * c.insize;
+        g.bias = conv_b[i - 1];
+        g.act = c.activation;
+        const bool last = i + 1 == desc.num_convs;
+        g.out = last ? x : cbuf[i] + (size_t)s.pad[i] * c.size;
+        g.out_m1 = s.t[i];
+        g.out_s0 = last ? (int64_t)s.t[i] * c.size : (int64_t)s.t_pad[i] * c.size;
+        g.out_s1 = c.size;
+        plan->convs.push_back(make_gemm_plan(g));
+    }
+    auto dense = [&](const __half* a, int K, const __half* w, int Nout, const float* bias, int act, __half* out, int ld_out,
+                     const __half* residual, float alpha) {
+        GemmDesc g{};
+        g.a = a;
+        g.batches = 1;
+        g.rows_per_batch = (int)rows;
+        g.a_row_stride = K;
+        g.a_batch_stride = (int64_t)rows * K;
+        g.w = w;
+        g.N = Nout;
+        g.K = K;
+        g.bias = bias;
+        g.act = act;
+        g.out = out;
+        g.out_m1 = 1;
+        g.out_s0 = ld_out;
+        g.out_s1 = 0;
+        g.residual = residual;
+        g.alpha = alpha;
+        return make_gemm_plan(g);
+    };
+    const int ff = desc.dim_feedforward;
+    for (int l = 0; l < desc.depth; ++l) {
+        const auto& lw = layers[l];
+        TxPlan::Layer L;
+        L.qkv = dense(x, 512, lw.wqkv, 1536, nullptr, GEMM_ACT_NONE, qkv, 1536, nullptr, 0.0f);
+        L.attn = AttnParams{qkv, att, rope, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
+        L.out_proj = dense(att, 512, lw.wo, 512, lw.bo, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
+        L.fc1 = dense(x, 512, lw.w1, 2 * ff, nullptr, GEMM_ACT_SWIGLU, hid, ff, nullptr, 0.0f);
+        L.fc2 = dense(hid, ff, lw.w2, 512, nullptr, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
+        L.n1 = lw.n1;
+        L.n2 = lw.n2;
+        plan->layers.push_back(L);
+    }
+    plan->upsample = dense(x, 512, wu, desc.upsample_scale * 512, bu, GEMM_ACT_NONE, ups, desc.upsample_scale * 512, nullptr, 0.0f);
+    {
+        GemmDesc g{};
+        g.a = ups;
+        g.batches = 1;
+        g.rows_per_batch = (int)(rows * desc.upsample_scale);
+        g.a_row_stride = 512;
+        g.a_batch_stride = (int64_t)rows * desc.upsample_scale * 512;
+        g.w = wc;
+        g.N = desc.outsize;
+        g.K = 512;
+        g.act = GEMM_ACT_NONE;
+        g.out = scores;
+        g.out_m1 = 1;
+        g.out_s0 = desc.outsize;
+        plan->crf = make_gemm_plan(g);
+    }
+    plan->x = x;
+    plan->y = y;
+    plan->rows = rows;
+    plan->N = N;
+    plan->T = T;
+    plan->H = desc.nhead;
+    plan->n_launches = 1 + (desc.num_convs - 1) + desc.depth * 7 + 2;
+    return plan;
+}
+
+void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
+    {
+        const long long total = (long long)conv1.N * conv1.T * (conv1.C1 / 8);
+        tx_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(conv1);
+        if (prof) prof->mark("tx_conv1", stream);
+    }
+    for (auto& c : convs) {
+        run_gemm(c, stream);
+        if (prof) prof->mark("tx_conv_gemm", stream);
+    }
+    const unsigned norm_grid = (unsigned)((rows + 7) / 8);
+    for (auto& L : layers) {
+        run_gemm(L.qkv, stream);
+        if (prof) prof->mark("qkv_gemm", stream);
+        tx_attention_kernel<<<dim3((unsigned)((T + 63) / 64), (unsigned)H, (unsigned)N), 128, 0, stream>>>(L.attn);
+        if (prof) prof->mark("tx_attention", stream);
+        run_gemm(L.out_proj, stream);
+        if (prof) prof->mark("out_proj_gemm", stream);
+        rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n1, rows);
+        if (prof) prof->mark("rmsnorm", stream);
+        run_gemm(L.fc1, stream);
+        if (prof) prof->mark("fc1_swiglu_gemm", stream);
+        run_gemm(L.fc2, stream);
+        if (prof) prof->mark("fc2_gemm", stream);
+        rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n2, rows);
+        if (prof) prof->mark("rmsnorm", stream);
+    }
+    run_gemm(upsample, stream);
+    if (prof) prof->mark("upsample_gemm", stream);
+    run_gemm(crf, stream);
+    if (prof) prof->mark("crf_gemm", stream);
+    B200_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+std::unique_ptr<Model> make_tx_model(const b200_model_desc& desc, const b200_tensor* tensors, int n) {
+    return std::make_unique<TxModel>(desc, tensors, n);
+}
+
 }  // namespace b200

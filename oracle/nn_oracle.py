@@ -125,35 +125,40 @@ def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_qui
     x = np.ascontiguousarray(signal, np.float32).reshape(signal.shape[0], 1, -1)
     inter = {}
     q = _q16 if emulate_fp16 else (lambda a: a)
+    w_in = w
     if emulate_fp16:
         w = {k: (_q16(v) if v.ndim >= 2 and not (k.startswith("0.conv") or k.startswith("1.conv")) else v)
              for k, v in w.items()}
     if cfg.is_tx_model:
         tx = cfg.tx
+        if emulate_fp16:
+            w = dict(w)
+            w["conv.0.conv.weight.tensor"] = w_in["conv.0.conv.weight.tensor"]  # conv1 runs in fp32
         for i, c in enumerate(cfg.convs):
-            x = conv1d(x, w[f"conv.{i}.conv.weight.tensor"], w[f"conv.{i}.conv.bias.tensor"], c.stride, c.activation)
+            x = q(conv1d(x, w[f"conv.{i}.conv.weight.tensor"], w[f"conv.{i}.conv.bias.tensor"], c.stride, c.activation))
         x = x.transpose(0, 2, 1)
         inter["conv"] = x
         N, T, d = x.shape
         H, D = tx.nhead, tx.d_model // tx.nhead
         alpha = np.float32(tx.deepnorm_alpha)
+        wc = q(w_in["crf.linear.weight.tensor"] * np.float32(tx.crf_scale))
         for l in range(tx.depth):
             p = f"transformer_encoder.{l}."
-            qkv = (x @ w[p + "self_attn.Wqkv.weight.tensor"].T).reshape(N, T, 3, H, D)
-            q, k, v = rope(qkv[:, :, 0], tx.theta), rope(qkv[:, :, 1], tx.theta), qkv[:, :, 2]
-            a = windowed_attention(q, k, v, tx.attn_window, cpu_split_quirk).reshape(N, T, d)
-            a = a @ w[p + "self_attn.out_proj.weight.tensor"].T + w[p + "self_attn.out_proj.bias.tensor"]
-            x = rmsnorm(a + x * alpha, w[p + "norm1.weight.tensor"]).astype(np.float32)
+            qkv = q(x @ w[p + "self_attn.Wqkv.weight.tensor"].T).reshape(N, T, 3, H, D)
+            qq, k, v = q(rope(qkv[:, :, 0], tx.theta)), q(rope(qkv[:, :, 1], tx.theta)), qkv[:, :, 2]
+            a = q(windowed_attention(qq, k, v, tx.attn_window, cpu_split_quirk).reshape(N, T, d))
+            a = q(a @ w[p + "self_attn.out_proj.weight.tensor"].T + w[p + "self_attn.out_proj.bias.tensor"] + x * alpha)
+            x = q(rmsnorm(a, w[p + "norm1.weight.tensor"]).astype(np.float32))
             t = x @ w[p + "ff.fc1.weight.tensor"].T
             y, gate = t[..., : tx.dim_feedforward], t[..., tx.dim_feedforward:]
-            f = ((gate * _sigmoid(gate)) * y) @ w[p + "ff.fc2.weight.tensor"].T
-            x = rmsnorm(f + x * alpha, w[p + "norm2.weight.tensor"]).astype(np.float32)
+            f = q(q((gate * _sigmoid(gate)) * y) @ w[p + "ff.fc2.weight.tensor"].T + x * alpha)
+            x = q(rmsnorm(f, w[p + "norm2.weight.tensor"]).astype(np.float32))
             if l == 0:
                 inter["layer0"] = x
         inter["encoder"] = x
-        u = x @ w["upsample.linear.weight.tensor"].T + w["upsample.linear.bias.tensor"]
+        u = q(x @ w["upsample.linear.weight.tensor"].T + w["upsample.linear.bias.tensor"])
         u = u.reshape(N, tx.upsample_scale * T, d)
-        scores = u @ (w["crf.linear.weight.tensor"] * np.float32(tx.crf_scale)).T
+        scores = q(u @ wc.T)
         scores = scores.astype(np.float32)
         return (scores, inter) if return_intermediates else scores
 

@@ -12,6 +12,8 @@ sig = np.random.default_rng(1234).standard_normal((N, runner.chunk_size())).asty
 for i in range(N): runner.accept_chunk(i, sig[i])
 got = runner.forward_scores(N).astype(np.float32)
 if cfg.clamp: got = np.clip(got, -5, 5)
+print("got finite", np.isfinite(got).all(), "std", got.std())
 for name, ref in [("fp32 oracle", nn_oracle.forward(cfg, w, sig.astype(np.float32))), ("fp16-storage oracle", nn_oracle.forward(cfg, w, sig.astype(np.float32), emulate_fp16=True))]:
     e = np.abs(got - ref); sc = np.abs(ref).max()
     print(f"{kind} vs {name}: scale {sc:.2f} max {e.max():.4f} mean {e.mean():.5f} relL2 {np.linalg.norm(got-ref)/np.linalg.norm(ref):.2e} frac>1e-3*scale {(e>1e-3*sc).mean():.4f} frac>4e-3*scale {(e>4e-3*sc).mean():.5f} p99.9 {np.quantile(e,0.999):.4f}")
+    print("   per-t mean err (every 16th)", np.round(e.mean(axis=(0,2))[::16], 4))
