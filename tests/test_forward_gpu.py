@@ -90,7 +90,7 @@ def test_call_chunks_end_to_end(crf_oracle, kind, N, T):
         assert len(c.moves) == runner.chunk_size() // cfg.stride
         assert len(c.sequence) == len(c.qstring) == int(c.moves.sum())
     # partial batch: the first k results do not depend on what the other slots hold
-    k = 5
+    k = min(5, N - 1)
     part = runner.call_chunks(k)
     assert [p.sequence for p in part] == [c.sequence for c in chunks[:k]]
     stats = runner.sample_stats()
