@@ -1,0 +1,171 @@
+"""CPU-only checks of the host side: C ABI symbols, loud failure without a GPU, config parsing, weight container,
+the numerics contract, and the multi-process sharding helpers (gloo, world_size 2)."""
+import ctypes as C
+import math
+import os
+import pathlib
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import MODELS, ROOT, model_dir
+
+
+def test_library_exports_every_declared_symbol():
+    from dorado_b200 import lib as L
+    header = (ROOT / "include" / "b200call.h").read_text()
+    declared = set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", header))
+    assert declared, "no B200_API declarations parsed"
+    lib = L.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libb200call.so does not export {name}"
+    assert set(L.EXPORTS) == declared
+    assert b"sm_100a" in lib.b200_version()
+
+
+def test_fails_loudly_without_a_gpu():
+    from dorado_b200 import lib as L
+    lib = L.load_library()
+    if lib.b200_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(L.B200Error) as e:
+        L.decode_scores(np.zeros((1, 4, 256), np.float16))
+    assert e.value.status == L.B200_ERR_CUDA and "no CPU fallback" in str(e.value)
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir("fast"))
+    with pytest.raises(L.B200Error) as e:
+        B200Caller(cfg, synthetic_weights(cfg, 1))
+    assert e.value.status == L.B200_ERR_CUDA
+
+
+def test_null_arguments_return_invalid():
+    from dorado_b200 import lib as L
+    lib = L.load_library()
+    assert lib.b200_engine_create(None, None, 0, 0, None) == L.B200_ERR_INVALID
+    assert b"null" in lib.b200_last_error()
+    assert lib.b200_runner_batch_size(None) == 0
+
+
+def test_model_configs_parse_like_the_reference():
+    """Expected values follow dorado/config/BasecallModelConfig.cpp (and its tests/BasecallModelConfigTest.cpp)."""
+    from dorado_b200.config import ACT_SWISH, ACT_TANH, load_model_config
+    fast, hac, sup = (load_model_config(model_dir(k)) for k in ("fast", "hac", "sup"))
+    assert (fast.stride, fast.lstm_size, fast.lstm_layers, fast.state_len, fast.outsize) == (6, 96, 5, 3, 256)
+    assert (hac.stride, hac.lstm_size, hac.state_len, hac.outsize, hac.clamp) == (6, 384, 4, 1024, True)
+    assert [c.activation for c in hac.convs] == [ACT_SWISH, ACT_SWISH, ACT_TANH]
+    assert hac.bias is False and hac.out_features is None
+    assert (hac.qscale, hac.qbias) == (1.1, -1.1)
+    assert sup.is_tx_model and sup.stride == 6 and sup.stride_inner() == 12 and sup.outsize == 4096
+    assert sup.tx.attn_window == (127, 128) and sup.tx.depth == 18 and abs(sup.tx.deepnorm_alpha - 2.4494897) < 1e-6
+    assert sup.chunk_size_granularity() == 192 and sup.normalise_chunk_size(10000) == 9984
+    assert fast.normalise_chunk_size(10000) == 9996 and fast.out_len(9996) == 1666
+
+
+def test_weight_names_follow_reference_file_list(tmp_path):
+    from dorado_b200.config import load_model_config
+    from dorado_b200.weights import load_b2w, save_b2w, synthetic_weights, tensor_specs
+    hac = load_model_config(model_dir("hac"))
+    names = list(tensor_specs(hac))
+    # dorado/basecall/crf_utils.cpp:34-95
+    assert names[:2] == ["0.conv.weight.tensor", "0.conv.bias.tensor"]
+    assert "4.rnn.weight_ih_l0.tensor" in names and "8.rnn.bias_hh_l0.tensor" in names
+    assert names[-1] == "9.linear.weight.tensor"
+    sup = load_model_config(model_dir("sup"))
+    sn = list(tensor_specs(sup))
+    assert sn[10] == "transformer_encoder.0.self_attn.Wqkv.weight.tensor" and sn[-1] == "crf.linear.weight.tensor"
+    assert len(sn) == 10 + 18 * 7 + 3
+    w = synthetic_weights(hac, 3)
+    save_b2w(tmp_path / "w.b2w", w)
+    back = load_b2w(tmp_path / "w.b2w")
+    assert list(back) == list(w) and all(np.array_equal(back[k], w[k]) for k in w)
+    assert not np.any(w["4.rnn.bias_hh_l0.tensor"])
+
+
+def test_numerics_contract_accuracy(crf_oracle):
+    lib = crf_oracle.lib
+    xs = np.concatenate([-np.logspace(-6, 1.9, 4000), [0.0]]).astype(np.float32)
+    got = np.array([lib.crf_math_expf(float(x)) for x in xs], np.float32)
+    ref = np.exp(xs.astype(np.float64))
+    assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-37)) < 3e-7
+    ys = np.logspace(-6, 3, 4000).astype(np.float32)
+    gl = np.array([lib.crf_math_logf(float(y)) for y in ys], np.float32)
+    rl = np.log(ys.astype(np.float64))
+    assert np.max(np.abs(gl - rl) / np.maximum(np.abs(rl), 1e-3)) < 3e-7
+    ps = np.linspace(0, 1, 1001).astype(np.float32)
+    gp = np.array([lib.crf_math_pow0p4f(float(p)) for p in ps], np.float32)
+    assert np.max(np.abs(gp - ps.astype(np.float64) ** 0.4)) < 2e-7
+    assert lib.crf_math_lse2(1.0, 1.0) == pytest.approx(1.0 + math.log(2.0), rel=2e-7)
+    assert lib.crf_math_lse2(30.0, 1.0) == 30.0  # 17.0 cut-off of beam_search.cpp:44
+    halfs = np.arange(0, 65536, 7, dtype=np.uint16)
+    halfs = halfs[~np.isnan(halfs.view(np.float16))]  # NaN payload quieting is implementation-defined
+    conv = np.array([lib.crf_half_to_float(int(h)) for h in halfs], np.float32)
+    np.testing.assert_array_equal(conv.view(np.uint32), halfs.view(np.float16).astype(np.float32).view(np.uint32))
+
+
+def test_oracle_decode_edge_cases(crf_oracle):
+    """T = 1, ties everywhere, saturated scores, narrow beams: the reference's edge behaviour, restated."""
+    r = crf_oracle.decode(np.zeros((2, 1, 256), np.float16))
+    assert r.n_bases.tolist() == [1, 1] and (r.moves[:, 0] == 1).all()
+    r = crf_oracle.decode(np.full((1, 50, 256), 5.0, np.float16), clamp_val=5.0)
+    assert r.n_bases[0] == 50  # every step beats the fixed stay score 2.0
+    r = crf_oracle.decode(np.full((1, 50, 256), -5.0, np.float16), clamp_val=5.0)
+    assert r.n_bases[0] == 1   # stays win everywhere; the first block always emits
+    r1 = crf_oracle.decode(np.random.default_rng(0).standard_normal((1, 80, 1024)).astype(np.float16), beam_width=1)
+    assert 1 <= r1.n_bases[0] <= 80 and set(r1.sequences[0]) <= set("ACGT")
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, os.environ["B200_ROOT"])
+import torch, torch.distributed as dist
+from dorado_b200 import parallel as P
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['B200_PORT']}",
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = P.shard_reads(103, world, rank)
+sizes = P.all_gather_int(len(mine))
+assert sum(sizes) == 103 and max(sizes) - min(sizes) <= 1, sizes
+t = P.max_over_ranks(1.0 + rank)
+assert t == float(world), t
+total = P.sum_over_ranks(len(mine))
+assert total == 103
+P.barrier()
+print("ok", rank, len(mine), t)
+"""
+
+
+def test_multi_rank_sharding_with_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", B200_ROOT=str(ROOT), B200_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", _WORKER], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_adapter_header_compiles_against_reference_headers():
+    """include/B200ModelRunner.h implements dorado::basecall::ModelRunnerBase; type-check it against the
+    reference's own headers where the reference tree is available (not on the GPU box)."""
+    d = pathlib.Path("/root/reference/dorado")
+    if not d.exists():
+        pytest.skip("reference tree not present")
+    import torch
+    t = pathlib.Path(torch.__file__).parent
+    src = ROOT / "tests" / "data" / "adapter_check.cpp"
+    src.write_text('#include "B200ModelRunner.h"\nint main() { return 0; }\n')
+    inc = [ROOT / "include", d, d / "basecall", d / "basecall/include", d / "nn/include", d / "config/include",
+           d / "torch_utils/include", d / "utils/include", d / "models/include", d / "3rdparty/spdlog/include",
+           d / "3rdparty/NVTX/c/include", d / "3rdparty/toml11/include"]
+    cmd = ["/usr/bin/g++", "-std=c++23", "-fsyntax-only", "-w", "-D_GLIBCXX_USE_CXX11_ABI=1", "-DDORADO_CUDA_BUILD=0",
+           "-DDORADO_METAL_BUILD=0", "-DDORADO_ORIN=0"] + [f"-I{p}" for p in inc] + \
+          ["-isystem", str(t / "include"), "-isystem", str(t / "include/torch/csrc/api/include"), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
