@@ -15,8 +15,8 @@
 //   bwd     fp32  [N][T+1][S]      written by kernel 1, read once by kernel 2
 //   beam    8 B   [N][T][32]       {state:16, prev:8, stay:8, block_prob:f32} per kept element
 //   out     u8    moves/seq/qstr [N][T], n_bases i32 [N]
-// Thread mapping: S/4 threads per chunk; in the backward scan thread q owns states {q + k*S/4},
-// in the forward scan states {4q..4q+3}; both touch the same 16 contiguous scores per block.
+// Thread mapping: one thread per state in both scans (two states per thread for S = 1024 in the forward
+// kernel); the forward kernel adds one beam-search warp per chunk that runs one block behind the scan.
 #include "decode.h"
 
 #include "b200_crf_math.h"
@@ -34,79 +34,68 @@ constexpr uint32_t kCrcSeed = 0x12345678u;
 template <int SL>
 struct Dims {
     static constexpr int S = 1 << (2 * SL);
-    static constexpr int P = S / 4;
     static constexpr int C = 4 * S;
 };
 
-__device__ __forceinline__ void unpack16(const uint4& r0, const uint4& r1, float clamp_val, float* sc) {
-    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
-        const float2 f = __half22float2(h);
-        sc[2 * i] = f.x;
-        sc[2 * i + 1] = f.y;
-    }
-    if (clamp_val > 0.0f) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            sc[i] = sc[i] < -clamp_val ? -clamp_val : (sc[i] > clamp_val ? clamp_val : sc[i]);
-        }
-    }
-}
-
-template <int GT>
-__device__ __forceinline__ void group_sync(int g) {
-    if constexpr (GT <= 32) {
-        __syncwarp();
-    } else {
-        named_bar_sync(1 + g, GT);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Kernel 1: backward scan (CPUDecoder.cpp:69-92).
+// Kernel 1: backward scan (CPUDecoder.cpp:69-92).  One thread per state.
+//   bwd[t][v] = LSE( bwd[t+1][v] + blank, bwd[t+1][succ_j] + M[t][succ_j*4 + top(v)] , j = 0..3 )
+// with v = q + top*S/4, succ_j = 4q + j.  The score row is staged through shared memory "transposed"
+// ([i % 16][i / 16]) so that both the coalesced global read (4 fp16 per thread) and the per-state
+// gather are bank-conflict free.
 // ------------------------------------------------------------------------------------------------
 template <int SL>
-__global__ void __launch_bounds__(256) crf_bwd_scan_kernel(const __half* __restrict__ scores,
-                                                           float* __restrict__ bwd,
-                                                           int N,
-                                                           int T,
-                                                           float clamp_val,
-                                                           float blank) {
-    constexpr int S = Dims<SL>::S, P = Dims<SL>::P, C = Dims<SL>::C;
-    constexpr int GROUPS = (256 / P) > 0 ? (256 / P) : 1;
-    constexpr int GT = P < 32 ? 32 : P;  // sync granularity (sub-warp groups share a warp)
+struct ScanCfg {
+    static constexpr int S = Dims<SL>::S, C = Dims<SL>::C, P4 = S / 4;
+    static constexpr int SPT = S > 512 ? S / 512 : 1;   // states per scan thread
+    static constexpr int NT = S / SPT;                  // scan threads per chunk
+    static constexpr int PITCH = P4 + 2;                // 4 * PITCH == 8 (mod 32): conflict-free staging
+};
+
+__device__ __forceinline__ float clampf(float v, float c) { return c > 0.0f ? (v < -c ? -c : (v > c ? c : v)) : v; }
+
+template <int SL>
+__global__ void __launch_bounds__(ScanCfg<SL>::S > 256 ? ScanCfg<SL>::S : 256)
+        crf_bwd_scan_kernel(const __half* __restrict__ scores, float* __restrict__ bwd, int N, int T, float clamp_val,
+                            float blank) {
+    using Cfg = ScanCfg<SL>;
+    constexpr int S = Cfg::S, C = Cfg::C, P4 = Cfg::P4, PITCH = Cfg::PITCH;
+    constexpr int CH = S >= 256 ? 1 : 256 / S;  // chunks per CTA
     constexpr int PF = 4;
-    constexpr int RS = C / 8;  // row stride in uint4
-
-    const int g = threadIdx.x / P;
-    const int q = threadIdx.x % P;
-    const int chunk = blockIdx.x * GROUPS + g;
-    __shared__ __align__(16) float a[GROUPS][2][S];
-
+    const int g = threadIdx.x / S;
+    const int v = threadIdx.x % S;
+    const int chunk = blockIdx.x * CH + g;
+    __shared__ __align__(16) float a[CH][2][S];
+    __shared__ float st[CH][2][16 * PITCH];
     const bool active = chunk < N;
-    const int chunk_c = active ? chunk : (N - 1);  // inactive groups shadow the last chunk, no stores
-    const uint4* srow = reinterpret_cast<const uint4*>(scores + (size_t)chunk_c * T * C) + 2 * q;
+    const int chunk_c = active ? chunk : N - 1;  // idle groups shadow the last chunk (no stores)
+    const uint2* srow = reinterpret_cast<const uint2*>(scores + (size_t)chunk_c * T * C) + v;
+    constexpr int RS = C / 4;  // row stride in uint2
     float* out = bwd + (size_t)chunk_c * (T + 1) * S;
+    const int q = v % P4, top = v / P4;
+    const int st_row = 4 * (v & 3), st_col = v >> 2;
 
-    uint4 pf[PF][2];
+    uint2 pf[PF];
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
         const int tt = T - 1 - k;
-        if (tt >= 0) {
-            pf[k][0] = ldg_nc_v4(srow + (size_t)tt * RS);
-            pf[k][1] = ldg_nc_v4(srow + (size_t)tt * RS + 1);
-        }
+        if (tt >= 0) pf[k] = __ldg(srow + (size_t)tt * RS);
     }
-    float own[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        own[k] = 0.0f;
-        a[g][0][q + k * P] = 0.0f;
-        if (active) out[(size_t)T * S + q + k * P] = 0.0f;
-    }
-    group_sync<GT>(g);
+    auto stage = [&](int buf, const uint2& r) {
+        const __half2 h0 = *reinterpret_cast<const __half2*>(&r.x), h1 = *reinterpret_cast<const __half2*>(&r.y);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        float* d = &st[g][buf][st_row * PITCH + st_col];
+        d[0] = clampf(f0.x, clamp_val);
+        d[PITCH] = clampf(f0.y, clamp_val);
+        d[2 * PITCH] = clampf(f1.x, clamp_val);
+        d[3 * PITCH] = clampf(f1.y, clamp_val);
+    };
+    float own = 0.0f;
+    a[g][0][v] = 0.0f;
+    if (active) out[(size_t)T * S + v] = 0.0f;
+    stage(0, pf[0]);
+    if (T - 1 - PF >= 0) pf[0] = __ldg(srow + (size_t)(T - 1 - PF) * RS);
+    if constexpr (S <= 32) __syncwarp(); else named_bar_sync(1 + g, S);
 
     int cur = 0;
     for (int t = T - 1; t >= 0; t -= PF) {
@@ -114,23 +103,18 @@ __global__ void __launch_bounds__(256) crf_bwd_scan_kernel(const __half* __restr
         for (int k = 0; k < PF; ++k) {
             const int tt = t - k;
             if (tt >= 0) {
-                const uint4 r0 = pf[k][0], r1 = pf[k][1];
-                if (tt - PF >= 0) {
-                    pf[k][0] = ldg_nc_v4(srow + (size_t)(tt - PF) * RS);
-                    pf[k][1] = ldg_nc_v4(srow + (size_t)(tt - PF) * RS + 1);
+                // stage the next block's scores while this block is computed
+                if (tt - 1 >= 0) {
+                    stage(cur ^ 1, pf[(k + 1) % PF]);
+                    if (tt - 1 - PF >= 0) pf[(k + 1) % PF] = __ldg(srow + (size_t)(tt - 1 - PF) * RS);
                 }
-                float sc[16];
-                unpack16(r0, r1, clamp_val, sc);
                 const float4 nx = *reinterpret_cast<const float4*>(&a[g][cur][4 * q]);
-#pragma unroll
-                for (int top = 0; top < 4; ++top) {
-                    own[top] = b200_lse5(B200_ADD(own[top], blank), B200_ADD(nx.x, sc[0 + top]),
-                                         B200_ADD(nx.y, sc[4 + top]), B200_ADD(nx.z, sc[8 + top]),
-                                         B200_ADD(nx.w, sc[12 + top]));
-                    a[g][cur ^ 1][q + top * P] = own[top];
-                    if (active) out[(size_t)tt * S + q + top * P] = own[top];
-                }
-                group_sync<GT>(g);
+                const float* sc = &st[g][cur][top * PITCH + q];
+                own = b200_lse5(B200_ADD(own, blank), B200_ADD(nx.x, sc[0]), B200_ADD(nx.y, sc[4 * PITCH]),
+                                B200_ADD(nx.z, sc[8 * PITCH]), B200_ADD(nx.w, sc[12 * PITCH]));
+                a[g][cur ^ 1][v] = own;
+                if (active) out[(size_t)tt * S + v] = own;
+                if constexpr (S <= 32) __syncwarp(); else named_bar_sync(1 + g, S);
                 cur ^= 1;
             }
         }
@@ -138,7 +122,10 @@ __global__ void __launch_bounds__(256) crf_bwd_scan_kernel(const __half* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel 2: forward scan + posteriors + beam search.
+// Kernel 2: forward scan + posteriors + beam search, pipelined.
+// Per chunk: NT scan threads (one state each; two for S = 1024) produce, for block t, the clamped score row, the
+// bwd[t+1] row and the posterior row into a double-buffered shared-memory slot; one beam warp (lane = beam
+// element) consumes the slot one block behind, so the scan of block t+1 overlaps the beam step of block t.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t crc_bits(uint32_t crc, uint32_t nb, int nbits) {
     for (int i = 0; i < nbits; ++i) {
@@ -158,12 +145,24 @@ __device__ __forceinline__ uint32_t crc2(uint32_t crc, uint32_t nb) {
     return crc;
 }
 
+// inverse of crc2 for known new bits: the hash a sequence must have had before `nb` was appended
+__device__ __forceinline__ uint32_t crc2_inv(uint32_t crc, uint32_t nb) {
+    uint32_t b = crc >> 31;  // the polynomial has bit 31 set, (x >> 1) does not
+    uint32_t t = crc ^ (b ? kCrcPoly : 0u);
+    crc = (t << 1) | (b ^ ((nb >> 1) & 1u));
+    b = crc >> 31;
+    t = crc ^ (b ? kCrcPoly : 0u);
+    crc = (t << 1) | (b ^ (nb & 1u));
+    return crc;
+}
+
 struct BeamSmem {
     float cand_score[5 * kBeamW];
     uint32_t cand_hash[5 * kBeamW];
     float new_score[kBeamW];
     uint32_t new_hash[kBeamW];
     uint32_t new_meta[kBeamW];  // state | prev << 16 | stay << 24
+    __align__(16) uint32_t prev_hash[kBeamW];
 };
 
 struct BeamLane {
@@ -230,7 +229,7 @@ __device__ int beam_init(const float* bw_row, BeamSmem& bs, BeamLane& me, int W,
 // One block of the beam search for one chunk, executed by one warp (lane = beam element).
 // Returns the new beam width; writes the kept elements (and their block probabilities) to beam_row.
 template <int SL>
-__device__ int beam_step(const float* sc_row,
+__device__ int beam_step(const __half* sc_row,
                          const float* bw_row,
                          const float* post_row,
                          BeamSmem& bs,
@@ -246,65 +245,85 @@ __device__ int beam_step(const float* sc_row,
     constexpr int SB = 2 * SL;
     constexpr uint32_t mask = S - 1;
     const bool valid = lane < width;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     // --- candidates (beam_search.cpp:225-262) ---
     uint32_t ns[4], hs[4];
+    float s[5];
     float lmax = B200_FLT_LOWEST;
     if (valid) {
         const uint32_t shifted = me.state << 2;
+        const uint32_t dropped = shifted >> SB;
 #pragma unroll
         for (uint32_t b = 0; b < 4; ++b) {
             ns[b] = (shifted & mask) | b;
-            const uint32_t move_idx = ((ns[b] << 2) + (shifted >> SB)) & 0xffffu;
-            const float v = B200_ADD(B200_ADD(me.score, sc_row[move_idx]), bw_row[ns[b]]);
+            const uint32_t move_idx = ((ns[b] << 2) + dropped) & 0xffffu;
+            s[b] = B200_ADD(B200_ADD(me.score, __half2float(sc_row[move_idx])), bw_row[ns[b]]);
             hs[b] = crc2(me.hash, b);
-            bs.cand_score[lane * 4 + b] = v;
-            bs.cand_hash[lane * 4 + b] = hs[b];
-            lmax = b200_fmaxf(lmax, v);
+            lmax = b200_fmaxf(lmax, s[b]);
         }
-        const float sv = B200_ADD(B200_ADD(me.score, blank), bw_row[me.state]);
-        bs.cand_score[4 * width + lane] = sv;
-        bs.cand_hash[4 * width + lane] = me.hash;
-        lmax = b200_fmaxf(lmax, sv);
+        s[4] = B200_ADD(B200_ADD(me.score, blank), bw_row[me.state]);
+        lmax = b200_fmaxf(lmax, s[4]);
     }
     float max_score = warp_max(lmax);
-    __syncwarp();
 
     // --- merge stays with equal-hash steps (beam_search.cpp:264-305) ---
-    bool dup = false;
+    // stay i matches step (j, b_i) iff hash_j == crc2_inv(hash_i, b_i): one lookup of the 32 previous hashes
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    bool dup = false;
+    if (valid) dup = __popc(__match_any_sync(vmask, me.hash)) > 1;
+    bs.prev_hash[lane] = valid ? me.hash : 0u;
     if (valid) {
-        dup = __popc(__match_any_sync(vmask, me.hash)) > 1;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bs.cand_score[lane * 4 + b] = s[b];
     }
+    __syncwarp();
     if (!__any_sync(0xffffffffu, dup)) {
-        // all hashes distinct: each stay can match at most one step and no step is shared
         float folded = B200_FLT_LOWEST;
         if (valid) {
-            const int latest = me.state & 3;
-            int jm = -1;
-            for (int j = 0; j < width; ++j) {
-                if (bs.cand_hash[j * 4 + latest] == me.hash) jm = j;
+            const uint32_t latest = me.state & 3u;
+            const uint32_t target = crc2_inv(me.hash, latest);
+            uint32_t hit = 0u;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const uint4 h = *reinterpret_cast<const uint4*>(&bs.prev_hash[4 * j4]);
+                hit |= (h.x == target ? 1u : 0u) << (4 * j4);
+                hit |= (h.y == target ? 1u : 0u) << (4 * j4 + 1);
+                hit |= (h.z == target ? 1u : 0u) << (4 * j4 + 2);
+                hit |= (h.w == target ? 1u : 0u) << (4 * j4 + 3);
             }
-            if (jm >= 0) {
-                const int si = 4 * width + lane, pi = jm * 4 + latest;
-                const float st = bs.cand_score[si], sp = bs.cand_score[pi];
+            hit &= vmask;
+            if (hit) {
+                const int jm = __ffs(hit) - 1;  // hashes are distinct: at most one bit
+                const int pi = jm * 4 + (int)latest;
+                const float st = s[4], sp = bs.cand_score[pi];
                 folded = b200_log_sum_exp(st, sp);
                 if (st > sp) {
-                    bs.cand_score[si] = folded;
+                    s[4] = folded;
                     bs.cand_score[pi] = B200_FLT_LOWEST;
                 } else {
                     bs.cand_score[pi] = folded;
-                    bs.cand_score[si] = B200_FLT_LOWEST;
+                    s[4] = B200_FLT_LOWEST;
                 }
             }
         }
         max_score = b200_fmaxf(max_score, warp_max(folded));
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) s[b] = bs.cand_score[lane * 4 + b];
+        }
     } else {
         // hash collision between beam elements (rare): replay the reference's sequential order
-        float m2 = max_score;
-        // gather the latest bases through shared memory so lane 0 can see them
+        if (valid) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bs.cand_hash[lane * 4 + b] = hs[b];
+            bs.cand_score[4 * width + lane] = s[4];
+            bs.cand_hash[4 * width + lane] = me.hash;
+        }
         bs.new_meta[lane] = valid ? (me.state & 3u) : 0u;
         __syncwarp();
+        float m2 = max_score;
         if (lane == 0) {
             for (int i = 0; i < width; ++i) {
                 const int si = 4 * width + i;
@@ -327,14 +346,12 @@ __device__ int beam_step(const float* sc_row,
             }
         }
         max_score = __shfl_sync(0xffffffffu, m2, 0);
-    }
-    __syncwarp();
-
-    float s[5];
-    if (valid) {
+        __syncwarp();
+        if (valid) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s[b] = bs.cand_score[lane * 4 + b];
-        s[4] = bs.cand_score[4 * width + lane];
+            for (int b = 0; b < 4; ++b) s[b] = bs.cand_score[lane * 4 + b];
+            s[4] = bs.cand_score[4 * width + lane];
+        }
     }
 
     // --- cutoff (beam_search.cpp:310-396) ---
@@ -372,19 +389,13 @@ __device__ int beam_step(const float* sc_row,
 
     // --- keep the first W candidates >= cutoff in candidate order (beam_search.cpp:398-409) ---
     bool f[5];
-    int c = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) f[k] = valid && (s[k] >= cutoff);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) c += f[k];
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int steps_total = __shfl_sync(0xffffffffu, incl, 31);
-    int pos = incl - c;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, f[0]), b1 = __ballot_sync(0xffffffffu, f[1]);
+    const uint32_t b2 = __ballot_sync(0xffffffffu, f[2]), b3 = __ballot_sync(0xffffffffu, f[3]);
+    const uint32_t b4 = __ballot_sync(0xffffffffu, f[4]);
+    int pos = __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+    const int steps_total = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         if (f[b]) {
@@ -396,9 +407,8 @@ __device__ int beam_step(const float* sc_row,
             ++pos;
         }
     }
-    const uint32_t stay_mask = __ballot_sync(0xffffffffu, f[4]);
     if (f[4]) {
-        const int sp = steps_total + __popc(stay_mask & ((1u << lane) - 1u));
+        const int sp = steps_total + __popc(b4 & lt_mask);
         if (sp < W) {
             bs.new_score[sp] = s[4];
             bs.new_hash[sp] = me.hash;
@@ -462,155 +472,162 @@ __device__ int beam_step(const float* sc_row,
     return cnt;
 }
 
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    __threadfence_block();  // publish this thread's shared-memory writes before signalling the consumer
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int SL>
-__global__ void __launch_bounds__(Dims<SL>::P < 32 ? 128 : (Dims<SL>::P < 256 ? 128 : 256))
-        crf_fwd_beam_kernel(const __half* __restrict__ scores,
-                            const float* __restrict__ bwd,
-                            uint2* __restrict__ beam,
-                            int N,
-                            int T,
-                            float clamp_val,
-                            float blank,
-                            int W,
-                            float log_beam_cut) {
-    constexpr int S = Dims<SL>::S, P = Dims<SL>::P, C = Dims<SL>::C;
-    constexpr int GT = P < 32 ? 32 : P;
-    constexpr int THREADS = P < 256 ? 128 : 256;
-    constexpr int GROUPS = THREADS / GT;
-    constexpr int NW = GT / 32;  // warps per group
+struct FwdCfg {
+    using Scan = ScanCfg<SL>;
+    static constexpr int GT = Scan::NT + 32;                 // threads per chunk: scan threads + beam warp
+    static constexpr int CH = GT <= 128 ? 2 : 1;             // chunks per CTA (barrier ids: 5 per chunk)
+    static constexpr int THREADS = GT * CH;
+};
+
+template <int SL>
+__global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const __half* __restrict__ scores,
+                                                                          const float* __restrict__ bwd,
+                                                                          uint2* __restrict__ beam,
+                                                                          int N,
+                                                                          int T,
+                                                                          float clamp_val,
+                                                                          float blank,
+                                                                          int W,
+                                                                          float log_beam_cut) {
+    using Cfg = ScanCfg<SL>;
+    using F = FwdCfg<SL>;
+    constexpr int S = Cfg::S, C = Cfg::C, P4 = Cfg::P4, SPT = Cfg::SPT, NT = Cfg::NT;
+    constexpr int GT = F::GT, CH = F::CH;
+    constexpr int NW = NT / 32;  // scan warps per chunk
     constexpr int PF = 4;
-    constexpr int RS = C / 8;
 
     const int g = threadIdx.x / GT;
-    const int q = threadIdx.x % GT;
+    const int tid = threadIdx.x % GT;
     const int lane = threadIdx.x & 31;
-    const int wg = q >> 5;  // warp within group
-    const int chunk = blockIdx.x * GROUPS + g;
-    const bool scan_thread = q < P;
+    const int chunk = blockIdx.x * CH + g;
+    // barrier ids of this chunk group
+    const int BAR_SCAN = 1 + 5 * g, BAR_FULL = 2 + 5 * g, BAR_EMPTY = 4 + 5 * g;
 
-    __shared__ __align__(16) float fa[GROUPS][2][S];
-    __shared__ __align__(16) float sc_row[GROUPS][C];
-    __shared__ __align__(16) float bw_row[GROUPS][S];
-    __shared__ __align__(16) float post_row[GROUPS][S];
-    __shared__ float red[GROUPS][2][NW];
-    __shared__ BeamSmem bsm[GROUPS];
+    __shared__ __align__(16) float fa[CH][2][S];
+    __shared__ __align__(16) __half sc_row[CH][2][C];  // clamped scores (clamping fp16 values is exact in fp16)
+    __shared__ __align__(16) float bw_row[CH][2][S];
+    __shared__ __align__(16) float post_row[CH][2][S];
+    __shared__ float red[CH][2][NW];
+    __shared__ BeamSmem bsm[CH];
 
-    if (chunk >= N) return;  // whole groups exit together; barriers are per group
-
-    const int qs = scan_thread ? q : 0;
-    const uint4* srow = reinterpret_cast<const uint4*>(scores + (size_t)chunk * T * C) + 2 * qs;
-    const float4* brow = reinterpret_cast<const float4*>(bwd + (size_t)chunk * (T + 1) * S) + qs;
-    constexpr int BRS = S / 4;
+    if (chunk >= N) return;  // whole chunk groups exit together; every barrier below is per group
+    const bool is_scan = tid < NT;
     uint2* beam_out = beam + (size_t)chunk * T * kBeamW;
 
-    // beam init from bwd[0]
-    if (scan_thread) {
-        const float4 b0 = brow[0];
-        *reinterpret_cast<float4*>(&bw_row[g][4 * q]) = b0;
+    if (is_scan) {
+        // ================= scan threads =================
+        const int v = tid;  // states SPT*v .. SPT*v + SPT-1
+        const int wv = v >> 5;
+        const __half* srow = scores + (size_t)chunk * T * C + (size_t)v * 4 * SPT;
+        const float* brow = bwd + (size_t)chunk * (T + 1) * S + (size_t)v * SPT;
+        // bwd[0] for the beam initialisation, forward guide 0
 #pragma unroll
-        for (int j = 0; j < 4; ++j) fa[g][0][4 * q + j] = 0.0f;
-    }
-    group_sync<GT>(g);
-    BeamLane me{0u, 0u, 0.0f};
-    int width = 0;
-    if (wg == 0) {
-        width = beam_init<SL>(bw_row[g], bsm[g], me, W, lane);
-    }
-    group_sync<GT>(g);
-
-    uint4 pf[PF][2];
-    float4 pb[PF];
-    if (scan_thread) {
+        for (int e = 0; e < SPT; ++e) {
+            bw_row[g][1][SPT * v + e] = brow[e];
+            fa[g][0][SPT * v + e] = 0.0f;
+        }
+        named_bar_sync(BAR_SCAN, GT);  // (a) bwd[0] visible to the beam warp
+        named_bar_sync(BAR_SCAN, GT);  // (b) beam warp has consumed it; slot 1 may be reused
+        uint2 pf[PF][SPT];
+        float pb[PF][SPT];
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
             if (k < T) {
-                pf[k][0] = ldg_nc_v4(srow + (size_t)k * RS);
-                pf[k][1] = ldg_nc_v4(srow + (size_t)k * RS + 1);
-                pb[k] = ldg_nc_f4(brow + (size_t)(k + 1) * BRS);
+#pragma unroll
+                for (int e = 0; e < SPT; ++e) {
+                    pf[k][e] = __ldg(reinterpret_cast<const uint2*>(srow + (size_t)k * C) + e);
+                    pb[k][e] = __ldg(brow + (size_t)(k + 1) * S + e);
+                }
             }
         }
-    }
-    float f[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    int cur = 0;
-
-    for (int t0 = 0; t0 < T; t0 += PF) {
+        float f[SPT];
 #pragma unroll
-        for (int k = 0; k < PF; ++k) {
-            const int t = t0 + k;
-            if (t < T) {
-                float e[4];
-                float lmax = B200_FLT_LOWEST;
-                if (scan_thread) {
-                    const uint4 r0 = pf[k][0], r1 = pf[k][1];
-                    const float4 bw = pb[k];
-                    if (t + PF < T) {
-                        pf[k][0] = ldg_nc_v4(srow + (size_t)(t + PF) * RS);
-                        pf[k][1] = ldg_nc_v4(srow + (size_t)(t + PF) * RS + 1);
-                        pb[k] = ldg_nc_f4(brow + (size_t)(t + PF + 1) * BRS);
-                    }
-                    float sc[16];
-                    unpack16(r0, r1, clamp_val, sc);
-                    float4* dst = reinterpret_cast<float4*>(&sc_row[g][16 * q]);
-                    dst[0] = make_float4(sc[0], sc[1], sc[2], sc[3]);
-                    dst[1] = make_float4(sc[4], sc[5], sc[6], sc[7]);
-                    dst[2] = make_float4(sc[8], sc[9], sc[10], sc[11]);
-                    dst[3] = make_float4(sc[12], sc[13], sc[14], sc[15]);
-                    *reinterpret_cast<float4*>(&bw_row[g][4 * q]) = bw;
-                    const float p0 = fa[g][cur][q], p1 = fa[g][cur][q + P], p2 = fa[g][cur][q + 2 * P],
-                                p3 = fa[g][cur][q + 3 * P];
-                    const float bwv[4] = {bw.x, bw.y, bw.z, bw.w};
+        for (int e = 0; e < SPT; ++e) f[e] = 0.0f;
+        int cur = 0;
+        for (int t0 = 0; t0 < T; t0 += PF) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        f[j] = b200_lse5(B200_ADD(f[j], blank), B200_ADD(p0, sc[4 * j + 0]),
-                                         B200_ADD(p1, sc[4 * j + 1]), B200_ADD(p2, sc[4 * j + 2]),
-                                         B200_ADD(p3, sc[4 * j + 3]));
-                        e[j] = B200_ADD(f[j], bwv[j]);  // v = fwd + bwd
-                        lmax = b200_fmaxf(lmax, e[j]);
+            for (int k = 0; k < PF; ++k) {
+                const int t = t0 + k;
+                if (t < T) {
+                    const int slot = t & 1;
+                    if (t >= 2) named_bar_sync(BAR_EMPTY + slot, GT);  // beam warp is done with this slot
+                    float vsum[SPT];
+                    float lmax = B200_FLT_LOWEST;
+#pragma unroll
+                    for (int e = 0; e < SPT; ++e) {
+                        const uint2 r = pf[k][e];
+                        const float bw = pb[k][e];
+                        if (t + PF < T) {
+                            pf[k][e] = __ldg(reinterpret_cast<const uint2*>(srow + (size_t)(t + PF) * C) + e);
+                            pb[k][e] = __ldg(brow + (size_t)(t + PF + 1) * S + e);
+                        }
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+                        const float s0 = clampf(f0.x, clamp_val), s1 = clampf(f0.y, clamp_val);
+                        const float s2 = clampf(f1.x, clamp_val), s3 = clampf(f1.y, clamp_val);
+                        const int st = SPT * v + e;
+                        {
+                            const __half2 c0 = __floats2half2_rn(s0, s1), c1 = __floats2half2_rn(s2, s3);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<const uint32_t*>(&c0);
+                            pk.y = *reinterpret_cast<const uint32_t*>(&c1);
+                            *reinterpret_cast<uint2*>(&sc_row[g][slot][4 * st]) = pk;
+                        }
+                        bw_row[g][slot][st] = bw;
+                        const int p = st >> 2;
+                        f[e] = b200_lse5(B200_ADD(f[e], blank), B200_ADD(fa[g][cur][p], s0), B200_ADD(fa[g][cur][p + P4], s1),
+                                         B200_ADD(fa[g][cur][p + 2 * P4], s2), B200_ADD(fa[g][cur][p + 3 * P4], s3));
+                        fa[g][cur ^ 1][st] = f[e];
+                        vsum[e] = B200_ADD(f[e], bw);  // fwd + bwd
+                        lmax = b200_fmaxf(lmax, vsum[e]);
                     }
-                }
-                // max over the group's states
-                float mx = warp_max(lmax);
-                if constexpr (NW > 1) {
-                    if (lane == 0) red[g][0][wg] = mx;
-                    group_sync<GT>(g);
+                    float mx = warp_max(lmax);
+                    if (lane == 0) red[g][0][wv] = mx;
+                    named_bar_sync(BAR_SCAN, NT);
                     mx = red[g][0][0];
 #pragma unroll
                     for (int w = 1; w < NW; ++w) mx = b200_fmaxf(mx, red[g][0][w]);
-                }
-                // sum of exp in the contract's order (see oracle/crf_oracle.c posts_row)
-                float part = 0.0f;
-                if (scan_thread) {
+                    // posterior normaliser in the contract's order: per-thread left-to-right, per-warp xor butterfly,
+                    // warps left to right (oracle/crf_oracle.c posts_row)
+                    float ex[SPT];
+                    float part = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) e[j] = b200_expf(B200_SUB(e[j], mx));
-                    part = B200_ADD(B200_ADD(B200_ADD(e[0], e[1]), e[2]), e[3]);
-                }
+                    for (int e = 0; e < SPT; ++e) {
+                        ex[e] = b200_expf(B200_SUB(vsum[e], mx));
+                        part = e == 0 ? ex[0] : B200_ADD(part, ex[e]);
+                    }
 #pragma unroll
-                for (int o = (P < 32 ? P / 2 : 16); o >= 1; o >>= 1) {
-                    part = B200_ADD(part, __shfl_xor_sync(0xffffffffu, part, o));
-                }
-                float z = part;
-                if constexpr (NW > 1) {
-                    if (lane == 0) red[g][1][wg] = part;
-                    group_sync<GT>(g);
-                    z = red[g][1][0];
+                    for (int o = 16; o >= 1; o >>= 1) part = B200_ADD(part, __shfl_xor_sync(0xffffffffu, part, o));
+                    if (lane == 0) red[g][1][wv] = part;
+                    named_bar_sync(BAR_SCAN, NT);
+                    float z = red[g][1][0];
 #pragma unroll
                     for (int w = 1; w < NW; ++w) z = B200_ADD(z, red[g][1][w]);
-                } else if constexpr (P < 32) {
-                    z = __shfl_sync(0xffffffffu, part, 0);
+#pragma unroll
+                    for (int e = 0; e < SPT; ++e) post_row[g][slot][SPT * v + e] = B200_DIV(ex[e], z);
+                    named_bar_arrive(BAR_FULL + slot, GT);  // slot t is complete
+                    cur ^= 1;
                 }
-                if (scan_thread) {
-                    *reinterpret_cast<float4*>(&post_row[g][4 * q]) =
-                            make_float4(B200_DIV(e[0], z), B200_DIV(e[1], z), B200_DIV(e[2], z), B200_DIV(e[3], z));
-                    *reinterpret_cast<float4*>(&fa[g][cur ^ 1][4 * q]) = make_float4(f[0], f[1], f[2], f[3]);
-                }
-                group_sync<GT>(g);
-                if (wg == 0) {
-                    width = beam_step<SL>(sc_row[g], bw_row[g], post_row[g], bsm[g], me, width, W, log_beam_cut,
-                                          blank, t == T - 1, beam_out + (size_t)t * kBeamW, lane);
-                }
-                group_sync<GT>(g);
-                cur ^= 1;
             }
+        }
+    } else {
+        // ================= beam warp =================
+        named_bar_sync(BAR_SCAN, GT);  // (a)
+        BeamLane me{0u, 0u, 0.0f};
+        int width = beam_init<SL>(bw_row[g][1], bsm[g], me, W, lane);
+        named_bar_sync(BAR_SCAN, GT);  // (b)
+        for (int t = 0; t < T; ++t) {
+            const int slot = t & 1;
+            named_bar_sync(BAR_FULL + slot, GT);
+            width = beam_step<SL>(sc_row[g][slot], bw_row[g][slot], post_row[g][slot], bsm[g], me, width, W, log_beam_cut,
+                                  blank, t == T - 1, beam_out + (size_t)t * kBeamW, lane);
+            if (t + 2 < T) named_bar_arrive(BAR_EMPTY + slot, GT);
         }
     }
 }
@@ -713,20 +730,18 @@ size_t traceback_smem_bytes(int T) {
 
 template <int SL>
 void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) {
-    constexpr int P = Dims<SL>::P;
     {
-        constexpr int GROUPS = (256 / P) > 0 ? (256 / P) : 1;
-        const int grid = (a.N + GROUPS - 1) / GROUPS;
-        crf_bwd_scan_kernel<SL><<<grid, P * GROUPS, 0, stream>>>(a.scores, a.bwd, a.N, a.T, a.clamp_val, a.blank);
+        constexpr int S = Dims<SL>::S;
+        constexpr int CH = S >= 256 ? 1 : 256 / S;
+        const int grid = (a.N + CH - 1) / CH;
+        crf_bwd_scan_kernel<SL><<<grid, S * CH, 0, stream>>>(a.scores, a.bwd, a.N, a.T, a.clamp_val, a.blank);
         if (prof) prof->mark("crf_bwd_scan", stream);
     }
     {
-        constexpr int GT = P < 32 ? 32 : P;
-        constexpr int THREADS = P < 256 ? 128 : 256;
-        constexpr int GROUPS = THREADS / GT;
-        const int grid = (a.N + GROUPS - 1) / GROUPS;
-        crf_fwd_beam_kernel<SL><<<grid, THREADS, 0, stream>>>(a.scores, a.bwd, a.beam, a.N, a.T, a.clamp_val,
-                                                                a.blank, a.beam_width, a.log_beam_cut);
+        using F = FwdCfg<SL>;
+        const int grid = (a.N + F::CH - 1) / F::CH;
+        crf_fwd_beam_kernel<SL><<<grid, F::THREADS, 0, stream>>>(a.scores, a.bwd, a.beam, a.N, a.T, a.clamp_val, a.blank,
+                                                                   a.beam_width, a.log_beam_cut);
         if (prof) prof->mark("crf_fwd_beam", stream);
     }
     {

@@ -104,24 +104,26 @@ void crf_backward_scan(const float* scores, int T, int S, float blank, float* bw
     }
 }
 
-/* softmax over states of fwd + bwd.  Reduction order (part of the numerics contract): partial sums
- * over each aligned group of 4 states, a xor-butterfly over groups of min(S/4, 32) partials, then a
- * left-to-right sum over those groups. */
+/* softmax over states of fwd + bwd.  Reduction order (part of the numerics contract, mirrors the CUDA kernel's
+ * one-thread-per-state layout): SPT = max(1, S/512) consecutive states are summed left to right, a xor-butterfly
+ * runs over each aligned group of min(S/SPT, 32) such partials, and the groups are summed left to right. */
 static void posts_row(const float* f, const float* b, int S, float* out) {
-    float v[1024], e[1024], part[256];
+    float v[1024], e[1024], part[512];
     float mx = B200_ADD(f[0], b[0]);
     for (int s = 0; s < S; ++s) {
         v[s] = B200_ADD(f[s], b[s]);
         mx = b200_fmaxf(mx, v[s]);
     }
-    const int P = S / 4;
+    const int SPT = S > 512 ? S / 512 : 1;
+    const int P = S / SPT;
     for (int q = 0; q < P; ++q) {
-        for (int j = 0; j < 4; ++j) e[4 * q + j] = b200_expf(B200_SUB(v[4 * q + j], mx));
-        part[q] = B200_ADD(B200_ADD(B200_ADD(e[4 * q], e[4 * q + 1]), e[4 * q + 2]), e[4 * q + 3]);
+        for (int j = 0; j < SPT; ++j) e[SPT * q + j] = b200_expf(B200_SUB(v[SPT * q + j], mx));
+        part[q] = e[SPT * q];
+        for (int j = 1; j < SPT; ++j) part[q] = B200_ADD(part[q], e[SPT * q + j]);
     }
     const int G = P < 32 ? P : 32;
     for (int o = G / 2; o >= 1; o >>= 1) {
-        float nxt[256];
+        float nxt[512];
         for (int q = 0; q < P; ++q) nxt[q] = B200_ADD(part[q], part[q ^ o]);
         memcpy(part, nxt, sizeof(float) * (size_t)P);
     }
