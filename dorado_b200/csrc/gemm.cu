@@ -4,9 +4,10 @@
 //   host_linear / cutlass conv     dorado/nn/ConvStack.cpp:257, dorado/nn/CRFModules.cpp:112
 //   koi_linear / koi_mm_swiglu     dorado/nn/TxModules.cpp:653-697
 //
-// One 128 x BN output tile per CTA.  Warp roles: warp 0 = TMA producer (A and W tiles, 128-byte swizzle,
-// 4-stage mbarrier ring), warp 1 = single-thread tcgen05.mma issuer (accumulator in TMEM), warps 2-5 =
-// epilogue (tcgen05.ld -> bias / activation / residual -> fp16 -> 16-byte global stores).
+// Persistent: one CTA per SM loops over 128 x BN output tiles.  Warp roles: warp 0 = TMA producer (A and W tiles,
+// 128-byte swizzle, 4-stage mbarrier ring that runs across tiles), warp 1 = single-thread tcgen05.mma issuer,
+// warps 2-5 = epilogue (tcgen05.ld -> bias / activation / residual -> fp16 -> 16-byte global stores).  The
+// accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // A is addressed through a 3-D tensor map (k, row, batch) so that overlapping-row views work: the last
 // conv of the LSTM models reads its im2col rows straight from the NTC activation buffer with row stride
 // = stride * C_in (the reference's "cutlass_conv" trick, ConvStack.cpp:236-275).
@@ -29,9 +30,12 @@ constexpr int GEMM_THREADS = 192;
 
 struct GemmKernelParams {
     int rows_per_batch, tiles_per_batch, N, num_k_blocks, bn, act;
+    int num_tiles, n_tiles;  // total tiles, tiles along N
     const float* bias;
     __half* out;
     long long out_m1, out_s0, out_s1;
+    long long out_col_m1, out_col_s0;
+    int bias_per_row;
     const __half* residual;
     float alpha;
     uint32_t tmem_cols;
@@ -58,8 +62,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     const uint32_t stage_bytes = a_bytes + w_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;   // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -69,7 +74,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
         }
-        tc::mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tmem_full[i], 1);
+            tc::mbar_init(&tmem_empty[i], 128);
+        }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_a);
         tc::prefetch_tmap(&tma_w);
@@ -80,97 +88,123 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    const int batch = blockIdx.x / p.tiles_per_batch;
-    const int r0 = (blockIdx.x % p.tiles_per_batch) * BM;
-    const int n0 = blockIdx.y * p.bn;
-
     if (warp == 0) {
         if (tc::elect_one()) {
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
-                uint8_t* a_s = smem + s * stage_bytes;
-                tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
-                tc::tma_load_2d(a_s + a_bytes, &tma_w, &full[s], kb * BK, n0);
+            long long it = 0;  // k-block counter across tiles
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+                const int batch = mt / p.tiles_per_batch;
+                const int r0 = (mt % p.tiles_per_batch) * BM;
+                const int n0 = nt * p.bn;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % STAGES);
+                    tc::mbar_wait(&empty[s], (uint32_t)(((it / STAGES) & 1) ^ 1));
+                    tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
+                    uint8_t* a_s = smem + s * stage_bytes;
+                    tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
+                    tc::tma_load_2d(a_s + a_bytes, &tma_w, &full[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             const uint32_t idesc = tc::umma_idesc_f16(BM, p.bn);
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                tc::mbar_wait(&full[s], (kb / STAGES) & 1);
+            long long it = 0;
+            int ti = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+                const int ab = ti & 1;
+                tc::mbar_wait(&tmem_empty[ab], (uint32_t)(((ti >> 1) & 1) ^ 1));
                 tc::tc_fence_after();
-                const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
-                const uint64_t adesc = tc::umma_desc_sw128(a_addr);
-                const uint64_t bdesc = tc::umma_desc_sw128(a_addr + a_bytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.bn);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % STAGES);
+                    tc::mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+                    tc::tc_fence_after();
+                    const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
+                    const uint64_t adesc = tc::umma_desc_sw128(a_addr);
+                    const uint64_t bdesc = tc::umma_desc_sw128(a_addr + a_bytes);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                    tc::umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        tc::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    tc::umma_commit(&empty[s]);
                 }
-                tc::umma_commit(&empty[s]);
+                tc::umma_commit(&tmem_full[ab]);
             }
-            tc::umma_commit(tmem_full);
         }
     } else {
         // epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
         const int lg = warp & 3;
-        const int row = r0 + lg * 32 + lane;
-        const bool valid = row < p.rows_per_batch;
-        const long long g = (long long)batch * p.rows_per_batch + row;
-        const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
         const int n_out_total = p.act == GEMM_ACT_SWIGLU ? p.N / 2 : p.N;
-        tc::mbar_wait(tmem_full, 0);
-        tc::tc_fence_after();
-        for (int c = 0; c < p.bn / 32; ++c) {
-            uint32_t r[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
-            tc::tmem_ld_wait();
-            const int nc = n0 + c * 32;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                v[j] = __uint_as_float(r[j]);
-                if (p.bias) v[j] += __ldg(p.bias + nc + j);
-            }
-            if (p.act == GEMM_ACT_SWIGLU) {
-                if (valid) {
-                    __half2 h[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float y0 = v[4 * j], g0 = v[4 * j + 1], y1 = v[4 * j + 2], g1 = v[4 * j + 3];
-                        h[j] = __floats2half2_rn(y0 * (g0 / (1.0f + __expf(-g0))), y1 * (g1 / (1.0f + __expf(-g1))));
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc / 2);
-                    dst[0] = *reinterpret_cast<uint4*>(&h[0]);
-                    dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+            const int ab = ti & 1;
+            const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const int batch = mt / p.tiles_per_batch;
+            const int r0 = (mt % p.tiles_per_batch) * BM;
+            const int n0 = nt * p.bn;
+            const int row = r0 + lg * 32 + lane;
+            const bool valid = row < p.rows_per_batch;
+            const long long g = (long long)batch * p.rows_per_batch + row;
+            const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
+            tc::mbar_wait(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
+            tc::tc_fence_after();
+            for (int c = 0; c < p.bn / 32; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + c * 32), r);
+                tc::tmem_ld_wait();
+                if (c == p.bn / 32 - 1) {
+                    // accumulator fully read: hand the TMEM buffer back before the (long) math + stores
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&tmem_empty[ab]);
                 }
-            } else {
-                if (p.residual && valid) {
-                    const uint4* res = reinterpret_cast<const uint4*>(p.residual + g * (long long)n_out_total + nc);
+                const int nc = n0 + c * 32;
+                const long long coff = p.out_col_m1 > 0 ? (nc / p.out_col_m1) * p.out_col_s0 + (nc % p.out_col_m1) : nc;
+                float v[32];
+                const float row_bias = (p.bias && p.bias_per_row && valid) ? __ldg(p.bias + g) : 0.0f;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint4 rv = __ldg(res + q);
-                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r[j]);
+                    if (p.bias) v[j] += p.bias_per_row ? row_bias : __ldg(p.bias + nc + j);
+                }
+                if (p.act == GEMM_ACT_SWIGLU) {
+                    if (valid) {
+                        __half2 h[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(rh[j]);
-                            v[q * 8 + 2 * j] += p.alpha * f.x;
-                            v[q * 8 + 2 * j + 1] += p.alpha * f.y;
+                        for (int j = 0; j < 8; ++j) {
+                            const float y0 = v[4 * j], g0 = v[4 * j + 1], y1 = v[4 * j + 2], g1 = v[4 * j + 3];
+                            h[j] = __floats2half2_rn(y0 * (g0 / (1.0f + __expf(-g0))), y1 * (g1 / (1.0f + __expf(-g1))));
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc / 2);
+                        dst[0] = *reinterpret_cast<uint4*>(&h[0]);
+                        dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    }
+                } else {
+                    if (p.residual && valid) {
+                        const uint4* res = reinterpret_cast<const uint4*>(p.residual + g * (long long)n_out_total + nc);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 rv = __ldg(res + q);
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(rh[j]);
+                                v[q * 8 + 2 * j] += p.alpha * f.x;
+                                v[q * 8 + 2 * j + 1] += p.alpha * f.y;
+                            }
                         }
                     }
-                }
-                if (valid) {
-                    __half2 h[16];
+                    if (valid) {
+                        __half2 h[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        h[j] = __floats2half2_rn(act_apply(v[2 * j], p.act), act_apply(v[2 * j + 1], p.act));
+                        for (int j = 0; j < 16; ++j) {
+                            h[j] = __floats2half2_rn(act_apply(v[2 * j], p.act), act_apply(v[2 * j + 1], p.act));
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + off + coff);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dst[q] = *reinterpret_cast<uint4*>(&h[4 * q]);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[q] = *reinterpret_cast<uint4*>(&h[4 * q]);
                 }
             }
         }
@@ -284,12 +318,18 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.out_m1 = p.d.out_m1;
     k.out_s0 = p.d.out_s0;
     k.out_s1 = p.d.out_s1;
+    k.out_col_m1 = p.d.out_col_m1;
+    k.out_col_s0 = p.d.out_col_s0;
+    k.bias_per_row = p.d.bias_per_row;
     k.residual = p.d.residual;
     k.alpha = p.d.alpha;
     uint32_t cols = 32;
-    while ((int)cols < p.bn) cols <<= 1;
+    while ((int)cols < 2 * p.bn) cols <<= 1;  // double-buffered accumulator
     k.tmem_cols = cols;
-    gemm_f16_tcgen05_kernel<<<p.grid, GEMM_THREADS, p.smem, stream>>>(p.tma_a, p.tma_w, k);
+    k.n_tiles = p.d.N / p.bn;
+    k.num_tiles = p.tiles_per_batch * p.d.batches * k.n_tiles;
+    const int grid = k.num_tiles < kNumSMs ? k.num_tiles : kNumSMs;
+    gemm_f16_tcgen05_kernel<<<grid, GEMM_THREADS, p.smem, stream>>>(p.tma_a, p.tma_w, k);
     B200_CUDA(cudaGetLastError());
 }
 

@@ -34,6 +34,11 @@ struct GemmDesc {
     int64_t out_m1 = 1;
     int64_t out_s0 = 0;
     int64_t out_s1 = 0;
+    // optional column blocking of the output: column n -> (n / out_col_m1) * out_col_s0 + (n % out_col_m1)
+    // (out_col_m1 = 0: plain contiguous columns).  out_col_m1 must be a multiple of 32.
+    int64_t out_col_m1 = 0;
+    int64_t out_col_s0 = 0;
+    int bias_per_row = 0;  // bias indexed by the global row g instead of the column
     // optional fused residual epilogue (deepnorm): v = v + alpha * residual[g][n]; requires act == NONE
     const __half* residual = nullptr;
     float alpha = 0.0f;
