@@ -251,8 +251,10 @@ def main():
     dom = max(agg, key=lambda k: agg[k][0] * agg[k][1])
     dom_ms, dom_cnt = agg[dom]
     C, T_out = cfg.outsize, runner.out_len()
-    if dom == "lstm_layer":
-        flops = 16.0 * cfg.lstm_size ** 2 * T_out * N  # 2*(2C)*(4C) per block per chunk per layer
+    if dom in ("lstm_layer", "lstm_rec"):
+        # 2*(2C)*(4C) FLOP per block per chunk per layer; the hoisted path's recurrent kernel does the
+        # W_hh half (the W_ih half is the lstm_gx_gemm launch)
+        flops = (16.0 if dom == "lstm_layer" else 8.0) * cfg.lstm_size ** 2 * T_out * N
         roof = {"kernel": dom, "bound": "tensor", "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": pk["tflops"],
                 "unit": "TFLOP/s", "traffic": None}
     elif dom.startswith("crf_"):

@@ -6,7 +6,7 @@
 //
 // Persistent: one CTA per SM loops over 128 x BN output tiles.  Warp roles: warp 0 = TMA producer (A and W tiles,
 // 128-byte swizzle, 4-stage mbarrier ring that runs across tiles), warp 1 = single-thread tcgen05.mma issuer,
-// warps 2-5 = epilogue (tcgen05.ld -> bias / activation / residual -> fp16 -> 16-byte global stores).  The
+// warps 2-9 = epilogue (tcgen05.ld -> bias / activation / residual -> fp16 -> 16-byte global stores).  The
 // accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // A is addressed through a 3-D tensor map (k, row, batch) so that overlapping-row views work: the last
 // conv of the LSTM models reads its im2col rows straight from the NTC activation buffer with row stride
@@ -26,7 +26,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 struct GemmKernelParams {
     int rows_per_batch, tiles_per_batch, N, num_k_blocks, bn, act;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tmem_full[i], 1);
-            tc::mbar_init(&tmem_empty[i], 128);
+            tc::mbar_init(&tmem_empty[i], 32 * GEMM_EPI_WARPS);
         }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_a);
@@ -136,6 +137,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     } else {
         // epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
         const int lg = warp & 3;
+        const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+        const int nch = p.bn / 32;
+        const int c_begin = chalf ? (nch + 1) / 2 : 0, c_end = chalf ? nch : (nch + 1) / 2;
         const int n_out_total = p.act == GEMM_ACT_SWIGLU ? p.N / 2 : p.N;
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
@@ -150,11 +154,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
             tc::mbar_wait(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after();
-            for (int c = 0; c < p.bn / 32; ++c) {
+            if (c_begin == c_end) {
+                tc::tc_fence_before();
+                tc::mbar_arrive(&tmem_empty[ab]);
+            }
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t r[32];
                 tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + c * 32), r);
                 tc::tmem_ld_wait();
-                if (c == p.bn / 32 - 1) {
+                if (c == c_end - 1) {
                     // accumulator fully read: hand the TMEM buffer back before the (long) math + stores
                     tc::tc_fence_before();
                     tc::mbar_arrive(&tmem_empty[ab]);

@@ -397,11 +397,212 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// LSTM layer for hidden sizes whose weights do not fit in one SM's shared memory (hac: C = 384).
+//
+// The x_t half of the gate pre-activations does not depend on the recurrence, so it is hoisted into one large
+// tcgen05 GEMM per layer (gemm.cu) that writes gx[t][chunk block][gate row][chunk] (fp16, bias included).  This
+// kernel then runs the recurrence with W_hh only: a CTA owns UN chunks for the whole sequence and streams the
+// permuted W_hh (4C x C fp16) from L2 through a TMA ring every step; being "fat" (UN up to 64 chunks) keeps the
+// number of CTAs re-reading the weights small.  Gate rows are permuted so that a warp's 32 TMEM lanes hold
+// (8 units x 4 gates); the 4 gates of a unit meet through a per-warp shared-memory exchange (no block barrier).
+// ------------------------------------------------------------------------------------------------
+constexpr int REC_GROUPS = 6;                      // epilogue groups (4 warps each); tile m -> group m % 6
+constexpr int REC_THREADS = 64 + 128 * REC_GROUPS; // warp 0 TMA, warp 1 MMA, 24 epilogue warps
+constexpr int REC_WSTAGES = 12;
+constexpr int REC_NBUF = 8;                        // TMEM accumulator buffers
+
+struct LstmRecParams {
+    __half* seq;          // [T][N][C] output h (in place over the layer input)
+    const __half* gx;     // [T][N / GB][4C][GB], GB = max(UN, 32)
+    int T, N, reverse;
+};
+
+template <int C, int UN>
+__global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(const __grid_constant__ CUtensorMap tma_w,
+                                                                 const LstmRecParams p) {
+    constexpr int MT = C / 32;            // gate tiles
+    constexpr int KBH = C / KBLK;         // K blocks (h only)
+    constexpr int ZB = UN * KBLK * 2;     // bytes of one Z block
+    constexpr int GB = UN < 32 ? 32 : UN; // chunk block of the gx layout
+    constexpr int TPG = MT / REC_GROUPS;  // tiles per epilogue group
+    constexpr uint32_t TMEM_COLS = REC_NBUF * UN < 32 ? 32 : REC_NBUF * UN;
+    static_assert(MT % REC_GROUPS == 0 && REC_NBUF * UN <= 512, "unsupported shape");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_s = smem;                                            // [REC_WSTAGES][8 KB]
+    uint8_t* z_s = w_s + (size_t)REC_WSTAGES * WBLK_BYTES;          // [2][KBH][ZB]
+    float* xs = reinterpret_cast<float*>(z_s + (size_t)2 * KBH * ZB);  // [24 warps][4][8][8] exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 24 * 256);
+    uint64_t* h_ready = bars;                    // [2]
+    uint64_t* acc_full = bars + 2;               // [REC_NBUF]
+    uint64_t* acc_empty = acc_full + REC_NBUF;   // [REC_NBUF]
+    uint64_t* w_full = acc_empty + REC_NBUF;     // [REC_WSTAGES]
+    uint64_t* w_empty = w_full + REC_WSTAGES;    // [REC_WSTAGES]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_empty + REC_WSTAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * UN;
+
+    for (int i = threadIdx.x; i < 2 * KBH * ZB / 16; i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) tc::mbar_init(&h_ready[i], 128 * REC_GROUPS);
+        for (int i = 0; i < REC_NBUF; ++i) {
+            tc::mbar_init(&acc_full[i], 1);
+            tc::mbar_init(&acc_empty[i], 128);
+        }
+        for (int i = 0; i < REC_WSTAGES; ++i) {
+            tc::mbar_init(&w_full[i], 1);
+            tc::mbar_init(&w_empty[i], 1);
+        }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_w);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            long long wj = 0;
+            for (int s = 0; s < p.T; ++s) {
+                for (int m = 0; m < MT; ++m) {
+                    for (int kb = 0; kb < KBH; ++kb, ++wj) {
+                        const int st = (int)(wj % REC_WSTAGES);
+                        tc::mbar_wait(&w_empty[st], (uint32_t)(((wj / REC_WSTAGES) & 1) ^ 1));
+                        tc::mbar_arrive_expect_tx(&w_full[st], WBLK_BYTES);
+                        tc::tma_load_2d(w_s + (size_t)st * WBLK_BYTES, &tma_w, &w_full[st], kb * KBLK, m * 128);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
+            const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
+            const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
+            long long wj = 0, j = 0;
+            for (int s = 0; s < p.T; ++s) {
+                const int buf = s & 1;
+                tc::mbar_wait(&h_ready[buf], (uint32_t)((s >> 1) & 1));
+                tc::tc_fence_after();
+                const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZB) >> 4);
+                for (int m = 0; m < MT; ++m, ++j) {
+                    const int ab = (int)(j % REC_NBUF);
+                    tc::mbar_wait(&acc_empty[ab], (uint32_t)(((j / REC_NBUF) & 1) ^ 1));
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ab * UN);
+#pragma unroll 1
+                    for (int kb = 0; kb < KBH; ++kb, ++wj) {
+                        const int st = (int)(wj % REC_WSTAGES);
+                        tc::mbar_wait(&w_full[st], (uint32_t)((wj / REC_WSTAGES) & 1));
+                        tc::tc_fence_after();
+                        const uint64_t adesc = wdesc0 + (uint64_t)((st * WBLK_BYTES) >> 4);
+                        const uint64_t bdesc = zd + (uint64_t)((kb * ZB) >> 4);
+                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                        tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                        tc::umma_commit(&w_empty[st]);
+                    }
+                    tc::umma_commit(&acc_full[ab]);
+                }
+            }
+        }
+    } else {
+        const int ewarp = warp - 2;
+        const int g = ewarp >> 2;   // group
+        const int qt = warp & 3;    // TMEM lane quarter of this warp
+        const int uk = lane >> 2;   // unit within the warp's 8 units (activation role)
+        const int gj = lane & 3;    // gate type of this lane's row: 0 i, 1 f, 2 g, 3 o
+        const int cp = lane & 3;    // column pair (cell-update role): columns 2cp, 2cp+1 of each 8-column chunk
+        float* xw = xs + ewarp * 256;
+        const float am = gj == 2 ? 2.0f : 1.0f;  // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
+        float c_reg[TPG][UN / 4];
+#pragma unroll
+        for (int i = 0; i < TPG; ++i)
+#pragma unroll
+            for (int k = 0; k < UN / 4; ++k) c_reg[i][k] = 0.0f;
+        tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0
+
+        for (int s = 0; s < p.T; ++s) {
+            const int t = p.reverse ? p.T - 1 - s : s;
+            const int nbuf = (s + 1) & 1;
+            uint8_t* zh_next = z_s + (size_t)nbuf * KBH * ZB;
+            __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
+            const __half* gx_t = p.gx + ((size_t)t * (p.N / GB) + (n0 / GB)) * (size_t)(4 * C) * GB + (n0 % GB);
+#pragma unroll
+            for (int i = 0; i < TPG; ++i) {
+                const int m = g + i * REC_GROUPS;
+                const long long j = (long long)s * MT + m;
+                const int ab = (int)(j % REC_NBUF);
+                const __half* gx_row = gx_t + (size_t)(m * 128 + qt * 32 + lane) * GB;
+                uint4 gxv = __ldg(reinterpret_cast<const uint4*>(gx_row));
+                tc::mbar_wait(&acc_full[ab], (uint32_t)((j / REC_NBUF) & 1));
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(ab * UN);
+#pragma unroll
+                for (int ch = 0; ch < UN / 8; ++ch) {
+                    uint32_t r[8];
+                    tc::tmem_ld_32x8(taddr + (uint32_t)(ch * 8), r);
+                    tc::tmem_ld_wait();
+                    if (ch == UN / 8 - 1) {
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&acc_empty[ab]);
+                    }
+                    const uint4 gcur = gxv;
+                    if (ch + 1 < UN / 8) gxv = __ldg(reinterpret_cast<const uint4*>(gx_row + (ch + 1) * 8));
+                    const __half2* gh = reinterpret_cast<const __half2*>(&gcur);
+                    float a[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 gf = __half22float2(gh[e]);
+                        const float v0 = __uint_as_float(r[2 * e]) + gf.x, v1 = __uint_as_float(r[2 * e + 1]) + gf.y;
+                        a[2 * e] = 1.0f - __fdividef(am, __expf(am * v0) + 1.0f);
+                        a[2 * e + 1] = 1.0f - __fdividef(am, __expf(am * v1) + 1.0f);
+                    }
+                    // per-warp exchange: xw[gate][unit][col]
+                    float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
+                    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+                    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+                    __syncwarp();
+                    const float2 ig = *reinterpret_cast<const float2*>(xw + (0 * 8 + uk) * 8 + 2 * cp);
+                    const float2 fg = *reinterpret_cast<const float2*>(xw + (1 * 8 + uk) * 8 + 2 * cp);
+                    const float2 gg = *reinterpret_cast<const float2*>(xw + (2 * 8 + uk) * 8 + 2 * cp);
+                    const float2 og = *reinterpret_cast<const float2*>(xw + (3 * 8 + uk) * 8 + 2 * cp);
+                    __syncwarp();
+                    const float c0 = fg.x * c_reg[i][2 * ch] + ig.x * gg.x;
+                    const float c1 = fg.y * c_reg[i][2 * ch + 1] + ig.y * gg.y;
+                    c_reg[i][2 * ch] = c0;
+                    c_reg[i][2 * ch + 1] = c1;
+                    const __half h0 = __float2half_rn(og.x * tanh_f(c0));
+                    const __half h1 = __float2half_rn(og.y * tanh_f(c1));
+                    const int u = qt * 8 + uk;           // unit within the tile
+                    const int nA = ch * 8 + 2 * cp;      // chunk (column) index within the CTA
+                    *reinterpret_cast<__half*>(zh_next + (size_t)m * ZB + sw64_offset(nA, u)) = h0;
+                    *reinterpret_cast<__half*>(zh_next + (size_t)m * ZB + sw64_offset(nA + 1, u)) = h1;
+                    y_t[(size_t)nA * C + m * 32 + u] = h0;
+                    y_t[(size_t)(nA + 1) * C + m * 32 + u] = h1;
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&h_ready[nbuf]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct LstmLayerWeights {
-    __half* w = nullptr;   // [4C][2C] permuted rows, [W_ih | W_hh]
+    __half* w = nullptr;   // resident path: [4C][2C] permuted rows, [W_ih | W_hh]
     float* bias = nullptr; // [4C] permuted
+    // hoisted path (lstm_rec_kernel): rows permuted as (tile, quarter, unit-in-quarter, gate)
+    __half* w_ih = nullptr;  // [4C][C]
+    __half* w_hh = nullptr;  // [4C][C]
 };
 
 class LstmModel;
@@ -409,7 +610,7 @@ class LstmModel;
 class LstmPlan final : public ForwardPlan {
 public:
     void run(cudaStream_t stream, ProfileSink* prof) override;
-    int launches() const override { return 1 + 1 + num_layers + num_linear; }
+    int launches() const override { return 1 + 1 + num_layers * (hoisted ? 2 : 1) + num_linear; }
 
     Conv12Params conv12{};
     dim3 conv12_grid;
@@ -419,6 +620,14 @@ public:
     int lstm_grid = 0, lstm_nbr = 16, lstm_groups = 3, lstm_threads = 0;
     size_t lstm_smem = 0;
     void launch_lstm(int l, cudaStream_t stream) const;
+    // hoisted path
+    bool hoisted = false;
+    int rec_un = 16;
+    size_t rec_smem = 0;
+    std::vector<GemmPlan> gx_gemm;
+    std::vector<CUtensorMap> rec_w;
+    std::vector<LstmRecParams> rec_p;
+    void launch_rec(int l, cudaStream_t stream) const;
     GemmPlan linear1, linear2;
     int num_layers = 0, num_linear = 1;
     const LstmModel* model = nullptr;
@@ -446,7 +655,8 @@ public:
 private:
     int pad3() const { return desc.convs[2].winlen / 2; }
     int t_pad(int T_in) const { return T_in + 2 * pad3() + 8; }
-    int n_pad(int N) const { return (N + 15) / 16 * 16; }
+    bool hoisted() const { return (size_t)4 * desc.lstm_size * 2 * desc.lstm_size * 2 > 150 * 1024; }
+    int n_pad(int N) const { return hoisted() ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16; }
 };
 
 LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : desc(d) {
@@ -512,8 +722,23 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
                     b[dst] = bih.data[src] + bhh.data[src];
                 }
         LstmLayerWeights lw;
-        lw.w = upload_f16(w);
-        lw.bias = upload_f32(b);
+        if ((size_t)4 * C * 2 * C * 2 <= 150 * 1024) {
+            lw.w = upload_f16(w);
+            lw.bias = upload_f32(b);
+        } else {
+            std::vector<float> wi((size_t)4 * C * C), wh((size_t)4 * C * C), b2((size_t)4 * C);
+            for (int m = 0; m < C / 32; ++m)
+                for (int r = 0; r < 128; ++r) {
+                    const int g = r & 3, unit = 32 * m + 8 * (r >> 5) + ((r & 31) >> 2);
+                    const int dst = m * 128 + r, src = g * C + unit;
+                    std::memcpy(&wi[(size_t)dst * C], &wih.data[(size_t)src * C], sizeof(float) * C);
+                    std::memcpy(&wh[(size_t)dst * C], &whh.data[(size_t)src * C], sizeof(float) * C);
+                    b2[dst] = bih.data[src] + bhh.data[src];
+                }
+            lw.w_ih = upload_f16(wi);
+            lw.w_hh = upload_f16(wh);
+            lw.bias = upload_f32(b2);
+        }
         layers.push_back(lw);
     }
     // linear(s)
@@ -544,6 +769,8 @@ LstmModel::~LstmModel() {
     for (auto& l : layers) {
         cudaFree(l.w);
         cudaFree(l.bias);
+        cudaFree(l.w_ih);
+        cudaFree(l.w_hh);
     }
     cudaFree(wl1);
     cudaFree(bl1);
@@ -555,7 +782,8 @@ size_t LstmModel::workspace_bytes(int N, int T_in) const {
     const size_t x2 = (size_t)N * t_pad(T_in) * 16 * 2 + 4096;
     const size_t seq = (size_t)(T_out + 1) * n_pad(N) * desc.lstm_size * 2 + 4096;
     const size_t mid = desc.out_features > 0 ? (size_t)T_out * n_pad(N) * desc.out_features * 2 + 4096 : 0;
-    return x2 + seq + mid;
+    const size_t gx = hoisted() ? (size_t)T_out * n_pad(N) * 4 * desc.lstm_size * 2 + 4096 : 0;
+    return x2 + seq + mid + gx;
 }
 
 std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
@@ -565,7 +793,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     const int Np = n_pad(N);
     if (Np != N) {
         // the reference's tensor-core LSTM has the same kind of constraint (multiples of 64, CudaCaller.h:60-63)
-        throw std::invalid_argument("batch_size must be a multiple of 16 for LSTM models");
+        throw std::invalid_argument(hoisted() ? "batch_size must be a multiple of 32 for this LSTM size"
+                                              : "batch_size must be a multiple of 16 for LSTM models");
     }
     auto plan = std::make_unique<LstmPlan>();
     plan->model = this;
@@ -580,6 +809,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     __half* x2 = reinterpret_cast<__half*>(take((size_t)N * Tp * 16 * 2));
     __half* seq = reinterpret_cast<__half*>(take((size_t)(T_out + 1) * Np * C * 2));
     __half* mid = desc.out_features > 0 ? reinterpret_cast<__half*>(take((size_t)T_out * Np * desc.out_features * 2)) : nullptr;
+    __half* gxbuf = hoisted() ? reinterpret_cast<__half*>(take((size_t)T_out * Np * 4 * C * 2)) : nullptr;
 
     // conv1 + conv2
     plan->conv12 = Conv12Params{signal, x2, conv_w, N, T_in, Tp, pad3(), desc.convs[0].size, desc.convs[0].winlen,
@@ -607,7 +837,46 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         plan->conv3 = make_gemm_plan(g);
     }
     // LSTM layers
-    {
+    if (hoisted()) {
+        plan->num_layers = desc.lstm_layers;
+        plan->hoisted = true;
+        if (C != 192 && C != 384) throw Unsupported("hoisted LSTM path is instantiated for lstm_size 192 and 384");
+        int un = Np >= 2048 ? 64 : (Np >= 512 ? 32 : 16);
+        while (Np % un != 0) un /= 2;
+        plan->rec_un = un;
+        const int GB = un < 32 ? 32 : un;
+        plan->lstm_grid = Np / un;
+        plan->rec_smem = 1024 + (size_t)REC_WSTAGES * WBLK_BYTES + (size_t)2 * (C / KBLK) * un * KBLK * 2 + 24 * 1024 + 1024;
+        for (int l = 0; l < desc.lstm_layers; ++l) {
+            GemmDesc g{};
+            g.a = layers[l].w_ih;  // gate rows are the M dimension, (t, chunk) the N dimension
+            g.batches = 1;
+            g.rows_per_batch = 4 * C;
+            g.a_row_stride = C;
+            g.a_batch_stride = (int64_t)4 * C * C;
+            g.w = seq;
+            g.N = T_out * Np;
+            g.K = C;
+            g.bias = layers[l].bias;
+            g.bias_per_row = 1;
+            g.act = GEMM_ACT_NONE;
+            g.out = gxbuf;
+            g.out_m1 = 1;
+            g.out_s0 = GB;
+            g.out_col_m1 = GB;
+            g.out_col_s0 = (int64_t)4 * C * GB;
+            plan->gx_gemm.push_back(make_gemm_plan(g));
+            plan->rec_w.push_back(make_tmap_2d(layers[l].w_hh, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C * 2, KBLK, 128));
+            LstmRecParams rp{};
+            rp.seq = seq;
+            rp.gx = gxbuf;
+            rp.T = T_out;
+            rp.N = Np;
+            rp.reverse = (l % 2 == 0) ? 1 : 0;
+            plan->rec_p.push_back(rp);
+        }
+        if (plan->rec_smem > 227 * 1024) throw Unsupported("LSTM shared-memory plan does not fit");
+    } else {
         plan->num_layers = desc.lstm_layers;
         const int MT = C / 32;
         const size_t w_bytes = (size_t)4 * C * 2 * C * 2;
@@ -707,6 +976,32 @@ static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
                                                                                         pl.lstm_p[l]);
 }
 
+template <int C, int UN>
+static void launch_rec_t(const LstmPlan& pl, int l, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<C, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    lstm_rec_kernel<C, UN><<<pl.lstm_grid, REC_THREADS, pl.rec_smem, stream>>>(pl.rec_w[l], pl.rec_p[l]);
+}
+
+template <int C>
+static void launch_rec_c(const LstmPlan& pl, int l, cudaStream_t stream) {
+    switch (pl.rec_un) {
+        case 64: launch_rec_t<C, 64>(pl, l, stream); break;
+        case 32: launch_rec_t<C, 32>(pl, l, stream); break;
+        default: launch_rec_t<C, 16>(pl, l, stream); break;
+    }
+}
+
+void LstmPlan::launch_rec(int l, cudaStream_t stream) const {
+    const int C = model->desc.lstm_size;
+    if (C == 384) launch_rec_c<384>(*this, l, stream);
+    else if (C == 192) launch_rec_c<192>(*this, l, stream);
+    else throw Unsupported("no hoisted LSTM kernel instantiation for this lstm_size");
+}
+
 template <int C>
 static void launch_lstm_c(const LstmPlan& pl, int l, cudaStream_t stream) {
     switch (pl.lstm_nbr) {
@@ -738,15 +1033,27 @@ void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
         nl = atoi(dbg);
         if (nl < num_layers) {
             for (int l = 0; l < nl; ++l) {
-                launch_lstm(l, stream);
+                if (hoisted) {
+                    run_gemm(gx_gemm[l], stream);
+                    launch_rec(l, stream);
+                } else {
+                    launch_lstm(l, stream);
+                }
             }
             B200_CUDA(cudaGetLastError());
             return;
         }
     }
     for (int l = 0; l < num_layers; ++l) {
-        launch_lstm(l, stream);
-        if (prof) prof->mark("lstm_layer", stream);
+        if (hoisted) {
+            run_gemm(gx_gemm[l], stream);
+            if (prof) prof->mark("lstm_gx_gemm", stream);
+            launch_rec(l, stream);
+            if (prof) prof->mark("lstm_rec", stream);
+        } else {
+            launch_lstm(l, stream);
+            if (prof) prof->mark("lstm_layer", stream);
+        }
     }
     run_gemm(linear1, stream);
     if (prof) prof->mark("linear_gemm", stream);
