@@ -595,6 +595,206 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weights-stationary LSTM recurrence over a thread-block cluster (hac: C = 384, cluster of 6 CTAs).
+//
+// W_hh (4C x C fp16 = 1.18 MB for C = 384) is split by gate tile across the CL CTAs of a cluster and stays in
+// their shared memory for the whole sequence; the cluster owns UN = 16 chunks.  Every step each CTA computes the
+// gates of its own 32*TPC hidden units from the full h_{t-1} (its private copy in shared memory), and all-gathers
+// its slice of h_t into every CTA's copy through distributed shared memory (st.shared::cluster), followed by one
+// cluster barrier.  No weight traffic after the prologue; the x_t half comes from the hoisted gx GEMM as in
+// lstm_rec_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int C, int CL>
+struct ClusterCfg {
+    static constexpr int MT = C / 32;
+    static constexpr int TPC = MT / CL;           // tiles per CTA
+    static constexpr int KBH = C / KBLK;
+    static constexpr int EW = 4 * TPC;            // epilogue warps
+    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr size_t W_BYTES = (size_t)TPC * KBH * WBLK_BYTES;
+    static constexpr size_t Z_BYTES = (size_t)2 * KBH * ZBLK;
+    static constexpr size_t SMEM = 1024 + W_BYTES + Z_BYTES + (size_t)EW * 1024 + 256;
+    static_assert(MT % CL == 0, "cluster size must divide the tile count");
+};
+
+template <int C, int CL>
+__global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_kernel(const __grid_constant__ CUtensorMap tma_w,
+                                                                                     const LstmRecParams p) {
+    using Cfg = ClusterCfg<C, CL>;
+    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH;
+    constexpr int GB = 32;  // chunk block of the gx layout (UN = 16 < 32)
+    constexpr uint32_t TMEM_COLS = 2 * TPC * UN <= 32 ? 32 : 64;
+    static_assert(2 * TPC * UN <= 64, "accumulators must fit the TMEM allocation");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_s = smem;                                           // [TPC][KBH][8 KB]
+    uint8_t* z_s = w_s + Cfg::W_BYTES;                             // [2][KBH][ZBLK]  full h, this CTA's copy
+    float* xs = reinterpret_cast<float*>(z_s + Cfg::Z_BYTES);      // [EW][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + Cfg::EW * 256);
+    uint64_t* w_full = bars;        // [1]
+    uint64_t* acc_full = bars + 1;  // [TPC]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + TPC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x / CL;
+    const int n0 = cluster_id * UN;
+
+    for (int i = threadIdx.x; i < (int)(Cfg::Z_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        tc::mbar_init(w_full, 1);
+        for (int i = 0; i < TPC; ++i) tc::mbar_init(&acc_full[i], 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_w);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0 && tc::elect_one()) {
+        // this CTA's gate tiles: m = rank * TPC + i
+        tc::mbar_arrive_expect_tx(w_full, (uint32_t)Cfg::W_BYTES);
+        for (int i = 0; i < TPC; ++i) {
+            for (int kb = 0; kb < KBH; ++kb) {
+                tc::tma_load_2d(w_s + (size_t)(i * KBH + kb) * WBLK_BYTES, &tma_w, w_full, kb * KBLK, ((int)rank * TPC + i) * 128);
+            }
+        }
+    }
+    __syncwarp();
+    // everybody in the cluster has zeroed its Z copy before any remote h store may land
+    cluster_arrive_release();
+    cluster_wait_acquire();
+
+    const bool is_mma = warp == 1;
+    const bool is_epi = warp >= 2;
+    const int ewarp = warp - 2;
+    const int ti = ewarp >> 2;       // which of this CTA's tiles the warp serves
+    const int qt = warp & 3;         // TMEM lane quarter
+    const int uk = lane >> 2, gj = lane & 3, cp = lane & 3;
+    float* xw = xs + (is_epi ? ewarp : 0) * 256;
+    const float am = gj == 2 ? 2.0f : 1.0f;
+    float c_reg[UN / 4];
+#pragma unroll
+    for (int k = 0; k < UN / 4; ++k) c_reg[k] = 0.0f;
+    const uint32_t z_local = tc::smem_u32(z_s);
+    const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
+    const uint64_t zdesc0 = umma_desc_sw64(z_local);
+    constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
+    if (is_mma) tc::mbar_wait(w_full, 0);
+
+    for (int s = 0; s < p.T; ++s) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const int buf = s & 1, nbuf = buf ^ 1;
+        if (is_mma) {
+            if (tc::elect_one()) {
+                tc::fence_proxy_async_smem();  // remote h stores (generic proxy) -> UMMA operand reads (async proxy)
+                tc::tc_fence_after();
+                const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZBLK) >> 4);
+                // 2 * TPC independent accumulation chains (tile x K-parity), interleaved so that the tensor pipe never
+                // waits on the previous MMA of the same accumulator; the epilogue adds the two K-halves
+#pragma unroll
+                for (int kb = 0; kb < KBH; ++kb) {
+#pragma unroll
+                    for (int i = 0; i < TPC; ++i) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((2 * i + (kb & 1)) * UN);
+                        const uint64_t adesc = wdesc0 + (uint64_t)(((i * KBH + kb) * WBLK_BYTES) >> 4);
+                        const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
+                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb >= 2);
+                        tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < TPC; ++i) tc::umma_commit(&acc_full[i]);
+            }
+            __syncwarp();
+        } else if (is_epi) {
+            const int m = (int)rank * TPC + ti;
+            const __half* gx_row = p.gx + ((size_t)t * (p.N / GB) + (n0 / GB)) * (size_t)(4 * C) * GB + (n0 % GB) +
+                                   (size_t)(m * 128 + qt * 32 + lane) * GB;
+            const uint4 gx0 = __ldg(reinterpret_cast<const uint4*>(gx_row));
+            const uint4 gx1 = __ldg(reinterpret_cast<const uint4*>(gx_row + 8));
+            __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
+            tc::mbar_wait(&acc_full[ti], (uint32_t)(s & 1));
+            tc::tc_fence_after();
+            uint32_t r[16], r2[16];
+            tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((2 * ti) * UN), r);
+            tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((2 * ti + 1) * UN), r2);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const uint4 gcur = ch == 0 ? gx0 : gx1;
+                const __half2* gh = reinterpret_cast<const __half2*>(&gcur);
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 gf = __half22float2(gh[e]);
+                    const float v0 = __uint_as_float(r[ch * 8 + 2 * e]) + gf.x, v1 = __uint_as_float(r[ch * 8 + 2 * e + 1]) + gf.y;
+                    a[2 * e] = 1.0f - __fdividef(am, __expf(am * v0) + 1.0f);
+                    a[2 * e + 1] = 1.0f - __fdividef(am, __expf(am * v1) + 1.0f);
+                }
+                float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
+                dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+                dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+                __syncwarp();
+                const float2 ig = *reinterpret_cast<const float2*>(xw + (0 * 8 + uk) * 8 + 2 * cp);
+                const float2 fg = *reinterpret_cast<const float2*>(xw + (1 * 8 + uk) * 8 + 2 * cp);
+                const float2 gg = *reinterpret_cast<const float2*>(xw + (2 * 8 + uk) * 8 + 2 * cp);
+                const float2 og = *reinterpret_cast<const float2*>(xw + (3 * 8 + uk) * 8 + 2 * cp);
+                __syncwarp();
+                const float c0 = fg.x * c_reg[2 * ch] + ig.x * gg.x;
+                const float c1 = fg.y * c_reg[2 * ch + 1] + ig.y * gg.y;
+                c_reg[2 * ch] = c0;
+                c_reg[2 * ch + 1] = c1;
+                const __half h0 = __float2half_rn(og.x * tanh_f(c0));
+                const __half h1 = __float2half_rn(og.y * tanh_f(c1));
+                const int u = qt * 8 + uk;
+                const int nA = ch * 8 + 2 * cp;
+                // all-gather: this unit's h goes into block m of every CTA's Z[nbuf]
+                const uint32_t off0 = (uint32_t)((nbuf * KBH + m) * ZBLK) + sw64_offset(nA, u);
+                const uint32_t off1 = (uint32_t)((nbuf * KBH + m) * ZBLK) + sw64_offset(nA + 1, u);
+#pragma unroll
+                for (int rr = 0; rr < CL; ++rr) {
+                    const uint32_t base = mapa_shared(z_local, (uint32_t)rr);
+                    st_cluster_u16(base + off0, __half_as_ushort(h0));
+                    st_cluster_u16(base + off1, __half_as_ushort(h1));
+                }
+                if (ch == 1) asm volatile("fence.proxy.async;" ::: "memory");  // generic writes -> async-proxy readers
+                y_t[(size_t)nA * C + m * 32 + u] = h0;
+                y_t[(size_t)(nA + 1) * C + m * 32 + u] = h1;
+            }
+        }
+        // h_t complete everywhere (and every accumulator drained) before the next step starts
+        cluster_arrive_release();
+        cluster_wait_acquire();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct LstmLayerWeights {
@@ -622,6 +822,7 @@ public:
     void launch_lstm(int l, cudaStream_t stream) const;
     // hoisted path
     bool hoisted = false;
+    bool use_cluster = false;
     int rec_un = 16;
     size_t rec_smem = 0;
     std::vector<GemmPlan> gx_gemm;
@@ -841,11 +1042,13 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         plan->num_layers = desc.lstm_layers;
         plan->hoisted = true;
         if (C != 192 && C != 384) throw Unsupported("hoisted LSTM path is instantiated for lstm_size 192 and 384");
-        int un = Np >= 2048 ? 64 : (Np >= 512 ? 32 : 16);
+        // C = 192 / 384: weights-stationary cluster kernel (6 CTAs x 16 chunks); otherwise the L2-streaming kernel
+        plan->use_cluster = true;
+        int un = plan->use_cluster ? 16 : (Np >= 2048 ? 64 : (Np >= 512 ? 32 : 16));
         while (Np % un != 0) un /= 2;
         plan->rec_un = un;
         const int GB = un < 32 ? 32 : un;
-        plan->lstm_grid = Np / un;
+        plan->lstm_grid = plan->use_cluster ? (Np / un) * 6 : Np / un;
         plan->rec_smem = 1024 + (size_t)REC_WSTAGES * WBLK_BYTES + (size_t)2 * (C / KBLK) * un * KBLK * 2 + 24 * 1024 + 1024;
         for (int l = 0; l < desc.lstm_layers; ++l) {
             GemmDesc g{};
@@ -995,8 +1198,37 @@ static void launch_rec_c(const LstmPlan& pl, int l, cudaStream_t stream) {
     }
 }
 
+template <int C, int CL>
+static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
+    using Cfg = ClusterCfg<C, CL>;
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<C, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)pl.lstm_grid, 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<C, CL>, pl.rec_w[l], pl.rec_p[l]));
+}
+
 void LstmPlan::launch_rec(int l, cudaStream_t stream) const {
     const int C = model->desc.lstm_size;
+    if (use_cluster) {
+        if (C == 384) launch_cluster_t<384, 6>(*this, l, stream);
+        else if (C == 192) launch_cluster_t<192, 6>(*this, l, stream);
+        else throw Unsupported("no cluster LSTM kernel instantiation for this lstm_size");
+        return;
+    }
     if (C == 384) launch_rec_c<384>(*this, l, stream);
     else if (C == 192) launch_rec_c<192>(*this, l, stream);
     else throw Unsupported("no hoisted LSTM kernel instantiation for this lstm_size");
