@@ -37,6 +37,8 @@ struct GemmKernelParams {
     long long out_m1, out_s0, out_s1;
     long long out_col_m1, out_col_s0;
     int bias_per_row;
+    const float* rope;
+    int rope_T, rope_cols;
     const __half* residual;
     float alpha;
     uint32_t tmem_cols;
@@ -157,6 +159,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             if (c_begin == c_end) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(&tmem_empty[ab]);
+            }
+            if (p.act == GEMM_ACT_ROPE) {
+                // head_dim 64 = two 32-column chunks (x1 | x2): out1 = cos*x1 - sin*x2, out2 = sin*x1 + cos*x2
+                const int tpos = (int)(g % p.rope_T);
+                const float4* tab = reinterpret_cast<const float4*>(p.rope) + (size_t)tpos * 16;  // (cos,sin) x 2 dims
+                for (int c = c_begin; c < c_end; c += 2) {
+                    uint32_t r0[32], r1[32];
+                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + c * 32), r0);
+                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + (c + 1) * 32), r1);
+                    tc::tmem_ld_wait();
+                    if (c + 2 >= c_end) {
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&tmem_empty[ab]);
+                    }
+                    const int nc = n0 + c * 32;
+                    if (valid) {
+                        __half2 h0[16], h1[16];
+                        const bool rot = nc < p.rope_cols;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a0 = __uint_as_float(r0[2 * j]), a1 = __uint_as_float(r0[2 * j + 1]);
+                            float b0 = __uint_as_float(r1[2 * j]), b1 = __uint_as_float(r1[2 * j + 1]);
+                            if (rot) {
+                                const float4 cs = __ldg(tab + j);
+                                const float x0 = cs.x * a0 - cs.y * b0, y0 = cs.y * a0 + cs.x * b0;
+                                const float x1 = cs.z * a1 - cs.w * b1, y1 = cs.w * a1 + cs.z * b1;
+                                a0 = x0; b0 = y0; a1 = x1; b1 = y1;
+                            }
+                            h0[j] = __floats2half2_rn(a0, a1);
+                            h1[j] = __floats2half2_rn(b0, b1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            dst[q] = *reinterpret_cast<uint4*>(&h0[4 * q]);
+                            dst[4 + q] = *reinterpret_cast<uint4*>(&h1[4 * q]);
+                        }
+                    }
+                }
+                continue;
             }
             for (int c = c_begin; c < c_end; ++c) {
                 uint32_t r[32];
@@ -298,6 +340,9 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
     }
     if (p.bn == 0) throw std::invalid_argument("gemm: no valid tile width");
     if (d.act == GEMM_ACT_SWIGLU && (p.bn % 64) != 0) throw std::invalid_argument("gemm: swiglu needs BN % 64 == 0");
+    if (d.act == GEMM_ACT_ROPE && ((p.bn % 128) != 0 || !d.rope || d.rope_T <= 0)) {
+        throw std::invalid_argument("gemm: rope epilogue needs BN % 128 == 0 and a table");
+    }
     p.tiles_per_batch = (d.rows_per_batch + BM - 1) / BM;
     p.grid = dim3((unsigned)(p.tiles_per_batch * d.batches), (unsigned)(d.N / p.bn), 1);
     p.smem = (size_t)STAGES * (BM * BK * 2 + (size_t)p.bn * BK * 2) + 256 + 1024;
@@ -329,6 +374,9 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.out_col_m1 = p.d.out_col_m1;
     k.out_col_s0 = p.d.out_col_s0;
     k.bias_per_row = p.d.bias_per_row;
+    k.rope = p.d.rope;
+    k.rope_T = p.d.rope_T;
+    k.rope_cols = p.d.rope_cols;
     k.residual = p.d.residual;
     k.alpha = p.d.alpha;
     uint32_t cols = 32;

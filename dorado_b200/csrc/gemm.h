@@ -13,6 +13,7 @@ enum GemmAct : int {
     GEMM_ACT_TANH = 2,         // TANH
     GEMM_ACT_TANH_X5 = 3,      // tanh(x) * 5 (pre-v4.x CRF linear, dorado/nn/CRFModules.cpp:27-31)
     GEMM_ACT_SWIGLU = 4,       // columns (2j, 2j+1) = (y, gate) -> silu(gate) * y, N/2 outputs (TxModules.cpp:170-176)
+    GEMM_ACT_ROPE = 5,         // output columns are [3][H][64] (q|k|v): rotary embedding on q and k (TxModules.cpp:220-250)
 };
 
 struct GemmDesc {
@@ -39,6 +40,10 @@ struct GemmDesc {
     int64_t out_col_m1 = 0;
     int64_t out_col_s0 = 0;
     int bias_per_row = 0;  // bias indexed by the global row g instead of the column
+    // GEMM_ACT_ROPE: (cos, sin) table [T_max][32][2], tokens per chunk, number of leading columns to rotate
+    const float* rope = nullptr;
+    int rope_T = 0;
+    int rope_cols = 0;
     // optional fused residual epilogue (deepnorm): v = v + alpha * residual[g][n]; requires act == NONE
     const __half* residual = nullptr;
     float alpha = 0.0f;

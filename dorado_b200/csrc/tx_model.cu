@@ -122,66 +122,63 @@ __device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t 
 }
 
 struct AttnParams {
-    const __half* qkv;
-    __half* out;
-    const float* rope;  // [T_max][32][2] (cos, sin)
+    const __half* qkv;  // [N*T][3][H][64], q and k already rotated (QKV GEMM epilogue)
+    __half* out;        // [N*T][H*64]
     int N, T, H;
     int win_upper, win_lower;  // keys j with -win_upper <= j - i <= win_lower
 };
 
-// load 64 rows x 64 dims of q or k (which = 0 / 1) for tokens [t0, t0+64) with rotary embedding into smem [64][PITCH]
-__device__ __forceinline__ void load_rope_tile(const AttnParams& p, int n, int h, int which, int t0, __half* dst) {
-    // thread handles (row, 8-dim group j in 0..3) pairs: needs dims [8j, 8j+8) and [32+8j, 32+8j+8)
-    for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
-        const int r = i >> 2, j = i & 3;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t* r, const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// copy 64 token rows x 64 dims (which = 0 q, 1 k, 2 v) for tokens [t0, t0+64) into smem [64][PITCH]; rows outside
+// [0, T) are zero-filled
+__device__ __forceinline__ void load_tile_async(const AttnParams& p, int n, int h, int which, int t0, __half* dst) {
+    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+        const int r = i >> 3, j = i & 7;
         const int t = t0 + r;
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
-        if (t >= 0 && t < p.T) {
-            const __half* src = p.qkv + (((size_t)n * p.T + t) * 3 + which) * p.H * ATT_D + (size_t)h * ATT_D;
-            const uint4 a = *reinterpret_cast<const uint4*>(src + 8 * j);
-            const uint4 b = *reinterpret_cast<const uint4*>(src + 32 + 8 * j);
-            const __half2* ah = reinterpret_cast<const __half2*>(&a);
-            const __half2* bh = reinterpret_cast<const __half2*>(&b);
-            const float2* cs = reinterpret_cast<const float2*>(p.rope + ((size_t)t * 32 + 8 * j) * 2);
-            __half2 ol[4], oh[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 x1 = __half22float2(ah[e]), x2 = __half22float2(bh[e]);
-                const float2 c0 = cs[2 * e], c1 = cs[2 * e + 1];  // (cos, sin) for dims 8j+2e, 8j+2e+1
-                ol[e] = __floats2half2_rn(c0.x * x1.x - c0.y * x2.x, c1.x * x1.y - c1.y * x2.y);
-                oh[e] = __floats2half2_rn(c0.y * x1.x + c0.x * x2.x, c1.y * x1.y + c1.x * x2.y);
-            }
-            lo = *reinterpret_cast<uint4*>(ol);
-            hi = *reinterpret_cast<uint4*>(oh);
-        }
-        *reinterpret_cast<uint4*>(dst + r * ATT_PITCH + 8 * j) = lo;
-        *reinterpret_cast<uint4*>(dst + r * ATT_PITCH + 32 + 8 * j) = hi;
+        const bool ok = t >= 0 && t < p.T;
+        const __half* src = p.qkv + (((size_t)n * p.T + (ok ? t : 0)) * 3 + which) * p.H * ATT_D + (size_t)h * ATT_D + 8 * j;
+        cp_async16(dst + r * ATT_PITCH + 8 * j, src, ok);
     }
 }
 
 __global__ void __launch_bounds__(128) tx_attention_kernel(const AttnParams p) {
     __shared__ __align__(16) __half q_s[64 * ATT_PITCH];
-    __shared__ __align__(16) __half k_s[64 * ATT_PITCH];
-    __shared__ __align__(16) __half vt_s[64 * ATT_PITCH];  // transposed: [d][key]
+    __shared__ __align__(16) __half k_s[2][64 * ATT_PITCH];
+    __shared__ __align__(16) __half v_s[2][64 * ATT_PITCH];
     const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
     const int q0 = qt * 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
 
-    load_rope_tile(p, n, h, 0, q0, q_s);
-    __syncthreads();
-    // Q fragments for this warp's 16 rows: 4 k-steps
-    uint32_t qa[4][4];
-    {
-        const __half* qb = q_s + (warp * 16) * ATT_PITCH;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            qa[ks][0] = *reinterpret_cast<const uint32_t*>(qb + g * ATT_PITCH + ks * 16 + 2 * tig);
-            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qb + (g + 8) * ATT_PITCH + ks * 16 + 2 * tig);
-            qa[ks][2] = *reinterpret_cast<const uint32_t*>(qb + g * ATT_PITCH + ks * 16 + 8 + 2 * tig);
-            qa[ks][3] = *reinterpret_cast<const uint32_t*>(qb + (g + 8) * ATT_PITCH + ks * 16 + 8 + 2 * tig);
-        }
-    }
+    int kstart = q0 - p.win_upper;
+    if (kstart < 0) kstart = 0;
+    kstart &= ~63;
+    int kend = q0 + 63 + p.win_lower + 1;
+    if (kend > p.T) kend = p.T;
+    const int nblk = (kend - kstart + 63) / 64;
+
+    load_tile_async(p, n, h, 0, q0, q_s);
+    load_tile_async(p, n, h, 1, kstart, k_s[0]);
+    load_tile_async(p, n, h, 2, kstart, v_s[0]);
+    cp_async_commit();
+
     float o[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -189,39 +186,45 @@ __global__ void __launch_bounds__(128) tx_attention_kernel(const AttnParams p) {
         for (int j = 0; j < 4; ++j) o[i][j] = 0.0f;
     float row_max[2] = {-INFINITY, -INFINITY}, row_sum[2] = {0.0f, 0.0f};
     const int qi[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+    uint32_t qa[4][4];
+    // ldmatrix address patterns (lane -> row/col of the 8x8 tiles)
+    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;  // A operand / V: rows 0-15
+    const int lm_col = (lane >> 4) * 8;                     // second pair of tiles: +8 columns
 
-    int kstart = q0 - p.win_upper;
-    if (kstart < 0) kstart = 0;
-    kstart &= ~63;
-    int kend = q0 + 63 + p.win_lower + 1;
-    if (kend > p.T) kend = p.T;
-
-    for (int kb = kstart; kb < kend; kb += 64) {
-        __syncthreads();  // previous block's smem reads done
-        load_rope_tile(p, n, h, 1, kb, k_s);
-        // V transposed: thread handles (key r, 8-dim group j)
-        for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-            const int r = i >> 3, j = i & 7;
-            const int t = kb + r;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (t < p.T) {
-                v = *reinterpret_cast<const uint4*>(p.qkv + (((size_t)n * p.T + t) * 3 + 2) * p.H * ATT_D + (size_t)h * ATT_D + 8 * j);
-            }
-            const __half* vh = reinterpret_cast<const __half*>(&v);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) vt_s[(8 * j + e) * ATT_PITCH + r] = vh[e];
+    for (int ib = 0; ib < nblk; ++ib) {
+        const int kb = kstart + ib * 64;
+        const int cur = ib & 1;
+        if (ib + 1 < nblk) {
+            load_tile_async(p, n, h, 1, kb + 64, k_s[cur ^ 1]);
+            load_tile_async(p, n, h, 2, kb + 64, v_s[cur ^ 1]);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        if (ib == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qa[ks], q_s + (warp * 16 + lm_row) * ATT_PITCH + ks * 16 + lm_col);
+        }
+        const __half* kt = k_s[cur];
+        const __half* vt = v_s[cur];
 
-        // S = Q K^T : 8 key tiles of 8
+        // S = Q K^T : 8 key tiles of 8.  B fragments of two key tiles per ldmatrix.x4:
+        //   matrices: (keys nt*8.., d ks*16..+7), (same keys, d +8), (keys +8, d ..+7), (keys +8, d +8)
         float s[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+        for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                const __half* kp = k_s + (nt * 8 + g) * ATT_PITCH + ks * 16 + 2 * tig;
-                mma_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+                uint32_t b[4];
+                const int krow = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int kcol = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(b, kt + krow * ATT_PITCH + kcol);
+                mma_16816(s[2 * np], qa[ks], b[0], b[1]);
+                mma_16816(s[2 * np + 1], qa[ks], b[2], b[3]);
             }
         }
         // scale, mask, online softmax
@@ -262,19 +265,26 @@ __global__ void __launch_bounds__(128) tx_attention_kernel(const AttnParams p) {
             pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&lo);
             pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
         }
-        // O = O * scale + P V
+        // O = O * scale + P V.  B[k = key][n = d] from row-major V via ldmatrix.trans:
+        //   matrices: (keys ks*16..+7, d dp*16..+7), (keys +8, d ..+7), (keys ..+7, d +8), (keys +8, d +8)
 #pragma unroll
         for (int dt = 0; dt < 8; ++dt) {
             o[dt][0] *= scale_old[0];
             o[dt][1] *= scale_old[0];
             o[dt][2] *= scale_old[1];
             o[dt][3] *= scale_old[1];
+        }
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                const __half* vp = vt_s + (dt * 8 + g) * ATT_PITCH + ks * 16 + 2 * tig;
-                mma_16816(o[dt], pa[ks], *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+                uint32_t b[4];
+                ldmatrix_x4_trans(b, vt + (ks * 16 + lm_row) * ATT_PITCH + dp * 16 + lm_col);
+                mma_16816(o[2 * dp], pa[ks], b[0], b[1]);
+                mma_16816(o[2 * dp + 1], pa[ks], b[2], b[3]);
             }
         }
+        __syncthreads();  // all warps done with k_s/v_s[cur] before it is refilled
     }
     // finalise: divide by the row sums (quad-reduced) and store
 #pragma unroll
@@ -536,14 +546,19 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
         g.out_s1 = 0;
         g.residual = residual;
         g.alpha = alpha;
+        if (act == GEMM_ACT_ROPE) {
+            g.rope = rope;
+            g.rope_T = T;
+            g.rope_cols = 2 * desc.nhead * 64;
+        }
         return make_gemm_plan(g);
     };
     const int ff = desc.dim_feedforward;
     for (int l = 0; l < desc.depth; ++l) {
         const auto& lw = layers[l];
         TxPlan::Layer L;
-        L.qkv = dense(x, 512, lw.wqkv, 1536, nullptr, GEMM_ACT_NONE, qkv, 1536, nullptr, 0.0f);
-        L.attn = AttnParams{qkv, att, rope, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
+        L.qkv = dense(x, 512, lw.wqkv, 1536, nullptr, GEMM_ACT_ROPE, qkv, 1536, nullptr, 0.0f);
+        L.attn = AttnParams{qkv, att, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
         L.out_proj = dense(att, 512, lw.wo, 512, lw.bo, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
         L.fc1 = dense(x, 512, lw.w1, 2 * ff, nullptr, GEMM_ACT_SWIGLU, hid, ff, nullptr, 0.0f);
         L.fc2 = dense(hid, ff, lw.w2, 512, nullptr, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
