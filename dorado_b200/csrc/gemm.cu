@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                                                                            const GemmKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages x (A 16 KB | W bn*128 B), then barriers
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_bytes = BM * BK * 2;
     const uint32_t w_bytes = (uint32_t)p.bn * BK * 2;
     const uint32_t stage_bytes = a_bytes + w_bytes;

@@ -16,6 +16,7 @@
 #include "gemm.h"
 #include "tc.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -127,6 +128,7 @@ struct LstmParams {
     const float* bias;  // [4C] permuted like the weight rows (b_ih + b_hh)
     int T, N, C, reverse;
     int w_stages;  // 0 => weights resident in shared memory
+    long long* dbg;  // optional timeline (clock64 stamps of CTA 0, steps 64..67); nullptr in production
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
     using Cfg = LstmCfg<C>;
     constexpr int MT = Cfg::MT, G = Cfg::G, KB = Cfg::KB, KBX = Cfg::KBX;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const bool resident = p.w_stages == 0;
     const int w_blocks = resident ? MT * KB : p.w_stages;
     uint8_t* w_s = smem;
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&x_full[i], 1);
             tc::mbar_init(&z_free[i], (uint32_t)mma_warps);
-            tc::mbar_init(&h_ready[i], G * 128);
-            tc::mbar_init(&acc_free[i], G * 128);
+            tc::mbar_init(&h_ready[i], G * 4);   // one arrival per epilogue warp
+            tc::mbar_init(&acc_free[i], G * 4);
         }
         for (int i = 0; i < 2 * MT; ++i) tc::mbar_init(&acc_full[i], 1);
         const int nwb = resident ? 1 : p.w_stages;
@@ -271,14 +274,17 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                     const int buf = s & 1;
                     const uint32_t par = (uint32_t)((s >> 1) & 1);
                     const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
+                    const bool dbg = p.dbg && blockIdx.x == 0 && mw == 0 && s >= 64 && s < 68;
                     tc::mbar_wait(&x_full[buf], par);
                     tc::mbar_wait(&acc_free[buf], par ^ 1);
                     tc::tc_fence_after();
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         if (half == 1) {
+                            if (dbg) p.dbg[(s - 64) * 16 + 0] = clock64();
                             tc::mbar_wait(&h_ready[buf], par);
                             tc::tc_fence_after();
+                            if (dbg) p.dbg[(s - 64) * 16 + 1] = clock64();
                         }
 #pragma unroll
                         for (int i = 0; i < MT / G; ++i) {
@@ -296,6 +302,7 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                         }
                     }
                     tc::umma_commit(&z_free[buf]);
+                    if (dbg) p.dbg[(s - 64) * 16 + 2] = clock64();
                 }
             } else {
                 long long wj = 0;
@@ -338,7 +345,10 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
         const int gate = warp & 3;   // TMEM lane quarter this warp may read == gate type (i,f,g,o)
         float* gs = g_s + (size_t)g * 4 * NBR * 32;
         constexpr int CPT = NBR / 4;
-        tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0 is in place (zeroed before the CTA-wide sync)
+        float bias_r[MT / G];
+#pragma unroll
+        for (int i = 0; i < MT / G; ++i) bias_r[i] = __ldg(p.bias + (g + i * G) * 128 + gate * 32 + lane);
+        if (lane == 0) tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0 is in place (zeroed before the CTA-wide sync)
 
         for (int s = 0; s < p.T; ++s) {
             const int t = p.reverse ? p.T - 1 - s : s;
@@ -346,11 +356,14 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
             const uint32_t par = (uint32_t)((s >> 1) & 1);
             uint8_t* zh_next = z_s + (size_t)(nbuf * KB + KBX) * ZBLK;
             __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
+            const bool dbg = p.dbg && blockIdx.x == 0 && ewarp == 0 && lane == 0 && s >= 64 && s < 68;
 #pragma unroll
             for (int i = 0; i < MT / G; ++i) {
                 const int m = g + i * G;
+                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 4] = clock64();
                 tc::mbar_wait(&acc_full[buf * MT + m], par);
                 tc::tc_fence_after();
+                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 5] = clock64();
                 uint32_t r[NBR];
                 const uint32_t taddr = tmem_base + ((uint32_t)(gate * 32) << 16) + (uint32_t)((buf * MT + m) * UN);
                 if constexpr (NBR == 16) {
@@ -361,13 +374,20 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                     tc::tmem_ld_32x4(taddr, r);
                 }
                 tc::tmem_ld_wait();
-                const float b = __ldg(p.bias + m * 128 + gate * 32 + lane);
+                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 6] = clock64();
+                const float b = bias_r[i];
+                const float am = gate == 2 ? 2.0f : 1.0f;  // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
 #pragma unroll
                 for (int n = 0; n < NBR; ++n) {
                     const float v = __uint_as_float(r[n]) + b;
-                    gs[(gate * NBR + n) * 32 + lane] = gate == 2 ? tanh_f(v) : sigmoid_f(v);
+                    gs[(gate * NBR + n) * 32 + lane] = 1.0f - __fdividef(am, __expf(am * v) + 1.0f);
                 }
+                float c_old[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) c_old[j] = c_s[((size_t)m * NBR + ew + 4 * j) * 32 + lane];
+                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 7] = clock64();
                 named_bar_sync(1 + g, 128);
+                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 8] = clock64();
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     const int n = ew + 4 * j;
@@ -375,19 +395,23 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                     const float fg = gs[(1 * NBR + n) * 32 + lane];
                     const float gg = gs[(2 * NBR + n) * 32 + lane];
                     const float og = gs[(3 * NBR + n) * 32 + lane];
-                    float* cp = &c_s[((size_t)m * NBR + n) * 32 + lane];  // owned by this thread for all steps
-                    const float cs = fg * (*cp) + ig * gg;
-                    *cp = cs;
+                    const float cs = fg * c_old[j] + ig * gg;
+                    c_s[((size_t)m * NBR + n) * 32 + lane] = cs;  // owned by this thread for all steps
                     const __half h = __float2half_rn(og * tanh_f(cs));
                     *reinterpret_cast<__half*>(zh_next + (size_t)m * ZBLK + sw64_offset(n, lane)) = h;
                     y_t[(size_t)n * C + m * 32 + lane] = h;
                 }
                 if (i + 1 < MT / G) named_bar_sync(1 + g, 128);  // gs reuse within the step
             }
+            if (dbg) p.dbg[(s - 64) * 16 + 9] = clock64();
             tc::tc_fence_before();
-            tc::mbar_arrive(&acc_free[buf]);
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&h_ready[nbuf]);
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(&acc_free[buf]);
+                tc::mbar_arrive(&h_ready[nbuf]);
+            }
+            if (dbg) p.dbg[(s - 64) * 16 + 10] = clock64();
             named_bar_sync(1 + g, 128);  // gs reuse across steps
         }
     }
@@ -428,7 +452,8 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(const __grid_c
     constexpr uint32_t TMEM_COLS = REC_NBUF * UN < 32 ? 32 : REC_NBUF * UN;
     static_assert(MT % REC_GROUPS == 0 && REC_NBUF * UN <= 512, "unsupported shape");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_s = smem;                                            // [REC_WSTAGES][8 KB]
     uint8_t* z_s = w_s + (size_t)REC_WSTAGES * WBLK_BYTES;          // [2][KBH][ZB]
     float* xs = reinterpret_cast<float*>(z_s + (size_t)2 * KBH * ZB);  // [24 warps][4][8][8] exchange
@@ -642,7 +667,8 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
     constexpr uint32_t TMEM_COLS = 2 * TPC * UN <= 32 ? 32 : 64;
     static_assert(2 * TPC * UN <= 64, "accumulators must fit the TMEM allocation");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_s = smem;                                           // [TPC][KBH][8 KB]
     uint8_t* z_s = w_s + Cfg::W_BYTES;                             // [2][KBH][ZBLK]  full h, this CTA's copy
     float* xs = reinterpret_cast<float*>(z_s + Cfg::Z_BYTES);      // [EW][256]
@@ -821,6 +847,7 @@ public:
     size_t lstm_smem = 0;
     void launch_lstm(int l, cudaStream_t stream) const;
     // hoisted path
+    long long* dbg_timeline = nullptr;
     bool hoisted = false;
     bool use_cluster = false;
     int rec_un = 16;
@@ -1115,6 +1142,12 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             lp.C = C;
             lp.reverse = (l % 2 == 0) ? 1 : 0;  // reverse_first = true (CRFModel.cpp:40, LSTMStack.cpp:31-41)
             lp.w_stages = w_stages;
+            lp.dbg = nullptr;
+            if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
+                B200_CUDA(cudaMalloc(&lp.dbg, 64 * sizeof(long long)));
+                B200_CUDA(cudaMemset(lp.dbg, 0, 64 * sizeof(long long)));
+                plan->dbg_timeline = lp.dbg;
+            }
             plan->lstm_p.push_back(lp);
         }
         if (plan->lstm_smem > 227 * 1024) throw Unsupported("LSTM shared-memory plan does not fit");
@@ -1285,6 +1318,17 @@ void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
         } else {
             launch_lstm(l, stream);
             if (prof) prof->mark("lstm_layer", stream);
+        }
+    }
+    if (dbg_timeline) {
+        long long h[64];
+        B200_CUDA(cudaStreamSynchronize(stream));
+        B200_CUDA(cudaMemcpy(h, dbg_timeline, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < 4; ++s) {
+            const long long* e = h + s * 16;
+            const long long t0 = e[0];
+            fprintf(stderr, "[lstm timeline step %d] mma: wait_h_start 0 wait_h_done %lld issue_done %lld | epi: wait_acc_start %lld acc_full %lld ld_done %lld act_done %lld bar_done %lld cells_done %lld arrive_done %lld\n",
+                    64 + s, e[1] - t0, e[2] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0, e[8] - t0, e[9] - t0, e[10] - t0);
         }
     }
     run_gemm(linear1, stream);
