@@ -126,8 +126,9 @@ constexpr int ZBLK = UN * KBLK * 2;
 struct LstmParams {
     __half* seq;        // [T][N][C] in place
     const float* bias;  // [4C] permuted like the weight rows (b_ih + b_hh)
+    const __half* w;    // [4C][2C] permuted weights (read directly when they are kept in tensor memory)
     int T, N, C, reverse;
-    int w_stages;  // 0 => weights resident in shared memory
+    int w_stages;  // 0 => weights resident on chip
     long long* dbg;  // optional timeline (clock64 stamps of CTA 0, steps 64..67); nullptr in production
 };
 
@@ -165,7 +166,12 @@ struct LstmCfg {
     static constexpr int KB = 2 * C / KBLK;
     static constexpr int KBX = C / KBLK;
     static constexpr int THREADS = 32 * (1 + G) + 128 * G;
-    static constexpr uint32_t TMEM_COLS = 2 * MT * UN <= 32 ? 32 : 2 * MT * UN <= 64 ? 64 : 2 * MT * UN <= 128 ? 128 : 2 * MT * UN <= 256 ? 256 : 512;
+    // weights in tensor memory: the MMA then reads only the tiny [16 x K] activation operand from shared memory
+    // instead of re-reading 4C x 2C weights every step (C = 96: 288 weight columns + 96 accumulator columns)
+    static constexpr bool WT = (MT * C + 2 * MT * UN) <= 512;
+    static constexpr int ACC_COLS = 2 * MT * UN;
+    static constexpr int NEED_COLS = ACC_COLS + (WT ? MT * C : 0);
+    static constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
     static_assert(MT % G == 0 && 2 * MT * UN <= 512, "unsupported LSTM size");
 };
 
@@ -178,8 +184,9 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr bool WT = Cfg::WT;
     const bool resident = p.w_stages == 0;
-    const int w_blocks = resident ? MT * KB : p.w_stages;
+    const int w_blocks = WT ? 0 : (resident ? MT * KB : p.w_stages);
     uint8_t* w_s = smem;
     uint8_t* z_s = w_s + (size_t)w_blocks * WBLK_BYTES;                   // [2][KB][ZBLK]
     float* g_s = reinterpret_cast<float*>(z_s + (size_t)2 * KB * ZBLK);   // [G][4][NBR][32]
@@ -224,11 +231,35 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_w = tmem_base + Cfg::ACC_COLS;  // [MT][C] columns: tile m, k-step ks at m*C + ks*8
+    if constexpr (WT) {
+        if (warp > G) {
+            // epilogue warp (group = tile, quarter = warp & 3): each thread owns one weight row of its tile
+            const int ew_ = warp - (1 + G);
+            const int m = ew_ >> 2, q = warp & 3;
+            static_assert(MT == G, "weights-in-TMEM path assumes one tile per epilogue group");
+            const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)(m * 128 + q * 32 + lane) * 2 * C);
+#pragma unroll
+            for (int cb = 0; cb < C / 32; ++cb) {
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const uint4 x = __ldg(src + cb * 8 + v);
+                    r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                }
+                tc::tmem_st_32x32(tmem_w + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * C + cb * 32), r);
+            }
+            tc::tmem_st_wait();
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+    }
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (tc::elect_one()) {
-            if (resident) {
+            if (resident && !WT) {
                 tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)(MT * KB * WBLK_BYTES));
                 for (int m = 0; m < MT; ++m) {
                     for (int kb = 0; kb < KB; ++kb) {
@@ -268,7 +299,7 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
             const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
             const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
             if (resident) {
-                tc::mbar_wait(&w_full[0], 0);
+                if constexpr (!WT) tc::mbar_wait(&w_full[0], 0);
                 // this warp owns tiles mw, mw + G, ...; descriptors are base + compile-time offsets
                 for (int s = 0; s < p.T; ++s) {
                     const int buf = s & 1;
@@ -293,10 +324,16 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                             const uint64_t wd = wdesc0 + (uint64_t)((m * KB * WBLK_BYTES) >> 4);
 #pragma unroll
                             for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb) {
-                                const uint64_t adesc = wd + (uint64_t)((kb * WBLK_BYTES) >> 4);
                                 const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
-                                tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
-                                tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                                if constexpr (WT) {
+                                    const uint32_t a_t = tmem_w + (uint32_t)(m * C + kb * 16);  // 16 columns per 32-element block
+                                    tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, kb != 0);
+                                    tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
+                                } else {
+                                    const uint64_t adesc = wd + (uint64_t)((kb * WBLK_BYTES) >> 4);
+                                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                                    tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                                }
                             }
                             if (half == 1) tc::umma_commit(&acc_full[buf * MT + m]);
                         }
@@ -1128,7 +1165,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         plan->lstm_grid = Np / nbr;
         const int KB = 2 * C / KBLK;
         const int w_stages = resident ? 0 : 12;
-        const size_t wsm = resident ? w_bytes : (size_t)w_stages * WBLK_BYTES;
+        const bool w_in_tmem = (C / 32) * C + 2 * (C / 32) * UN <= 512;
+        const size_t wsm = w_in_tmem ? 0 : (resident ? w_bytes : (size_t)w_stages * WBLK_BYTES);
         plan->lstm_smem = 1024 + wsm + (size_t)2 * KB * ZBLK + (size_t)G * 4 * nbr * 32 * 4 + (size_t)MT * nbr * 32 * 4 +
                           8 * (8 + 2 * MT + 2 * 16) + 64;
         for (int l = 0; l < desc.lstm_layers; ++l) {
@@ -1137,6 +1175,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             LstmParams lp{};
             lp.seq = seq;
             lp.bias = layers[l].bias;
+            lp.w = layers[l].w;
             lp.T = T_out;
             lp.N = Np;
             lp.C = C;
