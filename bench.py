@@ -57,7 +57,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -78,7 +78,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples whose nvidia-smi timestamp falls inside [t_begin, t_end] (time.time() values)."""
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -88,6 +90,10 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                if t_begin is not None:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                        continue
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
             except ValueError:
@@ -215,11 +221,15 @@ def main():
     runner.step_device(N, max(3, args.warmup))
     launches0 = caller.stats()["gpu_launches"]
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    time.sleep(0.3)  # let nvidia-smi reach its sampling loop before the timed region starts
+    barrier()
+    t_begin = time.time()
     tot_ms, fwd_ms, dec_ms = runner.step_device(N, args.steps)
     barrier()
-    clocks = sampler.stop()
+    t_end = time.time()
+    time.sleep(0.05)
+    clocks = sampler.stop(t_begin, t_end)
     launches = caller.stats()["gpu_launches"] - launches0
     tot_ms = max_over_ranks(tot_ms)
     value = world * samples_per_step * args.steps / (tot_ms * 1e-3)
@@ -251,20 +261,39 @@ def main():
     dom = max(agg, key=lambda k: agg[k][0] * agg[k][1])
     dom_ms, dom_cnt = agg[dom]
     C, T_out = cfg.outsize, runner.out_len()
-    if dom in ("lstm_layer", "lstm_rec"):
-        # 2*(2C)*(4C) FLOP per block per chunk per layer; the hoisted path's recurrent kernel does the
-        # W_hh half (the W_ih half is the lstm_gx_gemm launch)
-        flops = (16.0 if dom == "lstm_layer" else 8.0) * cfg.lstm_size ** 2 * T_out * N
-        roof = {"kernel": dom, "bound": "tensor", "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "traffic": None}
-    elif dom.startswith("crf_"):
-        byts = (2.0 * C + 3.0) * T_out * N  # scores read once + 3 output bytes per block
-        roof = {"kernel": dom, "bound": "hbm", "achieved": byts / (dom_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "traffic": None}
+    # algorithmic work of ONE launch of each kernel
+    work = {}
+    if cfg.is_tx_model:
+        M = N * (T // cfg.stride_inner())          # transformer tokens in the batch
+        d, ff = cfg.tx.d_model, cfg.tx.dim_feedforward
+        work = {"qkv_gemm": ("tensor", 2.0 * M * d * 3 * d), "out_proj_gemm": ("tensor", 2.0 * M * d * d),
+                "fc1_swiglu_gemm": ("tensor", 2.0 * M * d * 2 * ff), "fc2_gemm": ("tensor", 2.0 * M * ff * d),
+                "tx_attention": ("tensor", 4.0 * M * cfg.tx.nhead * 64 * (sum(cfg.tx.attn_window) + 1)),
+                "upsample_gemm": ("tensor", 2.0 * M * d * cfg.tx.upsample_scale * d),
+                "crf_gemm": ("tensor", 2.0 * M * cfg.tx.upsample_scale * d * C),
+                "rmsnorm": ("hbm", 2.0 * M * d * 2)}
     else:
-        flops = FLOP_PER_SAMPLE[kind] * samples_per_step
-        roof = {"kernel": dom, "bound": "tensor", "achieved": flops / (dom_ms * 1e-3) / 1e12, "peak": pk["tflops"],
+        Cl = cfg.lstm_size
+        work = {"lstm_layer": ("tensor", 16.0 * Cl * Cl * T_out * N),   # 2*(2C)*(4C) per chunk-step
+                "lstm_rec": ("tensor", 8.0 * Cl * Cl * T_out * N),      # W_hh half; the W_ih half is lstm_gx_gemm
+                "lstm_gx_gemm": ("tensor", 8.0 * Cl * Cl * T_out * N),
+                "conv3_gemm": ("tensor", 2.0 * cfg.convs[2].winlen * 16 * Cl * T_out * N),
+                "linear_gemm": ("tensor", 2.0 * Cl * C * T_out * N),
+                "conv12": ("hbm", (2.0 + 32.0) * T * N)}
+    for k in ("crf_bwd_scan", "crf_fwd_beam", "crf_traceback"):
+        work[k] = ("hbm", (2.0 * C + 3.0) * T_out * N)  # whole-decode algorithmic bytes, charged to each kernel
+    bound, amount = work.get(dom, ("tensor", FLOP_PER_SAMPLE[kind] * samples_per_step))
+    if bound == "tensor":
+        roof = {"kernel": dom, "bound": "tensor", "achieved": amount / (dom_ms * 1e-3) / 1e12, "peak": pk["tflops"],
                 "unit": "TFLOP/s", "traffic": None}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": amount / (dom_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "traffic": None}
+    roof["per_kernel"] = {k: {"bound": work[k][0], "ms_per_launch": round(agg[k][0], 4), "launches": agg[k][1],
+                              "achieved": round(work[k][1] / (agg[k][0] * 1e-3) / (1e12 if work[k][0] == "tensor" else 1e9), 2),
+                              "frac": round(work[k][1] / (agg[k][0] * 1e-3) /
+                                            ((pk["tflops"] * 1e12) if work[k][0] == "tensor" else (pk["hbm_gbs"] * 1e9)), 4)}
+                          for k in agg if k in work}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["peak_source"] = pk["source"]
     roof["ms_per_launch"] = dom_ms
