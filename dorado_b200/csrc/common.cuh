@@ -23,13 +23,12 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 
 constexpr int kNumSMs = 148;
 
+// exact warp-wide max of finite floats in one redux.sync: order-preserving float <-> uint32 key
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const float other = __shfl_xor_sync(0xffffffffu, v, o);
-        v = v > other ? v : other;
-    }
-    return v;
+    const uint32_t u = __float_as_uint(v);
+    const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const uint32_t m = __reduce_max_sync(0xffffffffu, key);
+    return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
 }
 
 __device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }

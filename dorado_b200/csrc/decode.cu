@@ -465,7 +465,7 @@ __device__ int beam_step(const __half* sc_row,
             if (count) prob = B200_ADD(prob, post_row[sh[k]]);
         }
         prob = prob < 0.0f ? 0.0f : (prob > 1.0f ? 1.0f : prob);
-        prob = b200_pow0p4f(prob);
+        // the pow(p, 0.4) of beam_search.cpp:503 is applied by the traceback kernel, only along the chosen path
         beam_row[lane] = make_uint2(meta, __float_as_uint(prob));
     }
     __syncwarp();
@@ -681,6 +681,8 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
         __syncwarp();
     }
     if (lane == 0) pmove[0] = 1;  // always step in the first block
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) pprob[t] = b200_pow0p4f(pprob[t]);  // "power fudge factor", beam_search.cpp:503
     __syncwarp();
 
     // base start blocks
