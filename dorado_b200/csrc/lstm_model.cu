@@ -679,6 +679,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
 __device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint16_t v) {
     asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -752,10 +755,11 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
     const int ewarp = warp - 2;
     const int ti = ewarp >> 2;       // which of this CTA's tiles the warp serves
     const int qt = warp & 3;         // TMEM lane quarter
-    const int uk = lane >> 2, gj = lane & 3, cp = lane & 3;
+    const int uk = lane >> 2, gj = lane & 3;   // activation role: unit within the warp's 8, gate type
+    const int up = lane >> 3, cc = lane & 7;   // cell-update role: unit pair (2up, 2up+1), column cc of each 8-column chunk
     float* xw = xs + (is_epi ? ewarp : 0) * 256;
     const float am = gj == 2 ? 2.0f : 1.0f;
-    float c_reg[UN / 4];
+    float c_reg[UN / 4];  // [chunk of 8 columns][unit of the pair]
 #pragma unroll
     for (int k = 0; k < UN / 4; ++k) c_reg[k] = 0.0f;
     const uint32_t z_local = tc::smem_u32(z_s);
@@ -769,8 +773,7 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
         const int buf = s & 1, nbuf = buf ^ 1;
         if (is_mma) {
             if (tc::elect_one()) {
-                tc::fence_proxy_async_smem();  // remote h stores (generic proxy) -> UMMA operand reads (async proxy)
-                tc::tc_fence_after();
+                tc::tc_fence_after();  // (the writers of h issued fence.proxy.async before the cluster barrier)
                 const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZBLK) >> 4);
                 // 2 * TPC independent accumulation chains (tile x K-parity), interleaved so that the tensor pipe never
                 // waits on the previous MMA of the same accumulator; the epilogue adds the two K-halves
@@ -821,31 +824,29 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
                 dst[0] = make_float4(a[0], a[1], a[2], a[3]);
                 dst[1] = make_float4(a[4], a[5], a[6], a[7]);
                 __syncwarp();
-                const float2 ig = *reinterpret_cast<const float2*>(xw + (0 * 8 + uk) * 8 + 2 * cp);
-                const float2 fg = *reinterpret_cast<const float2*>(xw + (1 * 8 + uk) * 8 + 2 * cp);
-                const float2 gg = *reinterpret_cast<const float2*>(xw + (2 * 8 + uk) * 8 + 2 * cp);
-                const float2 og = *reinterpret_cast<const float2*>(xw + (3 * 8 + uk) * 8 + 2 * cp);
+                float ig[2], fg[2], gg[2], og[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    ig[e] = xw[(0 * 8 + 2 * up + e) * 8 + cc];
+                    fg[e] = xw[(1 * 8 + 2 * up + e) * 8 + cc];
+                    gg[e] = xw[(2 * 8 + 2 * up + e) * 8 + cc];
+                    og[e] = xw[(3 * 8 + 2 * up + e) * 8 + cc];
+                }
                 __syncwarp();
-                const float c0 = fg.x * c_reg[2 * ch] + ig.x * gg.x;
-                const float c1 = fg.y * c_reg[2 * ch + 1] + ig.y * gg.y;
+                const float c0 = fg[0] * c_reg[2 * ch] + ig[0] * gg[0];
+                const float c1 = fg[1] * c_reg[2 * ch + 1] + ig[1] * gg[1];
                 c_reg[2 * ch] = c0;
                 c_reg[2 * ch + 1] = c1;
-                const __half h0 = __float2half_rn(og.x * tanh_f(c0));
-                const __half h1 = __float2half_rn(og.y * tanh_f(c1));
-                const int u = qt * 8 + uk;
-                const int nA = ch * 8 + 2 * cp;
-                // all-gather: this unit's h goes into block m of every CTA's Z[nbuf]
+                const __half2 hh = __floats2half2_rn(og[0] * tanh_f(c0), og[1] * tanh_f(c1));
+                const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hh);
+                const int u = qt * 8 + 2 * up;   // even unit within the tile
+                const int nA = ch * 8 + cc;      // chunk (row of the operand block)
+                // all-gather: units (u, u+1) of chunk nA go into block m of every CTA's Z[nbuf] as one 32-bit store
                 const uint32_t off0 = (uint32_t)((nbuf * KBH + m) * ZBLK) + sw64_offset(nA, u);
-                const uint32_t off1 = (uint32_t)((nbuf * KBH + m) * ZBLK) + sw64_offset(nA + 1, u);
 #pragma unroll
-                for (int rr = 0; rr < CL; ++rr) {
-                    const uint32_t base = mapa_shared(z_local, (uint32_t)rr);
-                    st_cluster_u16(base + off0, __half_as_ushort(h0));
-                    st_cluster_u16(base + off1, __half_as_ushort(h1));
-                }
+                for (int rr = 0; rr < CL; ++rr) st_cluster_u32(mapa_shared(z_local, (uint32_t)rr) + off0, hbits);
+                *reinterpret_cast<uint32_t*>(y_t + (size_t)nA * C + m * 32 + u) = hbits;
                 if (ch == 1) asm volatile("fence.proxy.async;" ::: "memory");  // generic writes -> async-proxy readers
-                y_t[(size_t)nA * C + m * 32 + u] = h0;
-                y_t[(size_t)(nA + 1) * C + m * 32 + u] = h1;
             }
         }
         // h_t complete everywhere (and every accumulator drained) before the next step starts
