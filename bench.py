@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--model", default="fast", choices=list(MODELS))
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--chunksize", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (batch sweeps)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -305,6 +306,8 @@ def main():
     roof["decode_gbs"] = (2.0 * C + 3.0) * T_out * N / (dec_ms / args.steps * 1e-3) / 1e9
 
     try:
+        if args.no_cpu_baseline:
+            raise RuntimeError("skipped (--no-cpu-baseline)")
         cpu = run_reference_cpu(kind, args.chunksize, budget_chunks_per_core=1, repeats=1)
         cpu_baseline = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     except Exception as e:  # the checker is optional for the headline number
