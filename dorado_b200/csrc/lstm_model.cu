@@ -685,88 +685,95 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-template <int C, int CL>
+template <int C, int CL, int UNC>
 struct ClusterCfg {
     static constexpr int MT = C / 32;
     static constexpr int TPC = MT / CL;           // tiles per CTA
     static constexpr int KBH = C / KBLK;
     static constexpr int EW = 4 * TPC;            // epilogue warps
     static constexpr int THREADS = 64 + 32 * EW;
-    static constexpr size_t W_BYTES = (size_t)TPC * KBH * WBLK_BYTES;
-    static constexpr size_t Z_BYTES = (size_t)2 * KBH * ZBLK;
-    static constexpr size_t SMEM = 1024 + W_BYTES + Z_BYTES + (size_t)EW * 1024 + 256;
+    static constexpr int ZB = UNC * KBLK * 2;     // bytes of one operand block (UNC chunk rows x 32 fp16)
+    static constexpr int WCOLS = C / 2;           // TMEM columns of one weight tile (two fp16 per column)
+    static constexpr int ACC0 = TPC * WCOLS;      // accumulators start behind the weights
+    static constexpr int NEED = ACC0 + 2 * TPC * UNC;
+    static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+    static constexpr size_t Z_BYTES = (size_t)2 * KBH * ZB;
+    static constexpr size_t SMEM = 1024 + Z_BYTES + (size_t)EW * 1024 + 256;
     static_assert(MT % CL == 0, "cluster size must divide the tile count");
+    static_assert(NEED <= 512, "weights + accumulators must fit tensor memory");
 };
 
-template <int C, int CL>
-__global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_kernel(const __grid_constant__ CUtensorMap tma_w,
-                                                                                     const LstmRecParams p) {
-    using Cfg = ClusterCfg<C, CL>;
-    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH;
-    constexpr int GB = 32;  // chunk block of the gx layout (UN = 16 < 32)
-    constexpr uint32_t TMEM_COLS = 2 * TPC * UN <= 32 ? 32 : 64;
-    static_assert(2 * TPC * UN <= 64, "accumulators must fit the TMEM allocation");
+// UNC = chunks per cluster (16 or 32).  W_hh tiles live in TENSOR MEMORY (A operand from TMEM): 2 tiles x C/2
+// columns for C = 384 plus 2 * TPC * UNC accumulator columns = 448 / 512 of the 512 columns.
+template <int C, int CL, int UNC>
+__global__ void __launch_bounds__(ClusterCfg<C, CL, UNC>::THREADS, 1) lstm_cluster_kernel(const __half* __restrict__ w_hh,
+                                                                                          const LstmRecParams p) {
+    using Cfg = ClusterCfg<C, CL, UNC>;
+    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH, ZB = Cfg::ZB;
+    constexpr int GB = 32;  // chunk block of the gx layout
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_s = smem;                                           // [TPC][KBH][8 KB]
-    uint8_t* z_s = w_s + Cfg::W_BYTES;                             // [2][KBH][ZBLK]  full h, this CTA's copy
+    uint8_t* z_s = smem;                                           // [2][KBH][ZB]  full h, this CTA's copy
     float* xs = reinterpret_cast<float*>(z_s + Cfg::Z_BYTES);      // [EW][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + Cfg::EW * 256);
-    uint64_t* w_full = bars;        // [1]
-    uint64_t* acc_full = bars + 1;  // [TPC]
+    uint64_t* acc_full = bars;  // [TPC]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + TPC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x / CL;
-    const int n0 = cluster_id * UN;
+    const int n0 = cluster_id * UNC;
 
     for (int i = threadIdx.x; i < (int)(Cfg::Z_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
     tc::fence_proxy_async_smem();
     if (threadIdx.x == 0) {
-        tc::mbar_init(w_full, 1);
         for (int i = 0; i < TPC; ++i) tc::mbar_init(&acc_full[i], 1);
         tc::fence_barrier_init();
-        tc::prefetch_tmap(&tma_w);
     }
-    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-
-    if (warp == 0 && tc::elect_one()) {
-        // this CTA's gate tiles: m = rank * TPC + i
-        tc::mbar_arrive_expect_tx(w_full, (uint32_t)Cfg::W_BYTES);
-        for (int i = 0; i < TPC; ++i) {
-            for (int kb = 0; kb < KBH; ++kb) {
-                tc::tma_load_2d(w_s + (size_t)(i * KBH + kb) * WBLK_BYTES, &tma_w, w_full, kb * KBLK, ((int)rank * TPC + i) * 128);
-            }
-        }
-    }
-    __syncwarp();
-    // everybody in the cluster has zeroed its Z copy before any remote h store may land
-    cluster_arrive_release();
-    cluster_wait_acquire();
 
     const bool is_mma = warp == 1;
     const bool is_epi = warp >= 2;
     const int ewarp = warp - 2;
     const int ti = ewarp >> 2;       // which of this CTA's tiles the warp serves
     const int qt = warp & 3;         // TMEM lane quarter
+    if (is_epi) {
+        // this thread's weight row (tile rank*TPC + ti, row 32*qt + lane) -> tensor memory, once
+        const int m = (int)rank * TPC + ti;
+        const uint4* src = reinterpret_cast<const uint4*>(w_hh + (size_t)(m * 128 + qt * 32 + lane) * C);
+#pragma unroll 1
+        for (int cb = 0; cb < C / 64; ++cb) {
+            uint32_t r[32];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const uint4 x = __ldg(src + cb * 8 + v);
+                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+            }
+            tc::tmem_st_32x32(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(ti * Cfg::WCOLS + cb * 32), r);
+        }
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    // everybody in the cluster has zeroed its Z copy before any remote h store may land
+    cluster_arrive_release();
+    cluster_wait_acquire();
+
     const int uk = lane >> 2, gj = lane & 3;   // activation role: unit within the warp's 8, gate type
     const int up = lane >> 3, cc = lane & 7;   // cell-update role: unit pair (2up, 2up+1), column cc of each 8-column chunk
     float* xw = xs + (is_epi ? ewarp : 0) * 256;
     const float am = gj == 2 ? 2.0f : 1.0f;
-    float c_reg[UN / 4];  // [chunk of 8 columns][unit of the pair]
+    float c_reg[UNC / 4];  // [chunk of 8 columns][unit of the pair]
 #pragma unroll
-    for (int k = 0; k < UN / 4; ++k) c_reg[k] = 0.0f;
+    for (int k = 0; k < UNC / 4; ++k) c_reg[k] = 0.0f;
     const uint32_t z_local = tc::smem_u32(z_s);
-    const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
     const uint64_t zdesc0 = umma_desc_sw64(z_local);
-    constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
-    if (is_mma) tc::mbar_wait(w_full, 0);
+    constexpr uint32_t idesc = tc::umma_idesc_f16(128, UNC);
 
     for (int s = 0; s < p.T; ++s) {
         const int t = p.reverse ? p.T - 1 - s : s;
@@ -774,18 +781,17 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
         if (is_mma) {
             if (tc::elect_one()) {
                 tc::tc_fence_after();  // (the writers of h issued fence.proxy.async before the cluster barrier)
-                const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZBLK) >> 4);
-                // 2 * TPC independent accumulation chains (tile x K-parity), interleaved so that the tensor pipe never
-                // waits on the previous MMA of the same accumulator; the epilogue adds the two K-halves
+                const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZB) >> 4);
+                // 2 * TPC independent accumulation chains (tile x K-parity), interleaved; the epilogue adds the halves
 #pragma unroll
                 for (int kb = 0; kb < KBH; ++kb) {
 #pragma unroll
                     for (int i = 0; i < TPC; ++i) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((2 * i + (kb & 1)) * UN);
-                        const uint64_t adesc = wdesc0 + (uint64_t)(((i * KBH + kb) * WBLK_BYTES) >> 4);
-                        const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
-                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb >= 2);
-                        tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(Cfg::ACC0 + (2 * i + (kb & 1)) * UNC);
+                        const uint32_t a_t = tmem_base + (uint32_t)(i * Cfg::WCOLS + kb * 16);
+                        const uint64_t bdesc = zd + (uint64_t)((kb * ZB) >> 4);
+                        tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, kb >= 2);
+                        tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
                     }
                 }
 #pragma unroll
@@ -796,58 +802,63 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
             const int m = (int)rank * TPC + ti;
             const __half* gx_row = p.gx + ((size_t)t * (p.N / GB) + (n0 / GB)) * (size_t)(4 * C) * GB + (n0 % GB) +
                                    (size_t)(m * 128 + qt * 32 + lane) * GB;
-            const uint4 gx0 = __ldg(reinterpret_cast<const uint4*>(gx_row));
-            const uint4 gx1 = __ldg(reinterpret_cast<const uint4*>(gx_row + 8));
+            uint4 gxv[UNC / 8];
+#pragma unroll
+            for (int k = 0; k < UNC / 8; ++k) gxv[k] = __ldg(reinterpret_cast<const uint4*>(gx_row + 8 * k));
             __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
             tc::mbar_wait(&acc_full[ti], (uint32_t)(s & 1));
             tc::tc_fence_after();
-            uint32_t r[16], r2[16];
-            tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((2 * ti) * UN), r);
-            tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((2 * ti + 1) * UN), r2);
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            for (int c16 = 0; c16 < UNC / 16; ++c16) {
+                uint32_t r[16], r2[16];
+                tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(Cfg::ACC0 + (2 * ti) * UNC + c16 * 16), r);
+                tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(Cfg::ACC0 + (2 * ti + 1) * UNC + c16 * 16), r2);
+                tc::tmem_ld_wait();
+                if (c16 == UNC / 16 - 1) tc::tc_fence_before();
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const uint4 gcur = ch == 0 ? gx0 : gx1;
-                const __half2* gh = reinterpret_cast<const __half2*>(&gcur);
-                float a[8];
+                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 gf = __half22float2(gh[e]);
-                    const float v0 = __uint_as_float(r[ch * 8 + 2 * e]) + gf.x, v1 = __uint_as_float(r[ch * 8 + 2 * e + 1]) + gf.y;
-                    a[2 * e] = 1.0f - __fdividef(am, __expf(am * v0) + 1.0f);
-                    a[2 * e + 1] = 1.0f - __fdividef(am, __expf(am * v1) + 1.0f);
+                for (int c8 = 0; c8 < 2; ++c8) {
+                    const int ch = c16 * 2 + c8;  // 8-column chunk index
+                    const uint4 gcur = gxv[ch];
+                    const __half2* gh = reinterpret_cast<const __half2*>(&gcur);
+                    float a[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 gf = __half22float2(gh[e]);
+                        const float v0 = __uint_as_float(r[c8 * 8 + 2 * e]) + gf.x, v1 = __uint_as_float(r[c8 * 8 + 2 * e + 1]) + gf.y;
+                        a[2 * e] = 1.0f - __fdividef(am, __expf(am * v0) + 1.0f);
+                        a[2 * e + 1] = 1.0f - __fdividef(am, __expf(am * v1) + 1.0f);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
+                    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+                    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+                    __syncwarp();
+                    float ig[2], fg[2], gg[2], og[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        ig[e] = xw[(0 * 8 + 2 * up + e) * 8 + cc];
+                        fg[e] = xw[(1 * 8 + 2 * up + e) * 8 + cc];
+                        gg[e] = xw[(2 * 8 + 2 * up + e) * 8 + cc];
+                        og[e] = xw[(3 * 8 + 2 * up + e) * 8 + cc];
+                    }
+                    __syncwarp();
+                    const float c0 = fg[0] * c_reg[2 * ch] + ig[0] * gg[0];
+                    const float c1 = fg[1] * c_reg[2 * ch + 1] + ig[1] * gg[1];
+                    c_reg[2 * ch] = c0;
+                    c_reg[2 * ch + 1] = c1;
+                    const __half2 hh = __floats2half2_rn(og[0] * tanh_f(c0), og[1] * tanh_f(c1));
+                    const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hh);
+                    const int u = qt * 8 + 2 * up;   // even unit within the tile
+                    const int nA = ch * 8 + cc;      // chunk (row of the operand block)
+                    // all-gather: units (u, u+1) of chunk nA go into block m of every CTA's Z[nbuf] as one 32-bit store
+                    const uint32_t off0 = (uint32_t)((nbuf * KBH + m) * ZB) + sw64_offset(nA, u);
+#pragma unroll
+                    for (int rr = 0; rr < CL; ++rr) st_cluster_u32(mapa_shared(z_local, (uint32_t)rr) + off0, hbits);
+                    *reinterpret_cast<uint32_t*>(y_t + (size_t)nA * C + m * 32 + u) = hbits;
                 }
-                float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
-                dst[0] = make_float4(a[0], a[1], a[2], a[3]);
-                dst[1] = make_float4(a[4], a[5], a[6], a[7]);
-                __syncwarp();
-                float ig[2], fg[2], gg[2], og[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    ig[e] = xw[(0 * 8 + 2 * up + e) * 8 + cc];
-                    fg[e] = xw[(1 * 8 + 2 * up + e) * 8 + cc];
-                    gg[e] = xw[(2 * 8 + 2 * up + e) * 8 + cc];
-                    og[e] = xw[(3 * 8 + 2 * up + e) * 8 + cc];
-                }
-                __syncwarp();
-                const float c0 = fg[0] * c_reg[2 * ch] + ig[0] * gg[0];
-                const float c1 = fg[1] * c_reg[2 * ch + 1] + ig[1] * gg[1];
-                c_reg[2 * ch] = c0;
-                c_reg[2 * ch + 1] = c1;
-                const __half2 hh = __floats2half2_rn(og[0] * tanh_f(c0), og[1] * tanh_f(c1));
-                const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hh);
-                const int u = qt * 8 + 2 * up;   // even unit within the tile
-                const int nA = ch * 8 + cc;      // chunk (row of the operand block)
-                // all-gather: units (u, u+1) of chunk nA go into block m of every CTA's Z[nbuf] as one 32-bit store
-                const uint32_t off0 = (uint32_t)((nbuf * KBH + m) * ZBLK) + sw64_offset(nA, u);
-#pragma unroll
-                for (int rr = 0; rr < CL; ++rr) st_cluster_u32(mapa_shared(z_local, (uint32_t)rr) + off0, hbits);
-                *reinterpret_cast<uint32_t*>(y_t + (size_t)nA * C + m * 32 + u) = hbits;
-                if (ch == 1) asm volatile("fence.proxy.async;" ::: "memory");  // generic writes -> async-proxy readers
             }
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic writes -> async-proxy readers
         }
         // h_t complete everywhere (and every accumulator drained) before the next step starts
         cluster_arrive_release();
@@ -855,7 +866,7 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL>::THREADS, 1) lstm_cluster_ke
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -892,6 +903,7 @@ public:
     size_t rec_smem = 0;
     std::vector<GemmPlan> gx_gemm;
     std::vector<CUtensorMap> rec_w;
+    std::vector<const __half*> rec_whh;
     std::vector<LstmRecParams> rec_p;
     void launch_rec(int l, cudaStream_t stream) const;
     GemmPlan linear1, linear2;
@@ -1109,7 +1121,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         if (C != 192 && C != 384) throw Unsupported("hoisted LSTM path is instantiated for lstm_size 192 and 384");
         // C = 192 / 384: weights-stationary cluster kernel (6 CTAs x 16 chunks); otherwise the L2-streaming kernel
         plan->use_cluster = true;
-        int un = plan->use_cluster ? 16 : (Np >= 2048 ? 64 : (Np >= 512 ? 32 : 16));
+        // cluster kernel: 32 chunks per cluster once 16 chunks would need more clusters than fit at once (~16)
+        int un = plan->use_cluster ? (Np > 256 ? 32 : 16) : (Np >= 2048 ? 64 : (Np >= 512 ? 32 : 16));
         while (Np % un != 0) un /= 2;
         plan->rec_un = un;
         const int GB = un < 32 ? 32 : un;
@@ -1134,6 +1147,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             g.out_col_m1 = GB;
             g.out_col_s0 = (int64_t)4 * C * GB;
             plan->gx_gemm.push_back(make_gemm_plan(g));
+            plan->rec_whh.push_back(layers[l].w_hh);
             plan->rec_w.push_back(make_tmap_2d(layers[l].w_hh, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C * 2, KBLK, 128));
             LstmRecParams rp{};
             rp.seq = seq;
@@ -1271,12 +1285,12 @@ static void launch_rec_c(const LstmPlan& pl, int l, cudaStream_t stream) {
     }
 }
 
-template <int C, int CL>
+template <int C, int CL, int UNC>
 static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    using Cfg = ClusterCfg<C, CL>;
+    using Cfg = ClusterCfg<C, CL, UNC>;
     static bool attr = false;
     if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<C, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        B200_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<C, CL, UNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -1291,14 +1305,20 @@ static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<C, CL>, pl.rec_w[l], pl.rec_p[l]));
+    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<C, CL, UNC>, pl.rec_whh[l], pl.rec_p[l]));
+}
+
+template <int C>
+static void launch_cluster_c(const LstmPlan& pl, int l, cudaStream_t stream) {
+    if (pl.rec_un == 32) launch_cluster_t<C, 6, 32>(pl, l, stream);
+    else launch_cluster_t<C, 6, 16>(pl, l, stream);
 }
 
 void LstmPlan::launch_rec(int l, cudaStream_t stream) const {
     const int C = model->desc.lstm_size;
     if (use_cluster) {
-        if (C == 384) launch_cluster_t<384, 6>(*this, l, stream);
-        else if (C == 192) launch_cluster_t<192, 6>(*this, l, stream);
+        if (C == 384) launch_cluster_c<384>(*this, l, stream);
+        else if (C == 192) launch_cluster_c<192>(*this, l, stream);
         else throw Unsupported("no cluster LSTM kernel instantiation for this lstm_size");
         return;
     }
