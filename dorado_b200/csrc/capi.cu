@@ -132,6 +132,13 @@ int b200_runner_upload(b200_runner* r) {
     });
 }
 
+int b200_runners_step_device(b200_runner** runners, int32_t n_runners, int32_t num_chunks, int32_t iters, float* total_ms) {
+    return guarded([&] {
+        if (!runners || !total_ms) throw std::invalid_argument("b200_runners_step_device: null argument");
+        b200::pipelined_steps(reinterpret_cast<b200::Runner**>(runners), n_runners, num_chunks, iters, total_ms);
+    });
+}
+
 int b200_runner_step_device(b200_runner* r, int32_t num_chunks, int32_t iters, float* total_ms, float* forward_ms,
                             float* decode_ms) {
     return guarded([&] {

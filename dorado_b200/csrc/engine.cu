@@ -127,6 +127,7 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     m_opts.q_shift = d.qbias;
 
     B200_CUDA(cudaSetDevice(engine.device()));
+    B200_CUDA(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
     const size_t in_bytes = (size_t)m_N * m_T_in * sizeof(uint16_t);
     m_out_bytes = nb_offset(m_N, m_T_out) + (size_t)m_N * sizeof(int32_t);
     B200_CUDA(cudaHostAlloc(&m_h_input, in_bytes, cudaHostAllocDefault));
@@ -149,9 +150,9 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     engine.arena_bytes += (int64_t)m_arena.capacity();
     // zero padding rows / unused slots once, on the engine's own (non-blocking) stream so it is ordered
     // before the first forward
-    B200_CUDA(cudaMemsetAsync(m_d_input, 0, in_bytes, engine.stream()));
-    B200_CUDA(cudaMemsetAsync(m_d_ws, 0, ws_b, engine.stream()));
-    B200_CUDA(cudaStreamSynchronize(engine.stream()));
+    B200_CUDA(cudaMemsetAsync(m_d_input, 0, in_bytes, m_stream));
+    B200_CUDA(cudaMemsetAsync(m_d_ws, 0, ws_b, m_stream));
+    B200_CUDA(cudaStreamSynchronize(m_stream));
     m_plan = engine.model().make_plan(m_N, m_T_in, m_d_input, m_d_scores, m_d_ws, ws_b);
     for (auto& e : m_ev) B200_CUDA(cudaEventCreate(&e));
 }
@@ -163,6 +164,10 @@ Runner::~Runner() {
     }
     if (m_h_input) cudaFreeHost(m_h_input);
     if (m_h_out) cudaFreeHost(m_h_out);
+    if (m_stream) {
+        cudaStreamSynchronize(m_stream);
+        cudaStreamDestroy(m_stream);
+    }
 }
 
 void Runner::set_decoder_options(const b200_decoder_options& o) {
@@ -186,7 +191,7 @@ void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
 
 void Runner::run_forward(int n) {
     (void)n;  // the whole batch is computed; only the first n chunks are decoded and returned
-    m_plan->run(m_engine.stream());
+    m_plan->run(m_stream);
     m_engine.gpu_launches += m_plan->launches();
 }
 
@@ -210,23 +215,23 @@ void Runner::run_decode(int n, ProfileSink* prof) {
     a.sequence = reinterpret_cast<char*>(m_d_out + (size_t)m_N * m_T_out);
     a.qstring = reinterpret_cast<char*>(m_d_out + (size_t)2 * m_N * m_T_out);
     a.n_bases = reinterpret_cast<int32_t*>(m_d_out + nb_offset(m_N, m_T_out));
-    decode_scores(a, m_engine.stream(), prof);
+    decode_scores(a, m_stream, prof);
     m_engine.gpu_launches += 3;
 }
 
 void Runner::upload() {
-    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
     B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)m_N * m_T_in * sizeof(uint16_t), cudaMemcpyHostToDevice,
-                              m_engine.stream()));
-    B200_CUDA(cudaStreamSynchronize(m_engine.stream()));
+                              m_stream));
+    B200_CUDA(cudaStreamSynchronize(m_stream));
 }
 
 b200_result Runner::call_chunks(int num_chunks) {
     if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("call_chunks: num_chunks out of range");
-    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
-    cudaStream_t s = m_engine.stream();
+    cudaStream_t s = m_stream;
     B200_CUDA(cudaEventRecord(m_ev[0], s));
     B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t),
                               cudaMemcpyHostToDevice, s));
@@ -237,13 +242,16 @@ b200_result Runner::call_chunks(int num_chunks) {
     B200_CUDA(cudaMemcpyAsync(m_h_out, m_d_out, m_out_bytes, cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaEventRecord(m_ev[3], s));
     B200_CUDA(cudaStreamSynchronize(s));
-    float ms = 0;
-    B200_CUDA(cudaEventElapsedTime(&ms, m_ev[0], m_ev[1]));
-    m_engine.h2d_ms += ms;
-    B200_CUDA(cudaEventElapsedTime(&ms, m_ev[1], m_ev[2]));
-    m_engine.model_decode_ms += ms;
-    B200_CUDA(cudaEventElapsedTime(&ms, m_ev[2], m_ev[3]));
-    m_engine.d2h_ms += ms;
+    float h2d = 0, md = 0, d2h = 0;
+    B200_CUDA(cudaEventElapsedTime(&h2d, m_ev[0], m_ev[1]));
+    B200_CUDA(cudaEventElapsedTime(&md, m_ev[1], m_ev[2]));
+    B200_CUDA(cudaEventElapsedTime(&d2h, m_ev[2], m_ev[3]));
+    {
+        std::lock_guard<std::mutex> sl(m_engine.gpu_mutex());
+        m_engine.h2d_ms += h2d;
+        m_engine.model_decode_ms += md;
+        m_engine.d2h_ms += d2h;
+    }
     ++m_engine.batches_called;
 
     b200_result r{};
@@ -258,9 +266,9 @@ b200_result Runner::call_chunks(int num_chunks) {
 
 void Runner::step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms) {
     if (num_chunks < 1 || num_chunks > m_N || iters < 1) throw std::invalid_argument("step_device: bad arguments");
-    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
-    cudaStream_t s = m_engine.stream();
+    cudaStream_t s = m_stream;
     float fwd = 0, dec = 0;
     for (int i = 0; i < iters; ++i) {
         B200_CUDA(cudaEventRecord(m_ev[0], s));
@@ -280,11 +288,45 @@ void Runner::step_device(int num_chunks, int iters, float* total_ms, float* forw
     if (decode_ms) *decode_ms = dec;
 }
 
+// Device-resident throughput with several runners in flight (the reference runs num_runners = 2 CudaModelRunners
+// per device, api/runner_creation.cpp:91-123, so one runner's decode overlaps the next one's network).  Step i goes
+// to runner i % R on that runner's own stream; the region is bracketed by events on runner 0's stream, which first
+// releases and finally joins the other streams.
+void pipelined_steps(Runner** rs, int R, int num_chunks, int iters, float* total_ms) {
+    if (R < 1 || !rs || iters < 1) throw std::invalid_argument("pipelined_steps: bad arguments");
+    for (int r = 0; r < R; ++r) {
+        if (!rs[r]) throw std::invalid_argument("pipelined_steps: null runner");
+        if (&rs[r]->m_engine != &rs[0]->m_engine) throw std::invalid_argument("pipelined_steps: runners of different engines");
+        if (num_chunks < 1 || num_chunks > rs[r]->m_N) throw std::invalid_argument("pipelined_steps: num_chunks out of range");
+        for (int q = 0; q < r; ++q) {
+            if (rs[q] == rs[r]) throw std::invalid_argument("pipelined_steps: the same runner twice");
+        }
+    }
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int r = 0; r < R; ++r) locks.emplace_back(rs[r]->m_mutex);
+    Runner& r0 = *rs[0];
+    B200_CUDA(cudaSetDevice(r0.m_engine.device()));
+    B200_CUDA(cudaEventRecord(r0.m_ev[0], r0.m_stream));
+    for (int r = 1; r < R; ++r) B200_CUDA(cudaStreamWaitEvent(rs[r]->m_stream, r0.m_ev[0], 0));
+    for (int i = 0; i < iters; ++i) {
+        Runner& ru = *rs[i % R];
+        ru.run_forward(num_chunks);
+        ru.run_decode(num_chunks);
+    }
+    for (int r = 1; r < R; ++r) {
+        B200_CUDA(cudaEventRecord(rs[r]->m_ev[2], rs[r]->m_stream));
+        B200_CUDA(cudaStreamWaitEvent(r0.m_stream, rs[r]->m_ev[2], 0));
+    }
+    B200_CUDA(cudaEventRecord(r0.m_ev[1], r0.m_stream));
+    B200_CUDA(cudaStreamSynchronize(r0.m_stream));
+    B200_CUDA(cudaEventElapsedTime(total_ms, r0.m_ev[0], r0.m_ev[1]));
+}
+
 void Runner::forward_scores_to_host(int num_chunks, uint16_t* scores_out) {
     if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("forward_scores: num_chunks out of range");
-    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
-    cudaStream_t s = m_engine.stream();
+    cudaStream_t s = m_stream;
     B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t),
                               cudaMemcpyHostToDevice, s));
     run_forward(num_chunks);
@@ -319,9 +361,9 @@ ProfileSink::~ProfileSink() {
 
 std::string Runner::profile(int num_chunks) {
     if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("profile: num_chunks out of range");
-    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
-    cudaStream_t s = m_engine.stream();
+    cudaStream_t s = m_stream;
     ProfileSink sink;
     sink.begin(s);
     m_plan->run(s, &sink);
@@ -335,9 +377,9 @@ std::string Runner::profile(int num_chunks) {
 
 void Runner::debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst) {
     if (offset + bytes > m_ws_bytes) throw std::invalid_argument("debug_read_workspace: out of range");
-    std::lock_guard<std::mutex> lock(m_engine.gpu_mutex());
+    std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
-    B200_CUDA(cudaStreamSynchronize(m_engine.stream()));
+    B200_CUDA(cudaStreamSynchronize(m_stream));
     B200_CUDA(cudaMemcpy(dst, static_cast<unsigned char*>(m_d_ws) + offset, bytes, cudaMemcpyDeviceToHost));
 }
 

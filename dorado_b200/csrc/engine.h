@@ -83,7 +83,7 @@ public:
     int device() const { return m_device; }
     cudaStream_t stream() const { return m_stream; }
     Model& model() { return *m_model; }
-    std::mutex& gpu_mutex() { return m_gpu_mutex; }  // one batch in flight per device (CudaCaller.cpp:204-214)
+    std::mutex& gpu_mutex() { return m_gpu_mutex; }  // guards the timing totals below
     b200_stats stats() const;
 
     std::atomic<int64_t> batches_called{0};
@@ -99,8 +99,14 @@ private:
     std::mutex m_gpu_mutex;
 };
 
+class Runner;
+void pipelined_steps(Runner** runners, int n_runners, int num_chunks, int iters, float* total_ms);
+
+// One runner = one batch in flight: its own stream, pinned host buffers, arena and launch plan (the reference's
+// CudaModelRunner owns a stream too, CudaModelRunner.cpp:13-19).  Runners of one engine run concurrently.
 class Runner {
 public:
+    friend void pipelined_steps(Runner** runners, int n_runners, int num_chunks, int iters, float* total_ms);
     Runner(Engine& engine, int batch_size, int chunk_size);
     ~Runner();
     int batch_size() const { return m_N; }
@@ -123,6 +129,8 @@ private:
     void run_decode(int n, ProfileSink* prof = nullptr);
 
     Engine& m_engine;
+    cudaStream_t m_stream = nullptr;
+    std::mutex m_mutex;  // a runner is driven by one thread at a time
     int m_N, m_T_in, m_T_out, m_C;
     b200_decoder_options m_opts;
     // pinned host (input and output are separate allocations; the reference aliases them)

@@ -67,7 +67,7 @@ EXPORTS = [
     "b200_engine_destroy", "b200_engine_get_stats", "b200_runner_create", "b200_runner_destroy",
     "b200_runner_set_decoder_options", "b200_runner_batch_size", "b200_runner_chunk_size", "b200_runner_out_len",
     "b200_runner_accept_chunk_f16", "b200_runner_accept_chunk_f32", "b200_runner_input", "b200_runner_call_chunks",
-    "b200_runner_upload", "b200_runner_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_debug_read_workspace", "b200_decode_scores",
+    "b200_runner_upload", "b200_runner_step_device", "b200_runners_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_debug_read_workspace", "b200_decode_scores",
     "b200_test_gemm",
 ]
 
@@ -108,6 +108,7 @@ def load_library() -> C.CDLL:
     lib.b200_runner_call_chunks.argtypes = [vp, i32, C.POINTER(Result)]
     lib.b200_runner_upload.argtypes = [vp]
     lib.b200_runner_step_device.argtypes = [vp, i32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]
+    lib.b200_runners_step_device.argtypes = [C.POINTER(vp), i32, i32, i32, C.POINTER(f32)]
     lib.b200_runner_forward_scores.argtypes = [vp, i32, vp]
     lib.b200_decode_scores.argtypes = [i32, vp, i32, i32, i32, f32, C.POINTER(DecoderOptions), vp, vp, vp, vp]
     lib.b200_runner_profile.argtypes = [vp, i32, C.c_char_p, C.c_uint64]

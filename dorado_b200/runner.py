@@ -97,7 +97,9 @@ class B200ModelRunner:
             c = c.astype(np.float32, copy=False)
             L.check(self._lib.b200_runner_accept_chunk_f32(self.handle, chunk_idx, c.ctypes.data, c.size))
 
-    def call_chunks(self, num_chunks: int) -> List[DecodedChunk]:
+    def call_chunks_raw(self, num_chunks: int):
+        """The bare C-ABI call (what the C++ adapter makes): H2D, forward, decode, D2H; returns views of the runner's
+        pinned result buffers (moves [N,T], sequence [N,T], qstring [N,T], n_bases [N]), valid until the next call."""
         r = L.Result()
         L.check(self._lib.b200_runner_call_chunks(self.handle, num_chunks, C.byref(r)))
         T = r.t_out
@@ -105,6 +107,10 @@ class B200ModelRunner:
         seq = np.ctypeslib.as_array(C.cast(r.sequence, C.POINTER(C.c_uint8)), shape=(self._N, T))
         qs = np.ctypeslib.as_array(C.cast(r.qstring, C.POINTER(C.c_uint8)), shape=(self._N, T))
         nb = np.ctypeslib.as_array(r.n_bases, shape=(self._N,))
+        return moves, seq, qs, nb
+
+    def call_chunks(self, num_chunks: int) -> List[DecodedChunk]:
+        moves, seq, qs, nb = self.call_chunks_raw(num_chunks)
         out = []
         for i in range(num_chunks):
             n = int(nb[i])
@@ -177,6 +183,15 @@ class B200ModelRunner:
         L.check(self._lib.b200_runner_step_device(self.handle, num_chunks, iters, C.byref(tot), C.byref(fwd),
                                                   C.byref(dec)))
         return tot.value, fwd.value, dec.value
+
+    @staticmethod
+    def step_device_runners(runners, num_chunks: int, iters: int = 1) -> float:
+        """`iters` device-resident passes round-robin over several runners of one caller, all in flight at once
+        (dorado keeps num_runners = 2 per device, api/runner_creation.cpp:91-123).  Returns device milliseconds."""
+        arr = (C.c_void_p * len(runners))(*[r.handle if isinstance(r.handle, int) else r.handle.value for r in runners])
+        tot = C.c_float()
+        L.check(runners[0]._lib.b200_runners_step_device(arr, len(runners), num_chunks, iters, C.byref(tot)))
+        return tot.value
 
     def out_len(self) -> int:
         return self._t_out

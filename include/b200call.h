@@ -149,6 +149,11 @@ B200_API int b200_runner_call_chunks(b200_runner* runner, int32_t num_chunks, b2
 B200_API int b200_runner_upload(b200_runner* runner);
 B200_API int b200_runner_step_device(b200_runner* runner, int32_t num_chunks, int32_t iters, float* total_ms,
                                      float* forward_ms, float* decode_ms);
+/* The same with several runners of one engine in flight (the reference creates num_runners = 2 runners per device,
+ * api/runner_creation.cpp:91-123): pass i runs on runners[i % n_runners], each on its own stream; total_ms is the
+ * device time from the first launch to the last completion. */
+B200_API int b200_runners_step_device(b200_runner** runners, int32_t n_runners, int32_t num_chunks, int32_t iters,
+                                      float* total_ms);
 
 /* Stage-level entry points so scores and decode can be parity-checked independently (host buffers). */
 B200_API int b200_runner_forward_scores(b200_runner* runner, int32_t num_chunks, uint16_t* scores_out /* [n,t_out,outsize] fp16 */);

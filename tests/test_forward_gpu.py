@@ -115,3 +115,39 @@ def test_runner_rejects_bad_shapes():
         r.accept_chunk(0, np.zeros(1199, np.float16))
     with pytest.raises(L.B200Error):
         r.call_chunks(17)
+
+
+@pytest.mark.parametrize("kind,N,T", [("fast", 64, 3000), ("hac", 64, 1200), ("sup", 4, 1920)])
+def test_concurrent_runners_match_serial(kind, N, T):
+    """Two runners of one caller (dorado's num_runners = 2 per device, api/runner_creation.cpp:91-123), each on its own
+    stream and driven from its own thread, must return exactly what they return one at a time."""
+    import threading
+    from dorado_b200.runner import B200ModelRunner
+    cfg, w, caller, r0, sig0 = _setup(kind, N, T, seed=5)
+    r1 = B200ModelRunner(caller, N, T)
+    sig1 = np.random.default_rng(6).standard_normal((N, r1.chunk_size())).astype(np.float16)
+    for i in range(N):
+        r1.accept_chunk(i, sig1[i])
+    runners = [r0, r1]
+    serial = [[(c.sequence, c.qstring, bytes(c.moves)) for c in r.call_chunks(N)] for r in runners]
+    assert serial[0] != serial[1]
+    got = [[], []]
+
+    def drive(i):
+        for _ in range(4):
+            got[i].append([(c.sequence, c.qstring, bytes(c.moves)) for c in runners[i].call_chunks(N)])
+
+    ths = [threading.Thread(target=drive, args=(i,)) for i in range(2)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    for i in range(2):
+        assert len(got[i]) == 4
+        for g in got[i]:
+            assert g == serial[i]
+    # the device-resident pipelined loop (bench.py's `value`) leaves each runner's result intact as well
+    ms = B200ModelRunner.step_device_runners(runners, N, 6)
+    assert ms > 0
+    for i, r in enumerate(runners):
+        assert [(c.sequence, c.qstring, bytes(c.moves)) for c in r.call_chunks(N)] == serial[i]
