@@ -148,7 +148,6 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
     return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3))) << 4) + ((col & 7) << 1));
 }
 
-__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float tanh_f(float v) { return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f); }
 
 // C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).
@@ -458,213 +457,28 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// LSTM layer for hidden sizes whose weights do not fit in one SM's shared memory (hac: C = 384).
+// LSTM layer for hidden sizes whose weights do not fit one SM (hac: C = 384): hoisted x-projection + cluster recurrence.
 //
 // The x_t half of the gate pre-activations does not depend on the recurrence, so it is hoisted into one large
-// tcgen05 GEMM per layer (gemm.cu) that writes gx[t][chunk block][gate row][chunk] (fp16, bias included).  This
-// kernel then runs the recurrence with W_hh only: a CTA owns UN chunks for the whole sequence and streams the
-// permuted W_hh (4C x C fp16) from L2 through a TMA ring every step; being "fat" (UN up to 64 chunks) keeps the
-// number of CTAs re-reading the weights small.  Gate rows are permuted so that a warp's 32 TMEM lanes hold
-// (8 units x 4 gates); the 4 gates of a unit meet through a per-warp shared-memory exchange (no block barrier).
+// tcgen05 GEMM per layer (gemm.cu) that writes gx[t][chunk block][gate row][chunk] (fp16, bias included).  Gate rows
+// are permuted so that a warp's 32 TMEM lanes hold (8 units x 4 gates); the 4 gates of a unit meet through a
+// per-warp shared-memory exchange (no block barrier).
 // ------------------------------------------------------------------------------------------------
-constexpr int REC_GROUPS = 6;                      // epilogue groups (4 warps each); tile m -> group m % 6
-constexpr int REC_THREADS = 64 + 128 * REC_GROUPS; // warp 0 TMA, warp 1 MMA, 24 epilogue warps
-constexpr int REC_WSTAGES = 12;
-constexpr int REC_NBUF = 8;                        // TMEM accumulator buffers
-
 struct LstmRecParams {
     __half* seq;          // [T][N][C] output h (in place over the layer input)
-    const __half* gx;     // [T][N / GB][4C][GB], GB = max(UN, 32)
+    const __half* gx;     // [T][N / 32][4C][32]
     int T, N, reverse;
 };
-
-template <int C, int UN>
-__global__ void __launch_bounds__(REC_THREADS, 1) lstm_rec_kernel(const __grid_constant__ CUtensorMap tma_w,
-                                                                 const LstmRecParams p) {
-    constexpr int MT = C / 32;            // gate tiles
-    constexpr int KBH = C / KBLK;         // K blocks (h only)
-    constexpr int ZB = UN * KBLK * 2;     // bytes of one Z block
-    constexpr int GB = UN < 32 ? 32 : UN; // chunk block of the gx layout
-    constexpr int TPG = MT / REC_GROUPS;  // tiles per epilogue group
-    constexpr uint32_t TMEM_COLS = REC_NBUF * UN < 32 ? 32 : REC_NBUF * UN;
-    static_assert(MT % REC_GROUPS == 0 && REC_NBUF * UN <= 512, "unsupported shape");
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
-    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_s = smem;                                            // [REC_WSTAGES][8 KB]
-    uint8_t* z_s = w_s + (size_t)REC_WSTAGES * WBLK_BYTES;          // [2][KBH][ZB]
-    float* xs = reinterpret_cast<float*>(z_s + (size_t)2 * KBH * ZB);  // [24 warps][4][8][8] exchange
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 24 * 256);
-    uint64_t* h_ready = bars;                    // [2]
-    uint64_t* acc_full = bars + 2;               // [REC_NBUF]
-    uint64_t* acc_empty = acc_full + REC_NBUF;   // [REC_NBUF]
-    uint64_t* w_full = acc_empty + REC_NBUF;     // [REC_WSTAGES]
-    uint64_t* w_empty = w_full + REC_WSTAGES;    // [REC_WSTAGES]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_empty + REC_WSTAGES);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * UN;
-
-    for (int i = threadIdx.x; i < 2 * KBH * ZB / 16; i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
-    tc::fence_proxy_async_smem();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) tc::mbar_init(&h_ready[i], 128 * REC_GROUPS);
-        for (int i = 0; i < REC_NBUF; ++i) {
-            tc::mbar_init(&acc_full[i], 1);
-            tc::mbar_init(&acc_empty[i], 128);
-        }
-        for (int i = 0; i < REC_WSTAGES; ++i) {
-            tc::mbar_init(&w_full[i], 1);
-            tc::mbar_init(&w_empty[i], 1);
-        }
-        tc::fence_barrier_init();
-        tc::prefetch_tmap(&tma_w);
-    }
-    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-
-    if (warp == 0) {
-        if (tc::elect_one()) {
-            long long wj = 0;
-            for (int s = 0; s < p.T; ++s) {
-                for (int m = 0; m < MT; ++m) {
-                    for (int kb = 0; kb < KBH; ++kb, ++wj) {
-                        const int st = (int)(wj % REC_WSTAGES);
-                        tc::mbar_wait(&w_empty[st], (uint32_t)(((wj / REC_WSTAGES) & 1) ^ 1));
-                        tc::mbar_arrive_expect_tx(&w_full[st], WBLK_BYTES);
-                        tc::tma_load_2d(w_s + (size_t)st * WBLK_BYTES, &tma_w, &w_full[st], kb * KBLK, m * 128);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
-            const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
-            const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
-            long long wj = 0, j = 0;
-            for (int s = 0; s < p.T; ++s) {
-                const int buf = s & 1;
-                tc::mbar_wait(&h_ready[buf], (uint32_t)((s >> 1) & 1));
-                tc::tc_fence_after();
-                const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZB) >> 4);
-                for (int m = 0; m < MT; ++m, ++j) {
-                    const int ab = (int)(j % REC_NBUF);
-                    tc::mbar_wait(&acc_empty[ab], (uint32_t)(((j / REC_NBUF) & 1) ^ 1));
-                    tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(ab * UN);
-#pragma unroll 1
-                    for (int kb = 0; kb < KBH; ++kb, ++wj) {
-                        const int st = (int)(wj % REC_WSTAGES);
-                        tc::mbar_wait(&w_full[st], (uint32_t)((wj / REC_WSTAGES) & 1));
-                        tc::tc_fence_after();
-                        const uint64_t adesc = wdesc0 + (uint64_t)((st * WBLK_BYTES) >> 4);
-                        const uint64_t bdesc = zd + (uint64_t)((kb * ZB) >> 4);
-                        tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
-                        tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
-                        tc::umma_commit(&w_empty[st]);
-                    }
-                    tc::umma_commit(&acc_full[ab]);
-                }
-            }
-        }
-    } else {
-        const int ewarp = warp - 2;
-        const int g = ewarp >> 2;   // group
-        const int qt = warp & 3;    // TMEM lane quarter of this warp
-        const int uk = lane >> 2;   // unit within the warp's 8 units (activation role)
-        const int gj = lane & 3;    // gate type of this lane's row: 0 i, 1 f, 2 g, 3 o
-        const int cp = lane & 3;    // column pair (cell-update role): columns 2cp, 2cp+1 of each 8-column chunk
-        float* xw = xs + ewarp * 256;
-        const float am = gj == 2 ? 2.0f : 1.0f;  // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
-        float c_reg[TPG][UN / 4];
-#pragma unroll
-        for (int i = 0; i < TPG; ++i)
-#pragma unroll
-            for (int k = 0; k < UN / 4; ++k) c_reg[i][k] = 0.0f;
-        tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0
-
-        for (int s = 0; s < p.T; ++s) {
-            const int t = p.reverse ? p.T - 1 - s : s;
-            const int nbuf = (s + 1) & 1;
-            uint8_t* zh_next = z_s + (size_t)nbuf * KBH * ZB;
-            __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
-            const __half* gx_t = p.gx + ((size_t)t * (p.N / GB) + (n0 / GB)) * (size_t)(4 * C) * GB + (n0 % GB);
-#pragma unroll
-            for (int i = 0; i < TPG; ++i) {
-                const int m = g + i * REC_GROUPS;
-                const long long j = (long long)s * MT + m;
-                const int ab = (int)(j % REC_NBUF);
-                const __half* gx_row = gx_t + (size_t)(m * 128 + qt * 32 + lane) * GB;
-                uint4 gxv = __ldg(reinterpret_cast<const uint4*>(gx_row));
-                tc::mbar_wait(&acc_full[ab], (uint32_t)((j / REC_NBUF) & 1));
-                tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(ab * UN);
-#pragma unroll
-                for (int ch = 0; ch < UN / 8; ++ch) {
-                    uint32_t r[8];
-                    tc::tmem_ld_32x8(taddr + (uint32_t)(ch * 8), r);
-                    tc::tmem_ld_wait();
-                    if (ch == UN / 8 - 1) {
-                        tc::tc_fence_before();
-                        tc::mbar_arrive(&acc_empty[ab]);
-                    }
-                    const uint4 gcur = gxv;
-                    if (ch + 1 < UN / 8) gxv = __ldg(reinterpret_cast<const uint4*>(gx_row + (ch + 1) * 8));
-                    const __half2* gh = reinterpret_cast<const __half2*>(&gcur);
-                    float a[8];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 gf = __half22float2(gh[e]);
-                        const float v0 = __uint_as_float(r[2 * e]) + gf.x, v1 = __uint_as_float(r[2 * e + 1]) + gf.y;
-                        a[2 * e] = 1.0f - __fdividef(am, __expf(am * v0) + 1.0f);
-                        a[2 * e + 1] = 1.0f - __fdividef(am, __expf(am * v1) + 1.0f);
-                    }
-                    // per-warp exchange: xw[gate][unit][col]
-                    float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
-                    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
-                    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
-                    __syncwarp();
-                    const float2 ig = *reinterpret_cast<const float2*>(xw + (0 * 8 + uk) * 8 + 2 * cp);
-                    const float2 fg = *reinterpret_cast<const float2*>(xw + (1 * 8 + uk) * 8 + 2 * cp);
-                    const float2 gg = *reinterpret_cast<const float2*>(xw + (2 * 8 + uk) * 8 + 2 * cp);
-                    const float2 og = *reinterpret_cast<const float2*>(xw + (3 * 8 + uk) * 8 + 2 * cp);
-                    __syncwarp();
-                    const float c0 = fg.x * c_reg[i][2 * ch] + ig.x * gg.x;
-                    const float c1 = fg.y * c_reg[i][2 * ch + 1] + ig.y * gg.y;
-                    c_reg[i][2 * ch] = c0;
-                    c_reg[i][2 * ch + 1] = c1;
-                    const __half h0 = __float2half_rn(og.x * tanh_f(c0));
-                    const __half h1 = __float2half_rn(og.y * tanh_f(c1));
-                    const int u = qt * 8 + uk;           // unit within the tile
-                    const int nA = ch * 8 + 2 * cp;      // chunk (column) index within the CTA
-                    *reinterpret_cast<__half*>(zh_next + (size_t)m * ZB + sw64_offset(nA, u)) = h0;
-                    *reinterpret_cast<__half*>(zh_next + (size_t)m * ZB + sw64_offset(nA + 1, u)) = h1;
-                    y_t[(size_t)nA * C + m * 32 + u] = h0;
-                    y_t[(size_t)(nA + 1) * C + m * 32 + u] = h1;
-                }
-            }
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&h_ready[nbuf]);
-        }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Weights-stationary LSTM recurrence over a thread-block cluster (hac: C = 384, cluster of 6 CTAs).
 //
 // W_hh (4C x C fp16 = 1.18 MB for C = 384) is split by gate tile across the CL CTAs of a cluster and stays in
-// their shared memory for the whole sequence; the cluster owns UN = 16 chunks.  Every step each CTA computes the
-// gates of its own 32*TPC hidden units from the full h_{t-1} (its private copy in shared memory), and all-gathers
-// its slice of h_t into every CTA's copy through distributed shared memory (st.shared::cluster), followed by one
-// cluster barrier.  No weight traffic after the prologue; the x_t half comes from the hoisted gx GEMM as in
-// lstm_rec_kernel.
+// their TENSOR MEMORY for the whole sequence (A operand of tcgen05.mma read from TMEM, written once with
+// tcgen05.st); the cluster owns UNC = 16 or 32 chunks.  Every step each CTA computes the gates of its own 32*TPC
+// hidden units from the full h_{t-1} (its private copy in shared memory), and all-gathers its slice of h_t into
+// every CTA's copy through distributed shared memory (st.shared::cluster), followed by one cluster barrier.  No
+// weight traffic after the prologue; the x_t half comes from the hoisted gx GEMM.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -675,9 +489,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
     return r;
-}
-__device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint16_t v) {
-    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -875,7 +686,7 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL, UNC>::THREADS, 1) lstm_clust
 struct LstmLayerWeights {
     __half* w = nullptr;   // resident path: [4C][2C] permuted rows, [W_ih | W_hh]
     float* bias = nullptr; // [4C] permuted
-    // hoisted path (lstm_rec_kernel): rows permuted as (tile, quarter, unit-in-quarter, gate)
+    // hoisted path (lstm_cluster_kernel): rows permuted as (tile, quarter, unit-in-quarter, gate)
     __half* w_ih = nullptr;  // [4C][C]
     __half* w_hh = nullptr;  // [4C][C]
 };
@@ -898,11 +709,8 @@ public:
     // hoisted path
     long long* dbg_timeline = nullptr;
     bool hoisted = false;
-    bool use_cluster = false;
     int rec_un = 16;
-    size_t rec_smem = 0;
     std::vector<GemmPlan> gx_gemm;
-    std::vector<CUtensorMap> rec_w;
     std::vector<const __half*> rec_whh;
     std::vector<LstmRecParams> rec_p;
     void launch_rec(int l, cudaStream_t stream) const;
@@ -1119,15 +927,13 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         plan->num_layers = desc.lstm_layers;
         plan->hoisted = true;
         if (C != 192 && C != 384) throw Unsupported("hoisted LSTM path is instantiated for lstm_size 192 and 384");
-        // C = 192 / 384: weights-stationary cluster kernel (6 CTAs x 16 chunks); otherwise the L2-streaming kernel
-        plan->use_cluster = true;
-        // cluster kernel: 32 chunks per cluster once 16 chunks would need more clusters than fit at once (~16)
-        int un = plan->use_cluster ? (Np > 256 ? 32 : 16) : (Np >= 2048 ? 64 : (Np >= 512 ? 32 : 16));
+        // weights-stationary cluster kernel (6 CTAs): 16 chunks per cluster, 32 once 16 would need more clusters than
+        // are co-resident (ncu: launch__cluster_max_active = 22 on B200)
+        int un = Np > 256 ? 32 : 16;
         while (Np % un != 0) un /= 2;
         plan->rec_un = un;
-        const int GB = un < 32 ? 32 : un;
-        plan->lstm_grid = plan->use_cluster ? (Np / un) * 6 : Np / un;
-        plan->rec_smem = 1024 + (size_t)REC_WSTAGES * WBLK_BYTES + (size_t)2 * (C / KBLK) * un * KBLK * 2 + 24 * 1024 + 1024;
+        const int GB = 32;  // chunk block of the gx layout (n_pad = 32 on this path)
+        plan->lstm_grid = (Np / un) * 6;
         for (int l = 0; l < desc.lstm_layers; ++l) {
             GemmDesc g{};
             g.a = layers[l].w_ih;  // gate rows are the M dimension, (t, chunk) the N dimension
@@ -1148,7 +954,6 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             g.out_col_s0 = (int64_t)4 * C * GB;
             plan->gx_gemm.push_back(make_gemm_plan(g));
             plan->rec_whh.push_back(layers[l].w_hh);
-            plan->rec_w.push_back(make_tmap_2d(layers[l].w_hh, (uint64_t)C, (uint64_t)4 * C, (uint64_t)C * 2, KBLK, 128));
             LstmRecParams rp{};
             rp.seq = seq;
             rp.gx = gxbuf;
@@ -1157,7 +962,6 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.reverse = (l % 2 == 0) ? 1 : 0;
             plan->rec_p.push_back(rp);
         }
-        if (plan->rec_smem > 227 * 1024) throw Unsupported("LSTM shared-memory plan does not fit");
     } else {
         plan->num_layers = desc.lstm_layers;
         const int MT = C / 32;
@@ -1266,25 +1070,6 @@ static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
                                                                                         pl.lstm_p[l]);
 }
 
-template <int C, int UN>
-static void launch_rec_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<C, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
-    lstm_rec_kernel<C, UN><<<pl.lstm_grid, REC_THREADS, pl.rec_smem, stream>>>(pl.rec_w[l], pl.rec_p[l]);
-}
-
-template <int C>
-static void launch_rec_c(const LstmPlan& pl, int l, cudaStream_t stream) {
-    switch (pl.rec_un) {
-        case 64: launch_rec_t<C, 64>(pl, l, stream); break;
-        case 32: launch_rec_t<C, 32>(pl, l, stream); break;
-        default: launch_rec_t<C, 16>(pl, l, stream); break;
-    }
-}
-
 template <int C, int CL, int UNC>
 static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
     using Cfg = ClusterCfg<C, CL, UNC>;
@@ -1316,15 +1101,9 @@ static void launch_cluster_c(const LstmPlan& pl, int l, cudaStream_t stream) {
 
 void LstmPlan::launch_rec(int l, cudaStream_t stream) const {
     const int C = model->desc.lstm_size;
-    if (use_cluster) {
-        if (C == 384) launch_cluster_c<384>(*this, l, stream);
-        else if (C == 192) launch_cluster_c<192>(*this, l, stream);
-        else throw Unsupported("no cluster LSTM kernel instantiation for this lstm_size");
-        return;
-    }
-    if (C == 384) launch_rec_c<384>(*this, l, stream);
-    else if (C == 192) launch_rec_c<192>(*this, l, stream);
-    else throw Unsupported("no hoisted LSTM kernel instantiation for this lstm_size");
+    if (C == 384) launch_cluster_c<384>(*this, l, stream);
+    else if (C == 192) launch_cluster_c<192>(*this, l, stream);
+    else throw Unsupported("no cluster LSTM kernel instantiation for this lstm_size");
 }
 
 template <int C>
