@@ -125,6 +125,40 @@ int b200_runner_call_chunks(b200_runner* r, int32_t num_chunks, b200_result* out
     });
 }
 
+int b200_generate_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap, uint64_t* offsets,
+                         uint64_t capacity, uint64_t* count) {
+    return guarded([&] {
+        if (!count || (!offsets && capacity)) throw std::invalid_argument("b200_generate_chunks: null argument");
+        *count = b200::generate_chunks(num_samples, chunk_size, stride, overlap, offsets, capacity);
+    });
+}
+
+int b200_stitch_chunks(const b200_called_chunk* chunks, uint64_t n_chunks, uint64_t raw_samples, int32_t stride,
+                       uint8_t* moves_out, char* sequence_out, char* qstring_out, uint64_t* n_moves_out,
+                       uint64_t* n_bases_out) {
+    return guarded([&] {
+        if (!moves_out || !sequence_out || !qstring_out || !n_moves_out || !n_bases_out) {
+            throw std::invalid_argument("b200_stitch_chunks: null argument");
+        }
+        b200::stitch_chunks(chunks, n_chunks, raw_samples, stride, moves_out, sequence_out, qstring_out, n_moves_out,
+                            n_bases_out);
+    });
+}
+
+int b200_runner_accept_raw_chunk(b200_runner* r, int32_t chunk_idx, const b200_raw_chunk* chunk) {
+    return guarded([&] {
+        if (!r || !chunk) throw std::invalid_argument("b200_runner_accept_raw_chunk: null argument");
+        reinterpret_cast<b200::Runner*>(r)->accept_raw_chunk(chunk_idx, *chunk);
+    });
+}
+
+int b200_runner_debug_read_input(b200_runner* r, int32_t num_chunks, uint16_t* input_out) {
+    return guarded([&] {
+        if (!r) throw std::invalid_argument("b200_runner_debug_read_input: null argument");
+        reinterpret_cast<b200::Runner*>(r)->debug_read_input(num_chunks, input_out);
+    });
+}
+
 int b200_runner_upload(b200_runner* r) {
     return guarded([&] {
         if (!r) throw std::invalid_argument("b200_runner_upload: null argument");

@@ -164,6 +164,10 @@ Runner::~Runner() {
     }
     if (m_h_input) cudaFreeHost(m_h_input);
     if (m_h_out) cudaFreeHost(m_h_out);
+    if (m_h_raw) cudaFreeHost(m_h_raw);
+    if (m_h_slots) cudaFreeHost(m_h_slots);
+    if (m_d_raw) cudaFree(m_d_raw);
+    if (m_d_slots) cudaFree(m_d_slots);
     if (m_stream) {
         cudaStreamSynchronize(m_stream);
         cudaStreamDestroy(m_stream);
@@ -179,14 +183,82 @@ void Runner::set_decoder_options(const b200_decoder_options& o) {
 void Runner::accept_chunk_f16(int idx, const uint16_t* samples, int64_t len) {
     if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
     if (len != m_T_in) throw std::invalid_argument("accept_chunk: chunk length != chunk_size");
+    clear_raw_slot(idx);
     std::memcpy(m_h_input + (size_t)idx * m_T_in, samples, (size_t)len * sizeof(uint16_t));
 }
 
 void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
     if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
     if (len != m_T_in) throw std::invalid_argument("accept_chunk: chunk length != chunk_size");
+    clear_raw_slot(idx);
     __half* dst = reinterpret_cast<__half*>(m_h_input + (size_t)idx * m_T_in);
     for (int64_t i = 0; i < len; ++i) dst[i] = __float2half_rn(samples[i]);
+}
+
+void Runner::clear_raw_slot(int idx) {
+    if (m_h_slots && m_h_slots[idx].slice_len > 0) {
+        m_h_slots[idx].slice_len = 0;
+        --m_num_raw;
+    }
+}
+
+// BasecallerNode's input slice (BasecallerNode.cpp:395-400): raw[offset : offset + chunk_size], clamped at the read
+// end.  Only the slice is staged; scaling and repeat-padding happen on the device (frontend.cu).
+void Runner::accept_raw_chunk(int idx, const b200_raw_chunk& c) {
+    if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_raw_chunk: chunk_idx out of range");
+    if (!c.raw || c.num_samples == 0) throw std::invalid_argument("accept_raw_chunk: empty read");
+    if (c.input_offset >= c.num_samples) throw std::invalid_argument("accept_raw_chunk: input_offset beyond the read");
+    if (!(c.scale != 0.0f) || c.scale != c.scale || c.shift != c.shift) {
+        throw std::invalid_argument("accept_raw_chunk: scale must be non-zero and finite");
+    }
+    std::lock_guard<std::mutex> lock(m_mutex);
+    if (!m_h_raw) {
+        B200_CUDA(cudaSetDevice(m_engine.device()));
+        const size_t raw_b = (size_t)m_N * m_T_in * sizeof(int16_t);
+        B200_CUDA(cudaHostAlloc(&m_h_raw, raw_b, cudaHostAllocDefault));
+        B200_CUDA(cudaHostAlloc(&m_h_slots, (size_t)m_N * sizeof(RawSlot), cudaHostAllocDefault));
+        std::memset(m_h_raw, 0, raw_b);
+        std::memset(m_h_slots, 0, (size_t)m_N * sizeof(RawSlot));
+        B200_CUDA(cudaMalloc(&m_d_raw, raw_b));
+        B200_CUDA(cudaMalloc(&m_d_slots, (size_t)m_N * sizeof(RawSlot)));
+        m_engine.arena_bytes += (int64_t)(raw_b + (size_t)m_N * sizeof(RawSlot));
+    }
+    const uint64_t avail = c.num_samples - c.input_offset;
+    const int slice = (int)std::min<uint64_t>(avail, (uint64_t)m_T_in);
+    std::memcpy(m_h_raw + (size_t)idx * m_T_in, c.raw + c.input_offset, (size_t)slice * sizeof(int16_t));
+    if (m_h_slots[idx].slice_len == 0) ++m_num_raw;
+    m_h_slots[idx].slice_len = slice;
+    m_h_slots[idx].shift = c.shift;
+    m_h_slots[idx].scale = c.scale;
+}
+
+// Input stage of a batch: fp16 rows by plain H2D; raw rows as staged int16 + descriptors, then one gather/scale
+// kernel writes their fp16 rows (it skips fp16 slots, so both kinds can share a batch).
+void Runner::stage_input(int n) {
+    int raw_in_n = 0;
+    if (m_num_raw > 0) {
+        for (int i = 0; i < n; ++i) raw_in_n += m_h_slots[i].slice_len > 0;
+    }
+    if (raw_in_n < n) {
+        B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)n * m_T_in * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                  m_stream));
+    }
+    if (raw_in_n > 0) {
+        B200_CUDA(cudaMemcpyAsync(m_d_raw, m_h_raw, (size_t)n * m_T_in * sizeof(int16_t), cudaMemcpyHostToDevice, m_stream));
+        B200_CUDA(cudaMemcpyAsync(m_d_slots, m_h_slots, (size_t)n * sizeof(RawSlot), cudaMemcpyHostToDevice, m_stream));
+        launch_raw_chunk_gather(m_d_raw, m_d_slots, m_d_input, n, m_T_in, m_stream);
+        ++m_engine.gpu_launches;
+    }
+}
+
+void Runner::debug_read_input(int num_chunks, uint16_t* input_out) {
+    if (num_chunks < 1 || num_chunks > m_N || !input_out) throw std::invalid_argument("debug_read_input: bad arguments");
+    std::lock_guard<std::mutex> lock(m_mutex);
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    stage_input(num_chunks);
+    B200_CUDA(cudaMemcpyAsync(input_out, m_d_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t), cudaMemcpyDeviceToHost,
+                              m_stream));
+    B200_CUDA(cudaStreamSynchronize(m_stream));
 }
 
 void Runner::run_forward(int n) {
@@ -222,8 +294,7 @@ void Runner::run_decode(int n, ProfileSink* prof) {
 void Runner::upload() {
     std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
-    B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)m_N * m_T_in * sizeof(uint16_t), cudaMemcpyHostToDevice,
-                              m_stream));
+    stage_input(m_N);
     B200_CUDA(cudaStreamSynchronize(m_stream));
 }
 
@@ -233,8 +304,7 @@ b200_result Runner::call_chunks(int num_chunks) {
     B200_CUDA(cudaSetDevice(m_engine.device()));
     cudaStream_t s = m_stream;
     B200_CUDA(cudaEventRecord(m_ev[0], s));
-    B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t),
-                              cudaMemcpyHostToDevice, s));
+    stage_input(num_chunks);
     B200_CUDA(cudaEventRecord(m_ev[1], s));
     run_forward(num_chunks);
     run_decode(num_chunks);
@@ -327,8 +397,7 @@ void Runner::forward_scores_to_host(int num_chunks, uint16_t* scores_out) {
     std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
     cudaStream_t s = m_stream;
-    B200_CUDA(cudaMemcpyAsync(m_d_input, m_h_input, (size_t)num_chunks * m_T_in * sizeof(uint16_t),
-                              cudaMemcpyHostToDevice, s));
+    stage_input(num_chunks);
     run_forward(num_chunks);
     B200_CUDA(cudaMemcpyAsync(scores_out, m_d_scores, (size_t)num_chunks * m_T_out * m_C * sizeof(__half),
                               cudaMemcpyDeviceToHost, s));

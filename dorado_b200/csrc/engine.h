@@ -3,6 +3,7 @@
 #pragma once
 
 #include "b200call.h"
+#include "frontend.h"
 #include "common.cuh"
 
 #include <atomic>
@@ -116,6 +117,9 @@ public:
     void set_decoder_options(const b200_decoder_options& o);
     void accept_chunk_f16(int idx, const uint16_t* samples, int64_t len);
     void accept_chunk_f32(int idx, const float* samples, int64_t len);
+    // raw int16 chunk: slice + scale + repeat-pad happen on the device (frontend.cu)
+    void accept_raw_chunk(int idx, const b200_raw_chunk& chunk);
+    void debug_read_input(int num_chunks, uint16_t* input_out);
     b200_result call_chunks(int num_chunks);
     void upload();
     void step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms);
@@ -125,6 +129,8 @@ public:
     std::string profile(int num_chunks);
 
 private:
+    void stage_input(int n);  // H2D of the first n slots (+ gather/scale kernel for raw slots), on m_stream
+    void clear_raw_slot(int idx);
     void run_forward(int n);
     void run_decode(int n, ProfileSink* prof = nullptr);
 
@@ -136,6 +142,12 @@ private:
     // pinned host (input and output are separate allocations; the reference aliases them)
     uint16_t* m_h_input = nullptr;
     unsigned char* m_h_out = nullptr;  // moves | sequence | qstring | n_bases
+    // raw-chunk staging (allocated on the first accept_raw_chunk): pinned int16 [N][T_in] + per-slot descriptors
+    int16_t* m_h_raw = nullptr;
+    RawSlot* m_h_slots = nullptr;
+    int16_t* m_d_raw = nullptr;
+    RawSlot* m_d_slots = nullptr;
+    int m_num_raw = 0;  // slots currently holding a raw chunk
     // device
     Arena m_arena;
     __half* m_d_input = nullptr;

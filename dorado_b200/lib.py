@@ -57,6 +57,18 @@ class Result(C.Structure):
                 ("n_bases", C.POINTER(C.c_int32)), ("t_out", C.c_int32), ("num_chunks", C.c_int32)]
 
 
+class RawChunk(C.Structure):
+    """b200_raw_chunk"""
+    _fields_ = [("raw", C.c_void_p), ("num_samples", C.c_uint64), ("input_offset", C.c_uint64), ("shift", C.c_float),
+                ("scale", C.c_float)]
+
+
+class CalledChunk(C.Structure):
+    """b200_called_chunk"""
+    _fields_ = [("input_offset", C.c_uint64), ("raw_chunk_size", C.c_uint64), ("moves", C.c_void_p),
+                ("n_moves", C.c_uint64), ("sequence", C.c_void_p), ("qstring", C.c_void_p), ("n_bases", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("batches_called", C.c_int64), ("model_decode_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("gpu_launches", C.c_int64), ("arena_bytes", C.c_int64)]
@@ -68,7 +80,8 @@ EXPORTS = [
     "b200_runner_set_decoder_options", "b200_runner_batch_size", "b200_runner_chunk_size", "b200_runner_out_len",
     "b200_runner_accept_chunk_f16", "b200_runner_accept_chunk_f32", "b200_runner_input", "b200_runner_call_chunks",
     "b200_runner_upload", "b200_runner_step_device", "b200_runners_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_debug_read_workspace", "b200_decode_scores",
-    "b200_test_gemm",
+    "b200_test_gemm", "b200_generate_chunks", "b200_stitch_chunks", "b200_runner_accept_raw_chunk",
+    "b200_runner_debug_read_input",
 ]
 
 _lib = None
@@ -114,6 +127,11 @@ def load_library() -> C.CDLL:
     lib.b200_runner_profile.argtypes = [vp, i32, C.c_char_p, C.c_uint64]
     lib.b200_runner_debug_read_workspace.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     lib.b200_test_gemm.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, vp]
+    u64 = C.c_uint64
+    lib.b200_generate_chunks.argtypes = [u64, u64, u64, u64, C.POINTER(u64), u64, C.POINTER(u64)]
+    lib.b200_stitch_chunks.argtypes = [C.POINTER(CalledChunk), u64, u64, i32, vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.b200_runner_accept_raw_chunk.argtypes = [vp, i32, C.POINTER(RawChunk)]
+    lib.b200_runner_debug_read_input.argtypes = [vp, i32, vp]
     _lib = lib
     return lib
 

@@ -97,6 +97,20 @@ class B200ModelRunner:
             c = c.astype(np.float32, copy=False)
             L.check(self._lib.b200_runner_accept_chunk_f32(self.handle, chunk_idx, c.ctypes.data, c.size))
 
+    def accept_raw_chunk(self, chunk_idx: int, raw: np.ndarray, input_offset: int, shift: float, scale: float) -> None:
+        """One chunk of a read given as its whole RAW int16 signal: ScalerNode's (x - shift) / scale
+        (ScalerNode.cpp:226-229), BasecallerNode's slice + repeat-padding (BasecallerNode.cpp:395-440) run on the
+        device at the next call_chunks.  `raw` is only read during this call."""
+        r = np.ascontiguousarray(raw, np.int16).reshape(-1)
+        c = L.RawChunk(r.ctypes.data, r.size, int(input_offset), float(shift), float(scale))
+        L.check(self._lib.b200_runner_accept_raw_chunk(self.handle, chunk_idx, C.byref(c)))
+
+    def debug_read_input(self, num_chunks: int) -> np.ndarray:
+        """Run only the input stage and read the device-side fp16 batch input back: [num_chunks, chunk_size]."""
+        out = np.empty((num_chunks, self._T), np.float16)
+        L.check(self._lib.b200_runner_debug_read_input(self.handle, num_chunks, out.ctypes.data))
+        return out
+
     def call_chunks_raw(self, num_chunks: int):
         """The bare C-ABI call (what the C++ adapter makes): H2D, forward, decode, D2H; returns views of the runner's
         pinned result buffers (moves [N,T], sequence [N,T], qstring [N,T], n_bases [N]), valid until the next call."""

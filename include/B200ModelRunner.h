@@ -174,6 +174,23 @@ public:
         }
     }
 
+    // Raw-signal variant of accept_chunk (not part of ModelRunnerBase): `raw` is the read's whole int16 signal as the
+    // DataLoader delivers it (ScalerNode.cpp:190 asserts kShort), shift/scale what ScalerNode computed for the read.
+    // Scaling, slicing and repeat-padding run on the device (b200call.h: b200_runner_accept_raw_chunk), so ScalerNode's
+    // in-place fp16 conversion and BasecallerNode's slice/concat (BasecallerNode.cpp:395-440) are skipped.
+    void accept_raw_chunk(int chunk_idx, const at::Tensor& raw, size_t input_offset, float shift, float scale) {
+        if (raw.scalar_type() != at::kShort || !raw.is_contiguous()) {
+            throw std::invalid_argument("B200ModelRunner::accept_raw_chunk expects a contiguous int16 tensor");
+        }
+        b200_raw_chunk c{};
+        c.raw = raw.data_ptr<int16_t>();
+        c.num_samples = static_cast<uint64_t>(raw.numel());
+        c.input_offset = static_cast<uint64_t>(input_offset);
+        c.shift = shift;
+        c.scale = scale;
+        B200Caller::check(b200_runner_accept_raw_chunk(m_runner, chunk_idx, &c));
+    }
+
     std::vector<decode::DecodedChunk> call_chunks(int num_chunks) final {
         b200_result r{};
         B200Caller::check(b200_runner_call_chunks(m_runner, num_chunks, &r));

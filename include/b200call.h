@@ -155,6 +155,62 @@ B200_API int b200_runner_step_device(b200_runner* runner, int32_t num_chunks, in
 B200_API int b200_runners_step_device(b200_runner** runners, int32_t n_runners, int32_t num_chunks, int32_t iters,
                                       float* total_ms);
 
+/* ---- Front end of the path: chunking, raw-signal scaling, stitching ------------------
+ *
+ * utils::generate_chunks (dorado/read_pipeline/base/chunk.cpp:11-47): chunk start offsets of a read of
+ * `num_samples` samples.  Writes at most `capacity` offsets and always reports the full count.  The reference throws
+ * on an empty read, stride 0, chunk_size 0 / not a multiple of stride / <= overlap, overlap not a multiple of stride:
+ * those return B200_ERR_INVALID. */
+B200_API int b200_generate_chunks(uint64_t num_samples,
+                                  uint64_t chunk_size,
+                                  uint64_t stride,
+                                  uint64_t overlap,
+                                  uint64_t* offsets,
+                                  uint64_t capacity,
+                                  uint64_t* count);
+
+/* One chunk of a read given as RAW int16 signal: the device does what ScalerNode + BasecallerNode do on the host
+ * in the reference --  x' = fp16((float(x) - shift) / scale)  (utils::shift_scale_tensor_i16_to_f16_inplace,
+ * dorado/torch_utils/tensor_utils.cpp:100-143, called at read_pipeline/nodes/ScalerNode.cpp:226-229), the slice
+ * raw[input_offset : input_offset + chunk_size] clamped at the read end, and repeat-padding of a short slice
+ * (BasecallerNode.cpp:395-440) -- so int16 crosses PCIe once and no fp16 copy of the read is ever made on the host. */
+typedef struct b200_raw_chunk {
+    const int16_t* raw;    /* the read's whole raw signal (host memory) */
+    uint64_t num_samples;  /* read length in samples */
+    uint64_t input_offset; /* chunk start within the read (b200_generate_chunks) */
+    float shift, scale;    /* ScalerNode's normalisation of this read */
+} b200_raw_chunk;
+/* accept_chunk for a raw chunk: stages the slice (only its un-padded samples) in pinned memory; the next
+ * b200_runner_call_chunks uploads the staged int16 and runs the gather/scale kernel into the batch input.
+ * Slots given through b200_runner_accept_chunk_f16/_f32 afterwards revert to the fp16 path. */
+B200_API int b200_runner_accept_raw_chunk(b200_runner* runner, int32_t chunk_idx, const b200_raw_chunk* chunk);
+/* Debug / test hook: run only the input stage (uploads + gather/scale kernel) for the first num_chunks slots and
+ * copy the device-side fp16 batch input [num_chunks, chunk_size] back. */
+B200_API int b200_runner_debug_read_input(b200_runner* runner, int32_t num_chunks, uint16_t* input_out);
+
+/* utils::stitch_chunks (dorado/read_pipeline/base/stitch.cpp:12-96): merge the called chunks of one read, cutting
+ * every overlap at its midpoint (in model-stride units), trimming a single short chunk to the read length and
+ * dropping the partial-stride overhang.  `raw_samples` = ReadCommon::get_raw_data_samples(). */
+typedef struct b200_called_chunk {
+    uint64_t input_offset;   /* utils::Chunk::input_offset */
+    uint64_t raw_chunk_size; /* utils::Chunk::raw_chunk_size */
+    const uint8_t* moves;    /* n_moves = raw_chunk_size / stride entries */
+    uint64_t n_moves;
+    const char* sequence;    /* n_bases characters */
+    const char* qstring;     /* n_bases characters */
+    uint64_t n_bases;
+} b200_called_chunk;
+/* Output buffers must hold the sums of the inputs' n_moves / n_bases (upper bounds). */
+B200_API int b200_stitch_chunks(const b200_called_chunk* chunks,
+                                uint64_t n_chunks,
+                                uint64_t raw_samples,
+                                int32_t stride,
+                                uint8_t* moves_out,
+                                char* sequence_out,
+                                char* qstring_out,
+                                uint64_t* n_moves_out,
+                                uint64_t* n_bases_out);
+
 /* Stage-level entry points so scores and decode can be parity-checked independently (host buffers). */
 B200_API int b200_runner_forward_scores(b200_runner* runner, int32_t num_chunks, uint16_t* scores_out /* [n,t_out,outsize] fp16 */);
 B200_API int b200_decode_scores(int32_t device,

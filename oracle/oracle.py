@@ -136,6 +136,14 @@ class Reference:
         lib.ref_decode_chunks.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                           C.c_float, C.c_float, _u8p, _u8p, _u8p, _i32p]
         lib.ref_set_num_threads.argtypes = [C.c_int]
+        u64 = C.c_uint64
+        _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+        lib.ref_generate_chunks.argtypes = [u64, u64, u64, u64, _u64p, u64]
+        lib.ref_generate_chunks.restype = C.c_long
+        lib.ref_make_chunk_input.argtypes = [np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), u64, u64, u64,
+                                             C.c_float, C.c_float, _u16p]
+        lib.ref_stitch_chunks.argtypes = [u64, _u64p, _u64p, _u8p, _u64p, C.c_char_p, C.c_char_p, _u64p, u64, C.c_int,
+                                          _u8p, _u8p, _u8p, C.POINTER(u64), C.POINTER(u64)]
 
     def _check(self, rc):
         if rc != 0:
@@ -143,6 +151,40 @@ class Reference:
 
     def set_num_threads(self, n):
         self.lib.ref_set_num_threads(n)
+
+    # ---- front end (chunk.cpp, stitch.cpp, tensor_utils.cpp through ref_driver.cpp) --------------------------
+    def generate_chunks(self, num_samples, chunk_size, stride, overlap):
+        """utils::generate_chunks; raises RuntimeError where the reference throws."""
+        cap = 1 << 16
+        out = np.zeros(cap, np.uint64)
+        n = self.lib.ref_generate_chunks(num_samples, chunk_size, stride, overlap, out, cap)
+        if n < 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return [int(v) for v in out[:n]]
+
+    def make_chunk_input(self, raw, input_offset, chunk_size, shift, scale):
+        """ScalerNode scaling + BasecallerNode slice/repeat-pad of one chunk -> fp16 [chunk_size]."""
+        r = np.ascontiguousarray(raw, np.int16)
+        out = np.zeros(chunk_size, np.uint16)
+        self._check(self.lib.ref_make_chunk_input(r, r.size, input_offset, chunk_size, shift, scale, out))
+        return out.view(np.float16)
+
+    def stitch_chunks(self, chunks, raw_samples, stride):
+        """chunks: (input_offset, raw_chunk_size, moves, sequence, qstring) -> (sequence, qstring, moves)."""
+        offs = np.array([c[0] for c in chunks], np.uint64)
+        sizes = np.array([c[1] for c in chunks], np.uint64)
+        moves = np.ascontiguousarray(np.concatenate([np.asarray(c[2], np.uint8) for c in chunks]))
+        mlen = np.array([len(c[2]) for c in chunks], np.uint64)
+        seq = "".join(c[3] for c in chunks).encode("ascii")
+        qs = "".join(c[4] for c in chunks).encode("ascii")
+        slen = np.array([len(c[3]) for c in chunks], np.uint64)
+        mo = np.zeros(max(1, moves.size), np.uint8)
+        so = np.zeros(max(1, len(seq)), np.uint8)
+        qo = np.zeros(max(1, len(seq)), np.uint8)
+        nm, nb = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.ref_stitch_chunks(len(chunks), offs, sizes, moves, mlen, seq, qs, slen, raw_samples, stride,
+                                               mo, so, qo, C.byref(nm), C.byref(nb)))
+        return bytes(so[: nb.value]).decode("ascii"), bytes(qo[: nb.value]).decode("ascii"), mo[: nm.value].copy()
 
     def load_model(self, config_dir, weights_file):
         h = self.lib.ref_model_create(str(config_dir).encode(), str(weights_file).encode())

@@ -8,12 +8,18 @@
 //   * CRF scans          dorado/basecall/decode/CPUDecoder.cpp:43-92   (inner::forward/backward_scores)
 //   * beam search        dorado/basecall/decode/beam_search.cpp:522    (beam_search_decode)
 //   * whole decode       dorado/basecall/decode/CPUDecoder.cpp:100     (CPUDecoder::beam_search_part_2)
+//   * front end          dorado/read_pipeline/base/chunk.cpp:11-47 (generate_chunks), stitch.cpp:12-96 (stitch_chunks),
+//                        dorado/torch_utils/tensor_utils.cpp:254 (shift_scale_tensor_i16_to_f16_inplace)
 // Everything here is glue written for this repo; no reference source is copied.
 #include "basecall/decode/CPUDecoder.h"
 #include "basecall/decode/beam_search.h"
 #include "basecall/model/CRFModel.h"
 #include "basecall/model/TxModel.h"
 #include "config/BasecallModelConfig.h"
+#include "read_pipeline/base/chunk.h"
+#include "read_pipeline/base/messages.h"
+#include "read_pipeline/base/stitch.h"
+#include "torch_utils/tensor_utils.h"
 
 #include <ATen/ATen.h>
 #include <torch/torch.h>
@@ -229,6 +235,91 @@ int ref_decode_chunks(const float* scores,
             std::memcpy(qstr + size_t(i) * T, res[i].qstring.data(), res[i].qstring.size());
             std::memcpy(moves + size_t(i) * T, res[i].moves.data(), res[i].moves.size());
         }
+    });
+}
+
+// utils::generate_chunks (read_pipeline/base/chunk.cpp:11-47).  Returns the number of offsets (written up to cap),
+// or -1 when the reference throws.
+long ref_generate_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap, uint64_t* out,
+                         uint64_t cap) {
+    long n = -1;
+    guarded([&] {
+        const auto v = dorado::utils::generate_chunks(num_samples, chunk_size, stride, overlap);
+        for (size_t i = 0; i < v.size() && i < cap; ++i) {
+            out[i] = v[i];
+        }
+        n = long(v.size());
+    });
+    return n;
+}
+
+// What the model input row of one chunk holds in the reference: ScalerNode scales the whole read in place
+// (shift_scale_tensor_i16_to_f16_inplace, ScalerNode.cpp:226-229), BasecallerNode slices
+// raw_data[offset : offset + chunk_size] (clamped at the read end) and repeat-pads a short slice with
+// at::concat({slice.repeat({1, n}), slice[:overhang]}) (BasecallerNode.cpp:395-440).  The torch calls below are the
+// same calls the node makes.
+int ref_make_chunk_input(const int16_t* raw, uint64_t num_samples, uint64_t offset, uint64_t chunk_size, float shift,
+                         float scale, uint16_t* out) {
+    return guarded([&] {
+        using at::indexing::Ellipsis;
+        using at::indexing::Slice;
+        at::Tensor t = at::from_blob(const_cast<int16_t*>(raw), {int64_t(num_samples)}, at::kShort).clone();
+        dorado::utils::shift_scale_tensor_i16_to_f16_inplace(t, shift, scale);
+        at::Tensor input_slice = t.index({Ellipsis, Slice(int64_t(offset), int64_t(offset + chunk_size))});
+        if (input_slice.ndimension() == 1) {
+            input_slice = input_slice.unsqueeze(0);
+        }
+        const size_t slice_size = input_slice.size(1);
+        if (slice_size != chunk_size) {
+            auto [n, overhang] = std::div((int)chunk_size, (int)slice_size);
+            input_slice = at::concat({input_slice.repeat({1, n}), input_slice.index({Ellipsis, Slice(0, overhang)})}, 1);
+        }
+        input_slice = input_slice.contiguous();
+        std::memcpy(out, input_slice.data_ptr(), chunk_size * 2);
+    });
+}
+
+// utils::stitch_chunks (read_pipeline/base/stitch.cpp:12-96) on n chunks given as flat arrays.
+// moves/seq/qstr are concatenations; *_len give the per-chunk lengths.  Outputs are sized by the caller
+// (total moves / total bases are upper bounds).
+int ref_stitch_chunks(uint64_t n,
+                      const uint64_t* input_offsets,
+                      const uint64_t* raw_chunk_sizes,
+                      const uint8_t* moves,
+                      const uint64_t* moves_len,
+                      const char* seq,
+                      const char* qstr,
+                      const uint64_t* seq_len,
+                      uint64_t raw_samples,
+                      int stride,
+                      uint8_t* moves_out,
+                      char* seq_out,
+                      char* qstr_out,
+                      uint64_t* n_moves_out,
+                      uint64_t* n_bases_out) {
+    return guarded([&] {
+        std::vector<std::unique_ptr<dorado::utils::Chunk>> owned;
+        std::vector<const dorado::utils::Chunk*> ptrs;
+        size_t mo = 0, so = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            auto c = std::make_unique<dorado::utils::Chunk>(input_offsets[i], raw_chunk_sizes[i]);
+            c->moves.assign(moves + mo, moves + mo + moves_len[i]);
+            c->seq.assign(seq + so, seq_len[i]);
+            c->qstring.assign(qstr + so, seq_len[i]);
+            mo += moves_len[i];
+            so += seq_len[i];
+            ptrs.push_back(c.get());
+            owned.push_back(std::move(c));
+        }
+        dorado::ReadCommon rc;
+        rc.attributes.model_stride = stride;
+        rc.raw_data = at::empty({int64_t(raw_samples)}, at::kShort);
+        dorado::utils::stitch_chunks(rc, ptrs);
+        *n_moves_out = rc.moves.size();
+        *n_bases_out = rc.seq.size();
+        std::memcpy(moves_out, rc.moves.data(), rc.moves.size());
+        std::memcpy(seq_out, rc.seq.data(), rc.seq.size());
+        std::memcpy(qstr_out, rc.qstring.data(), rc.qstring.size());
     });
 }
 

@@ -1,0 +1,184 @@
+"""Front end of the hot path on the CPU: the product's host logic (generate_chunks,
+stitch_chunks through the C ABI) and the numpy oracle of the device-side scaling, both pinned to
+  * the golden vectors of the reference's own tests (tests/ChunkTest.cpp, tests/StitchTest.cpp), restated below,
+  * the compiled reference (oracle/_ref: chunk.cpp, stitch.cpp, tensor_utils.cpp) on random inputs,
+  * the committed fixture tests/golden/frontend.npz (generated from the compiled reference).
+"""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from dorado_b200 import lib as L
+from dorado_b200.frontend import generate_chunks, stitch_chunks
+from oracle import frontend_oracle as fo
+
+
+# ---- generate_chunks -------------------------------------------------------------------------------------------
+def test_generate_chunks_invalid_input_like_ChunkTest():
+    # tests/ChunkTest.cpp "Invalid input": every one of these throws in the reference
+    for args in [(0, 9996, 6, 498), (12345, 0, 6, 498), (12345, 9996, 0, 498), (12345, 9996, 10, 498),
+                 (12345, 9996, 7, 498), (12345, 9996, 6, 9996), (12345, 9996, 6, 9997)]:
+        with pytest.raises(L.B200Error) as e:
+            generate_chunks(*args)
+        assert e.value.status == L.B200_ERR_INVALID
+        with pytest.raises((RuntimeError, ValueError)):
+            fo.generate_chunks(*args)
+
+
+def test_generate_chunks_golden_vectors_of_ChunkTest():
+    golden = [((9996 // 2, 9996, 6, 498), [0]), ((9996, 9996, 6, 498), [0]), ((9996 + 1, 9996, 6, 498), [0, 6]),
+              ((9996 + 9996 // 2, 9996, 6, 498), [0, 4998]), ((2 * 9996 + 9996 // 2, 9996, 1, 0), [0, 9996, 14994]),
+              ((3 * 9996, 9996, 6, 498), [0, 9498, 18996, 19992])]
+    for args, want in golden:
+        assert generate_chunks(*args) == want
+        assert fo.generate_chunks(*args) == want
+
+
+@pytest.mark.parametrize("chunk_size,stride,overlap", [(9996, 6, 498), (9996, 7, 497), (9996, 12, 492), (9996, 17, 510),
+                                                       (555, 5, 25), (83, 1, 13), (123, 1, 0)])
+def test_generate_chunks_properties_of_ChunkTest(chunk_size, stride, overlap):
+    rng = np.random.default_rng(42)
+    for num_samples in rng.integers(1024, 2097152, 16):
+        offs = generate_chunks(int(num_samples), chunk_size, stride, overlap)
+        assert offs and offs[0] == 0
+        for i in range(1, len(offs) - 1):
+            assert offs[i] % stride == 0 and offs[i] == i * (chunk_size - overlap)
+        assert offs[-1] % stride == 0 and offs[-1] < num_samples
+        if len(offs) > 1:
+            assert chunk_size - stride <= num_samples - offs[-1] <= chunk_size
+        assert offs == fo.generate_chunks(int(num_samples), chunk_size, stride, overlap)
+
+
+def test_generate_chunks_matches_compiled_reference(reference):
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        stride = int(rng.choice([1, 5, 6, 12]))
+        chunk = stride * int(rng.integers(2, 400))
+        overlap = stride * int(rng.integers(0, chunk // stride))
+        n = int(rng.integers(1, 40 * chunk))
+        want = reference.generate_chunks(n, chunk, stride, overlap)
+        assert generate_chunks(n, chunk, stride, overlap) == want
+        assert fo.generate_chunks(n, chunk, stride, overlap) == want
+    with pytest.raises(RuntimeError):
+        reference.generate_chunks(0, 9996, 6, 498)
+
+
+def test_generate_chunks_capacity_reports_full_count():
+    import ctypes as C
+    lib = L.load_library()
+    n = C.c_uint64()
+    buf = (C.c_uint64 * 2)()
+    L.check(lib.b200_generate_chunks(3 * 9996, 9996, 6, 498, buf, 2, C.byref(n)))
+    assert n.value == 4 and list(buf) == [0, 9498]
+    L.check(lib.b200_generate_chunks(3 * 9996, 9996, 6, 498, None, 0, C.byref(n)))
+    assert n.value == 4
+
+
+# ---- stitch_chunks ---------------------------------------------------------------------------------------------
+STITCH_MOVES = [[1, 0, 0, 1, 0, 0, 1, 0, 1, 0], [1, 0, 0, 1, 0, 0, 0, 1, 0, 1], [1, 0, 0, 1, 0, 1, 1, 0, 0, 0],
+                [1, 0, 0, 1, 0, 0, 1, 0, 1, 0], [0, 1, 0, 1, 0, 0, 1, 0, 1, 0], [1, 0, 0, 0, 0, 0, 1, 0, 1, 1],
+                [1, 0, 0, 1, 0, 0, 1, 0, 1, 0]]
+
+
+def _stitch_test_chunks():
+    # tests/StitchTest.cpp: RAW_SIGNAL_SIZE 50, CHUNK_SIZE 10, OVERLAP 3, seven chunks "ACGT" / "!&.-"
+    offs, off = [0], 0
+    while off + 10 < 50:
+        off = min(off + 7, 40)
+        offs.append(off)
+    return [(o, 10, np.array(STITCH_MOVES[i], np.uint8), "ACGT", "!&.-") for i, o in enumerate(offs)]
+
+
+def test_stitch_chunks_golden_vector_of_StitchTest():
+    want_seq, want_q = "ACGTCGCGTCGTCGTCCGT", "!&.-&.&.-&.-&.-&&.-"
+    want_moves = [1, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0,
+                  1, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 1, 0, 1]
+    # the reference test leaves raw_data empty (0 samples), which also exercises the overhang pop
+    for impl in (stitch_chunks, fo.stitch_chunks):
+        seq, q, moves = impl(_stitch_test_chunks(), 0, 1)
+        assert seq == want_seq and q == want_q and moves.tolist() == want_moves
+
+
+def _random_called_read(rng, n_samples, chunk, stride, overlap):
+    chunks = []
+    for off in fo.generate_chunks(n_samples, chunk, stride, overlap):
+        moves = (rng.random(chunk // stride) < 0.45).astype(np.uint8)
+        moves[0] = 1  # beam_search.cpp:447-455
+        nb = int(moves.sum())
+        seq = "".join(rng.choice(list("ACGT"), nb))
+        q = "".join(chr(33 + int(v)) for v in rng.integers(1, 50, nb))
+        chunks.append((off, chunk, moves, seq, q))
+    return chunks
+
+
+def test_stitch_chunks_matches_compiled_reference(reference):
+    rng = np.random.default_rng(11)
+    for it in range(200):
+        stride = int(rng.choice([1, 5, 6]))
+        chunk = stride * int(rng.integers(8, 120))
+        overlap = stride * int(rng.integers(0, max(1, chunk // stride // 2)))
+        n = int(rng.integers(1, 12 * chunk))
+        chunks = _random_called_read(rng, n, chunk, stride, overlap)
+        want = reference.stitch_chunks(chunks, n, stride)
+        for impl in (stitch_chunks, fo.stitch_chunks):
+            seq, q, moves = impl(chunks, n, stride)
+            assert (seq, q) == want[:2] and moves.tolist() == want[2].tolist(), (it, n, chunk, stride, overlap)
+        assert len(want[2]) == n // stride or len(chunks) > 1
+        assert int(want[2].sum()) == len(want[0])
+
+
+def test_stitch_chunks_rejects_bad_input():
+    with pytest.raises(L.B200Error):
+        stitch_chunks([], 100, 6)
+    a = (0, 60, np.ones(10, np.uint8), "A" * 10, "!" * 10)
+    b = (120, 60, np.ones(10, np.uint8), "A" * 10, "!" * 10)  # gap instead of an overlap
+    with pytest.raises(L.B200Error):
+        stitch_chunks([a, b], 180, 6)
+    c = (57, 60, np.ones(10, np.uint8), "A" * 10, "!" * 10)   # overlap not on a stride boundary
+    with pytest.raises(L.B200Error):
+        stitch_chunks([a, c], 117, 6)
+    with pytest.raises(L.B200Error):
+        stitch_chunks([a], 60, 0)
+
+
+# ---- raw int16 -> scaled, repeat-padded fp16 rows (numpy oracle of the device kernel) -----------------------------
+def test_scaling_oracle_like_TensorUtilsTest(reference):
+    # tests/TensorUtilsTest.cpp:121-143: random sizes < 100, shift in [-100, 100], scale in [0.1, 100], zero tolerance
+    rng = np.random.default_rng(42)
+    for _ in range(40):
+        n = int(rng.integers(1, 100))
+        shift, scale = float(rng.uniform(-100, 100)), float(rng.uniform(0.1, 100))
+        raw = (rng.random(n) * 1000).astype(np.int16)
+        want = reference.make_chunk_input(raw, 0, n, shift, scale)
+        got = fo.scale_i16_to_f16(raw, np.float32(shift), np.float32(scale))
+        assert (got.view(np.uint16) == want.view(np.uint16)).all()
+
+
+def test_chunk_input_oracle_matches_compiled_reference(reference):
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        chunk = 6 * int(rng.integers(2, 300))
+        n = int(rng.integers(1, 6 * chunk))
+        raw = rng.integers(-32768, 32768, n).astype(np.int16)
+        shift, scale = float(rng.uniform(-500, 900)), float(rng.uniform(0.5, 400))
+        for off in fo.generate_chunks(n, chunk, 6, 6 * int(rng.integers(0, chunk // 12 + 1))):
+            want = reference.make_chunk_input(raw, off, chunk, shift, scale)
+            got = fo.chunk_input(raw, off, chunk, shift, scale)
+            assert (got.view(np.uint16) == want.view(np.uint16)).all()
+
+
+def test_frontend_golden_fixture_matches_oracle():
+    g = np.load(ROOT / "tests" / "golden" / "frontend.npz")
+    chunk, stride, overlap = int(g["chunk_size"]), int(g["stride"]), int(g["overlap"])
+    row = 0
+    for r, n in enumerate(g["read_lens"]):
+        raw = g[f"raw_{r}"]
+        shift, scale = g[f"shift_scale_{r}"]
+        offs = generate_chunks(int(n), chunk, stride, overlap)
+        assert offs == g[f"offsets_{r}"].tolist() == fo.generate_chunks(int(n), chunk, stride, overlap)
+        for o in offs:
+            assert g["row_read_offset"][row].tolist() == [r, o]
+            got = fo.chunk_input(raw, o, chunk, shift, scale)
+            assert (got.view(np.uint16) == g["input_rows_f16_bits"][row]).all()
+            row += 1
+    assert row == g["input_rows_f16_bits"].shape[0]
