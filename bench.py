@@ -344,6 +344,8 @@ def main():
     try:
         if args.no_cpu_baseline:
             raise RuntimeError("skipped (--no-cpu-baseline)")
+        if world > 1:
+            raise RuntimeError("reported at N=1 only")
         cpu = run_reference_cpu(kind, args.chunksize, budget_chunks_per_core=1, repeats=1)
         cpu_baseline = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     except Exception as e:  # the checker is optional for the headline number
