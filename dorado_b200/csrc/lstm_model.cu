@@ -974,6 +974,13 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             if (Np / 16 < 100 && Np % 8 == 0) nbr = 8;
             if (Np / 8 < 100 && Np % 4 == 0) nbr = 4;
         }
+        // tuning override: with several runners in flight, fatter CTAs (fewer SMs per kernel) let the recurrences of
+        // different batches run side by side instead of queueing for the same SMs (tools/exp_inflight.sh)
+        if (const char* e = std::getenv("B200_LSTM_CHUNKS_PER_CTA")) {
+            const int v = std::atoi(e);
+            if ((v == 4 || v == 8 || v == 16) && Np % v == 0) nbr = v;
+            else throw std::invalid_argument("B200_LSTM_CHUNKS_PER_CTA must be 4, 8 or 16 and divide the padded batch");
+        }
         if (C != 96 && C != 128 && C != 192 && C != 256 && C != 384 && C != 512) {
             throw Unsupported("lstm_size must be one of 96, 128, 192, 256, 384, 512");
         }
