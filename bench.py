@@ -332,6 +332,17 @@ def main():
                                             ((pk["tflops"] * 1e12) if work[k][0] == "tensor" else (pk["hbm_gbs"] * 1e9)), 4)}
                           for k in agg if k in work}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    # (profiles/*_traffic.json, written by tools/ncu_summary.py); null for workloads that were not captured
+    capture = {("fast", 512, "lstm_layer"): "r01_lstm_layer_fast_n512",
+               ("hac", 512, "lstm_rec"): "r01_lstm_cluster_hac_n512_tmem",
+               ("sup", 128, "fc1_swiglu_gemm"): "r01_gemm_sup_n128"}.get((kind, N, dom))
+    try:
+        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())[capture]
+        roof["traffic"] = tr["dram_bytes"]
+        roof["traffic_source"] = f"profiles/{capture}.ncu-rep ({tr['kernel']})"
+    except (OSError, KeyError, ValueError):
+        pass
     roof["peak_source"] = pk["source"]
     roof["ms_per_launch"] = dom_ms
     roof["launches_per_step"] = dom_cnt

@@ -5,6 +5,7 @@ Usage: python tools/ncu_summary.py [round-prefix]   (default r01)
 """
 import csv
 import io
+import json
 import pathlib
 import subprocess
 import sys
@@ -33,6 +34,7 @@ def main():
     prefix = sys.argv[1] if len(sys.argv) > 1 else "r01"
     out = [f"# {prefix}: one `ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 python bench.py "
            f"--steps 1 --warmup 1` capture per kernel; regenerate with tools/ncu_summary.py", ""]
+    traffic = {}  # bench.py's roofline.traffic: DRAM bytes per launch of each captured kernel, keyed by capture name
     for rep in sorted((ROOT / "profiles").glob(f"{prefix}_*.ncu-rep")):
         raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
@@ -51,8 +53,17 @@ def main():
         for k in KEEP:
             if k in col:
                 out.append(f"{k} [{units[col[k]]}] = {vals[col[k]]}")
+        try:
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(vals[col["dram__bytes_read.sum"]]) * mult[units[col["dram__bytes_read.sum"]]]
+            wr = float(vals[col["dram__bytes_write.sum"]]) * mult[units[col["dram__bytes_write.sum"]]]
+            traffic[rep.stem] = {"kernel": name.split("(")[0].split("::")[-1].strip(), "dram_read_bytes": rd,
+                                 "dram_write_bytes": wr, "dram_bytes": rd + wr}
+        except (KeyError, ValueError):
+            pass
         out.append("")
     (ROOT / "profiles" / f"{prefix}_ncu_full_summary.txt").write_text("\n".join(out))
+    (ROOT / "profiles" / f"{prefix}_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
     print("\n".join(out))
 
 
