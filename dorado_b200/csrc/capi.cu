@@ -159,6 +159,30 @@ int b200_runner_debug_read_input(b200_runner* r, int32_t num_chunks, uint16_t* i
     });
 }
 
+int b200_engine_runner_bytes(b200_engine* e, int32_t batch_size, int32_t chunk_size, uint64_t* bytes) {
+    return guarded([&] {
+        if (!e || !bytes) throw std::invalid_argument("b200_engine_runner_bytes: null argument");
+        *bytes = b200::runner_device_bytes(*reinterpret_cast<b200::Engine*>(e), batch_size, chunk_size);
+    });
+}
+
+int b200_engine_benchmark_batch_sizes(b200_engine* e, int32_t chunk_size, int32_t granularity, int32_t max_batch_size,
+                                      int32_t* batch_sizes, float* ms_per_chunk, int32_t capacity, int32_t* count) {
+    return guarded([&] {
+        if (!e || !count || capacity < 0) throw std::invalid_argument("b200_engine_benchmark_batch_sizes: bad argument");
+        *count = b200::benchmark_batch_sizes(*reinterpret_cast<b200::Engine*>(e), chunk_size, granularity, max_batch_size,
+                                             batch_sizes, ms_per_chunk, capacity);
+    });
+}
+
+int b200_select_batch_size(const int32_t* batch_sizes, const float* ms_per_chunk, int32_t count, int32_t max_batch_size,
+                           int32_t granularity, float time_penalty, int32_t* selected) {
+    return guarded([&] {
+        if (!selected) throw std::invalid_argument("b200_select_batch_size: null argument");
+        *selected = b200::select_batch_size(batch_sizes, ms_per_chunk, count, max_batch_size, granularity, time_penalty);
+    });
+}
+
 int b200_runner_upload(b200_runner* r) {
     return guarded([&] {
         if (!r) throw std::invalid_argument("b200_runner_upload: null argument");

@@ -159,6 +159,8 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
 
 Runner::~Runner() {
     cudaSetDevice(m_engine.device());
+    m_engine.arena_bytes -= (int64_t)m_arena.capacity();
+    if (m_h_raw) m_engine.arena_bytes -= (int64_t)((size_t)m_N * m_T_in * sizeof(int16_t) + (size_t)m_N * sizeof(RawSlot));
     for (auto& e : m_ev) {
         if (e) cudaEventDestroy(e);
     }
@@ -450,6 +452,71 @@ void Runner::debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst) {
     B200_CUDA(cudaSetDevice(m_engine.device()));
     B200_CUDA(cudaStreamSynchronize(m_stream));
     B200_CUDA(cudaMemcpy(dst, static_cast<unsigned char*>(m_d_ws) + offset, bytes, cudaMemcpyDeviceToHost));
+}
+
+// ---- batch-size selection ------------------------------------------------------------------------------------------
+// Same arithmetic as the Runner constructor's arena reservation (checked against b200_stats.arena_bytes on the GPU).
+size_t runner_device_bytes(Engine& engine, int batch_size, int chunk_size) {
+    const auto& d = engine.desc();
+    if (batch_size < 1 || chunk_size < d.stride || chunk_size % d.stride != 0) {
+        throw std::invalid_argument("runner_device_bytes: bad batch or chunk size");
+    }
+    const int T_out = chunk_size / d.stride;
+    const size_t in_bytes = (size_t)batch_size * chunk_size * sizeof(uint16_t);
+    const size_t out_bytes = nb_offset(batch_size, T_out) + (size_t)batch_size * sizeof(int32_t);
+    size_t bwd_b = 0, beam_b = 0;
+    decode_scratch_bytes(batch_size, T_out, d.state_len, &bwd_b, &beam_b);
+    const size_t scores_b = (size_t)batch_size * T_out * d.outsize * sizeof(__half);
+    const size_t ws_b = engine.model().workspace_bytes(batch_size, chunk_size);
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    return al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(out_bytes) + 4096;
+}
+
+int benchmark_batch_sizes(Engine& engine, int chunk_size, int granularity, int max_batch_size, int32_t* batch_sizes,
+                          float* ms_per_chunk, int capacity) {
+    if (granularity < 1 || max_batch_size < granularity) throw std::invalid_argument("benchmark_batch_sizes: bad range");
+    int count = 0;
+    for (int bs = granularity; bs <= max_batch_size; bs += granularity, ++count) {
+        float best = std::numeric_limits<float>::max();
+        {
+            Runner scratch(engine, bs, chunk_size);  // input stays zero: the kernels' time does not depend on the data
+            for (int i = 0; i < 2; ++i) {            // run twice to eliminate outliers (CudaCaller.cpp:536)
+                float total = 0, fwd = 0, dec = 0;
+                scratch.step_device(bs, 1, &total, &fwd, &dec);
+                best = std::min(best, total / (float)bs);
+            }
+        }
+        if (count < capacity) {
+            if (batch_sizes) batch_sizes[count] = bs;
+            if (ms_per_chunk) ms_per_chunk[count] = best;
+        }
+    }
+    return count;
+}
+
+int select_batch_size(const int32_t* batch_sizes, const float* ms_per_chunk, int count, int max_batch_size, int granularity,
+                      float time_penalty) {
+    if (!batch_sizes || !ms_per_chunk || count < 1) throw std::invalid_argument("select_batch_size: empty table");
+    if (!(time_penalty >= 0.0f)) throw std::invalid_argument("select_batch_size: negative time penalty");
+    // entries that beat every smaller batch size, in ascending batch-size order
+    std::vector<int> kept;
+    float best = std::numeric_limits<float>::max();
+    for (int i = 0; i < count; ++i) {
+        if (i > 0 && batch_sizes[i] <= batch_sizes[i - 1]) throw std::invalid_argument("select_batch_size: batch sizes must ascend");
+        if (ms_per_chunk[i] < best) {
+            best = ms_per_chunk[i];
+            kept.push_back(i);
+        }
+    }
+    if (kept.empty()) throw std::invalid_argument("select_batch_size: no finite timing");
+    const float threshold = best * (1.0f + time_penalty);
+    size_t last = 0;
+    while (last < kept.size() && !(ms_per_chunk[kept[last]] <= threshold)) ++last;  // first entry under the threshold
+    int selected = granularity;
+    for (size_t k = 0; k <= last && k < kept.size(); ++k) {
+        if (batch_sizes[kept[k]] <= max_batch_size) selected = batch_sizes[kept[k]];
+    }
+    return selected;
 }
 
 void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C, float clamp_val,

@@ -168,6 +168,13 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
 void test_gemm_host(int device, const uint16_t* a, const uint16_t* b, const float* bias, int M, int N, int K,
                     int activation, uint16_t* c);
 
+// batch-size selection (CudaCaller::determine_batch_dims)
+size_t runner_device_bytes(Engine& engine, int batch_size, int chunk_size);
+int benchmark_batch_sizes(Engine& engine, int chunk_size, int granularity, int max_batch_size, int32_t* batch_sizes,
+                          float* ms_per_chunk, int capacity);
+int select_batch_size(const int32_t* batch_sizes, const float* ms_per_chunk, int count, int max_batch_size, int granularity,
+                      float time_penalty);
+
 float log_beam_cut_of(float beam_cut);
 void require_sm100(int device);
 

@@ -55,6 +55,22 @@ class B200Caller:
         self._keep = None  # the engine copied everything to the device
         self._terminated = False
 
+    def runner_bytes(self, batch_size: int, chunk_size: int) -> int:
+        """Device bytes a runner of this shape allocates (exact; CudaCaller::calculate_memory_requirements estimates it)."""
+        n = C.c_uint64()
+        L.check(L.load_library().b200_engine_runner_bytes(self.handle, batch_size, chunk_size, C.byref(n)))
+        return int(n.value)
+
+    def benchmark_batch_sizes(self, chunk_size: int, granularity: int, max_batch_size: int):
+        """determine_batch_dims' timing loop (CudaCaller.cpp:530-557): [(batch_size, ms per chunk), ...]."""
+        cap = max(1, max_batch_size // max(1, granularity))
+        bs = (C.c_int32 * cap)()
+        ms = (C.c_float * cap)()
+        n = C.c_int32()
+        L.check(L.load_library().b200_engine_benchmark_batch_sizes(self.handle, chunk_size, granularity, max_batch_size, bs, ms, cap,
+                                                            C.byref(n)))
+        return [(int(bs[i]), float(ms[i])) for i in range(min(cap, n.value))]
+
     def stats(self) -> dict:
         s = L.Stats()
         L.check(L.load_library().b200_engine_get_stats(self.handle, C.byref(s)))

@@ -211,6 +211,35 @@ B200_API int b200_stitch_chunks(const b200_called_chunk* chunks,
                                 uint64_t* n_moves_out,
                                 uint64_t* n_bases_out);
 
+/* ---- Batch-size selection (CudaCaller::determine_batch_dims, CudaCaller.cpp:372-632) --------
+ *
+ * Device bytes one runner of (batch_size, chunk_size) allocates: exact, from the launch plan.  (The reference estimates
+ * it from per-model tables of bytes per chunk-timestep, CudaCaller::calculate_memory_requirements, :323-370.) */
+B200_API int b200_engine_runner_bytes(b200_engine* engine, int32_t batch_size, int32_t chunk_size, uint64_t* bytes);
+/* The benchmark loop of determine_batch_dims (:530-557): for batch sizes granularity, 2*granularity, ... <=
+ * max_batch_size, run the path twice on a scratch runner and keep the smaller time per chunk.  The reference times
+ * the network forward only; here the decode runs on the device too, so forward + decode is timed.  Writes at most
+ * `capacity` entries and reports the full count. */
+B200_API int b200_engine_benchmark_batch_sizes(b200_engine* engine,
+                                               int32_t chunk_size,
+                                               int32_t granularity,
+                                               int32_t max_batch_size,
+                                               int32_t* batch_sizes,
+                                               float* ms_per_chunk,
+                                               int32_t capacity,
+                                               int32_t* count);
+/* The selection rule of determine_batch_dims (:487-631) on such a table (ascending batch sizes): keep the entries that
+ * improve on every smaller batch size, take the first of them within (1 + time_penalty) of the best time, and return
+ * the largest kept batch size up to that entry that does not exceed max_batch_size (the memory cap); `granularity` if
+ * none fits.  Pure host logic. */
+B200_API int b200_select_batch_size(const int32_t* batch_sizes,
+                                    const float* ms_per_chunk,
+                                    int32_t count,
+                                    int32_t max_batch_size,
+                                    int32_t granularity,
+                                    float time_penalty,
+                                    int32_t* selected);
+
 /* Stage-level entry points so scores and decode can be parity-checked independently (host buffers). */
 B200_API int b200_runner_forward_scores(b200_runner* runner, int32_t num_chunks, uint16_t* scores_out /* [n,t_out,outsize] fp16 */);
 B200_API int b200_decode_scores(int32_t device,

@@ -182,3 +182,49 @@ def test_frontend_golden_fixture_matches_oracle():
             assert (got.view(np.uint16) == g["input_rows_f16_bits"][row]).all()
             row += 1
     assert row == g["input_rows_f16_bits"].shape[0]
+
+
+# ---- batch-size selection rule (CudaCaller::determine_batch_dims, CudaCaller.cpp:487-631) -----------------------------
+def _select_like_reference(table, max_size, granularity, penalty):
+    """Restatement of the reference's loop: `times_and_batch_sizes` keeps entries that improve on best_time (:585-589),
+    the first entry under best * (1 + penalty) bounds the search (:604-607), the last kept batch size <= max_size up to it
+    wins (:619-631), starting from the granularity (:405)."""
+    best, kept = float("inf"), []
+    for bs, t in table:
+        if t < best:
+            best = t
+            kept.append((t, bs))
+    thr = np.float32(best) * (np.float32(1) + np.float32(penalty))
+    idx = next(i for i, (t, _) in enumerate(kept) if np.float32(t) <= thr)
+    final = granularity
+    for t, bs in kept[: idx + 1]:
+        if bs <= max_size:
+            final = bs
+    return final
+
+
+def test_select_batch_size_matches_reference_rule():
+    from dorado_b200.batching import select_batch_size
+    t = [(64, 1.0), (128, 0.6), (192, 0.65), (256, 0.5), (320, 0.49), (384, 0.495)]
+    assert select_batch_size(t, 10240, 64, 0.0) == 320          # the best time itself
+    assert select_batch_size(t, 10240, 64, 0.05) == 256         # first entry within 5 % of the best
+    assert select_batch_size(t, 200, 64, 0.0) == 128            # memory cap
+    assert select_batch_size(t, 32, 64, 0.0) == 64              # nothing fits: the granularity
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n = int(rng.integers(1, 40))
+        g = int(rng.choice([16, 32, 64]))
+        table = [(g * (i + 1), float(np.float32(rng.uniform(0.05, 2.0) / (1 + 0.1 * i)))) for i in range(n)]
+        cap = int(rng.integers(1, g * (n + 2)))
+        pen = float(rng.choice([0.0, 0.05, 0.1, 0.5]))
+        assert select_batch_size(table, cap, g, pen) == _select_like_reference(table, cap, g, pen)
+
+
+def test_select_batch_size_rejects_bad_tables():
+    from dorado_b200.batching import select_batch_size
+    with pytest.raises(L.B200Error):
+        select_batch_size([], 512, 64, 0.0)
+    with pytest.raises(L.B200Error):
+        select_batch_size([(128, 1.0), (64, 0.5)], 512, 64, 0.0)   # not ascending
+    with pytest.raises(L.B200Error):
+        select_batch_size([(64, 1.0)], 512, 64, -0.1)

@@ -115,3 +115,23 @@ def test_raw_chunk_argument_errors():
         r.accept_raw_chunk(16, raw, 0, 0.0, 1.0)      # slot out of range
     with pytest.raises(L.B200Error):
         r.accept_raw_chunk(0, np.zeros(0, np.int16), 0, 0.0, 1.0)
+
+
+def test_runner_bytes_and_batch_size_selection():
+    """b200_engine_runner_bytes is exactly what a runner allocates; the determine_batch_dims counterpart returns a batch
+    size from its own timing table that respects the memory cap."""
+    from dorado_b200.batching import determine_batch_size, max_batch_size_for_memory, select_batch_size
+    from dorado_b200.runner import B200ModelRunner
+    cfg, caller = _caller("fast")
+    before = caller.stats()["arena_bytes"]
+    r = B200ModelRunner(caller, 64, 1200)
+    assert caller.stats()["arena_bytes"] - before == caller.runner_bytes(64, 1200)
+    r.close()
+    assert caller.stats()["arena_bytes"] == before
+    assert caller.runner_bytes(128, 1200) > caller.runner_bytes(64, 1200)
+    limit = 3 * caller.runner_bytes(128, 6000)
+    cap = max_batch_size_for_memory(caller, 6000, limit, 64, num_runners=2)
+    assert cap % 64 == 0 and caller.runner_bytes(cap, 6000) * 2 <= limit < caller.runner_bytes(cap + 64, 6000) * 2
+    chosen, table = determine_batch_size(caller, 6000, limit, 64, time_penalty=0.05, num_runners=2, benchmark_limit=256)
+    assert [b for b, _ in table] == list(range(64, min(cap, 256) + 1, 64)) and all(t > 0 for _, t in table)
+    assert chosen == select_batch_size(table, cap, 64, 0.05) and 64 <= chosen <= cap
