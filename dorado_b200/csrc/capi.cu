@@ -133,6 +133,14 @@ int b200_generate_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t str
     });
 }
 
+int b200_generate_variable_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap,
+                                  uint64_t* intervals, uint64_t capacity, uint64_t* count) {
+    return guarded([&] {
+        if (!count || (!intervals && capacity)) throw std::invalid_argument("b200_generate_variable_chunks: null argument");
+        *count = b200::generate_variable_chunks(num_samples, chunk_size, stride, overlap, intervals, capacity);
+    });
+}
+
 int b200_stitch_chunks(const b200_called_chunk* chunks, uint64_t n_chunks, uint64_t raw_samples, int32_t stride,
                        uint8_t* moves_out, char* sequence_out, char* qstring_out, uint64_t* n_moves_out,
                        uint64_t* n_bases_out) {

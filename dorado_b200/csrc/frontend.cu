@@ -41,6 +41,41 @@ uint64_t generate_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t str
     return count;
 }
 
+// ---- utils::generate_variable_chunks (dorado/read_pipeline/base/chunk.cpp:49-113) --------------------------------
+// As few chunks as the fixed chunking would need, but of near-equal length: the read plus the (count - 1) overlaps is
+// split evenly (the first `total % count` chunks get one extra sample), then every interior start is rounded up and
+// every interior end rounded down to a stride multiple.
+uint64_t generate_variable_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap,
+                                  uint64_t* intervals, uint64_t capacity) {
+    if (num_samples == 0) throw std::invalid_argument("generate_variable_chunks: empty read");
+    if (stride == 0) throw std::invalid_argument("generate_variable_chunks: invalid stride 0");
+    if (chunk_size == 0 || chunk_size % stride != 0 || chunk_size == stride || chunk_size <= overlap) {
+        throw std::invalid_argument("generate_variable_chunks: invalid chunk size " + std::to_string(chunk_size) +
+                                    " with overlap " + std::to_string(overlap) + " and stride " + std::to_string(stride));
+    }
+    if (overlap % stride != 0 || (stride != 1 && overlap == 0)) {
+        throw std::invalid_argument("generate_variable_chunks: invalid overlap " + std::to_string(overlap) + " with stride " +
+                                    std::to_string(stride));
+    }
+    const uint64_t step = chunk_size - overlap;
+    const uint64_t count = 1 + (num_samples > chunk_size ? (num_samples - chunk_size + step - 1) / step : 0);
+    const uint64_t total = num_samples + (count - 1) * overlap;
+    const uint64_t base = total / count, longer = total % count;
+    uint64_t start = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint64_t end = start + base + (i < longer ? 1 : 0);
+        uint64_t first = start, second = end;
+        if (i > 0) first = (first + stride - 1) / stride * stride;
+        if (i + 1 < count) second -= second % stride;
+        if (i < capacity && intervals) {
+            intervals[2 * i] = first;
+            intervals[2 * i + 1] = second;
+        }
+        start = end - overlap;
+    }
+    return count;
+}
+
 // ---- utils::stitch_chunks (dorado/read_pipeline/base/stitch.cpp:12-96) --------------------------------------------
 // Each overlap (in stride units) is cut at its midpoint: the earlier chunk loses the last floor(ovl / 2) blocks, the
 // later one the first ovl - floor(ovl / 2).  Bases follow the moves: a chunk contributes the bases whose move lies in

@@ -17,6 +17,8 @@ struct RawSlot {
 
 uint64_t generate_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap,
                          uint64_t* offsets, uint64_t capacity);
+uint64_t generate_variable_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap,
+                                  uint64_t* intervals, uint64_t capacity);
 void stitch_chunks(const b200_called_chunk* chunks, uint64_t n_chunks, uint64_t raw_samples, int stride,
                    uint8_t* moves_out, char* seq_out, char* qstr_out, uint64_t* n_moves_out, uint64_t* n_bases_out);
 void launch_raw_chunk_gather(const int16_t* staged, const RawSlot* slots, __half* input, int num_chunks, int T_in,

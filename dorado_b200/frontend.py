@@ -28,6 +28,16 @@ def generate_chunks(num_samples: int, chunk_size: int, stride: int, overlap: int
     return [int(buf[i]) for i in range(n.value)]
 
 
+def generate_variable_chunks(num_samples: int, chunk_size: int, stride: int, overlap: int) -> List[Tuple[int, int]]:
+    """[first, second) intervals of the variable-chunk-size mode (utils::generate_variable_chunks, chunk.cpp:49-113)."""
+    lib = L.load_library()
+    n = C.c_uint64()
+    L.check(lib.b200_generate_variable_chunks(num_samples, chunk_size, stride, overlap, None, 0, C.byref(n)))
+    buf = (C.c_uint64 * (2 * n.value))()
+    L.check(lib.b200_generate_variable_chunks(num_samples, chunk_size, stride, overlap, buf, n.value, C.byref(n)))
+    return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n.value)]
+
+
 def stitch_chunks(chunks: Sequence[Tuple[int, int, np.ndarray, str, str]], raw_samples: int, stride: int):
     """chunks: (input_offset, raw_chunk_size, moves uint8 [T_out], sequence, qstring) per called chunk, in read order.
     Returns (sequence, qstring, moves) of the stitched read."""

@@ -82,7 +82,7 @@ EXPORTS = [
     "b200_runner_upload", "b200_runner_step_device", "b200_runners_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_debug_read_workspace", "b200_decode_scores",
     "b200_test_gemm", "b200_generate_chunks", "b200_stitch_chunks", "b200_runner_accept_raw_chunk",
     "b200_runner_debug_read_input", "b200_engine_runner_bytes", "b200_engine_benchmark_batch_sizes",
-    "b200_select_batch_size",
+    "b200_select_batch_size", "b200_generate_variable_chunks",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def load_library() -> C.CDLL:
     lib.b200_test_gemm.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, vp]
     u64 = C.c_uint64
     lib.b200_generate_chunks.argtypes = [u64, u64, u64, u64, C.POINTER(u64), u64, C.POINTER(u64)]
+    lib.b200_generate_variable_chunks.argtypes = [u64, u64, u64, u64, C.POINTER(u64), u64, C.POINTER(u64)]
     lib.b200_stitch_chunks.argtypes = [C.POINTER(CalledChunk), u64, u64, i32, vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]
     lib.b200_runner_accept_raw_chunk.argtypes = [vp, i32, C.POINTER(RawChunk)]
     lib.b200_runner_debug_read_input.argtypes = [vp, i32, vp]

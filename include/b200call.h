@@ -169,6 +169,19 @@ B200_API int b200_generate_chunks(uint64_t num_samples,
                                   uint64_t capacity,
                                   uint64_t* count);
 
+/* utils::generate_variable_chunks (dorado/read_pipeline/base/chunk.cpp:49-113), the chunking of the reference's
+ * variable-chunk-size mode: near-equal chunks <= chunk_size whose interior boundaries lie on stride multiples.  Writes at
+ * most `capacity` (first, second) pairs into intervals[2 * i], intervals[2 * i + 1] and always reports the full count.
+ * Invalid arguments (those the reference throws on, incl. chunk_size == stride and overlap == 0 with stride != 1)
+ * return B200_ERR_INVALID.  (The ragged batch layout that consumes these intervals is not implemented yet.) */
+B200_API int b200_generate_variable_chunks(uint64_t num_samples,
+                                           uint64_t chunk_size,
+                                           uint64_t stride,
+                                           uint64_t overlap,
+                                           uint64_t* intervals,
+                                           uint64_t capacity,
+                                           uint64_t* count);
+
 /* One chunk of a read given as RAW int16 signal: the device does what ScalerNode + BasecallerNode do on the host
  * in the reference --  x' = fp16((float(x) - shift) / scale)  (utils::shift_scale_tensor_i16_to_f16_inplace,
  * dorado/torch_utils/tensor_utils.cpp:100-143, called at read_pipeline/nodes/ScalerNode.cpp:226-229), the slice

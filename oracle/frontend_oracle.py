@@ -54,6 +54,32 @@ def generate_chunks(num_samples: int, chunk_size: int, stride: int, overlap: int
     return offsets
 
 
+def generate_variable_chunks(num_samples: int, chunk_size: int, stride: int, overlap: int):
+    """dorado/read_pipeline/base/chunk.cpp:49-113"""
+    import math
+    if num_samples == 0:
+        raise RuntimeError("empty read")
+    if stride == 0:
+        raise ValueError("invalid stride")
+    if chunk_size == 0 or chunk_size % stride or chunk_size == stride or chunk_size <= overlap:
+        raise ValueError("invalid chunk size")
+    if overlap % stride or (stride != 1 and overlap == 0):
+        raise ValueError("invalid overlap")
+    num_chunks = 1 + (math.ceil((num_samples - chunk_size) / float(chunk_size - overlap)) if num_samples > chunk_size else 0)
+    with_overlaps = num_samples + (num_chunks - 1) * overlap
+    longer, adjusted = with_overlaps % num_chunks, with_overlaps // num_chunks
+    iv, start = [], 0
+    for i in range(num_chunks):
+        iv.append([start, start + adjusted + (1 if i < longer else 0)])
+        start = iv[-1][1] - overlap
+    for i in range(1, num_chunks):
+        if iv[i][0] % stride:
+            iv[i][0] += stride - iv[i][0] % stride
+    for i in range(num_chunks - 1):
+        iv[i][1] -= iv[i][1] % stride
+    return [tuple(x) for x in iv]
+
+
 def stitch_chunks(chunks, raw_samples: int, stride: int):
     """chunks: list of (input_offset, raw_chunk_size, moves, sequence, qstring); returns (sequence, qstring, moves)."""
     start_pos, mid_front = 0, 0

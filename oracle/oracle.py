@@ -140,6 +140,8 @@ class Reference:
         _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
         lib.ref_generate_chunks.argtypes = [u64, u64, u64, u64, _u64p, u64]
         lib.ref_generate_chunks.restype = C.c_long
+        lib.ref_generate_variable_chunks.argtypes = [u64, u64, u64, u64, _u64p, u64]
+        lib.ref_generate_variable_chunks.restype = C.c_long
         lib.ref_make_chunk_input.argtypes = [np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), u64, u64, u64,
                                              C.c_float, C.c_float, _u16p]
         lib.ref_stitch_chunks.argtypes = [u64, _u64p, _u64p, _u8p, _u64p, C.c_char_p, C.c_char_p, _u64p, u64, C.c_int,
@@ -161,6 +163,15 @@ class Reference:
         if n < 0:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return [int(v) for v in out[:n]]
+
+    def generate_variable_chunks(self, num_samples, chunk_size, stride, overlap):
+        """utils::generate_variable_chunks -> [(first, second), ...]; raises RuntimeError where the reference throws."""
+        cap = 1 << 16
+        out = np.zeros(2 * cap, np.uint64)
+        n = self.lib.ref_generate_variable_chunks(num_samples, chunk_size, stride, overlap, out, cap)
+        if n < 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n)]
 
     def make_chunk_input(self, raw, input_offset, chunk_size, shift, scale):
         """ScalerNode scaling + BasecallerNode slice/repeat-pad of one chunk -> fp16 [chunk_size]."""

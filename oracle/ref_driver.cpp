@@ -253,6 +253,21 @@ long ref_generate_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t str
     return n;
 }
 
+// utils::generate_variable_chunks (read_pipeline/base/chunk.cpp:49-113): [first, second) intervals, flattened.
+long ref_generate_variable_chunks(uint64_t num_samples, uint64_t chunk_size, uint64_t stride, uint64_t overlap, uint64_t* out,
+                                  uint64_t cap) {
+    long n = -1;
+    guarded([&] {
+        const auto v = dorado::utils::generate_variable_chunks(num_samples, chunk_size, stride, overlap);
+        for (size_t i = 0; i < v.size() && i < cap; ++i) {
+            out[2 * i] = v[i].first;
+            out[2 * i + 1] = v[i].second;
+        }
+        n = long(v.size());
+    });
+    return n;
+}
+
 // What the model input row of one chunk holds in the reference: ScalerNode scales the whole read in place
 // (shift_scale_tensor_i16_to_f16_inplace, ScalerNode.cpp:226-229), BasecallerNode slices
 // raw_data[offset : offset + chunk_size] (clamped at the read end) and repeat-pads a short slice with

@@ -228,3 +228,32 @@ def test_select_batch_size_rejects_bad_tables():
         select_batch_size([(128, 1.0), (64, 0.5)], 512, 64, 0.0)   # not ascending
     with pytest.raises(L.B200Error):
         select_batch_size([(64, 1.0)], 512, 64, -0.1)
+
+
+# ---- generate_variable_chunks (first piece of SURVEY 8f row 1) -------------------------------------------------------
+def test_generate_variable_chunks_like_ChunkTest(reference):
+    from dorado_b200.frontend import generate_variable_chunks
+    for args in [(0, 9996, 6, 498), (12345, 0, 6, 498), (12345, 9996, 0, 498), (12345, 9996, 10, 498), (12345, 6, 6, 498),
+                 (12345, 9996, 7, 498), (12345, 9996, 7, 0), (12345, 9996, 6, 9996), (12345, 9996, 6, 9997)]:
+        with pytest.raises(L.B200Error):
+            generate_variable_chunks(*args)
+        with pytest.raises(RuntimeError):
+            reference.generate_variable_chunks(*args)
+    golden = [((9996 // 2, 9996, 6, 498), [(0, 4998)]), ((9996, 9996, 6, 498), [(0, 9996)]),
+              ((9996 + 1, 9996, 6, 498), [(0, 5244), (4752, 9997)]),
+              ((9996 + 9996 // 2, 9996, 6, 498), [(0, 7746), (7248, 14994)]),
+              ((2 * 9996 + 9996 // 2, 9996, 1, 0), [(0, 8330), (8330, 16660), (16660, 24990)]),
+              ((3 * 9996, 9996, 6, 498), [(0, 7866), (7374, 15240), (14748, 22614), (22122, 29988)])]
+    for args, want in golden:
+        assert generate_variable_chunks(*args) == want == fo.generate_variable_chunks(*args) == reference.generate_variable_chunks(*args)
+    rng = np.random.default_rng(42)
+    for chunk_size, stride, overlap in [(9996, 6, 498), (9996, 7, 497), (9996, 12, 492), (9996, 17, 510), (555, 5, 25),
+                                        (83, 1, 13), (123, 1, 0)]:
+        for n in rng.integers(1024, 2097152, 16):
+            iv = generate_variable_chunks(int(n), chunk_size, stride, overlap)
+            assert iv == reference.generate_variable_chunks(int(n), chunk_size, stride, overlap)
+            assert iv == fo.generate_variable_chunks(int(n), chunk_size, stride, overlap)
+            assert iv[0][0] == 0 and iv[-1][1] == n
+            assert all(a % stride == 0 for a, _ in iv[1:]) and all(b % stride == 0 for _, b in iv[:-1])
+            assert all(0 < b - a <= chunk_size for a, b in iv)
+            assert all(iv[i - 1][1] - iv[i][0] <= overlap for i in range(1, len(iv)))
