@@ -748,12 +748,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
     }
     {
         const size_t smem = traceback_smem_bytes(a.T);
-        static bool attr_set = false;
-        if (!attr_set && smem > 48 * 1024) {
-            B200_CUDA(cudaFuncSetAttribute(crf_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-            attr_set = true;
-        }
+        if (smem > 48 * 1024) ensure_dynamic_smem(crf_traceback_kernel, 200 * 1024);
         const int grid = (a.N + kTbWarps - 1) / kTbWarps;
         crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.q_scale, a.q_shift, a.moves,
                                                                     a.sequence, a.qstring, a.n_bases);

@@ -6,9 +6,12 @@
 
 #include "decode.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <set>
+#include <utility>
 #include <vector>
 
 namespace b200 {
@@ -30,6 +33,17 @@ void* Arena::take(size_t bytes) {
     void* p = m_base + m_off;
     m_off += aligned;
     return p;
+}
+
+void ensure_dynamic_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, kernel})) return;
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({dev, kernel});
 }
 
 // byte offset of the int32 n_bases array behind the three [N][T] byte planes
@@ -374,8 +388,10 @@ void pipelined_steps(Runner** rs, int R, int num_chunks, int iters, float* total
             if (rs[q] == rs[r]) throw std::invalid_argument("pipelined_steps: the same runner twice");
         }
     }
+    std::vector<Runner*> order(rs, rs + R);
+    std::sort(order.begin(), order.end());  // one global lock order, whatever order the callers list the runners in
     std::vector<std::unique_lock<std::mutex>> locks;
-    for (int r = 0; r < R; ++r) locks.emplace_back(rs[r]->m_mutex);
+    for (Runner* r : order) locks.emplace_back(r->m_mutex);
     Runner& r0 = *rs[0];
     B200_CUDA(cudaSetDevice(r0.m_engine.device()));
     B200_CUDA(cudaEventRecord(r0.m_ev[0], r0.m_stream));

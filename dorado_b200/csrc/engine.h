@@ -175,6 +175,14 @@ int benchmark_batch_sizes(Engine& engine, int chunk_size, int granularity, int m
 int select_batch_size(const int32_t* batch_sizes, const float* ms_per_chunk, int count, int max_batch_size, int granularity,
                       float time_penalty);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and per function: set it once for each (device, kernel)
+// pair, from whichever thread gets there first (several runners, and in dorado several devices, share one process).
+void ensure_dynamic_smem(const void* kernel, int bytes);
+template <typename K>
+inline void ensure_dynamic_smem(K* kernel, int bytes) {
+    ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 float log_beam_cut_of(float beam_cut);
 void require_sm100(int device);
 

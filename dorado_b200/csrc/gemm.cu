@@ -351,11 +351,7 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
     p.tma_a = make_tmap_3d(d.a, (uint64_t)(d.a_inner > 0 ? d.a_inner : d.K), (uint64_t)d.rows_per_batch, (uint64_t)d.batches, (uint64_t)d.a_row_stride * 2,
                            batch_stride, BK, BM, 1);
     p.tma_w = make_tmap_2d(d.w, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)d.K * 2, BK, (uint32_t)p.bn);
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    ensure_dynamic_smem(gemm_f16_tcgen05_kernel, 227 * 1024);
     return p;
 }
 

@@ -1068,11 +1068,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
 
 template <int C, int NBR>
 static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<C, NBR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    ensure_dynamic_smem(lstm_layer_kernel<C, NBR>, 227 * 1024);
     lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
                                                                                         pl.lstm_p[l]);
 }
@@ -1080,11 +1076,7 @@ static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
 template <int C, int CL, int UNC>
 static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
     using Cfg = ClusterCfg<C, CL, UNC>;
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<C, CL, UNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr = true;
-    }
+    ensure_dynamic_smem(lstm_cluster_kernel<C, CL, UNC>, (int)Cfg::SMEM);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)pl.lstm_grid, 1, 1);
     cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
