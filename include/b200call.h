@@ -5,7 +5,7 @@
  * include/B200ModelRunner.h implements that interface on top of the entry points below, replacing
  *   CudaModelRunner            dorado/basecall/CudaModelRunner.cpp:13-77
  *   CudaCaller                 dorado/basecall/CudaCaller.cpp:149-720
- *   CRFModel / TxModel (CUDA)  dorado/basecall/model/CRFModel.cpp:69-115, dorado/nn/*.cpp run_koi paths
+ *   CRFModel / TxModel (CUDA)  dorado/basecall/model/CRFModel.cpp:69-115, the run_koi paths under dorado/nn
  *   CUDADecoder                dorado/basecall/decode/CUDADecoder.cpp:17-173
  *   Koi                        cmake/Koi.cmake (closed libkoi.a)
  * No C++ types, exceptions or torch types cross this boundary: plain pointers and sizes only.

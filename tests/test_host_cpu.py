@@ -169,3 +169,17 @@ def test_adapter_header_compiles_against_reference_headers():
           ["-isystem", str(t / "include"), "-isystem", str(t / "include/torch/csrc/api/include"), str(src)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_c_abi_from_a_plain_c_client(tmp_path):
+    """include/b200call.h is a C header: a C11 program built with gcc links libb200call.so, exercises the host-side entry
+    points (golden vectors of the reference's ChunkTest) and sees the device entry points fail loudly without a GPU."""
+    exe = tmp_path / "abi_smoke"
+    lib_dir = ROOT / "dorado_b200"
+    cmd = ["/usr/bin/gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}",
+           str(ROOT / "tests" / "data" / "abi_smoke.c"), "-o", str(exe), f"-L{lib_dir}", "-lb200call",
+           f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi_smoke ok" in r.stdout, r.stdout + r.stderr
