@@ -8,7 +8,7 @@
  * div (all correctly rounded on x86-64 and on sm_100a) in a fixed order.  The CUDA kernels
  * (dorado_b200/csrc/decode.cu) and the CPU oracle (oracle/crf_oracle.c) both include this file, so
  * the two produce the same bits by construction.  Accuracy versus libm: <= 2 ulp over the ranges
- * the decoder uses (tests/test_oracle_math.py).
+ * the decoder uses (tests/test_host_cpu.py::test_numerics_contract_accuracy).
  *
  * Compile rules: C side with -ffp-contract=off (oracle/Makefile); CUDA side uses the explicit
  * __f*_rn intrinsics, which nvcc never contracts.
