@@ -333,7 +333,7 @@ b200_result Runner::call_chunks(int num_chunks) {
     B200_CUDA(cudaEventElapsedTime(&md, m_ev[1], m_ev[2]));
     B200_CUDA(cudaEventElapsedTime(&d2h, m_ev[2], m_ev[3]));
     {
-        std::lock_guard<std::mutex> sl(m_engine.gpu_mutex());
+        std::lock_guard<std::mutex> sl(m_engine.stats_mutex());
         m_engine.h2d_ms += h2d;
         m_engine.model_decode_ms += md;
         m_engine.d2h_ms += d2h;

@@ -84,20 +84,20 @@ public:
     int device() const { return m_device; }
     cudaStream_t stream() const { return m_stream; }
     Model& model() { return *m_model; }
-    std::mutex& gpu_mutex() { return m_gpu_mutex; }  // guards the timing totals below
+    std::mutex& stats_mutex() { return m_stats_mutex; }  // guards the timing totals below
     b200_stats stats() const;
 
     std::atomic<int64_t> batches_called{0};
     std::atomic<int64_t> gpu_launches{0};
     std::atomic<int64_t> arena_bytes{0};
-    double model_decode_ms = 0, h2d_ms = 0, d2h_ms = 0;  // guarded by gpu_mutex
+    double model_decode_ms = 0, h2d_ms = 0, d2h_ms = 0;  // guarded by stats_mutex
 
 private:
     b200_model_desc m_desc;
     int m_device;
     cudaStream_t m_stream = nullptr;
     std::unique_ptr<Model> m_model;
-    std::mutex m_gpu_mutex;
+    std::mutex m_stats_mutex;
 };
 
 class Runner;

@@ -145,7 +145,7 @@ B200_API int b200_runner_call_chunks(b200_runner* runner, int32_t num_chunks, b2
 
 /* Measurement hooks (bench.py): run `iters` forward+decode passes over the batch already resident on
  * the device (uploaded by the last call_chunks / upload) and report device time from CUDA events on the
- * engine's stream; decode_ms/forward_ms may be NULL. */
+ * runner's stream; decode_ms/forward_ms may be NULL. */
 B200_API int b200_runner_upload(b200_runner* runner);
 B200_API int b200_runner_step_device(b200_runner* runner, int32_t num_chunks, int32_t iters, float* total_ms,
                                      float* forward_ms, float* decode_ms);
