@@ -7,7 +7,8 @@
 // Contract kept:
 //   accept_chunk(idx, [C_in, chunk_size] half/float tensor)  -> copy into batch slot idx
 //   call_chunks(n) -> exactly n DecodedChunk{sequence, qstring, moves}; moves.size() == chunk_size / stride;
-//                     blocking; runners sharing a caller are serialised per GPU; errors -> std::runtime_error
+//                     blocking; runners sharing a caller run concurrently on their own streams (one thread per runner);
+//                     errors -> std::runtime_error
 //   config(), chunk_size(), batch_size(), batch_timeouts_ms(), is_low_latency(), terminate(), restart(),
 //   get_name() (unique), sample_stats() with the reference's keys "batches_called", "model_decode_ms".
 #pragma once
