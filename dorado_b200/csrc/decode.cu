@@ -13,7 +13,7 @@
 // Data layout in HBM (per batch of N chunks, T blocks, S = 4^state_len states, C = 4S):
 //   scores  fp16  [N][T][C]        read twice (once per scan direction), coalesced 32 B per thread
 //   bwd     fp32  [N][T+1][S]      written by kernel 1, read once by kernel 2
-//   beam    8 B   [N][T][32]       {state:16, prev:8, stay:8, block_prob:f32} per kept element
+//   beam    8 B   [N][T][32]       {state:16, prev:8, stay:8, posterior:f32 (before the ^0.4 of the qscore)} per kept element
 //   out     u8    moves/seq/qstr [N][T], n_bases i32 [N]
 // Thread mapping: one thread per state in both scans (two states per thread for S = 1024 in the forward
 // kernel); the forward kernel adds one beam-search warp per chunk that runs one block behind the scan.

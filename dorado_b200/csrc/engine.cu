@@ -1,7 +1,8 @@
 // Engine / Runner: see engine.h.  Mirrors the control flow of the reference's CudaCaller::call_chunks
 // (dorado/basecall/CudaCaller.cpp:224-271): H2D copy, forward, decode part 1 on the GPU, D2H of the
-// 3 x N x T byte result -- here without libtorch, Koi or a separate GPU worker thread (the per-device
-// mutex gives the same one-batch-in-flight FIFO behaviour as the reference's task queue).
+// 3 x N x T byte result -- here without libtorch, Koi or a separate GPU worker thread.  Every runner has its own stream,
+// so the runners of a device overlap (one batch's decode under the next batch's network) instead of queueing behind
+// the reference's per-device task queue (CudaCaller.cpp:204-214).
 #include "engine.h"
 
 #include "decode.h"

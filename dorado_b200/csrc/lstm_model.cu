@@ -3,7 +3,8 @@
 // Replaces, for the CUDA path of dorado/basecall/model/CRFModel.cpp:69-115:
 //   ConvStack layers 1,2   host_convolution_f16              dorado/nn/ConvStack.cpp:216-232
 //   ConvStack layer 3      host_linear "cutlass conv"        dorado/nn/ConvStack.cpp:236-275  -> gemm.cu
-//   LSTMStack              host_cutlass_lstm/host_small_lstm dorado/nn/LSTMStack.cpp:127-238 -> lstm_layer_kernel
+//   LSTMStack              host_cutlass_lstm/host_small_lstm dorado/nn/LSTMStack.cpp:127-238 -> lstm_layer_kernel (C = 96),
+//                                                                                         gx GEMM + lstm_cluster_kernel (C = 192, 384)
 //   LinearCRF              host_linear                       dorado/nn/CRFModules.cpp:49-122   -> gemm.cu
 // Semantics are those of the CPU modules (ConvStack.cpp:146-163, LSTMStack.cpp:29-41, CRFModules.cpp:24-34).
 //
