@@ -26,7 +26,7 @@ NOTES = {
                        "no GPU budget was left to re-capture",
     "crf_fwd_beam_fast": "captured at 25d6e20 (decode v2); the final kernel (35b17a9: redux max, deferred pow) takes 2.80 ms "
                          "(r01_launches_fast_n512.csv)",
-    "crf_bwd_scan_fast": "captured at 25d6e20 together with the forward kernel; the backward scan has not changed since",
+    "crf_bwd_scan_fast": "captured at 25d6e20 together with the forward kernel; the final backward scan takes 0.89 ms (r01_launches_fast_n512.csv)",
     "lstm_cluster_hac_n512_tmem": "final kernel (43cb863): W_hh in tensor memory, 32 chunks per cluster, 16 clusters",
 }
 
