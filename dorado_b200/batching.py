@@ -13,6 +13,12 @@ from typing import List, Sequence, Tuple
 from . import lib as L
 
 
+def batch_size_granularity(cfg) -> int:
+    """CudaCaller::get_batch_size_granularity (dorado/basecall/include/basecall/CudaCaller.h:60-63): 32 for transformer
+    models, 64 for LSTM models -- both are multiples of what the kernels here need (16 for fast, 32 for hac, 1 for sup)."""
+    return 32 if cfg.is_tx_model else 64
+
+
 def select_batch_size(table: Sequence[Tuple[int, float]], max_batch_size: int, granularity: int,
                       time_penalty: float = 0.0) -> int:
     """table: (batch_size, ms per chunk), ascending batch sizes.  Pure host logic in libb200call.so."""

@@ -257,3 +257,12 @@ def test_generate_variable_chunks_like_ChunkTest(reference):
             assert all(a % stride == 0 for a, _ in iv[1:]) and all(b % stride == 0 for _, b in iv[:-1])
             assert all(0 < b - a <= chunk_size for a, b in iv)
             assert all(iv[i - 1][1] - iv[i][0] <= overlap for i in range(1, len(iv)))
+
+
+def test_batch_size_granularity_like_the_reference():
+    from conftest import model_dir
+    from dorado_b200.batching import batch_size_granularity
+    from dorado_b200.config import load_model_config
+    assert batch_size_granularity(load_model_config(model_dir("fast"))) == 64   # CudaCaller.h:60-63
+    assert batch_size_granularity(load_model_config(model_dir("hac"))) == 64
+    assert batch_size_granularity(load_model_config(model_dir("sup"))) == 32
