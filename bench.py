@@ -13,12 +13,17 @@ embarrassingly; no collective on the data path) -> weak scaling; time = max over
   e2e    same metric through the C ABI call the adapter makes (b200_runner_call_chunks via
          B200ModelRunner.call_chunks_raw) from pinned host buffers, one host thread per runner:
          H2D of the fp16 batch and D2H of moves/sequence/qstring inside the timed region
-  roofline      dominant kernel of the step, timed live per launch with CUDA events
-  cpu_baseline  the reference's own CPU path (oracle/_ref, compiled from the reference sources) on a bounded
-                sample of the same workload, all host cores (torch intra-op threads = 1 per runner, one runner
-                per core, as dorado does)
+  roofline      dominant kernel of the step, timed live per launch with CUDA events; per-kernel table beside it
+                (each decode kernel is charged the bytes of its own interface; `decode` is the three together against the
+                algorithmic 2C+3 bytes per chunk-block of SURVEY.md 8d)
+  cpu_baseline  the reference's own CPU runner (dorado::basecall::ModelRunner::call_chunks, compiled from the reference
+                sources into oracle/_ref) on all host cores -- one runner per core, torch intra-op threads = 1 as dorado
+                configures it -- 4 chunks per runner per pass, median of 5 passes after a warm-up; plus the
+                single-runner N=1 / N=8 figures with ModelRunner's own model_ms / decode_ms split
+  configs       (default run only) the same measurement for hac@512 and sup@128: value / e2e / roofline per model
 
-`--impl reference` times only that CPU path and prints the same JSON line with "impl": "reference".
+`--impl reference` times only the CPU runner: a step is one pass of every runner over its 4 chunks; W warm-up passes,
+then exactly K timed passes, value = samples of the K passes / their wall time.
 """
 from __future__ import annotations
 
@@ -43,6 +48,8 @@ MODELS = {
 }
 # algorithmic FLOP per input sample
 FLOP_PER_SAMPLE = {"fast": 0.1435e6, "hac": 2.139e6, "sup": 14.35e6}
+SUB_MODELS = {"hac": dict(batch=512, steps=8), "sup": dict(batch=128, steps=6)}
+METRIC = "basecalled samples/s"
 
 
 def model_dir(kind):
@@ -83,7 +90,6 @@ class ClockSampler:
 
     def stop(self, t_begin=None, t_end=None):
         """Summarise the samples whose nvidia-smi timestamp falls inside [t_begin, t_end] (time.time() values)."""
-        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -118,46 +124,306 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference_cpu(kind, chunk_size, budget_chunks_per_core=2, repeats=1):
-    """The reference's own CPU path (ModelRunner::call_chunks semantics) on all host cores."""
-    from dorado_b200.config import load_model_config
-    from dorado_b200.weights import save_b2w, synthetic_weights
-    from oracle.oracle import Reference
-    import concurrent.futures as cf
-    import tempfile
-    cfg = load_model_config(model_dir(kind))
-    T = cfg.normalise_chunk_size(chunk_size)
-    cores = os.cpu_count() or 1
-    ref = Reference()
-    ref.set_num_threads(1)  # dorado/torch_utils/torch_utils.cpp:20
-    with tempfile.TemporaryDirectory() as td:
-        wpath = os.path.join(td, "w.b2w")
-        save_b2w(wpath, synthetic_weights(cfg, 42))
-        handles = [ref.load_model(model_dir(kind), wpath) for _ in range(cores)]
-    rng = np.random.default_rng(1234)
-    sig = rng.standard_normal((cores, budget_chunks_per_core, T)).astype(np.float32)
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: dorado::basecall::ModelRunner (oracle/_ref), the only place bench.py executes oracle/
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuReference:
+    """`runners` ModelRunners of batch `chunks_per_runner`, each driven by its own host thread (BasecallerNode drives every
+    runner from its own worker thread); torch intra-op threads = 1 (dorado/torch_utils/torch_utils.cpp:20)."""
 
-    def work(i):
-        n = 0
-        for c in range(budget_chunks_per_core):
-            scores = ref.forward(handles[i], sig[i, c:c + 1])
-            ref.decode(scores, q_shift=cfg.qbias, q_scale=cfg.qscale)
-            n += T
-        return n
+    def __init__(self, kind, chunk_size, runners, chunks_per_runner):
+        from dorado_b200.config import load_model_config
+        from dorado_b200.weights import synthetic_weights
+        from oracle.oracle import Reference, ReferenceRunner
+        self.kind = kind
+        self.cfg = load_model_config(model_dir(kind))
+        self.T = self.cfg.normalise_chunk_size(chunk_size)
+        self.ref = Reference()
+        self.ref.set_num_threads(1)
+        w = synthetic_weights(self.cfg, 42)
+        first = ReferenceRunner(self.ref, model_dir(kind), w, chunks_per_runner, chunk_size)
+        self.runners = [first] + [ReferenceRunner(self.ref, model_dir(kind), None, chunks_per_runner, chunk_size, share_with=first)
+                                  for _ in range(runners - 1)]
+        self.B = chunks_per_runner
+        rng = np.random.default_rng(1234)
+        for r in self.runners:
+            sig = rng.standard_normal((self.B, self.T)).astype(np.float32)
+            for i in range(self.B):
+                r.accept_chunk(i, sig[i])
 
-    with cf.ThreadPoolExecutor(cores) as ex:
-        list(ex.map(work, range(cores)))  # warm-up (also pages libtorch in)
-        best = None
-        for _ in range(repeats):
+    def passes(self, n):
+        """n passes; every runner calls call_chunks(B) once per pass, all runners start a pass together.  Returns the wall
+        time of each pass."""
+        R = len(self.runners)
+        bar = threading.Barrier(R + 1)
+        times = []
+
+        def drive(r):
+            for _ in range(n):
+                bar.wait()
+                r.call_chunks(self.B, want_output=False)
+                bar.wait()
+
+        ths = [threading.Thread(target=drive, args=(r,)) for r in self.runners]
+        for th in ths:
+            th.start()
+        for _ in range(n):
+            bar.wait()
             t0 = time.perf_counter()
-            total = sum(ex.map(work, range(cores)))
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    for h in handles:
-        ref.free_model(h)
-    return dict(value=total / best, unit="samples/s", cores=cores, kind="reference",
-                sample=f"{cores} runners x {budget_chunks_per_core} chunks of {T} samples, {kind} topology, "
-                       f"forward + CPUDecoder, torch threads=1 per runner", seconds=best, samples=total)
+            bar.wait()
+            times.append(time.perf_counter() - t0)
+        for th in ths:
+            th.join()
+        return times
+
+    def samples_per_pass(self):
+        return len(self.runners) * self.B * self.T
+
+    def close(self):
+        for r in self.runners[1:]:
+            r.close()
+        self.runners[0].close()
+
+
+def cpu_single_runner(kind, chunk_size, batch, iters=5):
+    """One ModelRunner, batch N: wall ms per call_chunks and ModelRunner's own model_ms / decode_ms (ModelRunner.cpp:32-57)."""
+    c = CpuReference(kind, chunk_size, 1, batch)
+    c.passes(1)
+    s0 = c.runners[0].sample_stats()
+    times = c.passes(iters)
+    s1 = c.runners[0].sample_stats()
+    c.close()
+    return {"batch": batch, "iters": iters, "ms_per_call": 1e3 * float(np.mean(times)),
+            "model_ms": (s1["model_ms"] - s0["model_ms"]) / iters, "decode_ms": (s1["decode_ms"] - s0["decode_ms"]) / iters,
+            "samples_per_s": batch * c.T / float(np.mean(times))}
+
+
+def cpu_reference_budget(kind):
+    """runners x chunks per runner for the all-cores figure, bounded so that six passes stay within ~30 s of wall time
+    and the replicas fit host memory (sup holds 315 MB of fp32 weights per runner)."""
+    cores = os.cpu_count() or 1
+    if kind == "fast":
+        return cores, 4
+    if kind == "hac":
+        return cores, 2
+    return min(cores, 32), 1
+
+
+def run_reference_arm(args, config):
+    kind = args.model
+    runners, per = cpu_reference_budget(kind)
+    c = CpuReference(kind, args.chunksize, runners, per)
+    W, K = max(0, args.warmup), max(1, args.steps)
+    c.passes(max(1, W))
+    t0 = time.perf_counter()
+    times = c.passes(K)
+    total = time.perf_counter() - t0
+    value = K * c.samples_per_pass() / total
+    sample = (f"{runners} ModelRunners (one per core, torch threads = 1) x {per} chunks of {c.T} samples per pass, {kind} topology, "
+              f"ModelRunner::call_chunks (forward + CPUDecoder); {K} passes after {max(1, W)} warm-up")
+    c.close()
+    config = dict(config, parallelism="host cores only", runners_per_gpu=0, batch_per_gpu=runners * per)
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": K,
+            "warmup": max(1, W), "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": runners, "kind": "reference", "sample": sample,
+                             "median_pass_ms": 1e3 * float(np.median(times))},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def cpu_baseline_leg(kind, chunksize):
+    """The bounded CPU sample reported next to the GPU line (rank 0, N=1 only)."""
+    runners, per = cpu_reference_budget(kind)
+    c = CpuReference(kind, chunksize, runners, per)
+    c.passes(1)
+    times = c.passes(5)
+    med = float(np.median(times))
+    out = {"value": c.samples_per_pass() / med, "unit": "samples/s", "cores": runners, "kind": "reference",
+           "sample": f"{runners} ModelRunners (one per core, torch threads = 1) x {per} chunks of {c.T} samples per pass, {kind} "
+                     f"topology, ModelRunner::call_chunks; median of 5 passes after 1 warm-up",
+           "pass_ms": [round(1e3 * t, 1) for t in times]}
+    c.close()
+    out["single_runner"] = {"n1": cpu_single_runner(kind, chunksize, 1), "n8": cpu_single_runner(kind, chunksize, 8, iters=3)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+def kernel_work(cfg, kind, N, T, T_out):
+    """Algorithmic work of ONE launch of each kernel: name -> (bound, amount)."""
+    C = cfg.outsize
+    S = C // 4
+    if cfg.is_tx_model:
+        M = N * (T // cfg.stride_inner())          # transformer tokens in the batch
+        d, ff = cfg.tx.d_model, cfg.tx.dim_feedforward
+        work = {"qkv_gemm": ("tensor", 2.0 * M * d * 3 * d), "out_proj_gemm": ("tensor", 2.0 * M * d * d),
+                "fc1_swiglu_gemm": ("tensor", 2.0 * M * d * 2 * ff), "fc2_gemm": ("tensor", 2.0 * M * ff * d),
+                "tx_attention": ("tensor", 4.0 * M * cfg.tx.nhead * 64 * (sum(cfg.tx.attn_window) + 1)),
+                "upsample_gemm": ("tensor", 2.0 * M * d * cfg.tx.upsample_scale * d),
+                "crf_gemm": ("tensor", 2.0 * M * cfg.tx.upsample_scale * d * C),
+                "rmsnorm": ("hbm", 2.0 * M * d * 2),
+                "tx_conv1": ("hbm", (2.0 + 2.0 * cfg.convs[0].size) * T * N)}
+    else:
+        Cl = cfg.lstm_size
+        work = {"lstm_layer": ("tensor", 16.0 * Cl * Cl * T_out * N),   # 2*(2C)*(4C) per chunk-step
+                "lstm_rec": ("tensor", 8.0 * Cl * Cl * T_out * N),      # W_hh half; the W_ih half is lstm_gx_gemm
+                "lstm_gx_gemm": ("tensor", 8.0 * Cl * Cl * T_out * N),
+                "conv3_gemm": ("tensor", 2.0 * cfg.convs[2].winlen * 16 * Cl * T_out * N),
+                "linear_gemm": ("tensor", 2.0 * Cl * C * T_out * N),
+                "conv12": ("hbm", (2.0 + 32.0) * T * N)}
+    # decode: every kernel is charged the bytes of its own interface (what it must read and write once)
+    work["crf_bwd_scan"] = ("hbm", (2.0 * C + 4.0 * S) * T_out * N)               # scores in, fp32 guides out
+    work["crf_fwd_beam"] = ("hbm", (2.0 * C + 4.0 * S + 8.0 * 32) * T_out * N)    # scores + guides in, beam records out
+    work["crf_traceback"] = ("hbm", (8.0 * 32 + 3.0) * T_out * N)                 # beam records in, moves/seq/qstring out
+    return work
+
+
+def bench_b200(kind, batch, chunksize, steps, warmup, R, rank, local_rank, world, sampler=None, want_cpu=False):
+    import torch
+    import torch.distributed as dist
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir(kind))
+    T = cfg.normalise_chunk_size(chunksize)
+    caller = B200Caller(cfg, synthetic_weights(cfg, 42), device=local_rank)
+    runners = [B200ModelRunner(caller, batch, chunksize) for _ in range(R)]
+    runner = runners[0]
+    rng = np.random.default_rng(1234 + rank)
+    for r in runners:
+        r.input_view()[:] = rng.standard_normal((batch, T)).astype(np.float16)
+    N = batch
+    samples_per_step = N * T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput: step i runs on runner i % R (own stream, own buffers) ----
+    for r in runners:
+        r.upload()
+    W = max(3, warmup)
+    B200ModelRunner.step_device_runners(runners, N, W * R)
+    launches0 = caller.stats()["gpu_launches"]
+    barrier()
+    t_begin = time.time()
+    tot_ms = B200ModelRunner.step_device_runners(runners, N, steps)
+    barrier()
+    t_end = time.time()
+    launches = caller.stats()["gpu_launches"] - launches0
+    clocks = None
+    if sampler is not None:
+        time.sleep(0.05)
+        clocks = sampler.stop(t_begin, t_end)
+    _, fwd_ms, dec_ms = runner.step_device(N, steps)  # un-overlapped stage split, outside the timed region
+    tot_ms = max_over_ranks(tot_ms)
+    value = world * samples_per_step * steps / (tot_ms * 1e-3)
+
+    # ---- end to end through the public API (host buffers), one host thread per runner ----
+    last = [None] * R
+
+    def drive(i, n_calls):
+        for _ in range(n_calls):
+            last[i] = runners[i].call_chunks_raw(N)  # the C-ABI call the C++ adapter makes; results land in pinned host memory
+
+    def run_calls(total):
+        ths = [threading.Thread(target=drive, args=(i, total // R + (1 if i < total % R else 0))) for i in range(R)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    run_calls(W * R)
+    barrier()
+    t0 = time.perf_counter()
+    run_calls(steps)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    bases_last = int(next(c for c in last if c is not None)[3][:N].sum())
+    e2e_value = world * samples_per_step * steps / e2e_s
+    h2d = N * T * 2
+    d2h = N * runner.out_len() * 3 + 4 * N
+    out = {"value": value, "ms_per_step": tot_ms / steps, "steps": steps, "warmup": W,
+           "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_s / steps * 1e3},
+           "gpu_launches": int(launches), "forward_ms_per_step": fwd_ms / steps, "decode_ms_per_step": dec_ms / steps,
+           "bases_called_last_step": bases_last, "batch_per_gpu": N, "chunk_samples": T, "runners_per_gpu": R}
+    if clocks is not None:
+        out["clocks"] = clocks
+    if rank != 0:
+        for r in runners:
+            r.close()
+        caller.close()
+        return out
+
+    # ---- roofline of the dominant kernel (rank 0, live CUDA events per launch) ----
+    pk = peaks()
+    prof = {}
+    for _ in range(3):
+        for name, ms in runner.profile(N):
+            prof.setdefault(name, []).append(ms)
+    agg = {k: (float(np.mean(v)), len(v) // 3) for k, v in prof.items()}  # mean ms per launch, launches per step
+    step_ms = sum(m * c for m, c in agg.values())
+    dom = max(agg, key=lambda k: agg[k][0] * agg[k][1])
+    dom_ms, dom_cnt = agg[dom]
+    C, T_out = cfg.outsize, runner.out_len()
+    work = kernel_work(cfg, kind, N, T, T_out)
+    bound, amount = work.get(dom, ("tensor", FLOP_PER_SAMPLE[kind] * samples_per_step))
+    unit_div, peak, unit = (1e12, pk["tflops"], "TFLOP/s") if bound == "tensor" else (1e9, pk["hbm_gbs"], "GB/s")
+    roof = {"kernel": dom, "bound": bound, "achieved": amount / (dom_ms * 1e-3) / unit_div, "peak": peak, "unit": unit,
+            "traffic": None}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+
+    def entry(k):
+        b, amt = work[k]
+        div, pkv = (1e12, pk["tflops"]) if b == "tensor" else (1e9, pk["hbm_gbs"])
+        ach = amt / (agg[k][0] * 1e-3) / div
+        return {"bound": b, "ms_per_launch": round(agg[k][0], 4), "launches": agg[k][1], "achieved": round(ach, 2),
+                "frac": round(ach / pkv, 4)}
+
+    roof["per_kernel"] = {k: entry(k) for k in agg if k in work}
+    dec_kernels = [k for k in ("crf_bwd_scan", "crf_fwd_beam", "crf_traceback") if k in agg]
+    dec_total_ms = sum(agg[k][0] * agg[k][1] for k in dec_kernels)
+    dec_alg = (2.0 * C + 3.0) * T_out * N
+    roof["decode"] = {"bound": "hbm", "algorithmic_bytes": dec_alg, "ms": round(dec_total_ms, 4),
+                      "achieved": round(dec_alg / (dec_total_ms * 1e-3) / 1e9, 2),
+                      "frac": round(dec_alg / (dec_total_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
+    # DRAM bytes per launch of the dominant kernel from this round's `ncu --set full` capture of the same workload
+    # (profiles/r02_traffic.json, written by tools/ncu_summary.py); null when that kernel was not captured
+    try:
+        tr = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())[f"{kind}_n{N}_{dom}"]
+        roof["traffic"] = tr["dram_bytes"]
+        roof["traffic_source"] = f"profiles/{tr['file']} ({tr['kernel']})"
+    except (OSError, KeyError, ValueError):
+        pass
+    roof["peak_source"] = pk["source"]
+    roof["ms_per_launch"] = dom_ms
+    roof["launches_per_step"] = dom_cnt
+    roof["share_of_step"] = dom_ms * dom_cnt / step_ms
+    roof["kernels_ms"] = {k: round(m * c, 4) for k, (m, c) in agg.items()}
+    roof["forward_tflops"] = FLOP_PER_SAMPLE[kind] * samples_per_step / (fwd_ms / steps * 1e-3) / 1e12
+    out["roofline"] = roof
+
+    if want_cpu:
+        try:
+            out["cpu_baseline"] = cpu_baseline_leg(kind, chunksize)
+        except Exception as e:  # the checker is optional for the headline number
+            out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": f"unavailable: {e}"}
+    for r in runners:
+        r.close()
+    caller.close()
+    return out
 
 
 def main():
@@ -172,6 +438,7 @@ def main():
     ap.add_argument("--runners", type=int, default=2,
                     help="runners (batches in flight) per GPU; dorado's default is 2 per device (api/runner_creation.cpp)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (batch sweeps)")
+    ap.add_argument("--no-sub-models", action="store_true", help="skip the hac@512 / sup@128 sub-results of the default run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,20 +454,11 @@ def main():
               "model": kind, "batch_per_gpu": args.batch, "chunk_samples": T, "parallelism": f"replica x{args.gpus}",
               "runners_per_gpu": args.runners,
               "l2": "per-step working set (conv activations + scores > 400 MB) exceeds the 126 MB L2; no explicit flush"}
-    metric = "basecalled samples/s"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        w = max(0, args.warmup)
-        res = run_reference_cpu(kind, args.chunksize, budget_chunks_per_core=1, repeats=max(1, min(args.steps, 3)))
-        line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "samples/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": w, "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(run_reference_arm(args, config)))
         return 0
 
     import torch
@@ -211,167 +469,37 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from dorado_b200.runner import B200Caller, B200ModelRunner
-    from dorado_b200.weights import synthetic_weights
-    weights = synthetic_weights(cfg, 42)
-    caller = B200Caller(cfg, weights, device=local_rank)
-    R = max(1, args.runners)
-    runners = [B200ModelRunner(caller, args.batch, args.chunksize) for _ in range(R)]
-    runner = runners[0]
-    rng = np.random.default_rng(1234 + rank)
-    for r in runners:
-        r.input_view()[:] = rng.standard_normal((args.batch, T)).astype(np.float16)
-    N = args.batch
-    samples_per_step = N * T
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident throughput -------------------------------------------------------------
-    # step i runs on runner i % R (own stream, own buffers); with R = 2 one batch's decode overlaps the next one's network
-    for r in runners:
-        r.upload()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)  # let nvidia-smi reach its sampling loop; warm-up and timed region then run back to back
-    B200ModelRunner.step_device_runners(runners, N, max(3, args.warmup) * R)
-    launches0 = caller.stats()["gpu_launches"]
-    barrier()
-    t_begin = time.time()
-    tot_ms = B200ModelRunner.step_device_runners(runners, N, args.steps)
-    barrier()
-    t_end = time.time()
-    time.sleep(0.05)
-    clocks = sampler.stop(t_begin, t_end)
-    launches = caller.stats()["gpu_launches"] - launches0
-    _, fwd_ms, dec_ms = runner.step_device(N, args.steps)  # un-overlapped stage split, outside the timed region
-    tot_ms = max_over_ranks(tot_ms)
-    value = world * samples_per_step * args.steps / (tot_ms * 1e-3)
-
-    # ---- end to end through the public API (host buffers) ----------------------------------------
-    # one host thread per runner (BasecallerNode drives each runner from its own thread); args.steps calls in total
-    import threading
-    last = [None] * R
-
-    def drive(i, n_calls):
-        for _ in range(n_calls):
-            last[i] = runners[i].call_chunks_raw(N)  # the C-ABI call the C++ adapter makes; results land in pinned host memory
-
-    def run_calls(total):
-        ths = [threading.Thread(target=drive, args=(i, total // R + (1 if i < total % R else 0))) for i in range(R)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-
-    run_calls(max(3, args.warmup) * R)
-    barrier()
-    t0 = time.perf_counter()
-    run_calls(args.steps)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    bases_last = int(next(c for c in last if c is not None)[3][:N].sum())
-    e2e_value = world * samples_per_step * args.steps / e2e_s
-    h2d = N * T * 2
-    d2h = N * runner.out_len() * 3 + 4 * N
-
+    time.sleep(0.3)  # let nvidia-smi reach its sampling loop
+    R = max(1, args.runners)
+    main_res = bench_b200(kind, args.batch, args.chunksize, args.steps, args.warmup, R, rank, local_rank, world, sampler=sampler,
+                          want_cpu=(world == 1 and not args.no_cpu_baseline))
+    subs = {}
+    default_run = kind == "fast" and args.batch == 512 and not args.no_sub_models
+    if default_run:
+        for sk, sc in SUB_MODELS.items():
+            res = bench_b200(sk, sc["batch"], args.chunksize, sc["steps"], 3, R, rank, local_rank, world)
+            if rank == 0:
+                keep = ("value", "ms_per_step", "steps", "e2e", "forward_ms_per_step", "decode_ms_per_step", "batch_per_gpu",
+                        "chunk_samples", "runners_per_gpu", "gpu_launches", "bases_called_last_step")
+                subs[sk] = {k: res[k] for k in keep}
+                r = res["roofline"]
+                subs[sk]["roofline"] = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step",
+                                                          "per_kernel", "decode", "forward_tflops", "traffic")}
     if rank != 0:
         return 0
-
-    # ---- roofline of the dominant kernel (rank 0, live CUDA events per launch) --------------------
-    pk = peaks()
-    prof = {}
-    for _ in range(3):
-        for name, ms in runner.profile(N):
-            prof.setdefault(name, []).append(ms)
-    agg = {k: (float(np.mean(v)), len(v) // 3) for k, v in prof.items()}  # mean ms per launch, launches per step
-    step_ms = sum(m * c for m, c in agg.values())
-    dom = max(agg, key=lambda k: agg[k][0] * agg[k][1])
-    dom_ms, dom_cnt = agg[dom]
-    C, T_out = cfg.outsize, runner.out_len()
-    # algorithmic work of ONE launch of each kernel
-    work = {}
-    if cfg.is_tx_model:
-        M = N * (T // cfg.stride_inner())          # transformer tokens in the batch
-        d, ff = cfg.tx.d_model, cfg.tx.dim_feedforward
-        work = {"qkv_gemm": ("tensor", 2.0 * M * d * 3 * d), "out_proj_gemm": ("tensor", 2.0 * M * d * d),
-                "fc1_swiglu_gemm": ("tensor", 2.0 * M * d * 2 * ff), "fc2_gemm": ("tensor", 2.0 * M * ff * d),
-                "tx_attention": ("tensor", 4.0 * M * cfg.tx.nhead * 64 * (sum(cfg.tx.attn_window) + 1)),
-                "upsample_gemm": ("tensor", 2.0 * M * d * cfg.tx.upsample_scale * d),
-                "crf_gemm": ("tensor", 2.0 * M * cfg.tx.upsample_scale * d * C),
-                "rmsnorm": ("hbm", 2.0 * M * d * 2)}
-    else:
-        Cl = cfg.lstm_size
-        work = {"lstm_layer": ("tensor", 16.0 * Cl * Cl * T_out * N),   # 2*(2C)*(4C) per chunk-step
-                "lstm_rec": ("tensor", 8.0 * Cl * Cl * T_out * N),      # W_hh half; the W_ih half is lstm_gx_gemm
-                "lstm_gx_gemm": ("tensor", 8.0 * Cl * Cl * T_out * N),
-                "conv3_gemm": ("tensor", 2.0 * cfg.convs[2].winlen * 16 * Cl * T_out * N),
-                "linear_gemm": ("tensor", 2.0 * Cl * C * T_out * N),
-                "conv12": ("hbm", (2.0 + 32.0) * T * N)}
-    for k in ("crf_bwd_scan", "crf_fwd_beam", "crf_traceback"):
-        work[k] = ("hbm", (2.0 * C + 3.0) * T_out * N)  # whole-decode algorithmic bytes, charged to each kernel
-    bound, amount = work.get(dom, ("tensor", FLOP_PER_SAMPLE[kind] * samples_per_step))
-    if bound == "tensor":
-        roof = {"kernel": dom, "bound": "tensor", "achieved": amount / (dom_ms * 1e-3) / 1e12, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "traffic": None}
-    else:
-        roof = {"kernel": dom, "bound": "hbm", "achieved": amount / (dom_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "traffic": None}
-    roof["per_kernel"] = {k: {"bound": work[k][0], "ms_per_launch": round(agg[k][0], 4), "launches": agg[k][1],
-                              "achieved": round(work[k][1] / (agg[k][0] * 1e-3) / (1e12 if work[k][0] == "tensor" else 1e9), 2),
-                              "frac": round(work[k][1] / (agg[k][0] * 1e-3) /
-                                            ((pk["tflops"] * 1e12) if work[k][0] == "tensor" else (pk["hbm_gbs"] * 1e9)), 4)}
-                          for k in agg if k in work}
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    # (profiles/*_traffic.json, written by tools/ncu_summary.py); null for workloads that were not captured
-    capture = {("fast", 512, "lstm_layer"): "r01_lstm_layer_fast_n512",
-               ("hac", 512, "lstm_rec"): "r01_lstm_cluster_hac_n512_tmem",
-               ("sup", 128, "fc1_swiglu_gemm"): "r01_gemm_sup_n128"}.get((kind, N, dom))
-    try:
-        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())[capture]
-        roof["traffic"] = tr["dram_bytes"]
-        roof["traffic_source"] = f"profiles/{capture}.ncu-rep ({tr['kernel']})"
-    except (OSError, KeyError, ValueError):
-        pass
-    roof["peak_source"] = pk["source"]
-    roof["ms_per_launch"] = dom_ms
-    roof["launches_per_step"] = dom_cnt
-    roof["share_of_step"] = dom_ms * dom_cnt / step_ms
-    roof["kernels_ms"] = {k: round(m * c, 4) for k, (m, c) in agg.items()}
-    # whole-forward tensor roofline for context
-    roof["forward_tflops"] = FLOP_PER_SAMPLE[kind] * samples_per_step / (fwd_ms / args.steps * 1e-3) / 1e12
-    roof["decode_gbs"] = (2.0 * C + 3.0) * T_out * N / (dec_ms / args.steps * 1e-3) / 1e9
-
-    try:
-        if args.no_cpu_baseline:
-            raise RuntimeError("skipped (--no-cpu-baseline)")
-        if world > 1:
-            raise RuntimeError("reported at N=1 only")
-        cpu = run_reference_cpu(kind, args.chunksize, budget_chunks_per_core=1, repeats=1)
-        cpu_baseline = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    except Exception as e:  # the checker is optional for the headline number
-        cpu_baseline = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
-                        "sample": f"unavailable: {e}"}
-
-    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
+    line = {"metric": METRIC, "value": main_res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": main_res["warmup"], "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate; fp32 decode)", "data": "synthetic",
-            "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": int(launches), "forward_ms_per_step": fwd_ms / args.steps,
-            "decode_ms_per_step": dec_ms / args.steps, "roofline": roof, "cpu_baseline": cpu_baseline,
-            "bases_called_last_step": bases_last}
+            "config": config, "clocks": main_res.get("clocks"), "e2e": main_res["e2e"],
+            "gpu_launches": main_res["gpu_launches"], "forward_ms_per_step": main_res["forward_ms_per_step"],
+            "decode_ms_per_step": main_res["decode_ms_per_step"], "roofline": main_res["roofline"],
+            "cpu_baseline": main_res.get("cpu_baseline", {"value": None, "unit": "samples/s", "cores": os.cpu_count(),
+                                                            "kind": "reference", "sample": "reported at N=1 only"}),
+            "bases_called_last_step": main_res["bases_called_last_step"]}
+    if subs:
+        line["configs"] = subs
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

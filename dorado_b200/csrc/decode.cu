@@ -641,13 +641,17 @@ constexpr int kTbWarps = 2;
 __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint2* __restrict__ beam,
                                                                       int N,
                                                                       int T,
-                                                                      float q_scale,
-                                                                      float q_shift,
+                                                                      const b200_qtable* __restrict__ qtable,
                                                                       uint8_t* __restrict__ moves_out,
                                                                       char* __restrict__ seq_out,
                                                                       char* __restrict__ qstr_out,
                                                                       int32_t* __restrict__ n_bases_out) {
     extern __shared__ __align__(16) unsigned char tb_smem[];
+    __shared__ b200_qtable qt;  // quality-character quantiser (bin edges placed by the host, b200_crf_math.h)
+    for (int i = threadIdx.x; i < (int)(sizeof(b200_qtable) / 4); i += blockDim.x) {
+        reinterpret_cast<uint32_t*>(&qt)[i] = reinterpret_cast<const uint32_t*>(qtable)[i];
+    }
+    __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x * kTbWarps + w;
     if (chunk >= N) return;
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
                 for (int k = 0; k < 4; ++k) tp = B200_ADD(tp, k == base ? prob : wrong);
             }
             sc = "ACGT"[pstate[b0] & 3];
-            qc = b200_qchar(bp, tp, q_scale, q_shift);
+            qc = b200_qtable_lookup(&qt, bp, tp);
         }
         so[p] = sc;
         qo[p] = qc;
@@ -750,7 +754,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         const size_t smem = traceback_smem_bytes(a.T);
         if (smem > 48 * 1024) ensure_dynamic_smem(crf_traceback_kernel, 200 * 1024);
         const int grid = (a.N + kTbWarps - 1) / kTbWarps;
-        crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.q_scale, a.q_shift, a.moves,
+        crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.qtable, a.moves,
                                                                     a.sequence, a.qstring, a.n_bases);
         if (prof) prof->mark("crf_traceback", stream);
     }
@@ -775,6 +779,7 @@ void decode_scores(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
     if (a.T < 1 || a.T > 65535 || a.N < 1) {
         throw std::invalid_argument("b200 decode: need 1 <= T <= 65535 and N >= 1");
     }
+    if (!a.qtable) throw std::invalid_argument("b200 decode: quality table missing");
     switch (a.state_len) {
         case 3: launch_decode<3>(a, stream, prof); break;
         case 4: launch_decode<4>(a, stream, prof); break;

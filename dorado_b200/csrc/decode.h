@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include "b200_crf_math.h"
 
 namespace b200 {
 
@@ -20,6 +21,7 @@ struct DecodeArgs {
     float blank;
     float q_shift;
     float q_scale;
+    const b200_qtable* qtable;  // device copy of b200_qtable_build(q_scale, q_shift) (include/b200_crf_math.h)
     // scratch
     float* bwd;   // decode_scratch_bytes() -> bwd_bytes
     uint2* beam;  //                        -> beam_bytes

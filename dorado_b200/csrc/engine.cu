@@ -5,6 +5,7 @@
 // the reference's per-device task queue (CudaCaller.cpp:204-214).
 #include "engine.h"
 
+#include "b200_crf_math.h"
 #include "decode.h"
 
 #include <algorithm>
@@ -155,6 +156,7 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     const size_t ws_b = engine.model().workspace_bytes(m_N, m_T_in);
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
     m_arena.reserve(al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(m_out_bytes) + 4096);
+    m_d_qtable = static_cast<b200_qtable*>(m_arena.take(sizeof(b200_qtable)));  // inside the 4096 bytes of slack
     m_d_input = static_cast<__half*>(m_arena.take(in_bytes));
     m_d_scores = static_cast<__half*>(m_arena.take(scores_b));
     m_d_ws = m_arena.take(ws_b);
@@ -170,6 +172,19 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     B200_CUDA(cudaStreamSynchronize(m_stream));
     m_plan = engine.model().make_plan(m_N, m_T_in, m_d_input, m_d_scores, m_d_ws, ws_b);
     for (auto& e : m_ev) B200_CUDA(cudaEventCreate(&e));
+    upload_qtable();
+}
+
+// The per-base quality character is a quantiser of err = 1 - p_called / p_total (beam_search.cpp:94-98); its bin edges
+// are placed on the host with the host's own log10f, so the device reproduces the reference's characters exactly.
+void Runner::upload_qtable() {
+    b200_qtable tb;
+    if (b200_qtable_build(m_opts.q_scale, m_opts.q_shift, &tb) != 0) {
+        throw std::invalid_argument("decoder options: q_scale and q_shift must be finite");
+    }
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    B200_CUDA(cudaMemcpyAsync(m_d_qtable, &tb, sizeof(tb), cudaMemcpyHostToDevice, m_stream));
+    B200_CUDA(cudaStreamSynchronize(m_stream));
 }
 
 Runner::~Runner() {
@@ -194,7 +209,9 @@ Runner::~Runner() {
 void Runner::set_decoder_options(const b200_decoder_options& o) {
     if (o.beam_width < 1 || o.beam_width > 32) throw std::invalid_argument("beam_width must be in [1, 32]");
     if (o.move_pad != 0) throw Unsupported("move_pad is not implemented");
+    std::lock_guard<std::mutex> lock(m_mutex);
     m_opts = o;
+    upload_qtable();
 }
 
 void Runner::accept_chunk_f16(int idx, const uint16_t* samples, int64_t len) {
@@ -297,6 +314,7 @@ void Runner::run_decode(int n, ProfileSink* prof) {
     a.blank = m_opts.blank_score;
     a.q_shift = m_opts.q_shift;
     a.q_scale = m_opts.q_scale;
+    a.qtable = m_d_qtable;
     a.bwd = m_d_bwd;
     a.beam = m_d_beam;
     // output rows are packed for the n chunks actually called
@@ -553,8 +571,13 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
     const size_t sc_b = (size_t)N * T * C * sizeof(__half);
     const size_t out_b = nb_offset(N, T) + (size_t)N * 4;
     Arena arena;
-    arena.reserve(sc_b + bwd_b + beam_b + out_b + 4096);
+    arena.reserve(sc_b + bwd_b + beam_b + out_b + 8192);
     auto* d_sc = static_cast<__half*>(arena.take(sc_b));
+    b200_qtable tb;
+    if (b200_qtable_build(opts.q_scale, opts.q_shift, &tb) != 0) {
+        throw std::invalid_argument("decoder options: q_scale and q_shift must be finite");
+    }
+    auto* d_tb = static_cast<b200_qtable*>(arena.take(sizeof(b200_qtable)));
     DecodeArgs a{};
     a.scores = d_sc;
     a.N = N;
@@ -566,6 +589,7 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
     a.blank = opts.blank_score;
     a.q_shift = opts.q_shift;
     a.q_scale = opts.q_scale;
+    a.qtable = d_tb;
     a.bwd = static_cast<float*>(arena.take(bwd_b));
     a.beam = static_cast<uint2*>(arena.take(beam_b));
     auto* d_out = static_cast<unsigned char*>(arena.take(out_b));
@@ -575,6 +599,7 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
     a.n_bases = reinterpret_cast<int32_t*>(d_out + nb_offset(N, T));
     try {
         B200_CUDA(cudaMemcpyAsync(d_sc, scores, sc_b, cudaMemcpyHostToDevice, s));
+        B200_CUDA(cudaMemcpyAsync(d_tb, &tb, sizeof(tb), cudaMemcpyHostToDevice, s));
         decode_scores(a, s);
         B200_CUDA(cudaMemcpyAsync(moves, a.moves, (size_t)N * T, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaMemcpyAsync(sequence, a.sequence, (size_t)N * T, cudaMemcpyDeviceToHost, s));

@@ -3,6 +3,7 @@
 #pragma once
 
 #include "b200call.h"
+#include "b200_crf_math.h"
 #include "frontend.h"
 #include "common.cuh"
 
@@ -157,6 +158,8 @@ private:
     std::unique_ptr<ForwardPlan> m_plan;
     float* m_d_bwd = nullptr;
     uint2* m_d_beam = nullptr;
+    b200_qtable* m_d_qtable = nullptr;  // quality-character quantiser for (q_scale, q_shift), include/b200_crf_math.h
+    void upload_qtable();
     unsigned char* m_d_out = nullptr;
     size_t m_out_bytes = 0;
     cudaEvent_t m_ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -410,7 +410,11 @@ int crf_generate_sequence(const uint8_t* moves,
             for (int j = 0; j < move; ++j) seq[pos++] = alphabet[base];
         }
     }
-    for (int i = 0; i < n_bases; ++i) qstr[i] = b200_qchar(base_p[i], total_p[i], scale, shift);
+    /* the reference expression itself, on this host's libm (the engine reproduces it with b200_qtable) */
+    for (int i = 0; i < n_bases; ++i) {
+        const float err = B200_SUB(1.0f, B200_DIV(base_p[i], total_p[i]));
+        qstr[i] = b200_qchar_libm(err, scale, shift);
+    }
     free(base_p);
     free(total_p);
     return n_bases;
@@ -526,3 +530,53 @@ float crf_math_log1pf(float x) { return b200_log1pf(x); }
 float crf_math_pow0p4f(float x) { return b200_pow0p4f(x); }
 float crf_math_lse2(float x, float y) { return b200_log_sum_exp(x, y); }
 float crf_half_to_float(uint16_t h) { return half_to_float(h); }
+
+/* quality-character quantiser (include/b200_crf_math.h): table construction and an audit of the table against the
+ * reference expression on every `stride`-th positive float up to 1.0 plus a dense window around every edge. */
+int crf_qtable_build(float scale, float shift, b200_qtable* tb) { return b200_qtable_build(scale, shift, tb); }
+char crf_qtable_lookup(const b200_qtable* tb, float base_prob, float total_prob) {
+    return b200_qtable_lookup(tb, base_prob, total_prob);
+}
+char crf_qchar_libm(float err, float scale, float shift) { return b200_qchar_libm(err, scale, shift); }
+static char qtable_at(const b200_qtable* tb, uint32_t u) {
+    uint32_t lo = 0, hi = tb->n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tb->edge[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    return (char)tb->ch[lo];
+}
+long crf_qtable_audit(float scale, float shift, uint32_t stride, uint32_t window) {
+    b200_qtable tb;
+    if (b200_qtable_build(scale, shift, &tb) != 0) return -1;
+    long bad = 0;
+    for (uint64_t u = 1; u <= 0x3f800000u; u += stride) {
+        bad += qtable_at(&tb, (uint32_t)u) != b200_qchar_libm(B200_U2F((uint32_t)u), scale, shift);
+    }
+    for (uint32_t i = 0; i < tb.n; ++i) {
+        const uint32_t c = tb.edge[i];
+        const uint32_t a = c > window ? c - window : 1, b = c + window < 0x3f800000u ? c + window : 0x3f800000u;
+        for (uint32_t u = a; u <= b; ++u) bad += qtable_at(&tb, u) != b200_qchar_libm(B200_U2F(u), scale, shift);
+    }
+    return bad;
+}
+/* disagreements of the pinned pow0p4 with the host powf and with the correctly rounded value, on every stride-th float
+ * in [2^-40, 1) */
+void crf_pow0p4_audit(uint32_t stride, long* n, long* vs_libm, long* vs_exact, long* max_ulp_libm) {
+    long c = 0, a = 0, b = 0, mu = 0;
+    for (uint32_t u = 0x2b800000u; u < 0x3f800000u; u += stride) {
+        const float x = B200_U2F(u);
+        const float mine = b200_pow0p4f(x);
+        const float lm = powf(x, 0.4f);
+        const float ex = (float)pow((double)x, (double)0.4f);
+        if (mine != lm) {
+            ++a;
+            long d = (long)B200_F2U(mine) - (long)B200_F2U(lm);
+            if (d < 0) d = -d;
+            if (d > mu) mu = d;
+        }
+        b += mine != ex;
+        ++c;
+    }
+    *n = c; *vs_libm = a; *vs_exact = b; *max_ulp_libm = mu;
+}

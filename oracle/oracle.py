@@ -136,6 +136,13 @@ class Reference:
         lib.ref_decode_chunks.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                           C.c_float, C.c_float, _u8p, _u8p, _u8p, _i32p]
         lib.ref_set_num_threads.argtypes = [C.c_int]
+        lib.ref_runner_create.restype = C.c_void_p
+        lib.ref_runner_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        lib.ref_runner_destroy.argtypes = [C.c_void_p]
+        lib.ref_runner_dims.argtypes = [C.c_void_p, _i32p]
+        lib.ref_runner_accept_chunk.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int]
+        lib.ref_runner_call_chunks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_runner_stats.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
         u64 = C.c_uint64
         _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
         lib.ref_generate_chunks.argtypes = [u64, u64, u64, u64, _u64p, u64]
@@ -254,6 +261,67 @@ class Reference:
         self._check(self.lib.ref_decode_chunks(s, N, T, Cc, beam_width, beam_cut, blank, q_shift, q_scale, seq,
                                                qstr, moves, nb))
         return DecodeResult(seq, qstr, moves, nb)
+
+
+class ReferenceRunner:
+    """The reference's CPU runner itself: dorado::basecall::ModelRunner (dorado/basecall/ModelRunner.cpp) with the
+    ModelRunnerBase methods accept_chunk / call_chunks / sample_stats, on the synthetic weights written out as the
+    reference's own *.tensor files."""
+
+    def __init__(self, ref: "Reference", config_dir, weights, batch_size: int, chunk_size: int, share_with=None):
+        """weights: name -> array; share_with: another ReferenceRunner of the same model whose *.tensor files are reused."""
+        import tempfile
+        from dorado_b200.weights import save_b2w
+        self.ref = ref
+        if share_with is not None:
+            self._tmp = share_with._tmp
+            self.h = ref.lib.ref_runner_create(str(config_dir).encode(), b"", self._tmp.name.encode(), batch_size, chunk_size)
+        else:
+            self._tmp = tempfile.TemporaryDirectory()
+            wpath = os.path.join(self._tmp.name, "w.b2w")
+            save_b2w(wpath, weights)
+            self.h = ref.lib.ref_runner_create(str(config_dir).encode(), wpath.encode(), self._tmp.name.encode(),
+                                               batch_size, chunk_size)
+            os.remove(wpath)
+        if not self.h:
+            raise RuntimeError(ref.lib.ref_last_error().decode())
+        self._owns_tmp = share_with is None
+        d = np.zeros(3, np.int32)
+        ref.lib.ref_runner_dims(self.h, d)
+        self.batch_size, self.chunk_size, self.stride = int(d[0]), int(d[1]), int(d[2])
+        self.t_out = self.chunk_size // self.stride
+
+    def accept_chunk(self, idx: int, chunk: np.ndarray) -> None:
+        c = np.ascontiguousarray(chunk, np.float32).reshape(-1)
+        self.ref._check(self.ref.lib.ref_runner_accept_chunk(self.h, idx, c, c.size))
+
+    def call_chunks(self, num_chunks: int, want_output: bool = True):
+        if not want_output:
+            self.ref._check(self.ref.lib.ref_runner_call_chunks(self.h, num_chunks, None, None, None, None))
+            return None
+        seq, qstr, moves = (np.zeros((num_chunks, self.t_out), np.uint8) for _ in range(3))
+        nb = np.zeros(num_chunks, np.int32)
+        self.ref._check(self.ref.lib.ref_runner_call_chunks(self.h, num_chunks, seq.ctypes.data, qstr.ctypes.data,
+                                                            moves.ctypes.data, nb.ctypes.data))
+        return DecodeResult(seq, qstr, moves, nb)
+
+    def sample_stats(self) -> dict:
+        st = np.zeros(3, np.float64)
+        self.ref._check(self.ref.lib.ref_runner_stats(self.h, st))
+        return {"batches_called": st[0], "model_ms": st[1], "decode_ms": st[2]}
+
+    def close(self):
+        if self.h:
+            self.ref.lib.ref_runner_destroy(self.h)
+            self.h = None
+            if self._owns_tmp:
+                self._tmp.cleanup()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def reference_available() -> bool:

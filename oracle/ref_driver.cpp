@@ -8,9 +8,11 @@
 //   * CRF scans          dorado/basecall/decode/CPUDecoder.cpp:43-92   (inner::forward/backward_scores)
 //   * beam search        dorado/basecall/decode/beam_search.cpp:522    (beam_search_decode)
 //   * whole decode       dorado/basecall/decode/CPUDecoder.cpp:100     (CPUDecoder::beam_search_part_2)
+//   * the CPU runner     dorado/basecall/ModelRunner.cpp:10-65       (ModelRunner: accept_chunk / call_chunks / sample_stats)
 //   * front end          dorado/read_pipeline/base/chunk.cpp:11-47 (generate_chunks), stitch.cpp:12-96 (stitch_chunks),
 //                        dorado/torch_utils/tensor_utils.cpp:254 (shift_scale_tensor_i16_to_f16_inplace)
 // Everything here is glue written for this repo; no reference source is copied.
+#include "basecall/ModelRunner.h"
 #include "basecall/decode/CPUDecoder.h"
 #include "basecall/decode/beam_search.h"
 #include "basecall/model/CRFModel.h"
@@ -24,8 +26,11 @@
 #include <ATen/ATen.h>
 #include <torch/torch.h>
 
+#include <torch/serialize.h>
+
 #include <cstdint>
 #include <cstdio>
+#include <filesystem>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -335,6 +340,114 @@ int ref_stitch_chunks(uint64_t n,
         std::memcpy(moves_out, rc.moves.data(), rc.moves.size());
         std::memcpy(seq_out, rc.seq.data(), rc.seq.size());
         std::memcpy(qstr_out, rc.qstring.data(), rc.qstring.size());
+    });
+}
+
+// ---- the reference's CPU runner itself (dorado/basecall/ModelRunner.cpp) ------------------------------------------
+// ModelRunner loads its weights from <model dir>/*.tensor with torch::load (crf_utils.cpp:26-150,
+// tensor_utils.cpp:154-163), so the B2W1 tensors are first written out in that format next to a copy of config.toml,
+// under a directory that carries the model's own (non-deprecated) name.  An empty `weights` path reuses the directory a
+// previous call wrote under the same work_dir (many runners, one copy of the files).
+struct RefRunner {
+    std::unique_ptr<dorado::basecall::ModelRunner> runner;
+    std::filesystem::path dir;
+};
+
+void* ref_runner_create(const char* config_dir, const char* weights, const char* work_dir, int batch_size, int chunk_size) {
+    RefRunner* out = nullptr;
+    guarded([&] {
+        namespace fs = std::filesystem;
+        const fs::path src(config_dir);
+        const fs::path dst = fs::path(work_dir) / src.filename();
+        if (weights && weights[0]) {
+            fs::create_directories(dst);
+            fs::copy_file(src / "config.toml", dst / "config.toml", fs::copy_options::overwrite_existing);
+            {
+                std::ifstream f(weights, std::ios::binary);
+                if (!f) throw std::runtime_error(std::string("cannot open weights file ") + weights);
+                char magic[4];
+                uint32_t n = 0;
+                f.read(magic, 4);
+                f.read(reinterpret_cast<char*>(&n), 4);
+                for (uint32_t i = 0; i < n; ++i) {
+                    uint32_t name_len = 0, ndim = 0;
+                    f.read(reinterpret_cast<char*>(&name_len), 4);
+                    std::string name(name_len, '\0');
+                    f.read(name.data(), name_len);
+                    f.read(reinterpret_cast<char*>(&ndim), 4);
+                    std::vector<int64_t> dims(ndim);
+                    int64_t numel = 1;
+                    for (uint32_t d = 0; d < ndim; ++d) {
+                        uint32_t v = 0;
+                        f.read(reinterpret_cast<char*>(&v), 4);
+                        dims[d] = v;
+                        numel *= v;
+                    }
+                    at::Tensor t = at::empty(dims, at::kFloat);
+                    f.read(reinterpret_cast<char*>(t.data_ptr<float>()), numel * 4);
+                    if (!f) throw std::runtime_error("truncated weights file");
+                    torch::save(std::vector<at::Tensor>{t}, (dst / name).string());
+                }
+            }
+        }  // else: work_dir already holds the model directory written by an earlier runner
+        auto config = dorado::config::load_model_config(dst);
+        config.basecaller.set_batch_size(batch_size);
+        config.basecaller.set_chunk_size(chunk_size);
+        config.normalise_basecaller_params();
+        auto owned = std::make_unique<RefRunner>();
+        owned->dir = dst;
+        owned->runner = std::make_unique<dorado::basecall::ModelRunner>(config, "cpu");
+        out = owned.release();
+    });
+    return out;
+}
+
+void ref_runner_destroy(void* h) {
+    auto* r = static_cast<RefRunner*>(h);
+    delete r;  // the caller owns (and removes) work_dir
+}
+
+// dims[0..2] = batch_size, chunk_size, stride
+int ref_runner_dims(void* h, int* dims) {
+    auto* r = static_cast<RefRunner*>(h);
+    dims[0] = int(r->runner->batch_size());
+    dims[1] = int(r->runner->chunk_size());
+    dims[2] = r->runner->config().stride;
+    return 0;
+}
+
+// ModelRunner::accept_chunk (ModelRunner.cpp:47-49): chunk [1, chunk_size] fp32 (the CPU decoder's dtype)
+int ref_runner_accept_chunk(void* h, int idx, const float* samples, int len) {
+    auto* r = static_cast<RefRunner*>(h);
+    return guarded([&] {
+        at::Tensor c = at::from_blob(const_cast<float*>(samples), {1, len}, at::kFloat);
+        r->runner->accept_chunk(idx, c);
+    });
+}
+
+// ModelRunner::call_chunks (ModelRunner.cpp:32-45); outputs have row pitch T_out = chunk_size / stride (may be NULL)
+int ref_runner_call_chunks(void* h, int num_chunks, char* seq, char* qstr, uint8_t* moves, int* n_bases) {
+    auto* r = static_cast<RefRunner*>(h);
+    return guarded([&] {
+        auto res = r->runner->call_chunks(num_chunks);
+        const size_t T = r->runner->chunk_size() / size_t(r->runner->config().stride);
+        for (size_t i = 0; i < res.size(); ++i) {
+            if (n_bases) n_bases[i] = int(res[i].sequence.size());
+            if (seq) std::memcpy(seq + i * T, res[i].sequence.data(), res[i].sequence.size());
+            if (qstr) std::memcpy(qstr + i * T, res[i].qstring.data(), res[i].qstring.size());
+            if (moves) std::memcpy(moves + i * T, res[i].moves.data(), res[i].moves.size());
+        }
+    });
+}
+
+// ModelRunner::sample_stats (ModelRunner.cpp:51-57): batches_called, model_ms, decode_ms
+int ref_runner_stats(void* h, double* out3) {
+    auto* r = static_cast<RefRunner*>(h);
+    return guarded([&] {
+        const auto st = r->runner->sample_stats();
+        out3[0] = st.at("batches_called");
+        out3[1] = st.at("model_ms");
+        out3[2] = st.at("decode_ms");
     });
 }
 

@@ -107,6 +107,37 @@ def test_numerics_contract_accuracy(crf_oracle):
     np.testing.assert_array_equal(conv.view(np.uint32), halfs.view(np.float16).astype(np.float32).view(np.uint32))
 
 
+def test_pow0p4_against_libm(crf_oracle):
+    """The contract's pow(p, 0.4f) (binary64 exp(0.4f * log p), one rounding) is the correctly rounded powf on every
+    sampled argument; the host libm's powf is within 1 ulp of it and differs on < 0.2 % of the arguments."""
+    import ctypes as C
+    n, a, b, m = C.c_long(), C.c_long(), C.c_long(), C.c_long()
+    crf_oracle.lib.crf_pow0p4_audit(C.c_uint32(61), C.byref(n), C.byref(a), C.byref(b), C.byref(m))
+    assert n.value > 5_000_000
+    assert b.value == 0, f"{b.value} of {n.value} differ from the correctly rounded powf"
+    assert m.value <= 1 and a.value <= 2e-3 * n.value, (a.value, m.value)
+    lib = crf_oracle.lib
+    assert lib.crf_math_pow0p4f(0.0) == 0.0 and lib.crf_math_pow0p4f(1.0) == 1.0 and lib.crf_math_pow0p4f(-0.0) == 0.0
+    tiny = float(np.float32(1e-42))  # subnormal argument: handled exactly
+    assert lib.crf_math_pow0p4f(tiny) == pytest.approx(tiny ** float(np.float32(0.4)), rel=1e-6)
+
+
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (0.97, -0.05), (1.04, 0.4), (0.9, -0.2), (0.5, 3.0), (1.1, -1.1)])
+def test_quality_character_quantiser_is_exact(crf_oracle, scale, shift):
+    """b200_qtable (bin edges bisected on the host libm) reproduces the reference expression
+    char(33.5 + clamp(-10 log10(err) * scale + shift, 1, 50)) on every 29th float of (0, 1] and on +-4096 ulp around
+    every edge -- the engine's traceback kernel looks characters up in this table."""
+    import ctypes as C
+    lib = crf_oracle.lib
+    lib.crf_qtable_audit.restype = C.c_long
+    lib.crf_qtable_audit.argtypes = [C.c_float, C.c_float, C.c_uint32, C.c_uint32]
+    assert lib.crf_qtable_audit(scale, shift, 29, 4096) == 0
+    lib.crf_qchar_libm.restype = C.c_char
+    lib.crf_qchar_libm.argtypes = [C.c_float, C.c_float, C.c_float]
+    assert lib.crf_qchar_libm(0.0, scale, shift) == bytes([33 + 50])   # err = 0 -> +inf -> clamps to 50
+    assert lib.crf_qchar_libm(1.0, scale, shift) == bytes([int(33.5 + min(50.0, max(1.0, shift)))])
+
+
 def test_oracle_decode_edge_cases(crf_oracle):
     """T = 1, ties everywhere, saturated scores, narrow beams: the reference's edge behaviour, restated."""
     r = crf_oracle.decode(np.zeros((2, 1, 256), np.float16))

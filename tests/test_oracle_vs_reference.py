@@ -56,7 +56,9 @@ def test_beam_search_matches_reference_on_same_guides(crf_oracle, reference, sta
         assert len(rq) == len(oq)
         mism += sum(a != c for a, c in zip(rq, oq))
         total += len(rq)
-    assert mism <= 0.01 * total, f"{mism}/{total} qstring characters differ from the reference"
+    # glibc's powf differs from the correctly rounded value on 0.06 % of its arguments; a character only moves when that
+    # last ulp also crosses a quantiser edge, so at most an isolated character may differ
+    assert mism <= 1, f"{mism}/{total} qstring characters differ from the reference"
 
 
 @pytest.mark.parametrize("beam_width,beam_cut", [(32, 100.0), (8, 20.0), (32, 0.0)])
@@ -66,6 +68,7 @@ def test_beam_options_match_reference(crf_oracle, reference, beam_width, beam_cu
     rs, rq, rm = reference.beam_search_decode(s, b, p, beam_width=beam_width, beam_cut=beam_cut)
     os_, oq, om = crf_oracle.beam_search(s, b, p, beam_width=beam_width, beam_cut=beam_cut)
     assert rs == os_ and (rm == om).all()
+    assert sum(a != c for a, c in zip(rq, oq)) <= 1
 
 
 def test_full_decode_matches_reference_cpu_decoder(crf_oracle, reference):
@@ -81,7 +84,7 @@ def test_full_decode_matches_reference_cpu_decoder(crf_oracle, reference):
         if sa == sb:
             q_tot += len(a)
             q_bad += sum(x != y for x, y in zip(a, b))
-    assert q_bad <= 0.02 * q_tot
+    assert q_bad <= 0.002 * q_tot + 1
 
 
 @pytest.mark.parametrize("kind,N,T", [("fast", 2, 1200), ("hac", 2, 900), ("sup", 1, 1536)])
@@ -102,3 +105,34 @@ def test_forward_matches_reference(reference, tmp_path, kind, N, T):
         d = np.abs(true_win - ref)
         assert d.max() <= 2e-2 and (d > 1e-3).mean() <= 5e-3
     reference.free_model(h)
+
+
+@pytest.mark.parametrize("kind", ["fast", "hac"])
+def test_reference_model_runner_reproduces_full_length_fixture(reference, kind):
+    """dorado::basecall::ModelRunner (accept_chunk / call_chunks, ModelRunner.cpp:32-49) driven through the shim gives
+    exactly the strings committed in tests/golden/full_<kind>.npz for the same chunk, and keeps its model_ms / decode_ms
+    accounting (:51-57).  One chunk per call, as the fixture was generated: libtorch's fp32 kernels are not batch-invariant
+    (a different GEMM blocking at batch 2 changes last bits of the scores, and these ill-conditioned synthetic models then
+    flip a base), so only equal batch shapes are comparable bit for bit."""
+    import pathlib
+    from conftest import unpack_rows
+    from dorado_b200.config import load_model_config
+    from dorado_b200.weights import synthetic_weights
+    from oracle.oracle import ReferenceRunner
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / f"full_{kind}.npz")
+    cfg = load_model_config(model_dir(kind))
+    reference.set_num_threads(1)
+    r = ReferenceRunner(reference, model_dir(kind), synthetic_weights(cfg, int(g["weights_seed"])), 1, 10000)
+    assert r.chunk_size == int(g["T"]) and r.t_out == int(g["T_out"]) and r.batch_size == 1
+    sig = np.random.default_rng(int(g["signal_seed"])).standard_normal((int(g["M"]), r.chunk_size)).astype(np.float16)
+    nb = g["ref_n_bases"]
+    seqs, qs = unpack_rows(g["ref_seq"], nb), unpack_rows(g["ref_qstr"], nb)
+    mv = np.unpackbits(g["ref_moves"], axis=1)[:, : r.t_out]
+    for i in (3, 0):
+        r.accept_chunk(0, sig[i])
+        out = r.call_chunks(1)
+        assert out.sequences[0].encode() == seqs[i] and out.qstrings[0].encode() == qs[i]
+        np.testing.assert_array_equal(out.moves[0], mv[i])
+    st = r.sample_stats()
+    assert st["batches_called"] == 2 and st["model_ms"] > 0 and st["decode_ms"] > 0
+    r.close()
