@@ -58,6 +58,7 @@ void b200_default_decoder_options(b200_decoder_options* o) {
     o->blank_score = 2.0f;
     o->q_shift = 0.0f;
     o->q_scale = 1.0f;
+    o->temperature = 1.0f;
     o->move_pad = 0;
 }
 
@@ -77,6 +78,39 @@ int b200_engine_get_stats(const b200_engine* e, b200_stats* out) {
     return guarded([&] {
         if (!e || !out) throw std::invalid_argument("b200_engine_get_stats: null argument");
         *out = reinterpret_cast<const b200::Engine*>(e)->stats();
+    });
+}
+
+int b200_engine_terminate(b200_engine* e) {
+    return guarded([&] {
+        if (!e) throw std::invalid_argument("b200_engine_terminate: null argument");
+        reinterpret_cast<b200::Engine*>(e)->terminate();
+    });
+}
+
+int b200_engine_restart(b200_engine* e) {
+    return guarded([&] {
+        if (!e) throw std::invalid_argument("b200_engine_restart: null argument");
+        reinterpret_cast<b200::Engine*>(e)->restart();
+    });
+}
+
+int b200_engine_set_low_latency(b200_engine* e, int32_t on) {
+    return guarded([&] {
+        if (!e) throw std::invalid_argument("b200_engine_set_low_latency: null argument");
+        reinterpret_cast<b200::Engine*>(e)->set_low_latency(on != 0);
+    });
+}
+
+int32_t b200_engine_is_low_latency(const b200_engine* e) { return e && reinterpret_cast<const b200::Engine*>(e)->low_latency(); }
+
+int b200_engine_batch_timeouts_ms(const b200_engine* e, int32_t* first_chunk_ms, int32_t* last_chunk_ms) {
+    return guarded([&] {
+        if (!e) throw std::invalid_argument("b200_engine_batch_timeouts_ms: null argument");
+        int a = 0, b = 0;
+        reinterpret_cast<const b200::Engine*>(e)->batch_timeouts_ms(&a, &b);
+        if (first_chunk_ms) *first_chunk_ms = a;
+        if (last_chunk_ms) *last_chunk_ms = b;
     });
 }
 

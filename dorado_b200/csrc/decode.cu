@@ -22,6 +22,9 @@
 #include "b200_crf_math.h"
 #include "common.cuh"
 #include "engine.h"
+#include "nvtx.h"
+
+#include <string>
 
 namespace b200 {
 
@@ -740,12 +743,14 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         constexpr int S = Dims<SL>::S;
         constexpr int CH = S >= 256 ? 1 : 256 / S;
         const int grid = (a.N + CH - 1) / CH;
+        NvtxRange r("back_guides");
         crf_bwd_scan_kernel<SL><<<grid, S * CH, 0, stream>>>(a.scores, a.bwd, a.N, a.T, a.clamp_val, a.blank);
         if (prof) prof->mark("crf_bwd_scan", stream);
     }
     {
         using F = FwdCfg<SL>;
         const int grid = (a.N + F::CH - 1) / F::CH;
+        NvtxRange r("beam_search");  // forward scan + posteriors (the reference's "compute_posts") are fused in
         crf_fwd_beam_kernel<SL><<<grid, F::THREADS, 0, stream>>>(a.scores, a.bwd, a.beam, a.N, a.T, a.clamp_val, a.blank,
                                                                    a.beam_width, a.log_beam_cut);
         if (prof) prof->mark("crf_fwd_beam", stream);
@@ -754,6 +759,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         const size_t smem = traceback_smem_bytes(a.T);
         if (smem > 48 * 1024) ensure_dynamic_smem(crf_traceback_kernel, 200 * 1024);
         const int grid = (a.N + kTbWarps - 1) / kTbWarps;
+        NvtxRange r("decode");
         crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.qtable, a.moves,
                                                                     a.sequence, a.qstring, a.n_bases);
         if (prof) prof->mark("crf_traceback", stream);
@@ -762,6 +768,12 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
 }
 
 }  // namespace
+
+size_t decode_max_blocks() {
+    int T = 65535;
+    while (traceback_smem_bytes(T) > 200 * 1024) T -= 64;
+    return (size_t)T;
+}
 
 size_t decode_scratch_bytes(int N, int T, int state_len, size_t* bwd_bytes, size_t* beam_bytes) {
     const size_t S = (size_t)1 << (2 * state_len);
@@ -780,6 +792,10 @@ void decode_scores(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         throw std::invalid_argument("b200 decode: need 1 <= T <= 65535 and N >= 1");
     }
     if (!a.qtable) throw std::invalid_argument("b200 decode: quality table missing");
+    if (traceback_smem_bytes(a.T) > 200 * 1024) {
+        throw std::invalid_argument("b200 decode: " + std::to_string(a.T) + " blocks per chunk exceed what the traceback kernel "
+                                    "holds in shared memory (about 10 700); use a smaller chunk size");
+    }
     switch (a.state_len) {
         case 3: launch_decode<3>(a, stream, prof); break;
         case 4: launch_decode<4>(a, stream, prof); break;

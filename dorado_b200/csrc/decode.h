@@ -32,6 +32,7 @@ struct DecodeArgs {
     int32_t* n_bases;
 };
 
+size_t decode_max_blocks();  // largest T the traceback kernel's shared-memory plan holds
 size_t decode_scratch_bytes(int N, int T, int state_len, size_t* bwd_bytes, size_t* beam_bytes);
 struct ProfileSink;
 void decode_scores(const DecodeArgs& args, cudaStream_t stream, ProfileSink* prof = nullptr);

@@ -7,6 +7,7 @@
 
 #include "b200_crf_math.h"
 #include "decode.h"
+#include "nvtx.h"
 
 #include <algorithm>
 #include <cmath>
@@ -99,6 +100,8 @@ Engine::Engine(const b200_model_desc& desc, const b200_tensor* tensors, int num_
         : m_desc(desc), m_device(device) {
     if (desc.state_len < 3 || desc.state_len > 5) throw std::invalid_argument("state_len must be 3..5");
     if (desc.outsize != (1 << (2 * (desc.state_len + 1)))) throw std::invalid_argument("outsize != 4^(state_len+1)");
+    if (desc.num_convs < 1 || desc.num_convs > 8) throw std::invalid_argument("num_convs must be in [1, 8]");
+    if (desc.stride < 1) throw std::invalid_argument("stride must be positive");
     require_sm100(device);
     B200_CUDA(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
     if (desc.model_type == B200_MODEL_LSTM) {
@@ -116,8 +119,38 @@ Engine::~Engine() {
     if (m_stream) cudaStreamDestroy(m_stream);
 }
 
+void Engine::terminate() {
+    m_terminated.store(true);
+    std::unique_lock<std::mutex> lock(m_life_mutex);
+    m_life_cv.wait(lock, [&] { return m_in_flight == 0; });
+}
+
+void Engine::restart() { m_terminated.store(false); }
+
+void Engine::batch_timeouts_ms(int* first_chunk_ms, int* last_chunk_ms) const {
+    // CudaCaller.cpp:121-138, 216-222
+    const bool ll = m_low_latency.load();
+    if (first_chunk_ms) *first_chunk_ms = ll ? 350 : 300000;
+    if (last_chunk_ms) *last_chunk_ms = ll ? 350 : 30000;
+}
+
+Engine::CallGuard::CallGuard(Engine& e) : eng(e) {
+    std::lock_guard<std::mutex> lock(e.m_life_mutex);
+    if (e.m_terminated.load()) throw std::logic_error("call_chunks on a terminated caller (restart() it first)");
+    ++e.m_in_flight;
+}
+
+Engine::CallGuard::~CallGuard() {
+    {
+        std::lock_guard<std::mutex> lock(eng.m_life_mutex);
+        --eng.m_in_flight;
+    }
+    eng.m_life_cv.notify_all();
+}
+
 b200_stats Engine::stats() const {
     b200_stats s{};
+    std::lock_guard<std::mutex> lock(m_stats_mutex);
     s.batches_called = batches_called.load();
     s.model_decode_ms = model_decode_ms;
     s.h2d_ms = h2d_ms;
@@ -128,6 +161,20 @@ b200_stats Engine::stats() const {
 }
 
 Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine), m_N(batch_size), m_T_in(chunk_size) {
+    try {
+        init();
+    } catch (...) {
+        release();  // the destructor does not run for a half-built object: hand back pinned memory, stream, events
+        throw;
+    }
+    // only a fully built runner is charged to the engine's statistics
+    engine.arena_bytes += (int64_t)m_arena.capacity();
+    m_counted = true;
+}
+
+void Runner::init() {
+    Engine& engine = m_engine;
+    const int batch_size = m_N, chunk_size = m_T_in;
     const auto& d = engine.desc();
     if (batch_size < 1) throw std::invalid_argument("batch_size must be >= 1");
     const int stride_inner = d.model_type == B200_MODEL_TX ? d.stride * d.upsample_scale : d.stride;
@@ -137,13 +184,21 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
         throw std::invalid_argument("chunk_size must be a positive multiple of " + std::to_string(gran));
     }
     m_T_out = chunk_size / d.stride;
+    if ((size_t)m_T_out > decode_max_blocks()) {
+        throw std::invalid_argument("chunk_size / stride = " + std::to_string(m_T_out) + " blocks exceed the decoder's limit of " +
+                                    std::to_string(decode_max_blocks()));
+    }
     m_C = d.outsize;
     b200_default_decoder_options(&m_opts);
     m_opts.q_scale = d.qscale;
     m_opts.q_shift = d.qbias;
 
     B200_CUDA(cudaSetDevice(engine.device()));
-    B200_CUDA(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;  // numerically lowest value = highest priority
+        B200_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        B200_CUDA(cudaStreamCreateWithPriority(&m_stream, cudaStreamNonBlocking, engine.low_latency() ? greatest : least));
+    }
     const size_t in_bytes = (size_t)m_N * m_T_in * sizeof(uint16_t);
     m_out_bytes = nb_offset(m_N, m_T_out) + (size_t)m_N * sizeof(int32_t);
     B200_CUDA(cudaHostAlloc(&m_h_input, in_bytes, cudaHostAllocDefault));
@@ -164,7 +219,6 @@ Runner::Runner(Engine& engine, int batch_size, int chunk_size) : m_engine(engine
     m_d_bwd = static_cast<float*>(m_arena.take(bwd_b));
     m_d_beam = static_cast<uint2*>(m_arena.take(beam_b));
     m_d_out = static_cast<unsigned char*>(m_arena.take(m_out_bytes));
-    engine.arena_bytes += (int64_t)m_arena.capacity();
     // zero padding rows / unused slots once, on the engine's own (non-blocking) stream so it is ordered
     // before the first forward
     B200_CUDA(cudaMemsetAsync(m_d_input, 0, in_bytes, m_stream));
@@ -187,28 +241,39 @@ void Runner::upload_qtable() {
     B200_CUDA(cudaStreamSynchronize(m_stream));
 }
 
-Runner::~Runner() {
+Runner::~Runner() { release(); }
+
+void Runner::release() {
     cudaSetDevice(m_engine.device());
-    m_engine.arena_bytes -= (int64_t)m_arena.capacity();
+    if (m_stream) cudaStreamSynchronize(m_stream);
+    if (m_counted) m_engine.arena_bytes -= (int64_t)m_arena.capacity();
     if (m_h_raw) m_engine.arena_bytes -= (int64_t)((size_t)m_N * m_T_in * sizeof(int16_t) + (size_t)m_N * sizeof(RawSlot));
+    m_counted = false;
     for (auto& e : m_ev) {
         if (e) cudaEventDestroy(e);
+        e = nullptr;
     }
+    m_plan.reset();
     if (m_h_input) cudaFreeHost(m_h_input);
     if (m_h_out) cudaFreeHost(m_h_out);
     if (m_h_raw) cudaFreeHost(m_h_raw);
     if (m_h_slots) cudaFreeHost(m_h_slots);
     if (m_d_raw) cudaFree(m_d_raw);
     if (m_d_slots) cudaFree(m_d_slots);
-    if (m_stream) {
-        cudaStreamSynchronize(m_stream);
-        cudaStreamDestroy(m_stream);
-    }
+    m_h_input = nullptr;
+    m_h_out = nullptr;
+    m_h_raw = nullptr;
+    m_h_slots = nullptr;
+    m_d_raw = nullptr;
+    m_d_slots = nullptr;
+    if (m_stream) cudaStreamDestroy(m_stream);
+    m_stream = nullptr;
 }
 
 void Runner::set_decoder_options(const b200_decoder_options& o) {
     if (o.beam_width < 1 || o.beam_width > 32) throw std::invalid_argument("beam_width must be in [1, 32]");
-    if (o.move_pad != 0) throw Unsupported("move_pad is not implemented");
+    if (o.move_pad != 0) throw Unsupported("move_pad: only the closed Koi kernel defines it; the reference never sets it");
+    if (o.temperature != 1.0f) throw Unsupported("temperature != 1: no decoder of the reference reads this option");
     std::lock_guard<std::mutex> lock(m_mutex);
     m_opts = o;
     upload_qtable();
@@ -217,6 +282,7 @@ void Runner::set_decoder_options(const b200_decoder_options& o) {
 void Runner::accept_chunk_f16(int idx, const uint16_t* samples, int64_t len) {
     if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
     if (len != m_T_in) throw std::invalid_argument("accept_chunk: chunk length != chunk_size");
+    std::lock_guard<std::mutex> lock(m_mutex);
     clear_raw_slot(idx);
     std::memcpy(m_h_input + (size_t)idx * m_T_in, samples, (size_t)len * sizeof(uint16_t));
 }
@@ -224,6 +290,7 @@ void Runner::accept_chunk_f16(int idx, const uint16_t* samples, int64_t len) {
 void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
     if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
     if (len != m_T_in) throw std::invalid_argument("accept_chunk: chunk length != chunk_size");
+    std::lock_guard<std::mutex> lock(m_mutex);
     clear_raw_slot(idx);
     __half* dst = reinterpret_cast<__half*>(m_h_input + (size_t)idx * m_T_in);
     for (int64_t i = 0; i < len; ++i) dst[i] = __float2half_rn(samples[i]);
@@ -297,11 +364,13 @@ void Runner::debug_read_input(int num_chunks, uint16_t* input_out) {
 
 void Runner::run_forward(int n) {
     (void)n;  // the whole batch is computed; only the first n chunks are decoded and returned
+    NvtxRange range("nn_forward");
     m_plan->run(m_stream);
     m_engine.gpu_launches += m_plan->launches();
 }
 
 void Runner::run_decode(int n, ProfileSink* prof) {
+    NvtxRange range("gpu_decode");
     const auto& d = m_engine.desc();
     DecodeArgs a{};
     a.scores = m_d_scores;
@@ -326,6 +395,20 @@ void Runner::run_decode(int n, ProfileSink* prof) {
     m_engine.gpu_launches += 3;
 }
 
+// Deterministic pseudo-random fp16 signal in [-2, 2) for the batch-size benchmark (an LCG: no <random> state to share).
+void Runner::fill_synthetic_input() {
+    std::lock_guard<std::mutex> lock(m_mutex);
+    uint32_t x = 0x2545f491u;
+    __half* dst = reinterpret_cast<__half*>(m_h_input);
+    for (size_t i = 0; i < (size_t)m_N * m_T_in; ++i) {
+        x = x * 1664525u + 1013904223u;
+        dst[i] = __float2half_rn((float)(int32_t)(x >> 8 & 0xffff) * (4.0f / 65536.0f) - 2.0f);
+    }
+    B200_CUDA(cudaSetDevice(m_engine.device()));
+    stage_input(m_N);
+    B200_CUDA(cudaStreamSynchronize(m_stream));
+}
+
 void Runner::upload() {
     std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
@@ -335,6 +418,8 @@ void Runner::upload() {
 
 b200_result Runner::call_chunks(int num_chunks) {
     if (num_chunks < 1 || num_chunks > m_N) throw std::invalid_argument("call_chunks: num_chunks out of range");
+    NvtxRange range("call_chunks");  // CudaCaller::call_chunks, NVTX3_FUNC_RANGE (CudaCaller.cpp:228)
+    Engine::CallGuard in_flight(m_engine);
     std::lock_guard<std::mutex> lock(m_mutex);
     B200_CUDA(cudaSetDevice(m_engine.device()));
     cudaStream_t s = m_stream;
@@ -358,6 +443,12 @@ b200_result Runner::call_chunks(int num_chunks) {
         m_engine.d2h_ms += d2h;
     }
     ++m_engine.batches_called;
+    // a raw chunk is valid for one batch: afterwards every slot is an fp16 slot again (rows written straight into
+    // b200_runner_input() must not be overwritten by a stale gather)
+    if (m_num_raw > 0) {
+        for (int i = 0; i < m_N; ++i) m_h_slots[i].slice_len = 0;
+        m_num_raw = 0;
+    }
 
     b200_result r{};
     r.moves = m_h_out;
@@ -514,7 +605,8 @@ int benchmark_batch_sizes(Engine& engine, int chunk_size, int granularity, int m
     for (int bs = granularity; bs <= max_batch_size; bs += granularity, ++count) {
         float best = std::numeric_limits<float>::max();
         {
-            Runner scratch(engine, bs, chunk_size);  // input stays zero: the kernels' time does not depend on the data
+            Runner scratch(engine, bs, chunk_size);
+            scratch.fill_synthetic_input();  // beam-search time depends on the data: time a non-degenerate signal
             for (int i = 0; i < 2; ++i) {            // run twice to eliminate outliers (CudaCaller.cpp:536)
                 float total = 0, fwd = 0, dec = 0;
                 scratch.step_device(bs, 1, &total, &fwd, &dec);
@@ -562,7 +654,8 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
         if (C == (1 << (2 * (sl + 1)))) state_len = sl;
     }
     if (!state_len) throw std::invalid_argument("decode: C must be 4^(state_len+1) with state_len 3..5");
-    if (opts.move_pad != 0) throw Unsupported("move_pad is not implemented");
+    if (opts.move_pad != 0) throw Unsupported("move_pad: only the closed Koi kernel defines it; the reference never sets it");
+    if (opts.temperature != 1.0f) throw Unsupported("temperature != 1: no decoder of the reference reads this option");
     require_sm100(device);
     cudaStream_t s;
     B200_CUDA(cudaStreamCreate(&s));

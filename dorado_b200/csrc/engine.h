@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -88,6 +89,24 @@ public:
     std::mutex& stats_mutex() { return m_stats_mutex; }  // guards the timing totals below
     b200_stats stats() const;
 
+    // Lifecycle of CudaCaller (CudaCaller.cpp:126-138, 216-222, 273-287).  The reference parks a GPU worker thread per
+    // caller; here calls run on the callers' own threads, so terminate() refuses new batches and waits for the ones in
+    // flight, restart() (idempotent, callable once per runner sharing the engine) admits batches again.
+    void terminate();
+    void restart();
+    bool terminated() const { return m_terminated.load(); }
+    // Low-latency callers (adaptive sampling): 350 ms batch timeouts instead of 5 min / 30 s, and -- where the reference
+    // gives them a task queue of their own (CudaCaller.cpp:204-214) -- their runners get CUDA streams of the highest
+    // priority, so their kernels are scheduled ahead of the throughput runners sharing the GPU.  Set before creating runners.
+    void set_low_latency(bool on) { m_low_latency.store(on); }
+    bool low_latency() const { return m_low_latency.load(); }
+    void batch_timeouts_ms(int* first_chunk_ms, int* last_chunk_ms) const;
+    struct CallGuard {  // brackets one call_chunks
+        explicit CallGuard(Engine& e);
+        ~CallGuard();
+        Engine& eng;
+    };
+
     std::atomic<int64_t> batches_called{0};
     std::atomic<int64_t> gpu_launches{0};
     std::atomic<int64_t> arena_bytes{0};
@@ -98,7 +117,12 @@ private:
     int m_device;
     cudaStream_t m_stream = nullptr;
     std::unique_ptr<Model> m_model;
-    std::mutex m_stats_mutex;
+    mutable std::mutex m_stats_mutex;
+    std::atomic<bool> m_terminated{false};
+    std::atomic<bool> m_low_latency{false};
+    std::mutex m_life_mutex;
+    std::condition_variable m_life_cv;
+    int m_in_flight = 0;  // guarded by m_life_mutex
 };
 
 class Runner;
@@ -123,6 +147,7 @@ public:
     void debug_read_input(int num_chunks, uint16_t* input_out);
     b200_result call_chunks(int num_chunks);
     void upload();
+    void fill_synthetic_input();
     void step_device(int num_chunks, int iters, float* total_ms, float* forward_ms, float* decode_ms);
     void forward_scores_to_host(int num_chunks, uint16_t* scores_out);
     void debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst);
@@ -130,6 +155,9 @@ public:
     std::string profile(int num_chunks);
 
 private:
+    void init();     // everything the constructor allocates; may throw
+    void release();  // idempotent teardown shared by the destructor and a failed constructor
+    bool m_counted = false;
     void stage_input(int n);  // H2D of the first n slots (+ gather/scale kernel for raw slots), on m_stream
     void clear_raw_slot(int idx);
     void run_forward(int n);

@@ -270,14 +270,14 @@ using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, voi
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeFn get_encode_fn() {
-    static EncodeFn fn = nullptr;
-    if (!fn) {
+    // function-local static: initialised once, thread-safe (runners are created concurrently)
+    static const EncodeFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
         if (q != cudaDriverEntryPointSuccess || !p) throw CudaError("cuTensorMapEncodeTiled entry point not available");
-        fn = reinterpret_cast<EncodeFn>(p);
-    }
+        return reinterpret_cast<EncodeFn>(p);
+    }();
     return fn;
 }
 

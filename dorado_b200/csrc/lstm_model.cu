@@ -15,6 +15,7 @@
 //   scores  [N][T_out][outsize]
 #include "engine.h"
 #include "gemm.h"
+#include "nvtx.h"
 #include "tc.cuh"
 
 #include <cstdio>
@@ -709,6 +710,7 @@ public:
     void launch_lstm(int l, cudaStream_t stream) const;
     // hoisted path
     long long* dbg_timeline = nullptr;
+    int debug_layers = -1;  // >= 0: stop after that many LSTM layers (B200_DEBUG_LSTM_LAYERS, read once at plan creation)
     bool hoisted = false;
     int rec_un = 16;
     std::vector<GemmPlan> gx_gemm;
@@ -837,7 +839,7 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
         std::vector<float> w((size_t)out1 * Cp, 0.0f);
         for (int o = 0; o < out1; ++o) std::memcpy(&w[(size_t)o * Cp], &tw.data[(size_t)o * C], sizeof(float) * C);
         wl1 = upload_f16(w);
-        if (d.linear_bias || (d.out_features == 0 && false)) {
+        if (d.linear_bias) {
             const auto& tb = find_tensor(tensors, n, std::to_string(layer) + ".linear.bias.tensor");
             bl1 = upload_f32(std::vector<float>(tb.data, tb.data + out1));
         }
@@ -885,6 +887,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     }
     auto plan = std::make_unique<LstmPlan>();
     plan->model = this;
+    if (const char* dbg = std::getenv("B200_DEBUG_LSTM_LAYERS")) plan->debug_layers = std::atoi(dbg);
     uint8_t* base = static_cast<uint8_t*>(ws);
     auto take = [&](size_t bytes) {
         uint8_t* p = base;
@@ -1128,35 +1131,31 @@ void LstmPlan::launch_lstm(int l, cudaStream_t stream) const {
 }
 
 void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
-    conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
-    if (prof) prof->mark("conv12", stream);
-    run_gemm(conv3, stream);
-    if (prof) prof->mark("conv3_gemm", stream);
-    int nl = num_layers;
-    if (const char* dbg = getenv("B200_DEBUG_LSTM_LAYERS")) {  // debug: stop after k LSTM layers (tools/debug_forward.py)
-        nl = atoi(dbg);
-        if (nl < num_layers) {
-            for (int l = 0; l < nl; ++l) {
-                if (hoisted) {
-                    run_gemm(gx_gemm[l], stream);
-                    launch_rec(l, stream);
-                } else {
-                    launch_lstm(l, stream);
-                }
+    {
+        NvtxRange r("conv");
+        conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
+        if (prof) prof->mark("conv12", stream);
+        run_gemm(conv3, stream);
+        if (prof) prof->mark("conv3_gemm", stream);
+    }
+    {
+        NvtxRange lstm_range("lstm_stack");
+        const int nl = debug_layers >= 0 && debug_layers < num_layers ? debug_layers : num_layers;
+        for (int l = 0; l < nl; ++l) {
+            NvtxRange r("lstm_layer");
+            if (hoisted) {
+                run_gemm(gx_gemm[l], stream);
+                if (prof) prof->mark("lstm_gx_gemm", stream);
+                launch_rec(l, stream);
+                if (prof) prof->mark("lstm_rec", stream);
+            } else {
+                launch_lstm(l, stream);
+                if (prof) prof->mark("lstm_layer", stream);
             }
+        }
+        if (nl < num_layers) {  // debug: stop after nl layers (tools/debug_forward.py reads the sequence buffer)
             B200_CUDA(cudaGetLastError());
             return;
-        }
-    }
-    for (int l = 0; l < num_layers; ++l) {
-        if (hoisted) {
-            run_gemm(gx_gemm[l], stream);
-            if (prof) prof->mark("lstm_gx_gemm", stream);
-            launch_rec(l, stream);
-            if (prof) prof->mark("lstm_rec", stream);
-        } else {
-            launch_lstm(l, stream);
-            if (prof) prof->mark("lstm_layer", stream);
         }
     }
     if (dbg_timeline) {
@@ -1170,6 +1169,7 @@ void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
                     64 + s, e[1] - t0, e[2] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0, e[8] - t0, e[9] - t0, e[10] - t0);
         }
     }
+    NvtxRange r("linear");
     run_gemm(linear1, stream);
     if (prof) prof->mark("linear_gemm", stream);
     if (num_linear == 2) {

@@ -15,6 +15,7 @@
 // x <- RMSNorm(sublayer(x) + alpha * x) with the "+ alpha * x" fused into the GEMM epilogue.
 #include "engine.h"
 #include "gemm.h"
+#include "nvtx.h"
 
 #include <cmath>
 #include <cstring>
@@ -594,6 +595,7 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
 }
 
 void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
+    nvtxRangePushA("Conv");
     {
         const long long total = (long long)conv1.N * conv1.T * (conv1.C1 / 8);
         tx_conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(conv1);
@@ -603,27 +605,58 @@ void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
         run_gemm(c, stream);
         if (prof) prof->mark("tx_conv_gemm", stream);
     }
+    nvtxRangePop();
     const unsigned norm_grid = (unsigned)((rows + 7) / 8);
+    nvtxRangePushA("TransEnc");
     for (auto& L : layers) {
-        run_gemm(L.qkv, stream);
-        if (prof) prof->mark("qkv_gemm", stream);
-        tx_attention_kernel<<<dim3((unsigned)((T + 63) / 64), (unsigned)H, (unsigned)N), 128, 0, stream>>>(L.attn);
-        if (prof) prof->mark("tx_attention", stream);
-        run_gemm(L.out_proj, stream);
-        if (prof) prof->mark("out_proj_gemm", stream);
-        rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n1, rows);
-        if (prof) prof->mark("rmsnorm", stream);
-        run_gemm(L.fc1, stream);
-        if (prof) prof->mark("fc1_swiglu_gemm", stream);
-        run_gemm(L.fc2, stream);
-        if (prof) prof->mark("fc2_gemm", stream);
-        rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n2, rows);
-        if (prof) prof->mark("rmsnorm", stream);
+        NvtxRange layer("TxLayerKoiTiled");
+        {
+            NvtxRange r("QKV+ROTE");
+            run_gemm(L.qkv, stream);
+            if (prof) prof->mark("qkv_gemm", stream);
+        }
+        {
+            NvtxRange r("MEA");
+            tx_attention_kernel<<<dim3((unsigned)((T + 63) / 64), (unsigned)H, (unsigned)N), 128, 0, stream>>>(L.attn);
+            if (prof) prof->mark("tx_attention", stream);
+        }
+        {
+            NvtxRange r("OUTP");
+            run_gemm(L.out_proj, stream);
+            if (prof) prof->mark("out_proj_gemm", stream);
+        }
+        {
+            NvtxRange r("LNORM1");
+            rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n1, rows);
+            if (prof) prof->mark("rmsnorm", stream);
+        }
+        {
+            NvtxRange r("FC1+SILU");
+            run_gemm(L.fc1, stream);
+            if (prof) prof->mark("fc1_swiglu_gemm", stream);
+        }
+        {
+            NvtxRange r("FC2");
+            run_gemm(L.fc2, stream);
+            if (prof) prof->mark("fc2_gemm", stream);
+        }
+        {
+            NvtxRange r("LNORM2");
+            rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n2, rows);
+            if (prof) prof->mark("rmsnorm", stream);
+        }
     }
-    run_gemm(upsample, stream);
-    if (prof) prof->mark("upsample_gemm", stream);
-    run_gemm(crf, stream);
-    if (prof) prof->mark("crf_gemm", stream);
+    nvtxRangePop();
+    {
+        NvtxRange r("TransDec");
+        run_gemm(upsample, stream);
+        if (prof) prof->mark("upsample_gemm", stream);
+    }
+    {
+        NvtxRange r("CRF");
+        run_gemm(crf, stream);
+        if (prof) prof->mark("crf_gemm", stream);
+    }
     B200_CUDA(cudaGetLastError());
 }
 

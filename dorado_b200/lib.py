@@ -49,7 +49,7 @@ class Tensor(C.Structure):
 
 class DecoderOptions(C.Structure):
     _fields_ = [("beam_width", C.c_int32), ("beam_cut", C.c_float), ("blank_score", C.c_float),
-                ("q_shift", C.c_float), ("q_scale", C.c_float), ("move_pad", C.c_int32)]
+                ("q_shift", C.c_float), ("q_scale", C.c_float), ("temperature", C.c_float), ("move_pad", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -82,7 +82,8 @@ EXPORTS = [
     "b200_runner_upload", "b200_runner_step_device", "b200_runners_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_debug_read_workspace", "b200_decode_scores",
     "b200_test_gemm", "b200_generate_chunks", "b200_stitch_chunks", "b200_runner_accept_raw_chunk",
     "b200_runner_debug_read_input", "b200_engine_runner_bytes", "b200_engine_benchmark_batch_sizes",
-    "b200_select_batch_size", "b200_generate_variable_chunks",
+    "b200_select_batch_size", "b200_generate_variable_chunks", "b200_engine_terminate", "b200_engine_restart",
+    "b200_engine_set_low_latency", "b200_engine_is_low_latency", "b200_engine_batch_timeouts_ms",
 ]
 
 _lib = None
@@ -106,6 +107,12 @@ def load_library() -> C.CDLL:
     lib.b200_last_error.restype = C.c_char_p
     lib.b200_version.restype = C.c_char_p
     lib.b200_default_decoder_options.argtypes = [C.POINTER(DecoderOptions)]
+    lib.b200_engine_terminate.argtypes = [vp]
+    lib.b200_engine_restart.argtypes = [vp]
+    lib.b200_engine_set_low_latency.argtypes = [vp, i32]
+    lib.b200_engine_is_low_latency.argtypes = [vp]
+    lib.b200_engine_is_low_latency.restype = i32
+    lib.b200_engine_batch_timeouts_ms.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.b200_engine_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(Tensor), i32, i32, C.POINTER(vp)]
     lib.b200_engine_destroy.argtypes = [vp]
     lib.b200_engine_get_stats.argtypes = [vp, C.POINTER(Stats)]

@@ -35,7 +35,7 @@ class DecodedChunk:
 class B200Caller:
     """One model replica on one GPU (CudaCaller, dorado/basecall/CudaCaller.cpp:149-202)."""
 
-    def __init__(self, cfg: BasecallModelConfig, weights: dict, device: int = 0):
+    def __init__(self, cfg: BasecallModelConfig, weights: dict, device: int = 0, low_latency: bool = False):
         self.cfg = cfg
         self.device = device
         lib = L.load_library()
@@ -53,7 +53,23 @@ class B200Caller:
         self.handle = C.c_void_p()
         L.check(lib.b200_engine_create(C.byref(desc), arr, len(weights), device, C.byref(self.handle)))
         self._keep = None  # the engine copied everything to the device
-        self._terminated = False
+        L.check(lib.b200_engine_set_low_latency(self.handle, int(low_latency)))
+
+    def terminate(self) -> None:
+        """CudaCaller::terminate (CudaCaller.cpp:273-280): refuse new batches, wait for the ones in flight."""
+        L.check(L.load_library().b200_engine_terminate(self.handle))
+
+    def restart(self) -> None:
+        """CudaCaller::restart (CudaCaller.cpp:282-287); idempotent."""
+        L.check(L.load_library().b200_engine_restart(self.handle))
+
+    def is_low_latency(self) -> bool:
+        return bool(L.load_library().b200_engine_is_low_latency(self.handle))
+
+    def batch_timeouts_ms(self):
+        a, b = C.c_int32(), C.c_int32()
+        L.check(L.load_library().b200_engine_batch_timeouts_ms(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def runner_bytes(self, batch_size: int, chunk_size: int) -> int:
         """Device bytes a runner of this shape allocates (exact; CudaCaller::calculate_memory_requirements estimates it)."""
@@ -161,16 +177,16 @@ class B200ModelRunner:
         return False
 
     def batch_timeouts_ms(self):
-        return (300000, 30000)  # CudaCaller.cpp:126-138, non low-latency
+        return self.caller.batch_timeouts_ms()  # CudaCaller.cpp:216-222
 
     def is_low_latency(self) -> bool:
-        return False
+        return self.caller.is_low_latency()
 
     def terminate(self) -> None:
-        pass
+        self.caller.terminate()  # CudaModelRunner::terminate -> CudaCaller::terminate (CudaModelRunner.cpp:62)
 
     def restart(self) -> None:
-        pass
+        self.caller.restart()
 
     def get_name(self) -> str:
         return self._name

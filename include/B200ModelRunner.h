@@ -32,7 +32,8 @@ namespace dorado::basecall {
 // One model replica on one device; shared by the runners of that device (the reference's CudaCaller).
 class B200Caller {
 public:
-    B200Caller(const config::BasecallModelConfig& model_config, int device_index)
+    // low_latency: params.pipeline_type == PipelineType::simplex_low_latency (CudaCaller.cpp:149-152)
+    B200Caller(const config::BasecallModelConfig& model_config, int device_index, bool low_latency = false)
             : m_config(model_config), m_device(device_index) {
         b200_model_desc d{};
         d.model_type = model_config.is_tx_model() ? B200_MODEL_TX : B200_MODEL_LSTM;
@@ -85,6 +86,7 @@ public:
             }
         }
         check(b200_engine_create(&d, bt.data(), static_cast<int32_t>(bt.size()), device_index, &m_engine));
+        check(b200_engine_set_low_latency(m_engine, low_latency ? 1 : 0));
     }
     ~B200Caller() { b200_engine_destroy(m_engine); }
     B200Caller(const B200Caller&) = delete;
@@ -209,10 +211,14 @@ public:
     const config::BasecallModelConfig& config() const final { return m_caller->config(); }
     size_t chunk_size() const final { return static_cast<size_t>(b200_runner_chunk_size(m_runner)); }
     size_t batch_size() const final { return static_cast<size_t>(b200_runner_batch_size(m_runner)); }
-    std::pair<int, int> batch_timeouts_ms() const final { return {300000, 30000}; }  // CudaCaller.cpp:126-138
-    bool is_low_latency() const final { return false; }
-    void terminate() final {}
-    void restart() final {}
+    std::pair<int, int> batch_timeouts_ms() const final {  // CudaCaller.cpp:216-222
+        int32_t first = 0, last = 0;
+        B200Caller::check(b200_engine_batch_timeouts_ms(m_caller->engine(), &first, &last));
+        return {first, last};
+    }
+    bool is_low_latency() const final { return b200_engine_is_low_latency(m_caller->engine()) != 0; }
+    void terminate() final { B200Caller::check(b200_engine_terminate(m_caller->engine())); }  // CudaModelRunner.cpp:62
+    void restart() final { B200Caller::check(b200_engine_restart(m_caller->engine())); }      // CudaModelRunner.cpp:64
     std::string get_name() const final { return m_name; }
 
     stats::NamedStats sample_stats() const final {

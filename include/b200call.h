@@ -82,7 +82,11 @@ typedef struct b200_decoder_options {
     float blank_score;
     float q_shift;
     float q_scale;
-    int32_t move_pad; /* accepted for ABI parity; must be 0 */
+    float temperature; /* DecodedChunk.h:21; no decoder of the reference reads it (CPU, CUDA and Metal paths); kept so the
+                          struct mirrors DecoderOptions field for field.  Must be 1. */
+    int32_t move_pad;  /* DecodedChunk.h:22: never set in the reference tree and only forwarded to the closed Koi kernel
+                          host_run_decode (CUDADecoder.cpp:100-104), so its meaning is not defined by any open source;
+                          0 is accepted, anything else returns B200_ERR_UNSUPPORTED. */
 } b200_decoder_options;
 
 /* Result of one call_chunks(): pinned host arrays owned by the runner, rows of t_out bytes.
@@ -122,6 +126,18 @@ B200_API int b200_engine_create(const b200_model_desc* desc,
                                 b200_engine** out);
 B200_API int b200_engine_destroy(b200_engine* engine);
 B200_API int b200_engine_get_stats(const b200_engine* engine, b200_stats* out);
+
+/* CudaCaller lifecycle (CudaCaller.cpp:273-287): terminate refuses new batches and returns once the batches in flight have
+ * finished; restart (idempotent, callable once per runner sharing the engine) admits batches again.  A call_chunks on a
+ * terminated engine returns B200_ERR_INTERNAL ("terminated"). */
+B200_API int b200_engine_terminate(b200_engine* engine);
+B200_API int b200_engine_restart(b200_engine* engine);
+/* Low-latency callers (PipelineType::simplex_low_latency, CudaCaller.cpp:126-138, 204-222): batch timeouts of 350 ms
+ * instead of (300000, 30000), and runners created afterwards get highest-priority CUDA streams (the reference gives
+ * low-latency callers a task queue of their own).  Call before creating runners. */
+B200_API int b200_engine_set_low_latency(b200_engine* engine, int32_t on);
+B200_API int32_t b200_engine_is_low_latency(const b200_engine* engine);
+B200_API int b200_engine_batch_timeouts_ms(const b200_engine* engine, int32_t* first_chunk_ms, int32_t* last_chunk_ms);
 
 /* CudaModelRunner::CudaModelRunner (CudaModelRunner.cpp:13-19) + CudaCaller::create_input/output_tensor
  * (CudaCaller.cpp:289-314): pinned fp16 input [batch, 1, chunk_size], pinned output, device arena. */

@@ -151,3 +151,50 @@ def test_concurrent_runners_match_serial(kind, N, T):
     assert ms > 0
     for i, r in enumerate(runners):
         assert [(c.sequence, c.qstring, bytes(c.moves)) for c in r.call_chunks(N)] == serial[i]
+
+
+def test_caller_lifecycle_and_low_latency():
+    """CudaCaller::terminate / restart (CudaCaller.cpp:273-287) and the low-latency variant (:126-138, 216-222)."""
+    from dorado_b200 import lib as L
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir("fast"))
+    w = synthetic_weights(cfg, 42)
+    caller = B200Caller(cfg, w)
+    runner = B200ModelRunner(caller, 16, 1200)
+    assert runner.batch_timeouts_ms() == (300000, 30000) and not runner.is_low_latency()
+    sig = np.random.default_rng(0).standard_normal((16, runner.chunk_size())).astype(np.float16)
+    for i in range(16):
+        runner.accept_chunk(i, sig[i])
+    first = runner.call_chunks(16)
+    runner.terminate()
+    runner.terminate()                      # once per runner sharing the caller
+    with pytest.raises(L.B200Error) as e:
+        runner.call_chunks(16)
+    assert "terminated" in str(e.value)
+    runner.restart()
+    runner.restart()                        # idempotent
+    again = runner.call_chunks(16)
+    assert [c.sequence for c in again] == [c.sequence for c in first]
+    assert [c.qstring for c in again] == [c.qstring for c in first]
+    # low-latency caller: 350 ms timeouts, highest-priority streams, same results
+    ll = B200Caller(cfg, w, low_latency=True)
+    r2 = B200ModelRunner(ll, 16, 1200)
+    assert r2.batch_timeouts_ms() == (350, 350) and r2.is_low_latency()
+    for i in range(16):
+        r2.accept_chunk(i, sig[i])
+    assert [c.sequence for c in r2.call_chunks(16)] == [c.sequence for c in first]
+
+
+def test_decoder_options_struct_mirrors_the_reference():
+    from dorado_b200 import lib as L
+    o = L.default_decoder_options()
+    assert (o.beam_width, o.beam_cut, o.blank_score, o.q_shift, o.q_scale, o.temperature, o.move_pad) == (32, 100.0, 2.0, 0.0, 1.0, 1.0, 0)
+    scores = np.zeros((1, 8, 256), np.float16)
+    for field, val in (("move_pad", 1), ("temperature", 0.5)):
+        o = L.default_decoder_options()
+        setattr(o, field, val)
+        with pytest.raises(L.B200Error) as e:
+            L.decode_scores(scores, opts=o)
+        assert e.value.status == L.B200_ERR_UNSUPPORTED
