@@ -459,6 +459,241 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// LSTM layer, second generation for the small hidden size (fast: C = 96).  Same orientation as above (weights = M
+// operand, a CTA owns NBR chunks for the whole sequence), rebuilt around the length of the per-step dependent chain
+// h_{t-1} -> MMA -> gates -> h_t, which is what bounds a layer (1666 steps, a few hundred FLOP/cycle of actual work):
+//   * gate rows are permuted so that a warp's 32 TMEM lanes hold (8 units x 4 gates): the four gates of a cell meet by
+//     a 4 x 4 quad transpose in registers (shuffles); no shared-memory exchange, no block barrier on the chain;
+//   * cell states live in registers;
+//   * only the recurrent half of the weights (W_hh, the half on the chain) sits in tensor memory; the x_t half is
+//     read from shared memory by MMAs issued one step ahead.  That brings a CTA down to 256 tensor-memory columns,
+//     < 64 registers per thread and ~90 KB of shared memory, so TWO CTAs share an SM: the recurrences of two batches in
+//     flight (runners) run side by side instead of queueing for the SMs;
+//   * h_t leaves for HBM as one TMA store per tile from the operand block it was written to (no scattered stores).
+// ------------------------------------------------------------------------------------------------
+template <int C>
+struct Lstm2Cfg {
+    static constexpr int MT = C / 32;              // gate tiles (128 rows = 32 units x 4 gates)
+    static constexpr int KBX = C / KBLK;           // operand blocks of the x half (= of the h half)
+    static constexpr int KB = 2 * KBX;
+    static constexpr int THREADS = 32 * (1 + MT) + 128 * MT;   // TMA warp, MT MMA warps, MT epilogue groups of 4 warps
+    static constexpr int WCOLS = C / 2;            // TMEM columns of the W_hh half of one tile
+    static constexpr int ACC_COLS = 2 * MT * UN;   // double-buffered accumulators
+    static constexpr int NEED = ACC_COLS + MT * WCOLS;
+    static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+    static constexpr size_t WX_BYTES = (size_t)MT * KBX * WBLK_BYTES;   // W_ih half in shared memory
+    static constexpr size_t Z_BYTES = (size_t)2 * KB * ZBLK;
+    static constexpr size_t SMEM = 1024 + WX_BYTES + Z_BYTES + 8 * (8 + 2 * MT) + 64;
+    static_assert(NEED <= 512 && C % 32 == 0 && C % 16 == 0, "unsupported LSTM size");
+};
+
+template <int C, int NBR>
+__global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <= 256 ? 2 : 1)
+        lstm_layer2_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w, const LstmParams p) {
+    using Cfg = Lstm2Cfg<C>;
+    constexpr int MT = Cfg::MT, KB = Cfg::KB, KBX = Cfg::KBX;
+    constexpr int CPL = NBR / 4;  // cells per lane
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_s = smem;                                   // [MT][KBX][128 x 64 B]  W_ih, K-major, 64-byte swizzle
+    uint8_t* z_s = w_s + Cfg::WX_BYTES;                    // [2][KB][ZBLK]          [x_t ; h_{t-1}] operand blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(z_s + Cfg::Z_BYTES);
+    uint64_t* x_full = bars;          // [2]  TMA -> MMA
+    uint64_t* z_free = bars + 2;      // [2]  MMAs done with Z[buf] -> TMA
+    uint64_t* h_ready = bars + 4;     // [2]  epilogue wrote h into Z[buf] -> MMA
+    uint64_t* acc_free = bars + 6;    // [2]  epilogue done reading accumulator set -> MMA
+    uint64_t* acc_full = bars + 8;    // [2][MT] MMA -> epilogue
+    uint64_t* w_full = acc_full + 2 * MT;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * NBR;
+
+    // zero Z (padding rows, h_{-1}) before anything asynchronous starts
+    for (int i = threadIdx.x; i < (int)(Cfg::Z_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&x_full[i], 1);
+            tc::mbar_init(&z_free[i], MT);          // one commit per MMA warp
+            tc::mbar_init(&h_ready[i], MT * 4);     // one arrival per epilogue warp
+            tc::mbar_init(&acc_free[i], MT * 4);
+        }
+        for (int i = 0; i < 2 * MT; ++i) tc::mbar_init(&acc_full[i], 1);
+        tc::mbar_init(&w_full[0], 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_x);
+        tc::prefetch_tmap(&tma_w);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_w = tmem_base + Cfg::ACC_COLS;     // [MT][WCOLS]: tile m, 16-element k-step ks at m*WCOLS + ks*8
+
+    const bool is_epi = warp > MT;
+    const int ewarp = warp - (1 + MT);
+    const int em = ewarp >> 2;      // tile served by this epilogue warp
+    const int qt = warp & 3;        // TMEM lane quarter (the 4 warps of a tile cover all four)
+    if (is_epi) {
+        // this thread's W_hh row (tile em, row 32*qt + lane): columns C..2C-1 of the packed [W_ih | W_hh] row
+        const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)(em * 128 + qt * 32 + lane) * 2 * C + C);
+#pragma unroll 1
+        for (int cb = 0; cb < C / 32; ++cb) {
+            uint32_t r[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint4 x = __ldg(src + cb * 4 + v);
+                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+            }
+            tc::tmem_st_32x16(tmem_w + ((uint32_t)(qt * 32) << 16) + (uint32_t)(em * Cfg::WCOLS + cb * 16), r);
+        }
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+
+    if (warp == 0) {
+        // ---------------- TMA producer: W_ih once, then x_t one step ahead ----------------
+        if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)Cfg::WX_BYTES);
+            for (int m = 0; m < MT; ++m) {
+                for (int kb = 0; kb < KBX; ++kb) {
+                    tc::tma_load_2d(w_s + (size_t)(m * KBX + kb) * WBLK_BYTES, &tma_w, &w_full[0], kb * KBLK, m * 128);
+                }
+            }
+            for (int s = 0; s < p.T; ++s) {
+                const int t = p.reverse ? p.T - 1 - s : s;
+                const int buf = s & 1;
+                tc::mbar_wait(&z_free[buf], ((s >> 1) & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&x_full[buf], (uint32_t)(KBX * NBR * KBLK * 2));
+                for (int kb = 0; kb < KBX; ++kb) {
+                    tc::tma_load_2d(z_s + (size_t)(buf * KB + kb) * ZBLK, &tma_x, &x_full[buf], kb * KBLK, t * p.N + n0);
+                }
+            }
+        }
+    } else if (!is_epi) {
+        // ---------------- MMA issuers: warp mw owns tile mw ----------------
+        const int mw = warp - 1;
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
+            const uint64_t wdesc = umma_desc_sw64(tc::smem_u32(w_s)) + (uint64_t)((mw * KBX * WBLK_BYTES) >> 4);
+            const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
+            tc::mbar_wait(&w_full[0], 0);
+            for (int s = 0; s < p.T; ++s) {
+                const int buf = s & 1;
+                const uint32_t par = (uint32_t)((s >> 1) & 1);
+                const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
+                const uint32_t d_tmem = tmem_base + (uint32_t)((buf * MT + mw) * UN);
+                tc::mbar_wait(&x_full[buf], par);
+                tc::mbar_wait(&acc_free[buf], par ^ 1);
+                tc::tc_fence_after();
+                // x half: independent of the recurrence, runs under the previous step's gate math
+#pragma unroll
+                for (int kb = 0; kb < KBX; ++kb) {
+                    const uint64_t adesc = wdesc + (uint64_t)((kb * WBLK_BYTES) >> 4);
+                    const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
+                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                    tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
+                }
+                tc::mbar_wait(&h_ready[buf], par);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < KBX; ++kb) {
+                    const uint32_t a_t = tmem_w + (uint32_t)(mw * Cfg::WCOLS + kb * 16);
+                    const uint64_t bdesc = zd + (uint64_t)(((KBX + kb) * ZBLK) >> 4);
+                    tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, true);
+                    tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
+                }
+                tc::umma_commit(&acc_full[buf * MT + mw]);
+                tc::umma_commit(&z_free[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue: gates, cell update, h_t ----------------
+        const int uk = lane >> 2, gj = lane & 3;   // unit within the warp's 8, gate type (i, f, g, o)
+        const int g0 = gj & 1, g1 = gj >> 1;
+        const float am = gj == 2 ? 2.0f : 1.0f;    // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
+        const float bias = __ldg(p.bias + em * 128 + qt * 32 + lane);
+        const bool storer = qt == 0 && lane == 0;
+        float c_reg[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) c_reg[c] = 0.0f;
+        if (lane == 0) tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0 is in place (zeroed before the CTA-wide sync)
+
+        for (int s = 0; s < p.T; ++s) {
+            const int t = p.reverse ? p.T - 1 - s : s;
+            const int buf = s & 1, nbuf = buf ^ 1;
+            const uint32_t par = (uint32_t)((s >> 1) & 1);
+            uint8_t* zh = z_s + (size_t)(nbuf * KB + KBX + em) * ZBLK;   // block of this tile's 32 units in the next operand
+            tc::mbar_wait(&acc_full[buf * MT + em], par);
+            tc::tc_fence_after();
+            uint32_t r[NBR];
+            const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((buf * MT + em) * UN);
+            if constexpr (NBR == 16) {
+                tc::tmem_ld_32x16(taddr, r);
+            } else if constexpr (NBR == 8) {
+                tc::tmem_ld_32x8(taddr, r);
+            } else {
+                tc::tmem_ld_32x4(taddr, r);
+            }
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            float a[NBR];
+#pragma unroll
+            for (int n = 0; n < NBR; ++n) {
+                const float v = __uint_as_float(r[n]) + bias;
+                a[n] = 1.0f - __fdividef(am, __expf(am * v) + 1.0f);
+            }
+            // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float s0 = g0 ? a[4 * c + 0] : a[4 * c + 1];
+                float s1 = g0 ? a[4 * c + 2] : a[4 * c + 3];
+                float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                if (g0) { a[4 * c + 0] = r0; a[4 * c + 2] = r1; } else { a[4 * c + 1] = r0; a[4 * c + 3] = r1; }
+                s0 = g1 ? a[4 * c + 0] : a[4 * c + 2];
+                s1 = g1 ? a[4 * c + 1] : a[4 * c + 3];
+                r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+                r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+                if (g1) { a[4 * c + 0] = r0; a[4 * c + 1] = r1; } else { a[4 * c + 2] = r0; a[4 * c + 3] = r1; }
+            }
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const float cs = a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2];
+                c_reg[c] = cs;
+                const __half h = __float2half_rn(a[4 * c + 3] * tanh_f(cs));
+                // units (uk, uk ^ 1) of chunk 4c + gj leave as one 32-bit store from the even lane
+                const uint32_t mine = (uint32_t)__half_as_ushort(h);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 4);
+                if (!(uk & 1)) {
+                    *reinterpret_cast<uint32_t*>(zh + sw64_offset(4 * c + gj, qt * 8 + uk)) = mine | (other << 16);
+                }
+            }
+            tc::fence_proxy_async_smem();   // h_t -> visible to the MMAs and the TMA store (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(&acc_free[buf]);
+                tc::mbar_arrive(&h_ready[nbuf]);
+            }
+            // off the chain: h_t of this tile to HBM, one TMA store of the operand block (rows = the CTA's chunks)
+            if (storer) tc::bulk_wait_group_read<0>();   // the store of the previous step has read Z[buf]'s block: it may be rewritten next step
+            named_bar_sync(1 + em, 128);
+            if (storer) {
+                tc::tma_store_2d(&tma_x, zh, em * 32, t * p.N + n0);
+                tc::bulk_commit_group();
+            }
+        }
+        if (storer) tc::bulk_wait_group<0>();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSTM layer for hidden sizes whose weights do not fit one SM (hac: C = 384): hoisted x-projection + cluster recurrence.
 //
 // The x_t half of the gate pre-activations does not depend on the recurrence, so it is hoisted into one large
@@ -683,6 +918,253 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL, UNC>::THREADS, 1) lstm_clust
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cluster recurrence, second generation (the default): same weights-stationary decomposition, restructured around
+// what bounds a step -- the tensor pipe (2 * TPC tiles of 128 x 16 x C per group) and the SFU (5 transcendentals per
+// cell) -- instead of around barriers:
+//   * the cluster's chunks form NG = 2 independent groups of 16; the MMA issuer ping-pongs between them, so group A's
+//     gate math and all-gather run under group B's MMAs (a single group has nothing to overlap with);
+//   * h_t travels as BULK ASYNC COPIES (cp.async.bulk shared::cta -> shared::cluster): an epilogue tile stages its
+//     32 units x 16 chunks in the swizzled operand layout in local shared memory and one thread sends the 1 KB block to
+//     every CTA of the cluster; the bytes complete on the destination's mbarrier, which is what its MMA issuer waits on.
+//     No cluster barrier, no remote scalar stores, and the operand is written and read by the async proxy (no
+//     generic->async fence on the receiving side);
+//   * the same staged block leaves for HBM as one TMA store (no per-thread global stores);
+//   * the four gates of a cell meet by quad transposes in registers (shuffles) instead of a shared-memory exchange.
+// Safety of buffer reuse without extra barriers (Z and staging are double-buffered): a CTA starts step s+2 for a group
+// only after every CTA's slice of h_{s+1} has landed, which those CTAs sent only after their step-(s+1) MMAs completed,
+// which needed every slice of h_s to have landed everywhere -- so by then nobody reads Z[(s) & 1] of step s or the
+// staging block sent at step s any more.
+// ------------------------------------------------------------------------------------------------
+template <int C, int CL, int NG>
+struct Cluster2Cfg {
+    static constexpr int MT = C / 32;
+    static constexpr int TPC = MT / CL;            // gate tiles per CTA
+    static constexpr int KBH = C / KBLK;           // operand blocks (32 hidden units each)
+    static constexpr int GN = 16;                  // chunks per group = UMMA N
+    static constexpr int UNC = NG * GN;            // chunks per cluster
+    static constexpr int EW = 4 * TPC * NG;        // epilogue warps: (group, tile, TMEM lane quarter)
+    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr int ZB = GN * KBLK * 2;       // bytes of one operand block (16 chunk rows x 32 fp16)
+    static constexpr int WCOLS = C / 2;            // TMEM columns of one weight tile
+    static constexpr int ACC0 = TPC * WCOLS;       // accumulators start behind the weights
+    static constexpr int NEED = ACC0 + NG * TPC * GN;
+    static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+    static constexpr size_t Z_BYTES = (size_t)NG * 2 * KBH * ZB;      // [group][buffer][block]
+    static constexpr size_t ST_BYTES = (size_t)NG * 2 * TPC * ZB;     // [group][buffer][tile] staging
+    static constexpr size_t SMEM = 1024 + Z_BYTES + ST_BYTES + 256;
+    static_assert(MT % CL == 0 && NEED <= 512, "tile split / tensor memory budget");
+};
+
+template <int C, int CL, int NG>
+__global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_cluster2_kernel(const __grid_constant__ CUtensorMap tma_y,
+                                                                                          const __half* __restrict__ w_hh,
+                                                                                          const LstmRecParams p) {
+    using Cfg = Cluster2Cfg<C, CL, NG>;
+    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH, ZB = Cfg::ZB, GN = Cfg::GN;
+    constexpr int GB = 32;  // chunk block of the gx layout
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* z_s = smem;                                   // [NG][2][KBH][ZB]  this CTA's copy of the full h
+    uint8_t* st_s = z_s + Cfg::Z_BYTES;                    // [NG][2][TPC][ZB]  h_t of this CTA's units, staged for sending
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + Cfg::ST_BYTES);
+    uint64_t* h_full = bars;                               // [NG][2]   bytes of h landed -> MMA issuer
+    uint64_t* acc_full = bars + NG * 2;                    // [NG][TPC] MMA -> epilogue
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + NG * TPC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x / CL;
+    const int n0 = cluster_id * Cfg::UNC;
+
+    for (int i = threadIdx.x; i < (int)((Cfg::Z_BYTES + Cfg::ST_BYTES) / 16); i += blockDim.x) {
+        reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
+    }
+    tc::fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NG * 2; ++i) tc::mbar_init(&h_full[i], 1);
+        for (int i = 0; i < NG * TPC; ++i) tc::mbar_init(&acc_full[i], 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_y);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const bool is_epi = warp >= 2;
+    const int ew = warp - 2;
+    const int eg = ew / (4 * TPC);        // group served by this epilogue warp
+    const int ti = (ew >> 2) % TPC;       // tile of this CTA
+    const int qt = warp & 3;              // TMEM lane quarter (the 4 warps of a (group, tile) cover all four)
+    if (is_epi && eg == 0) {
+        // this thread's weight row (tile rank*TPC + ti, row 32*qt + lane) -> tensor memory, once
+        const int m = (int)rank * TPC + ti;
+        const uint4* src = reinterpret_cast<const uint4*>(w_hh + (size_t)(m * 128 + qt * 32 + lane) * C);
+#pragma unroll 1
+        for (int cb = 0; cb < C / 64; ++cb) {
+            uint32_t r[32];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const uint4 x = __ldg(src + cb * 8 + v);
+                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+            }
+            tc::tmem_st_32x32(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(ti * Cfg::WCOLS + cb * 32), r);
+        }
+        tc::tmem_st_wait();
+    }
+    if (threadIdx.x == 0) {
+        // h_{-1} = 0 is in place: complete phase 0 of the buffer-0 barriers without bytes
+        for (int g = 0; g < NG; ++g) tc::mbar_arrive(&h_full[g * 2 + 0]);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    // every CTA of the cluster has zeroed its operand buffers and initialised its barriers before any remote copy lands
+    cluster_arrive_release();
+    cluster_wait_acquire();
+
+    const uint32_t z_local = tc::smem_u32(z_s);
+    if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (tc::elect_one()) {
+            const uint64_t zdesc0 = umma_desc_sw64(z_local);
+            constexpr uint32_t idesc = tc::umma_idesc_f16(128, GN);
+            for (int s = 0; s < p.T; ++s) {
+                const int buf = s & 1, nbuf = buf ^ 1;
+                const uint32_t par = (uint32_t)((s >> 1) & 1);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    // arm the barrier the slices of h_s will complete on (all CL CTAs x TPC tiles, this group)
+                    if (s + 1 < p.T) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
+                    tc::mbar_wait(&h_full[g * 2 + buf], par);
+                    tc::tc_fence_after();
+                    const uint64_t zd = zdesc0 + (uint64_t)(((g * 2 + buf) * KBH * ZB) >> 4);
+#pragma unroll
+                    for (int i = 0; i < TPC; ++i) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(Cfg::ACC0 + (g * TPC + i) * GN);
+#pragma unroll
+                        for (int kb = 0; kb < KBH; ++kb) {
+                            const uint32_t a_t = tmem_base + (uint32_t)(i * Cfg::WCOLS + kb * 16);
+                            const uint64_t bdesc = zd + (uint64_t)((kb * ZB) >> 4);
+                            tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, kb != 0);
+                            tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
+                        }
+                        tc::umma_commit(&acc_full[g * TPC + i]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (is_epi) {
+        // ---------------- epilogue: gates, cell update, h_t out ----------------
+        const int uk = lane >> 2, gj = lane & 3;   // unit within the warp's 8, gate type (i, f, g, o)
+        const int g0 = gj & 1, g1 = gj >> 1;
+        const int m = (int)rank * TPC + ti;        // global tile = operand block this warp's units belong to
+        const float am = gj == 2 ? 2.0f : 1.0f;    // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
+        const bool sender = qt == 0 && lane == 0;
+        const int bar_id = 1 + eg * TPC + ti;
+        float c_reg[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // cells (unit uk, chunk 4c + gj)
+        const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(Cfg::ACC0 + (eg * TPC + ti) * GN);
+        const size_t gx_row_off = (size_t)(m * 128 + qt * 32 + lane) * GB + (size_t)(n0 % GB) + (size_t)eg * GN;
+        const size_t gx_step = (size_t)(p.N / GB) * (size_t)(4 * C) * GB;
+        const __half* gx_base = p.gx + (size_t)(n0 / GB) * (size_t)(4 * C) * GB + gx_row_off;
+        // remote addresses of this tile's operand block and of the barrier it completes on, per buffer
+        uint32_t dst_z[2], dst_bar[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            dst_z[b] = z_local + (uint32_t)(((eg * 2 + b) * KBH + m) * ZB);
+            dst_bar[b] = tc::smem_u32(&h_full[eg * 2 + b]);
+        }
+        for (int s = 0; s < p.T; ++s) {
+            const int t = p.reverse ? p.T - 1 - s : s;
+            const int nbuf = (s & 1) ^ 1;
+            const uint4* gp = reinterpret_cast<const uint4*>(gx_base + (size_t)t * gx_step);
+            const uint4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
+            uint8_t* stage = st_s + (size_t)((eg * 2 + (s & 1)) * TPC + ti) * ZB;
+            tc::mbar_wait(&acc_full[eg * TPC + ti], (uint32_t)(s & 1));
+            tc::tc_fence_after();
+            uint32_t r[16];
+            tc::tmem_ld_32x16(taddr, r);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            float a[16];
+            {
+                const __half2* h0 = reinterpret_cast<const __half2*>(&gx0);
+                const __half2* h1 = reinterpret_cast<const __half2*>(&gx1);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f0 = __half22float2(h0[e]), f1 = __half22float2(h1[e]);
+                    a[2 * e] = __uint_as_float(r[2 * e]) + f0.x;
+                    a[2 * e + 1] = __uint_as_float(r[2 * e + 1]) + f0.y;
+                    a[8 + 2 * e] = __uint_as_float(r[8 + 2 * e]) + f1.x;
+                    a[8 + 2 * e + 1] = __uint_as_float(r[8 + 2 * e + 1]) + f1.y;
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 16; ++n) a[n] = 1.0f - __fdividef(am, __expf(am * a[n]) + 1.0f);
+            // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float s0 = g0 ? a[4 * c + 0] : a[4 * c + 1];
+                float s1 = g0 ? a[4 * c + 2] : a[4 * c + 3];
+                float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                if (g0) { a[4 * c + 0] = r0; a[4 * c + 2] = r1; } else { a[4 * c + 1] = r0; a[4 * c + 3] = r1; }
+                s0 = g1 ? a[4 * c + 0] : a[4 * c + 2];
+                s1 = g1 ? a[4 * c + 1] : a[4 * c + 3];
+                r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+                r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+                if (g1) { a[4 * c + 0] = r0; a[4 * c + 1] = r1; } else { a[4 * c + 2] = r0; a[4 * c + 3] = r1; }
+            }
+            float hv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float cs = a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2];
+                c_reg[c] = cs;
+                hv[c] = a[4 * c + 3] * tanh_f(cs);
+            }
+            // pair the units (uk, uk ^ 1): the even lane stores chunks c = 0, 1 of both units, the odd lane c = 2, 3
+            {
+                const __half2 mine_lo = __floats2half2_rn(hv[0], hv[1]), mine_hi = __floats2half2_rn(hv[2], hv[3]);
+                const bool odd = uk & 1;
+                const uint32_t send = odd ? *reinterpret_cast<const uint32_t*>(&mine_lo) : *reinterpret_cast<const uint32_t*>(&mine_hi);
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 4);
+                const uint32_t keep = odd ? *reinterpret_cast<const uint32_t*>(&mine_hi) : *reinterpret_cast<const uint32_t*>(&mine_lo);
+                // keep = my h for chunks (cb, cb+1), got = the partner unit's h for the same chunks; cb = odd ? 2 : 0
+                const uint32_t even_unit = odd ? got : keep, odd_unit = odd ? keep : got;
+                const int cb = odd ? 2 : 0;
+                const int ucol = qt * 8 + (uk & ~1);
+                const uint32_t w0 = (even_unit & 0xffffu) | (odd_unit << 16);          // chunk 4*cb + gj
+                const uint32_t w1 = (even_unit >> 16) | (odd_unit & 0xffff0000u);      // chunk 4*(cb+1) + gj
+                *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * cb + gj, ucol)) = w0;
+                *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * (cb + 1) + gj, ucol)) = w1;
+            }
+            tc::fence_proxy_async_smem();            // staged block -> visible to the bulk copy / TMA store
+            if (sender) tc::bulk_wait_group_read<0>();  // the store issued a step ago has read the other staging buffer
+            named_bar_sync(bar_id, 128);
+            if (sender) {
+                if (s + 1 < p.T) {
+#pragma unroll
+                    for (int rr = 0; rr < CL; ++rr) {
+                        tc::bulk_copy_smem_to_cluster(mapa_shared(dst_z[nbuf], (uint32_t)rr), tc::smem_u32(stage), (uint32_t)ZB,
+                                                      mapa_shared(dst_bar[nbuf], (uint32_t)rr));
+                    }
+                }
+                tc::tma_store_2d(&tma_y, stage, m * 32, t * p.N + n0 + eg * GN);
+                tc::bulk_commit_group();
+            }
+        }
+        if (sender) tc::bulk_wait_group<0>();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // nobody leaves while a peer may still address this CTA's shared memory
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct LstmLayerWeights {
@@ -706,6 +1188,7 @@ public:
     std::vector<CUtensorMap> lstm_x, lstm_w;
     std::vector<LstmParams> lstm_p;
     int lstm_grid = 0, lstm_nbr = 16, lstm_groups = 3, lstm_threads = 0;
+    bool lstm_v1 = false;
     size_t lstm_smem = 0;
     void launch_lstm(int l, cudaStream_t stream) const;
     // hoisted path
@@ -716,6 +1199,8 @@ public:
     std::vector<GemmPlan> gx_gemm;
     std::vector<const __half*> rec_whh;
     std::vector<LstmRecParams> rec_p;
+    bool rec_v1 = false;   // B200_CLUSTER_V1=1: the first-generation cluster kernel (A/B comparisons)
+    CUtensorMap rec_y_map; // seq as [T_out * Np][C], box 32 units x 16 chunks: the TMA store of h_t
     void launch_rec(int l, cudaStream_t stream) const;
     GemmPlan linear1, linear2;
     int num_layers = 0, num_linear = 1;
@@ -731,6 +1216,7 @@ public:
                                            size_t ws_bytes) override;
 
     b200_model_desc desc;
+    bool lstm_v1 = false;     // B200_LSTM_V1=1: first-generation single-CTA LSTM kernel (A/B comparisons)
     float* conv_w = nullptr;  // packed conv1 / conv2 weights (see Conv12Params::w)
     __half* w3 = nullptr;               // [C][K3p]
     float* b3 = nullptr;
@@ -756,7 +1242,12 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
         throw Unsupported("conv stack shape outside what conv12_kernel implements");
     }
     const int C = d.lstm_size;
-    if (C != c3.size || C % 32 != 0 || C > 512) throw Unsupported("lstm_size must be a multiple of 32, <= 512");
+    if (C != c3.size) throw std::invalid_argument("last convolution size != lstm_size");
+    if (C != 96 && C != 192 && C != 384) {
+        // kernels are instantiated for the sizes of the reference's model zoo this engine covers
+        throw Unsupported("lstm_size " + std::to_string(C) + " is not supported (96, 192 and 384 are)");
+    }
+    if (const char* e = std::getenv("B200_LSTM_V1")) lstm_v1 = std::atoi(e) != 0;
     if (d.lstm_layers < 1 || d.lstm_layers > 8) throw std::invalid_argument("bad lstm_layers");
 
     // conv1: torch [c1][1][w] -> [c1][w]; conv2: torch [co][ci][k] -> [k][ci][co]
@@ -812,6 +1303,20 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
                 }
         LstmLayerWeights lw;
         if ((size_t)4 * C * 2 * C * 2 <= 150 * 1024) {
+            if (!lstm_v1) {
+                // lstm_layer2_kernel: rows ordered (tile, TMEM lane quarter, unit within the quarter's 8, gate)
+                std::vector<float> w2((size_t)4 * C * 2 * C), b2((size_t)4 * C);
+                for (int m = 0; m < C / 32; ++m)
+                    for (int r = 0; r < 128; ++r) {
+                        const int g = r & 3, unit = 32 * m + 8 * (r >> 5) + ((r & 31) >> 2);
+                        const int dst = m * 128 + r, src = g * C + unit;
+                        std::memcpy(&w2[(size_t)dst * 2 * C], &wih.data[(size_t)src * C], sizeof(float) * C);
+                        std::memcpy(&w2[(size_t)dst * 2 * C + C], &whh.data[(size_t)src * C], sizeof(float) * C);
+                        b2[dst] = bih.data[src] + bhh.data[src];
+                    }
+                w.swap(w2);
+                b.swap(b2);
+            }
             lw.w = upload_f16(w);
             lw.bias = upload_f32(b);
         } else {
@@ -936,6 +1441,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         int un = Np > 256 ? 32 : 16;
         while (Np % un != 0) un /= 2;
         plan->rec_un = un;
+        if (const char* e = std::getenv("B200_CLUSTER_V1")) plan->rec_v1 = std::atoi(e) != 0;
+        plan->rec_y_map = make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, 32, 16);
         const int GB = 32;  // chunk block of the gx layout (n_pad = 32 on this path)
         plan->lstm_grid = (Np / un) * 6;
         for (int l = 0; l < desc.lstm_layers; ++l) {
@@ -985,9 +1492,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             if ((v == 4 || v == 8 || v == 16) && Np % v == 0) nbr = v;
             else throw std::invalid_argument("B200_LSTM_CHUNKS_PER_CTA must be 4, 8 or 16 and divide the padded batch");
         }
-        if (C != 96 && C != 128 && C != 192 && C != 256 && C != 384 && C != 512) {
-            throw Unsupported("lstm_size must be one of 96, 128, 192, 256, 384, 512");
-        }
+        if (C != 96) throw Unsupported("the single-CTA LSTM kernels are instantiated for lstm_size 96");
+        plan->lstm_v1 = lstm_v1;
         const int G = (MT % 6 == 0) ? 6 : (MT % 4 == 0) ? 4 : 3;
         plan->lstm_nbr = nbr;
         plan->lstm_groups = G;
@@ -1072,9 +1578,15 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
 
 template <int C, int NBR>
 static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    ensure_dynamic_smem(lstm_layer_kernel<C, NBR>, 227 * 1024);
-    lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
-                                                                                        pl.lstm_p[l]);
+    if (pl.lstm_v1) {
+        ensure_dynamic_smem(lstm_layer_kernel<C, NBR>, 227 * 1024);
+        lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
+                                                                                            pl.lstm_p[l]);
+    } else {
+        ensure_dynamic_smem(lstm_layer2_kernel<C, NBR>, (int)Lstm2Cfg<C>::SMEM);
+        lstm_layer2_kernel<C, NBR><<<pl.lstm_grid, Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::SMEM, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
+                                                                                                      pl.lstm_p[l]);
+    }
 }
 
 template <int C, int CL, int UNC>
@@ -1096,10 +1608,34 @@ static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
     B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<C, CL, UNC>, pl.rec_whh[l], pl.rec_p[l]));
 }
 
+template <int C, int CL, int NG>
+static void launch_cluster2_t(const LstmPlan& pl, int l, cudaStream_t stream) {
+    using Cfg = Cluster2Cfg<C, CL, NG>;
+    ensure_dynamic_smem(lstm_cluster2_kernel<C, CL, NG>, (int)Cfg::SMEM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)pl.lstm_grid, 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster2_kernel<C, CL, NG>, pl.rec_y_map, pl.rec_whh[l], pl.rec_p[l]));
+}
+
 template <int C>
 static void launch_cluster_c(const LstmPlan& pl, int l, cudaStream_t stream) {
-    if (pl.rec_un == 32) launch_cluster_t<C, 6, 32>(pl, l, stream);
-    else launch_cluster_t<C, 6, 16>(pl, l, stream);
+    if (pl.rec_v1) {
+        if (pl.rec_un == 32) launch_cluster_t<C, 6, 32>(pl, l, stream);
+        else launch_cluster_t<C, 6, 16>(pl, l, stream);
+    } else {
+        if (pl.rec_un == 32) launch_cluster2_t<C, 6, 2>(pl, l, stream);
+        else launch_cluster2_t<C, 6, 1>(pl, l, stream);
+    }
 }
 
 void LstmPlan::launch_rec(int l, cudaStream_t stream) const {
@@ -1121,11 +1657,6 @@ static void launch_lstm_c(const LstmPlan& pl, int l, cudaStream_t stream) {
 void LstmPlan::launch_lstm(int l, cudaStream_t stream) const {
     switch (lstm_p[l].C) {
         case 96: launch_lstm_c<96>(*this, l, stream); break;
-        case 128: launch_lstm_c<128>(*this, l, stream); break;
-        case 192: launch_lstm_c<192>(*this, l, stream); break;
-        case 256: launch_lstm_c<256>(*this, l, stream); break;
-        case 384: launch_lstm_c<384>(*this, l, stream); break;
-        case 512: launch_lstm_c<512>(*this, l, stream); break;
         default: throw Unsupported("no LSTM kernel instantiation for this lstm_size");
     }
 }
