@@ -114,6 +114,45 @@ int b200_engine_batch_timeouts_ms(const b200_engine* e, int32_t* first_chunk_ms,
     });
 }
 
+int b200_pool_create(const b200_model_desc* desc, const b200_tensor* tensors, int32_t num_tensors, const int32_t* devices,
+                     int32_t num_devices, int32_t runners_per_device, int32_t batch_size, int32_t chunk_size, b200_pool** out) {
+    return guarded([&] {
+        if (!desc || !tensors || !devices || !out) throw std::invalid_argument("b200_pool_create: null argument");
+        *out = reinterpret_cast<b200_pool*>(
+                new b200::Pool(*desc, tensors, num_tensors, devices, num_devices, runners_per_device, batch_size, chunk_size));
+    });
+}
+
+int b200_pool_destroy(b200_pool* p) {
+    return guarded([&] { delete reinterpret_cast<b200::Pool*>(p); });
+}
+
+int32_t b200_pool_num_runners(const b200_pool* p) { return p ? reinterpret_cast<const b200::Pool*>(p)->num_runners() : 0; }
+int32_t b200_pool_out_len(const b200_pool* p) { return p ? reinterpret_cast<const b200::Pool*>(p)->out_len() : 0; }
+
+b200_runner* b200_pool_runner(b200_pool* p, int32_t index) {
+    return p ? reinterpret_cast<b200_runner*>(reinterpret_cast<b200::Pool*>(p)->runner(index)) : nullptr;
+}
+
+int b200_pool_runner_info(const b200_pool* p, int32_t index, int32_t* numa_node, int64_t* batches) {
+    return guarded([&] {
+        if (!p) throw std::invalid_argument("b200_pool_runner_info: null argument");
+        const auto* pool = reinterpret_cast<const b200::Pool*>(p);
+        if (index < 0 || index >= pool->num_runners()) throw std::invalid_argument("b200_pool_runner_info: index out of range");
+        if (numa_node) *numa_node = pool->runner_numa_node(index);
+        if (batches) *batches = pool->runner_batches(index);
+    });
+}
+
+int b200_pool_call_chunks(b200_pool* p, const uint16_t* chunks, int64_t num_chunks, uint8_t* moves, char* sequence,
+                          char* qstring, int32_t* n_bases, double* seconds) {
+    return guarded([&] {
+        if (!p) throw std::invalid_argument("b200_pool_call_chunks: null argument");
+        const double s = reinterpret_cast<b200::Pool*>(p)->call_chunks(chunks, num_chunks, moves, sequence, qstring, n_bases);
+        if (seconds) *seconds = s;
+    });
+}
+
 int b200_runner_create(b200_engine* e, int32_t batch_size, int32_t chunk_size, b200_runner** out) {
     return guarded([&] {
         if (!e || !out) throw std::invalid_argument("b200_runner_create: null argument");

@@ -243,9 +243,11 @@ __device__ int beam_step(const __half* sc_row,
                          float blank,
                          bool last_block,
                          uint2* beam_row,
-                         int lane) {
+                         int lane,
+                         long long* dbg) {
     constexpr int S = Dims<SL>::S;
     constexpr int SB = 2 * SL;
+    if (dbg && lane == 0) dbg[0] = clock64();
     constexpr uint32_t mask = S - 1;
     const bool valid = lane < width;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -269,6 +271,7 @@ __device__ int beam_step(const __half* sc_row,
         lmax = b200_fmaxf(lmax, s[4]);
     }
     float max_score = warp_max(lmax);
+    if (dbg && lane == 0) dbg[1] = clock64();
 
     // --- merge stays with equal-hash steps (beam_search.cpp:264-305) ---
     // stay i matches step (j, b_i) iff hash_j == crc2_inv(hash_i, b_i): one lookup of the 32 previous hashes
@@ -357,6 +360,7 @@ __device__ int beam_step(const __half* sc_row,
         }
     }
 
+    if (dbg && lane == 0) dbg[2] = clock64();
     // --- cutoff (beam_search.cpp:310-396) ---
     float cutoff = B200_SUB(max_score, log_beam_cut);
     auto count_ge = [&](float c) {
@@ -390,6 +394,7 @@ __device__ int beam_step(const __half* sc_row,
         if (cnt > W) cnt = W;
     }
 
+    if (dbg && lane == 0) dbg[3] = clock64();
     // --- keep the first W candidates >= cutoff in candidate order (beam_search.cpp:398-409) ---
     bool f[5];
 #pragma unroll
@@ -429,6 +434,7 @@ __device__ int beam_step(const __half* sc_row,
         me.state = meta & 0xffffu;
     }
 
+    if (dbg && lane == 0) dbg[4] = clock64();
     // --- last block: best element to slot 0 (beam_search.cpp:413-424) ---
     if (last_block) {
         const float best = warp_max(nvalid ? me.score : B200_FLT_LOWEST);
@@ -472,6 +478,10 @@ __device__ int beam_step(const __half* sc_row,
         beam_row[lane] = make_uint2(meta, __float_as_uint(prob));
     }
     __syncwarp();
+    if (dbg && lane == 0) {
+        dbg[5] = clock64();
+        dbg[6] = cnt;
+    }
     return cnt;
 }
 
@@ -497,7 +507,8 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
                                                                           float clamp_val,
                                                                           float blank,
                                                                           int W,
-                                                                          float log_beam_cut) {
+                                                                          float log_beam_cut,
+                                                                          long long* dbg) {
     using Cfg = ScanCfg<SL>;
     using F = FwdCfg<SL>;
     constexpr int S = Cfg::S, C = Cfg::C, P4 = Cfg::P4, SPT = Cfg::SPT, NT = Cfg::NT;
@@ -559,7 +570,10 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
                 const int t = t0 + k;
                 if (t < T) {
                     const int slot = t & 1;
+                    long long* d = (dbg && chunk == 0 && tid == 0 && t >= 100 && t < 108) ? dbg + (t - 100) * 16 : nullptr;
+                    if (d) d[8] = clock64();
                     if (t >= 2) named_bar_sync(BAR_EMPTY + slot, GT);  // beam warp is done with this slot
+                    if (d) d[9] = clock64();
                     float vsum[SPT];
                     float lmax = B200_FLT_LOWEST;
 #pragma unroll
@@ -615,6 +629,7 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
 #pragma unroll
                     for (int e = 0; e < SPT; ++e) post_row[g][slot][SPT * v + e] = B200_DIV(ex[e], z);
                     named_bar_arrive(BAR_FULL + slot, GT);  // slot t is complete
+                    if (d) d[10] = clock64();
                     cur ^= 1;
                 }
             }
@@ -627,9 +642,11 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
         named_bar_sync(BAR_SCAN, GT);  // (b)
         for (int t = 0; t < T; ++t) {
             const int slot = t & 1;
+            long long* d = (dbg && chunk == 0 && t >= 100 && t < 108) ? dbg + (t - 100) * 16 : nullptr;
+            if (d && lane == 0) d[7] = clock64();
             named_bar_sync(BAR_FULL + slot, GT);
             width = beam_step<SL>(sc_row[g][slot], bw_row[g][slot], post_row[g][slot], bsm[g], me, width, W, log_beam_cut,
-                                  blank, t == T - 1, beam_out + (size_t)t * kBeamW, lane);
+                                  blank, t == T - 1, beam_out + (size_t)t * kBeamW, lane, d);
             if (t + 2 < T) named_bar_arrive(BAR_EMPTY + slot, GT);
         }
     }
@@ -752,7 +769,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         const int grid = (a.N + F::CH - 1) / F::CH;
         NvtxRange r("beam_search");  // forward scan + posteriors (the reference's "compute_posts") are fused in
         crf_fwd_beam_kernel<SL><<<grid, F::THREADS, 0, stream>>>(a.scores, a.bwd, a.beam, a.N, a.T, a.clamp_val, a.blank,
-                                                                   a.beam_width, a.log_beam_cut);
+                                                                   a.beam_width, a.log_beam_cut, a.dbg);
         if (prof) prof->mark("crf_fwd_beam", stream);
     }
     {

@@ -21,7 +21,8 @@ struct DecodeArgs {
     float blank;
     float q_shift;
     float q_scale;
-    const b200_qtable* qtable;  // device copy of b200_qtable_build(q_scale, q_shift) (include/b200_crf_math.h)
+    const b200_qtable* qtable;
+    long long* dbg;  // optional clock64 timeline of chunk 0 (B200_DEBUG_BEAM_TIMELINE, test hook only); nullptr in production  // device copy of b200_qtable_build(q_scale, q_shift) (include/b200_crf_math.h)
     // scratch
     float* bwd;   // decode_scratch_bytes() -> bwd_bytes
     uint2* beam;  //                        -> beam_bytes

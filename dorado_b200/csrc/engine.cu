@@ -10,6 +10,8 @@
 #include "nvtx.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -296,6 +298,15 @@ void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
     for (int64_t i = 0; i < len; ++i) dst[i] = __float2half_rn(samples[i]);
 }
 
+uint16_t* Runner::input() {
+    std::lock_guard<std::mutex> lock(m_mutex);
+    if (m_num_raw > 0) {
+        for (int i = 0; i < m_N; ++i) m_h_slots[i].slice_len = 0;
+        m_num_raw = 0;
+    }
+    return m_h_input;
+}
+
 void Runner::clear_raw_slot(int idx) {
     if (m_h_slots && m_h_slots[idx].slice_len > 0) {
         m_h_slots[idx].slice_len = 0;
@@ -443,13 +454,6 @@ b200_result Runner::call_chunks(int num_chunks) {
         m_engine.d2h_ms += d2h;
     }
     ++m_engine.batches_called;
-    // a raw chunk is valid for one batch: afterwards every slot is an fp16 slot again (rows written straight into
-    // b200_runner_input() must not be overwritten by a stale gather)
-    if (m_num_raw > 0) {
-        for (int i = 0; i < m_N; ++i) m_h_slots[i].slice_len = 0;
-        m_num_raw = 0;
-    }
-
     b200_result r{};
     r.moves = m_h_out;
     r.sequence = reinterpret_cast<const char*>(m_h_out + (size_t)m_N * m_T_out);
@@ -693,7 +697,26 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
     try {
         B200_CUDA(cudaMemcpyAsync(d_sc, scores, sc_b, cudaMemcpyHostToDevice, s));
         B200_CUDA(cudaMemcpyAsync(d_tb, &tb, sizeof(tb), cudaMemcpyHostToDevice, s));
+        long long* d_dbg = nullptr;
+        if (std::getenv("B200_DEBUG_BEAM_TIMELINE")) {  // test hook only: clock64 stamps of chunk 0, blocks 100..107
+            B200_CUDA(cudaMalloc(&d_dbg, 128 * sizeof(long long)));
+            B200_CUDA(cudaMemsetAsync(d_dbg, 0, 128 * sizeof(long long), s));
+            a.dbg = d_dbg;
+        }
         decode_scores(a, s);
+        if (d_dbg) {
+            long long h[128];
+            B200_CUDA(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, s));
+            B200_CUDA(cudaStreamSynchronize(s));
+            for (int t = 0; t < 8; ++t) {
+                const long long* e = h + t * 16;
+                fprintf(stderr, "[beam timeline block %d] beam: wait %lld cand %lld merge %lld cutoff %lld compact %lld tail %lld (kept %lld) | "
+                                "scan: wait_empty %lld work %lld | period %lld\n",
+                        100 + t, e[0] - e[7], e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4], e[6], e[9] - e[8],
+                        e[10] - e[9], t > 0 ? e[0] - (e - 16)[0] : 0LL);
+            }
+            cudaFree(d_dbg);
+        }
         B200_CUDA(cudaMemcpyAsync(moves, a.moves, (size_t)N * T, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaMemcpyAsync(sequence, a.sequence, (size_t)N * T, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaMemcpyAsync(qstring, a.qstring, (size_t)N * T, cudaMemcpyDeviceToHost, s));

@@ -138,7 +138,10 @@ public:
     int batch_size() const { return m_N; }
     int chunk_size() const { return m_T_in; }
     int out_len() const { return m_T_out; }
-    uint16_t* input() { return m_h_input; }
+    // Direct access to the pinned fp16 batch.  Slots keep what they were given until they are given something else (as the
+    // reference's input tensor does), so asking for the buffer turns every raw slot back into an fp16 slot: rows written
+    // through the pointer are what the next call_chunks uploads.  Ask again after accept_raw_chunk before writing rows.
+    uint16_t* input();
     void set_decoder_options(const b200_decoder_options& o);
     void accept_chunk_f16(int idx, const uint16_t* samples, int64_t len);
     void accept_chunk_f32(int idx, const float* samples, int64_t len);
@@ -191,6 +194,46 @@ private:
     unsigned char* m_d_out = nullptr;
     size_t m_out_bytes = 0;
     cudaEvent_t m_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// One process, several devices: see pool.cu.
+class Pool {
+public:
+    Pool(const b200_model_desc& desc, const b200_tensor* tensors, int num_tensors, const int* devices, int num_devices,
+         int runners_per_device, int batch_size, int chunk_size);
+    ~Pool();
+    int num_runners() const;
+    Runner* runner(int i);
+    int runner_numa_node(int i) const;
+    int64_t runner_batches(int i) const;
+    int out_len() const { return m_t_out; }
+    // Feeds `num_chunks` host chunks (fp16 [num_chunks][chunk_size]) through all runners from a shared cursor; blocking.
+    // Output rows have pitch out_len(); any output pointer may be null.  Returns wall seconds.
+    double call_chunks(const uint16_t* chunks, int64_t num_chunks, uint8_t* moves, char* sequence, char* qstring,
+                       int32_t* n_bases);
+
+private:
+    struct Worker;
+    struct Job {
+        const uint16_t* chunks = nullptr;
+        int64_t num_chunks = 0;
+        uint8_t* moves = nullptr;
+        char* sequence = nullptr;
+        char* qstring = nullptr;
+        int32_t* n_bases = nullptr;
+    };
+    void worker_main(Worker& w);
+    void shutdown();
+    int m_batch, m_chunk, m_t_out = 0;
+    std::vector<std::unique_ptr<Engine>> m_engines;
+    std::vector<std::unique_ptr<Worker>> m_workers;
+    std::mutex m_mutex, m_job_mutex;
+    std::condition_variable m_cv_job, m_cv_done;
+    long long m_job_id = 0;
+    int m_ready = 0, m_done = 0;
+    bool m_stop = false;
+    Job m_job;
+    std::atomic<int64_t> m_cursor{0};
 };
 
 void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C, float clamp_val,

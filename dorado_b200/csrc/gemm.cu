@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "engine.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,7 +26,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;  // default ring depth
 constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
@@ -42,7 +43,15 @@ struct GemmKernelParams {
     const __half* residual;
     float alpha;
     uint32_t tmem_cols;
+    // staged epilogue: the fp16 tile goes through swizzled shared memory and leaves as TMA stores (tma_o)
+    int staged;      // 0 = per-thread global stores
+    int stages;      // TMA->MMA ring depth (3 when the staging tile needs the room)
+    int sw;          // columns of a staging sub-tile: 64 (128-byte swizzle) or 32 (64-byte swizzle)
+    int out_kind;    // coordinates of a sub-tile: 0 (col, row, batch)  1 (col, g % out_P, g / out_P)  2 (0, row, col / 32)
+    int out_P;
 };
+
+constexpr int kMaxStages = 4;
 
 __device__ __forceinline__ float act_apply(float v, int act) {
     switch (act) {
@@ -56,6 +65,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                            const __grid_constant__ CUtensorMap tma_w,
+                                                                           const __grid_constant__ CUtensorMap tma_o,
                                                                            const GemmKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages x (A 16 KB | W bn*128 B), then barriers
@@ -64,9 +74,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     const uint32_t a_bytes = BM * BK * 2;
     const uint32_t w_bytes = (uint32_t)p.bn * BK * 2;
     const uint32_t stage_bytes = a_bytes + w_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;   // [2]
+    const int NST = p.stages;
+    // staging tile of the epilogue: two column halves (one per epilogue warp set), 128 rows x bn/2 fp16 each
+    uint8_t* stage_out = smem + NST * stage_bytes;
+    const uint32_t half_bytes = p.staged ? (uint32_t)(BM * (((p.bn / 32 + 1) / 2) * 32) * 2) : 0u;  // the wider half
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 2 * half_bytes);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tmem_full = empty + kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -74,7 +88,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
         }
@@ -85,6 +99,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_a);
         tc::prefetch_tmap(&tma_w);
+        if (p.staged) tc::prefetch_tmap(&tma_o);
     }
     if (warp == 1) tc::tmem_alloc(tmem_holder, p.tmem_cols);
     tc::tc_fence_before();
@@ -101,8 +116,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                 const int r0 = (mt % p.tiles_per_batch) * BM;
                 const int n0 = nt * p.bn;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-                    const int s = (int)(it % STAGES);
-                    tc::mbar_wait(&empty[s], (uint32_t)(((it / STAGES) & 1) ^ 1));
+                    const int s = (int)(it % NST);
+                    tc::mbar_wait(&empty[s], (uint32_t)(((it / NST) & 1) ^ 1));
                     tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
                     uint8_t* a_s = smem + s * stage_bytes;
                     tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
@@ -121,8 +136,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.bn);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-                    const int s = (int)(it % STAGES);
-                    tc::mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+                    const int s = (int)(it % NST);
+                    tc::mbar_wait(&full[s], (uint32_t)((it / NST) & 1));
                     tc::tc_fence_after();
                     const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
                     const uint64_t adesc = tc::umma_desc_sw128(a_addr);
@@ -144,6 +159,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
         const int nch = p.bn / 32;
         const int c_begin = chalf ? (nch + 1) / 2 : 0, c_end = chalf ? nch : (nch + 1) / 2;
         const int n_out_total = p.act == GEMM_ACT_SWIGLU ? p.N / 2 : p.N;
+        // staged epilogue: this warp set (chalf) owns one half of the staging tile; thread = tile row
+        const bool staged = p.staged != 0;
+        const int out_div = p.act == GEMM_ACT_SWIGLU ? 2 : 1;            // output columns per accumulator column
+        uint8_t* my_stage = stage_out + (size_t)chalf * half_bytes;
+        const int trow = lg * 32 + lane;
+        const bool storer = staged && lg == 0 && lane == 0;
+        const int bar_free = 1 + 2 * chalf, bar_full = 2 + 2 * chalf;
+        const uint32_t sub_bytes = (uint32_t)(BM * p.sw * 2);
+        // 16-byte piece `piece` of output column block starting at half-relative column hc (multiple of 8) -> staging address
+        auto stage_ptr = [&](int hc) -> uint4* {
+            const int sub = hc / p.sw, cin = hc % p.sw;
+            const int piece = cin >> 3;
+            const uint32_t sw_xor = p.sw == 64 ? (uint32_t)(trow & 7) : (uint32_t)((trow >> 1) & 3);
+            return reinterpret_cast<uint4*>(my_stage + (size_t)sub * sub_bytes + (size_t)trow * (p.sw * 2) +
+                                            (((uint32_t)piece ^ sw_xor) << 4));
+        };
         int ti = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
             const int ab = ti & 1;
@@ -155,6 +186,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             const bool valid = row < p.rows_per_batch;
             const long long g = (long long)batch * p.rows_per_batch + row;
             const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
+            if (staged) {
+                // the stores of this set's previous tile have read the staging half: it may be rewritten
+                if (storer) tc::bulk_wait_group_read<0>();
+                named_bar_sync(bar_free, 128);
+            }
             tc::mbar_wait(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after();
             if (c_begin == c_end) {
@@ -175,7 +211,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                         tc::mbar_arrive(&tmem_empty[ab]);
                     }
                     const int nc = n0 + c * 32;
-                    if (valid) {
+                    if (valid || staged) {
                         __half2 h0[16], h1[16];
                         const bool rot = nc < p.rope_cols;
 #pragma unroll
@@ -191,74 +227,118 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                             h0[j] = __floats2half2_rn(a0, a1);
                             h1[j] = __floats2half2_rn(b0, b1);
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc);
+                        if (staged) {
+                            const int hc = (c - c_begin) * 32;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            dst[q] = *reinterpret_cast<uint4*>(&h0[4 * q]);
-                            dst[4 + q] = *reinterpret_cast<uint4*>(&h1[4 * q]);
-                        }
-                    }
-                }
-                continue;
-            }
-            for (int c = c_begin; c < c_end; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + c * 32), r);
-                tc::tmem_ld_wait();
-                if (c == c_end - 1) {
-                    // accumulator fully read: hand the TMEM buffer back before the (long) math + stores
-                    tc::tc_fence_before();
-                    tc::mbar_arrive(&tmem_empty[ab]);
-                }
-                const int nc = n0 + c * 32;
-                const long long coff = p.out_col_m1 > 0 ? (nc / p.out_col_m1) * p.out_col_s0 + (nc % p.out_col_m1) : nc;
-                float v[32];
-                const float row_bias = (p.bias && p.bias_per_row && valid) ? __ldg(p.bias + g) : 0.0f;
+                            for (int q = 0; q < 4; ++q) {
+                                *stage_ptr(hc + 8 * q) = *reinterpret_cast<uint4*>(&h0[4 * q]);
+                                *stage_ptr(hc + 32 + 8 * q) = *reinterpret_cast<uint4*>(&h1[4 * q]);
+                            }
+                        } else {
+                            uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = __uint_as_float(r[j]);
-                    if (p.bias) v[j] += p.bias_per_row ? row_bias : __ldg(p.bias + nc + j);
-                }
-                if (p.act == GEMM_ACT_SWIGLU) {
-                    if (valid) {
-                        __half2 h[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float y0 = v[4 * j], g0 = v[4 * j + 1], y1 = v[4 * j + 2], g1 = v[4 * j + 3];
-                            h[j] = __floats2half2_rn(y0 * (g0 / (1.0f + __expf(-g0))), y1 * (g1 / (1.0f + __expf(-g1))));
-                        }
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc / 2);
-                        dst[0] = *reinterpret_cast<uint4*>(&h[0]);
-                        dst[1] = *reinterpret_cast<uint4*>(&h[4]);
-                    }
-                } else {
-                    if (p.residual && valid) {
-                        const uint4* res = reinterpret_cast<const uint4*>(p.residual + g * (long long)n_out_total + nc);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 rv = __ldg(res + q);
-                            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = __half22float2(rh[j]);
-                                v[q * 8 + 2 * j] += p.alpha * f.x;
-                                v[q * 8 + 2 * j + 1] += p.alpha * f.y;
+                            for (int q = 0; q < 4; ++q) {
+                                dst[q] = *reinterpret_cast<uint4*>(&h0[4 * q]);
+                                dst[4 + q] = *reinterpret_cast<uint4*>(&h1[4 * q]);
                             }
                         }
                     }
-                    if (valid) {
-                        __half2 h[16];
+                }
+            } else {
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + c * 32), r);
+                    tc::tmem_ld_wait();
+                    if (c == c_end - 1) {
+                        // accumulator fully read: hand the TMEM buffer back before the (long) math + stores
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&tmem_empty[ab]);
+                    }
+                    const int nc = n0 + c * 32;
+                    const long long coff = p.out_col_m1 > 0 ? (nc / p.out_col_m1) * p.out_col_s0 + (nc % p.out_col_m1) : nc;
+                    float v[32];
+                    const float row_bias = (p.bias && p.bias_per_row && valid) ? __ldg(p.bias + g) : 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            h[j] = __floats2half2_rn(act_apply(v[2 * j], p.act), act_apply(v[2 * j + 1], p.act));
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(r[j]);
+                        if (p.bias) v[j] += p.bias_per_row ? row_bias : __ldg(p.bias + nc + j);
+                    }
+                    if (p.act == GEMM_ACT_SWIGLU) {
+                        if (valid || staged) {
+                            __half2 h[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float y0 = v[4 * j], g0 = v[4 * j + 1], y1 = v[4 * j + 2], g1 = v[4 * j + 3];
+                                h[j] = __floats2half2_rn(y0 * (g0 / (1.0f + __expf(-g0))), y1 * (g1 / (1.0f + __expf(-g1))));
+                            }
+                            if (staged) {
+                                const int hc = (c - c_begin) * 16;
+                                *stage_ptr(hc) = *reinterpret_cast<uint4*>(&h[0]);
+                                *stage_ptr(hc + 8) = *reinterpret_cast<uint4*>(&h[4]);
+                            } else {
+                                uint4* dst = reinterpret_cast<uint4*>(p.out + off + nc / 2);
+                                dst[0] = *reinterpret_cast<uint4*>(&h[0]);
+                                dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+                            }
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + off + coff);
+                    } else {
+                        if (p.residual && valid) {
+                            const uint4* res = reinterpret_cast<const uint4*>(p.residual + g * (long long)n_out_total + nc);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) dst[q] = *reinterpret_cast<uint4*>(&h[4 * q]);
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 rv = __ldg(res + q);
+                                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 f = __half22float2(rh[j]);
+                                    v[q * 8 + 2 * j] += p.alpha * f.x;
+                                    v[q * 8 + 2 * j + 1] += p.alpha * f.y;
+                                }
+                            }
+                        }
+                        if (valid || staged) {
+                            __half2 h[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                h[j] = __floats2half2_rn(act_apply(v[2 * j], p.act), act_apply(v[2 * j + 1], p.act));
+                            }
+                            if (staged) {
+                                const int hc = (c - c_begin) * 32;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) *stage_ptr(hc + 8 * q) = *reinterpret_cast<uint4*>(&h[4 * q]);
+                            } else {
+                                uint4* dst = reinterpret_cast<uint4*>(p.out + off + coff);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) dst[q] = *reinterpret_cast<uint4*>(&h[4 * q]);
+                            }
+                        }
                     }
                 }
             }
+            if (staged) {
+                tc::fence_proxy_async_smem();   // staged tile -> visible to the TMA store
+                named_bar_sync(bar_full, 128);
+                if (storer) {
+                    // this set's output columns [oc0, oc1) of the tile, as sub-tiles of p.sw columns
+                    const int oc0 = c_begin * 32 / out_div, oc1 = c_end * 32 / out_div;
+                    const int col0 = n0 / out_div + oc0;
+                    const int nsub = (oc1 - oc0) / p.sw;
+                    for (int k = 0; k < nsub; ++k) {
+                        const uint8_t* src = my_stage + (size_t)k * sub_bytes;
+                        const int col = col0 + k * p.sw;
+                        if (p.out_kind == 0) {
+                            tc::tma_store_3d(&tma_o, src, col, r0, batch);
+                        } else if (p.out_kind == 1) {
+                            tc::tma_store_3d(&tma_o, src, col, r0 % p.out_P, r0 / p.out_P);
+                        } else {
+                            tc::tma_store_3d(&tma_o, src, 0, r0, col / 32);
+                        }
+                    }
+                    tc::bulk_commit_group();
+                }
+            }
         }
+        if (storer) tc::bulk_wait_group<0>();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -318,6 +398,57 @@ CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2
     return encode(base, 3, dims, strides, box, swz);
 }
 
+// Decide whether the epilogue can leave through shared memory + TMA stores: the output must be expressible as a 3-D tensor
+// (columns, rows, outer) whose 128-row tiles never straddle the outer dimension, and each epilogue warp set's column range
+// must split into sub-tiles of 64 (128-byte swizzle) or 32 (64-byte swizzle) columns.
+static void plan_output_staging(GemmPlan& p) {
+    const GemmDesc& d = p.d;
+    p.staged = 0;
+    static const bool direct = [] {
+        const char* e = std::getenv("B200_GEMM_DIRECT");  // A/B switch: per-thread global stores
+        return e && std::atoi(e) != 0;
+    }();
+    if (direct) return;
+    const int nch = p.bn / 32;
+    if (nch < 2) return;
+    const int out_div = d.act == GEMM_ACT_SWIGLU ? 2 : 1;
+    const int w0 = ((nch + 1) / 2) * 32 / out_div, w1 = (nch - (nch + 1) / 2) * 32 / out_div;
+    int sw = (w0 % 64 == 0 && w1 % 64 == 0) ? 64 : (w0 % 32 == 0 && w1 % 32 == 0) ? 32 : 0;
+    if (!sw) return;
+    const uint64_t ncols = (uint64_t)(d.N / out_div);
+    uint64_t dims[3], strides[2];
+    uint32_t box[3] = {(uint32_t)sw, (uint32_t)BM, 1};
+    if (d.out_col_m1 > 0) {
+        if (d.out_col_m1 != 32 || d.out_m1 != 1 || d.batches != 1 || out_div != 1) return;
+        sw = 32;
+        box[0] = 32;
+        dims[0] = 32; dims[1] = (uint64_t)d.rows_per_batch; dims[2] = ncols / 32;
+        strides[0] = (uint64_t)d.out_s0 * 2; strides[1] = (uint64_t)d.out_col_s0 * 2;
+        p.out_kind = 2;
+    } else if (d.batches > 1) {
+        if (d.out_m1 != d.rows_per_batch) return;
+        dims[0] = ncols; dims[1] = (uint64_t)d.rows_per_batch; dims[2] = (uint64_t)d.batches;
+        strides[0] = (uint64_t)d.out_s1 * 2; strides[1] = (uint64_t)d.out_s0 * 2;
+        p.out_kind = 0;
+    } else if (d.out_m1 == 1) {
+        dims[0] = ncols; dims[1] = (uint64_t)d.rows_per_batch; dims[2] = 1;
+        strides[0] = (uint64_t)d.out_s0 * 2; strides[1] = (uint64_t)d.out_s0 * 2 * (uint64_t)d.rows_per_batch;
+        p.out_kind = 0;
+    } else if (d.out_m1 % BM == 0 && d.rows_per_batch % d.out_m1 == 0) {
+        dims[0] = ncols; dims[1] = (uint64_t)d.out_m1; dims[2] = (uint64_t)(d.rows_per_batch / d.out_m1);
+        strides[0] = (uint64_t)d.out_s1 * 2; strides[1] = (uint64_t)d.out_s0 * 2;
+        p.out_kind = 1;
+        p.out_P = (int)d.out_m1;
+    } else {
+        return;
+    }
+    if (strides[0] % 16 != 0 || strides[1] % 16 != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0) return;
+    if (dims[2] > 1 && strides[1] == 0) return;
+    p.tma_o = encode(d.out, 3, dims, strides, box, sw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    p.sw = sw;
+    p.staged = 1;
+}
+
 static int pick_bn(int N) {
     // largest tile width <= 256 that divides N and is a multiple of 32
     for (int bn = 256; bn >= 32; bn -= 32) {
@@ -346,7 +477,17 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
     }
     p.tiles_per_batch = (d.rows_per_batch + BM - 1) / BM;
     p.grid = dim3((unsigned)(p.tiles_per_batch * d.batches), (unsigned)(d.N / p.bn), 1);
-    p.smem = (size_t)STAGES * (BM * BK * 2 + (size_t)p.bn * BK * 2) + 256 + 1024;
+    plan_output_staging(p);
+    const size_t stage_bytes = BM * BK * 2 + (size_t)p.bn * BK * 2;
+    const size_t staging = p.staged ? (size_t)2 * BM * (((p.bn / 32 + 1) / 2) * 32) * 2 : 0;
+    p.stages = STAGES;
+    if ((size_t)p.stages * stage_bytes + staging + 256 + 1024 > 227 * 1024) p.stages = 3;
+    p.smem = (size_t)p.stages * stage_bytes + staging + 256 + 1024;
+    if (p.smem > 227 * 1024) {
+        p.staged = 0;
+        p.stages = STAGES;
+        p.smem = (size_t)p.stages * stage_bytes + 256 + 1024;
+    }
     const uint64_t batch_stride = d.batches > 1 ? (uint64_t)d.a_batch_stride * 2 : (uint64_t)d.a_row_stride * 2 * d.rows_per_batch;
     p.tma_a = make_tmap_3d(d.a, (uint64_t)(d.a_inner > 0 ? d.a_inner : d.K), (uint64_t)d.rows_per_batch, (uint64_t)d.batches, (uint64_t)d.a_row_stride * 2,
                            batch_stride, BK, BM, 1);
@@ -381,8 +522,13 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.tmem_cols = cols;
     k.n_tiles = p.d.N / p.bn;
     k.num_tiles = p.tiles_per_batch * p.d.batches * k.n_tiles;
+    k.staged = p.staged;
+    k.stages = p.stages;
+    k.sw = p.sw;
+    k.out_kind = p.out_kind;
+    k.out_P = p.out_P > 0 ? p.out_P : 1;
     const int grid = k.num_tiles < kNumSMs ? k.num_tiles : kNumSMs;
-    gemm_f16_tcgen05_kernel<<<grid, GEMM_THREADS, p.smem, stream>>>(p.tma_a, p.tma_w, k);
+    gemm_f16_tcgen05_kernel<<<grid, GEMM_THREADS, p.smem, stream>>>(p.tma_a, p.tma_w, p.staged ? p.tma_o : p.tma_a, k);
     B200_CUDA(cudaGetLastError());
 }
 

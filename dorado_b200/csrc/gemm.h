@@ -51,11 +51,13 @@ struct GemmDesc {
 
 struct GemmPlan {
     CUtensorMap tma_a, tma_w;
+    CUtensorMap tma_o;   // output, when the epilogue leaves through shared memory + TMA stores (staged)
     GemmDesc d;
     int bn = 128;
     int tiles_per_batch = 0;
     dim3 grid;
     size_t smem = 0;
+    int staged = 0, stages = 4, sw = 64, out_kind = 0, out_P = 1;
 };
 
 GemmPlan make_gemm_plan(const GemmDesc& d);

@@ -598,8 +598,11 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
                     tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
                     tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
                 }
+                const bool dbg = p.dbg && blockIdx.x == 0 && mw == 0 && s >= 64 && s < 68;
+                if (dbg) p.dbg[(s - 64) * 16 + 0] = clock64();
                 tc::mbar_wait(&h_ready[buf], par);
                 tc::tc_fence_after();
+                if (dbg) p.dbg[(s - 64) * 16 + 1] = clock64();
 #pragma unroll
                 for (int kb = 0; kb < KBX; ++kb) {
                     const uint32_t a_t = tmem_w + (uint32_t)(mw * Cfg::WCOLS + kb * 16);
@@ -609,6 +612,7 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
                 }
                 tc::umma_commit(&acc_full[buf * MT + mw]);
                 tc::umma_commit(&z_free[buf]);
+                if (dbg) p.dbg[(s - 64) * 16 + 2] = clock64();
             }
         }
     } else {
@@ -628,8 +632,11 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
             const int buf = s & 1, nbuf = buf ^ 1;
             const uint32_t par = (uint32_t)((s >> 1) & 1);
             uint8_t* zh = z_s + (size_t)(nbuf * KB + KBX + em) * ZBLK;   // block of this tile's 32 units in the next operand
+            long long* d = (p.dbg && blockIdx.x == 0 && ewarp == 0 && lane == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 16 : nullptr;
+            if (d) d[4] = clock64();
             tc::mbar_wait(&acc_full[buf * MT + em], par);
             tc::tc_fence_after();
+            if (d) d[5] = clock64();
             uint32_t r[NBR];
             const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((buf * MT + em) * UN);
             if constexpr (NBR == 16) {
@@ -641,12 +648,14 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
             }
             tc::tmem_ld_wait();
             tc::tc_fence_before();
+            if (d) d[6] = clock64();
             float a[NBR];
 #pragma unroll
             for (int n = 0; n < NBR; ++n) {
                 const float v = __uint_as_float(r[n]) + bias;
                 a[n] = 1.0f - __fdividef(am, __expf(am * v) + 1.0f);
             }
+            if (d) d[7] = clock64();
             // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
@@ -660,6 +669,7 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
                 r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
                 if (g1) { a[4 * c + 0] = r0; a[4 * c + 1] = r1; } else { a[4 * c + 2] = r0; a[4 * c + 3] = r1; }
             }
+            if (d) d[8] = clock64();
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const float cs = a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2];
@@ -672,12 +682,15 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
                     *reinterpret_cast<uint32_t*>(zh + sw64_offset(4 * c + gj, qt * 8 + uk)) = mine | (other << 16);
                 }
             }
+            if (d) d[9] = clock64();
             tc::fence_proxy_async_smem();   // h_t -> visible to the MMAs and the TMA store (async proxy)
             __syncwarp();
+            if (d) d[10] = clock64();
             if (lane == 0) {
                 tc::mbar_arrive(&acc_free[buf]);
                 tc::mbar_arrive(&h_ready[nbuf]);
             }
+            if (d) d[11] = clock64();
             // off the chain: h_t of this tile to HBM, one TMA store of the operand block (rows = the CTA's chunks)
             if (storer) tc::bulk_wait_group_read<0>();   // the store of the previous step has read Z[buf]'s block: it may be rewritten next step
             named_bar_sync(1 + em, 128);
@@ -685,6 +698,7 @@ __global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <
                 tc::tma_store_2d(&tma_x, zh, em * 32, t * p.N + n0);
                 tc::bulk_commit_group();
             }
+            if (d) d[12] = clock64();
         }
         if (storer) tc::bulk_wait_group<0>();
     }
@@ -705,6 +719,7 @@ struct LstmRecParams {
     __half* seq;          // [T][N][C] output h (in place over the layer input)
     const __half* gx;     // [T][N / 32][4C][32]
     int T, N, reverse;
+    long long* dbg;       // optional clock64 timeline of CTA 0, steps 64..67 (B200_DEBUG_LSTM_TIMELINE); nullptr in production
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1037,8 +1052,11 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                 for (int g = 0; g < NG; ++g) {
                     // arm the barrier the slices of h_s will complete on (all CL CTAs x TPC tiles, this group)
                     if (s + 1 < p.T) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
+                    long long* d = (p.dbg && blockIdx.x == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + g * 4 : nullptr;
+                    if (d) d[0] = clock64();
                     tc::mbar_wait(&h_full[g * 2 + buf], par);
                     tc::tc_fence_after();
+                    if (d) d[1] = clock64();
                     const uint64_t zd = zdesc0 + (uint64_t)(((g * 2 + buf) * KBH * ZB) >> 4);
 #pragma unroll
                     for (int i = 0; i < TPC; ++i) {
@@ -1052,6 +1070,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                         }
                         tc::umma_commit(&acc_full[g * TPC + i]);
                     }
+                    if (d) d[2] = clock64();
                 }
             }
         }
@@ -1082,12 +1101,16 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             const uint4* gp = reinterpret_cast<const uint4*>(gx_base + (size_t)t * gx_step);
             const uint4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
             uint8_t* stage = st_s + (size_t)((eg * 2 + (s & 1)) * TPC + ti) * ZB;
+            long long* d = (p.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + 8 : nullptr;
+            if (d) d[0] = clock64();
             tc::mbar_wait(&acc_full[eg * TPC + ti], (uint32_t)(s & 1));
             tc::tc_fence_after();
+            if (d) d[1] = clock64();
             uint32_t r[16];
             tc::tmem_ld_32x16(taddr, r);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
+            if (d) d[2] = clock64();
             float a[16];
             {
                 const __half2* h0 = reinterpret_cast<const __half2*>(&gx0);
@@ -1103,6 +1126,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             }
 #pragma unroll
             for (int n = 0; n < 16; ++n) a[n] = 1.0f - __fdividef(am, __expf(am * a[n]) + 1.0f);
+            if (d) d[3] = clock64();
             // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -1116,6 +1140,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                 r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
                 if (g1) { a[4 * c + 0] = r0; a[4 * c + 1] = r1; } else { a[4 * c + 2] = r0; a[4 * c + 3] = r1; }
             }
+            if (d) d[4] = clock64();
             float hv[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -1139,9 +1164,13 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                 *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * cb + gj, ucol)) = w0;
                 *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * (cb + 1) + gj, ucol)) = w1;
             }
+            if (d) d[5] = clock64();
             tc::fence_proxy_async_smem();            // staged block -> visible to the bulk copy / TMA store
+            if (d) d[6] = clock64();
             if (sender) tc::bulk_wait_group_read<0>();  // the store issued a step ago has read the other staging buffer
+            if (d) d[7] = clock64();
             named_bar_sync(bar_id, 128);
+            if (d) d[8] = clock64();
             if (sender) {
                 if (s + 1 < p.T) {
 #pragma unroll
@@ -1153,6 +1182,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                 tc::tma_store_2d(&tma_y, stage, m * 32, t * p.N + n0 + eg * GN);
                 tc::bulk_commit_group();
             }
+            if (d) d[9] = clock64();
         }
         if (sender) tc::bulk_wait_group<0>();
     }
@@ -1471,6 +1501,12 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.T = T_out;
             rp.N = Np;
             rp.reverse = (l % 2 == 0) ? 1 : 0;
+            rp.dbg = nullptr;
+            if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
+                B200_CUDA(cudaMalloc(&rp.dbg, 128 * sizeof(long long)));
+                B200_CUDA(cudaMemset(rp.dbg, 0, 128 * sizeof(long long)));
+                plan->dbg_timeline = rp.dbg;
+            }
             plan->rec_p.push_back(rp);
         }
     } else {
@@ -1690,14 +1726,26 @@ void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
         }
     }
     if (dbg_timeline) {
-        long long h[64];
+        long long h[128];
         B200_CUDA(cudaStreamSynchronize(stream));
-        B200_CUDA(cudaMemcpy(h, dbg_timeline, sizeof(h), cudaMemcpyDeviceToHost));
+        B200_CUDA(cudaMemcpy(h, dbg_timeline, hoisted ? sizeof(h) : 64 * sizeof(long long), cudaMemcpyDeviceToHost));
         for (int s = 0; s < 4; ++s) {
-            const long long* e = h + s * 16;
-            const long long t0 = e[0];
-            fprintf(stderr, "[lstm timeline step %d] mma: wait_h_start 0 wait_h_done %lld issue_done %lld | epi: wait_acc_start %lld acc_full %lld ld_done %lld act_done %lld bar_done %lld cells_done %lld arrive_done %lld\n",
-                    64 + s, e[1] - t0, e[2] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0, e[8] - t0, e[9] - t0, e[10] - t0);
+            if (hoisted) {
+                const long long* e = h + s * 32;
+                const long long t0 = e[0];
+                fprintf(stderr, "[cluster timeline step %d] mma g0: wait %lld..%lld issued %lld | g1: wait %lld..%lld issued %lld | epi(g0,t0): "
+                                "wait_acc %lld..%lld ld %lld act %lld transpose %lld cells+stage %lld fence %lld wait_read %lld bar %lld sent %lld | "
+                                "period %lld\n",
+                        64 + s, e[0] - t0, e[1] - t0, e[2] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[8] - t0, e[9] - t0, e[10] - t0, e[11] - t0,
+                        e[12] - t0, e[13] - t0, e[14] - t0, e[15] - t0, e[16] - t0, e[17] - t0, s > 0 ? e[0] - (e - 32)[0] : 0LL);
+            } else {
+                const long long* e = h + s * 16;
+                const long long t0 = e[0];
+                fprintf(stderr, "[lstm timeline step %d] mma: wait_h 0..%lld issued %lld | epi: wait_acc %lld..%lld ld %lld act %lld "
+                                "transpose/bar %lld cells %lld fence %lld arrive %lld store %lld | period %lld\n",
+                        64 + s, e[1] - t0, e[2] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0, e[8] - t0, e[9] - t0, e[10] - t0, e[11] - t0,
+                        e[12] - t0, s > 0 ? e[0] - (e - 16)[0] : 0LL);
+            }
         }
     }
     NvtxRange r("linear");

@@ -84,6 +84,8 @@ EXPORTS = [
     "b200_runner_debug_read_input", "b200_engine_runner_bytes", "b200_engine_benchmark_batch_sizes",
     "b200_select_batch_size", "b200_generate_variable_chunks", "b200_engine_terminate", "b200_engine_restart",
     "b200_engine_set_low_latency", "b200_engine_is_low_latency", "b200_engine_batch_timeouts_ms",
+    "b200_pool_create", "b200_pool_destroy", "b200_pool_num_runners", "b200_pool_runner", "b200_pool_out_len",
+    "b200_pool_runner_info", "b200_pool_call_chunks",
 ]
 
 _lib = None
@@ -107,6 +109,15 @@ def load_library() -> C.CDLL:
     lib.b200_last_error.restype = C.c_char_p
     lib.b200_version.restype = C.c_char_p
     lib.b200_default_decoder_options.argtypes = [C.POINTER(DecoderOptions)]
+    lib.b200_pool_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(Tensor), i32, C.POINTER(i32), i32, i32, i32, i32,
+                                     C.POINTER(vp)]
+    lib.b200_pool_destroy.argtypes = [vp]
+    lib.b200_pool_num_runners.argtypes = [vp]
+    lib.b200_pool_out_len.argtypes = [vp]
+    lib.b200_pool_runner.argtypes = [vp, i32]
+    lib.b200_pool_runner.restype = vp
+    lib.b200_pool_runner_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_int64)]
+    lib.b200_pool_call_chunks.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(C.c_double)]
     lib.b200_engine_terminate.argtypes = [vp]
     lib.b200_engine_restart.argtypes = [vp]
     lib.b200_engine_set_low_latency.argtypes = [vp, i32]

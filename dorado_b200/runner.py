@@ -104,6 +104,75 @@ class B200Caller:
             pass
 
 
+def _weight_array(weights: dict):
+    keep = []
+    arr = (L.Tensor * len(weights))()
+    for i, (name, w) in enumerate(weights.items()):
+        w = np.ascontiguousarray(w, np.float32)
+        keep.append(w)
+        arr[i].name = name.encode()
+        arr[i].data = w.ctypes.data_as(C.POINTER(C.c_float))
+        arr[i].ndim = w.ndim
+        for k, dim in enumerate(w.shape):
+            arr[i].dims[k] = dim
+    return arr, keep
+
+
+class B200Pool:
+    """Several devices in one process: api::create_basecall_runners + BasecallerNode's worker loop
+    (dorado/api/runner_creation.cpp:46-130, read_pipeline/nodes/BasecallerNode.cpp:300-352) -- one engine per device,
+    `runners_per_device` runners each, one pinned host thread per runner, batches taken from one shared cursor."""
+
+    def __init__(self, cfg: BasecallModelConfig, weights: dict, devices, runners_per_device: int, batch_size: int,
+                 chunk_size: int):
+        self.cfg = cfg
+        self._lib = lib = L.load_library()
+        desc = L.model_desc_from_config(cfg)
+        arr, keep = _weight_array(weights)
+        devs = (C.c_int32 * len(devices))(*devices)
+        self.chunk_size = cfg.normalise_chunk_size(chunk_size)
+        self.batch_size = batch_size
+        self.handle = C.c_void_p()
+        L.check(lib.b200_pool_create(C.byref(desc), arr, len(weights), devs, len(devices), runners_per_device, batch_size,
+                                     self.chunk_size, C.byref(self.handle)))
+        del keep
+        self.t_out = lib.b200_pool_out_len(self.handle)
+
+    def num_runners(self) -> int:
+        return self._lib.b200_pool_num_runners(self.handle)
+
+    def runner_info(self, i: int):
+        node, batches = C.c_int32(), C.c_int64()
+        L.check(self._lib.b200_pool_runner_info(self.handle, i, C.byref(node), C.byref(batches)))
+        return {"numa_node": node.value, "batches": batches.value}
+
+    def call_chunks(self, chunks: np.ndarray, want_output: bool = True):
+        """chunks: fp16 [n, chunk_size].  Returns (seconds, moves, sequence, qstring, n_bases)."""
+        c = np.ascontiguousarray(chunks, np.float16)
+        n = c.shape[0]
+        assert c.shape[1] == self.chunk_size
+        secs = C.c_double()
+        if not want_output:
+            L.check(self._lib.b200_pool_call_chunks(self.handle, c.ctypes.data, n, None, None, None, None, C.byref(secs)))
+            return secs.value, None, None, None, None
+        moves, seq, qs = (np.zeros((n, self.t_out), np.uint8) for _ in range(3))
+        nb = np.zeros(n, np.int32)
+        L.check(self._lib.b200_pool_call_chunks(self.handle, c.ctypes.data, n, moves.ctypes.data, seq.ctypes.data,
+                                                qs.ctypes.data, nb.ctypes.data, C.byref(secs)))
+        return secs.value, moves, seq, qs, nb
+
+    def close(self):
+        if self.handle:
+            self._lib.b200_pool_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class B200ModelRunner:
     _ids = itertools.count()
 
@@ -197,7 +266,8 @@ class B200ModelRunner:
 
     # --- stage-level / measurement hooks -------------------------------------------------------
     def input_view(self) -> np.ndarray:
-        """Pinned fp16 [batch, chunk_size] input buffer."""
+        """Pinned fp16 [batch, chunk_size] input buffer (asking for it turns raw slots back into fp16 slots)."""
+        self._lib.b200_runner_input(self.handle)
         return self._input
 
     def forward_scores(self, num_chunks: int) -> np.ndarray:

@@ -153,7 +153,9 @@ B200_API int32_t b200_runner_out_len(const b200_runner* runner); /* chunk_size /
 B200_API int b200_runner_accept_chunk_f16(b200_runner* runner, int32_t chunk_idx, const uint16_t* samples, int64_t len);
 /* Same, converting from fp32 on the way in (CPU ModelRunner's dtype, ModelRunner.cpp:47-49). */
 B200_API int b200_runner_accept_chunk_f32(b200_runner* runner, int32_t chunk_idx, const float* samples, int64_t len);
-/* Direct access to the pinned input (what the reference's accept_chunk writes through index_put_). */
+/* Direct access to the pinned input (what the reference's accept_chunk writes through index_put_).  Slots keep their
+ * content across calls; the call also turns every slot that holds a raw chunk back into an fp16 slot, so rows written
+ * through the pointer are what the next call uploads (ask again after b200_runner_accept_raw_chunk). */
 B200_API uint16_t* b200_runner_input(b200_runner* runner);
 
 /* ModelRunnerBase::call_chunks (CudaCaller.cpp:224-271): H2D, forward, decode, D2H; blocking. */
@@ -268,6 +270,42 @@ B200_API int b200_select_batch_size(const int32_t* batch_sizes,
                                     int32_t granularity,
                                     float time_penalty,
                                     int32_t* selected);
+
+/* ---- Several devices in one process ---------------------------------------------------------------
+ *
+ * api::create_basecall_runners (dorado/api/runner_creation.cpp:46-130) creates one CudaCaller per device and num_runners
+ * CudaModelRunners on each; BasecallerNode drives every runner from its own worker thread, all fed from shared chunk
+ * queues (read_pipeline/nodes/BasecallerNode.cpp:300-352).  b200_pool_create is that: one engine per listed device,
+ * runners_per_device runners each, one pinned host thread per runner (on the NUMA node of its device).
+ * b200_pool_runner() hands out the runners for the adapter to wrap as ModelRunnerBase objects (runner_creation.cpp:115-123);
+ * b200_pool_call_chunks is the worker loop itself for callers without a pipeline (bench, tests): `num_chunks` host chunks
+ * (fp16 bits, [num_chunks][chunk_size]) are taken batch by batch from ONE shared cursor by whichever runner is free
+ * (dynamic load balance; no collective, no inter-GPU traffic), results land in the caller's arrays with row pitch
+ * b200_pool_out_len().  Blocking; returns the wall time in *seconds. */
+typedef struct b200_pool b200_pool;
+B200_API int b200_pool_create(const b200_model_desc* desc,
+                              const b200_tensor* tensors,
+                              int32_t num_tensors,
+                              const int32_t* devices,
+                              int32_t num_devices,
+                              int32_t runners_per_device,
+                              int32_t batch_size,
+                              int32_t chunk_size,
+                              b200_pool** out);
+B200_API int b200_pool_destroy(b200_pool* pool);
+B200_API int32_t b200_pool_num_runners(const b200_pool* pool);
+B200_API b200_runner* b200_pool_runner(b200_pool* pool, int32_t index);
+B200_API int32_t b200_pool_out_len(const b200_pool* pool);
+/* per runner: host NUMA node its thread is pinned to (-1 = not pinned) and batches it has taken so far */
+B200_API int b200_pool_runner_info(const b200_pool* pool, int32_t index, int32_t* numa_node, int64_t* batches);
+B200_API int b200_pool_call_chunks(b200_pool* pool,
+                                   const uint16_t* chunks,
+                                   int64_t num_chunks,
+                                   uint8_t* moves,
+                                   char* sequence,
+                                   char* qstring,
+                                   int32_t* n_bases,
+                                   double* seconds);
 
 /* Stage-level entry points so scores and decode can be parity-checked independently (host buffers). */
 B200_API int b200_runner_forward_scores(b200_runner* runner, int32_t num_chunks, uint16_t* scores_out /* [n,t_out,outsize] fp16 */);

@@ -198,3 +198,36 @@ def test_decoder_options_struct_mirrors_the_reference():
         with pytest.raises(L.B200Error) as e:
             L.decode_scores(scores, opts=o)
         assert e.value.status == L.B200_ERR_UNSUPPORTED
+
+
+def test_pool_feeds_every_runner_and_matches_a_single_runner():
+    """b200_pool (one process, an engine per listed device, runners fed from one shared cursor) returns, chunk for chunk,
+    what a single runner returns; every runner takes part.  Listing device 0 twice exercises the multi-engine code on the
+    one-GPU test box (tools/bench_pool.py runs it across real devices)."""
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner, B200Pool
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir("fast"))
+    w = synthetic_weights(cfg, 42)
+    n, B, T = 150, 16, 1200
+    pool = B200Pool(cfg, w, [0, 0], 2, B, T)
+    assert pool.num_runners() == 4
+    sig = np.random.default_rng(5).standard_normal((n, pool.chunk_size)).astype(np.float16)
+    secs, moves, seq, qs, nb = pool.call_chunks(sig)
+    assert secs > 0
+    secs2, *_ = pool.call_chunks(sig, want_output=False)      # a second job on the same pool
+    taken = [pool.runner_info(i)["batches"] for i in range(4)]
+    assert sum(taken) == 2 * ((n + B - 1) // B) and min(taken) >= 1, taken
+    caller = B200Caller(cfg, w)
+    runner = B200ModelRunner(caller, B, T)
+    for start in range(0, n, B):
+        cnt = min(B, n - start)
+        for i in range(cnt):
+            runner.accept_chunk(i, sig[start + i])
+        ref = runner.call_chunks(cnt)
+        for i, c in enumerate(ref):
+            k = start + i
+            assert nb[k] == len(c.sequence)
+            assert bytes(seq[k, :nb[k]]).decode() == c.sequence and bytes(qs[k, :nb[k]]).decode() == c.qstring
+            assert (moves[k] == c.moves).all()
+    pool.close()
