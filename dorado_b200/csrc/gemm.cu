@@ -109,35 +109,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
 
     if (warp == 0) {
         if (tc::elect_one()) {
-            long long it = 0;  // k-block counter across tiles
+            int s = 0;            // ring slot and its phase, advanced incrementally (the ring depth is a run-time value)
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
                 const int batch = mt / p.tiles_per_batch;
                 const int r0 = (mt % p.tiles_per_batch) * BM;
                 const int n0 = nt * p.bn;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-                    const int s = (int)(it % NST);
-                    tc::mbar_wait(&empty[s], (uint32_t)(((it / NST) & 1) ^ 1));
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
                     uint8_t* a_s = smem + s * stage_bytes;
                     tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
                     tc::tma_load_2d(a_s + a_bytes, &tma_w, &full[s], kb * BK, n0);
+                    if (++s == NST) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             const uint32_t idesc = tc::umma_idesc_f16(BM, p.bn);
-            long long it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             int ti = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
                 const int ab = ti & 1;
                 tc::mbar_wait(&tmem_empty[ab], (uint32_t)(((ti >> 1) & 1) ^ 1));
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.bn);
-                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-                    const int s = (int)(it % NST);
-                    tc::mbar_wait(&full[s], (uint32_t)((it / NST) & 1));
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    tc::mbar_wait(&full[s], ph);
                     tc::tc_fence_after();
                     const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
                     const uint64_t adesc = tc::umma_desc_sw128(a_addr);
@@ -148,6 +152,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                         tc::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
                     tc::umma_commit(&empty[s]);
+                    if (++s == NST) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
                 tc::umma_commit(&tmem_full[ab]);
             }

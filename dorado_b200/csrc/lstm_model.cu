@@ -459,255 +459,6 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// LSTM layer, second generation for the small hidden size (fast: C = 96).  Same orientation as above (weights = M
-// operand, a CTA owns NBR chunks for the whole sequence), rebuilt around the length of the per-step dependent chain
-// h_{t-1} -> MMA -> gates -> h_t, which is what bounds a layer (1666 steps, a few hundred FLOP/cycle of actual work):
-//   * gate rows are permuted so that a warp's 32 TMEM lanes hold (8 units x 4 gates): the four gates of a cell meet by
-//     a 4 x 4 quad transpose in registers (shuffles); no shared-memory exchange, no block barrier on the chain;
-//   * cell states live in registers;
-//   * only the recurrent half of the weights (W_hh, the half on the chain) sits in tensor memory; the x_t half is
-//     read from shared memory by MMAs issued one step ahead.  That brings a CTA down to 256 tensor-memory columns,
-//     < 64 registers per thread and ~90 KB of shared memory, so TWO CTAs share an SM: the recurrences of two batches in
-//     flight (runners) run side by side instead of queueing for the SMs;
-//   * h_t leaves for HBM as one TMA store per tile from the operand block it was written to (no scattered stores).
-// ------------------------------------------------------------------------------------------------
-template <int C>
-struct Lstm2Cfg {
-    static constexpr int MT = C / 32;              // gate tiles (128 rows = 32 units x 4 gates)
-    static constexpr int KBX = C / KBLK;           // operand blocks of the x half (= of the h half)
-    static constexpr int KB = 2 * KBX;
-    static constexpr int THREADS = 32 * (1 + MT) + 128 * MT;   // TMA warp, MT MMA warps, MT epilogue groups of 4 warps
-    static constexpr int WCOLS = C / 2;            // TMEM columns of the W_hh half of one tile
-    static constexpr int ACC_COLS = 2 * MT * UN;   // double-buffered accumulators
-    static constexpr int NEED = ACC_COLS + MT * WCOLS;
-    static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
-    static constexpr size_t WX_BYTES = (size_t)MT * KBX * WBLK_BYTES;   // W_ih half in shared memory
-    static constexpr size_t Z_BYTES = (size_t)2 * KB * ZBLK;
-    static constexpr size_t SMEM = 1024 + WX_BYTES + Z_BYTES + 8 * (8 + 2 * MT) + 64;
-    static_assert(NEED <= 512 && C % 32 == 0 && C % 16 == 0, "unsupported LSTM size");
-};
-
-template <int C, int NBR>
-__global__ void __launch_bounds__(Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::TMEM_COLS <= 256 ? 2 : 1)
-        lstm_layer2_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w, const LstmParams p) {
-    using Cfg = Lstm2Cfg<C>;
-    constexpr int MT = Cfg::MT, KB = Cfg::KB, KBX = Cfg::KBX;
-    constexpr int CPL = NBR / 4;  // cells per lane
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_s = smem;                                   // [MT][KBX][128 x 64 B]  W_ih, K-major, 64-byte swizzle
-    uint8_t* z_s = w_s + Cfg::WX_BYTES;                    // [2][KB][ZBLK]          [x_t ; h_{t-1}] operand blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(z_s + Cfg::Z_BYTES);
-    uint64_t* x_full = bars;          // [2]  TMA -> MMA
-    uint64_t* z_free = bars + 2;      // [2]  MMAs done with Z[buf] -> TMA
-    uint64_t* h_ready = bars + 4;     // [2]  epilogue wrote h into Z[buf] -> MMA
-    uint64_t* acc_free = bars + 6;    // [2]  epilogue done reading accumulator set -> MMA
-    uint64_t* acc_full = bars + 8;    // [2][MT] MMA -> epilogue
-    uint64_t* w_full = acc_full + 2 * MT;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * NBR;
-
-    // zero Z (padding rows, h_{-1}) before anything asynchronous starts
-    for (int i = threadIdx.x; i < (int)(Cfg::Z_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
-    tc::fence_proxy_async_smem();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&x_full[i], 1);
-            tc::mbar_init(&z_free[i], MT);          // one commit per MMA warp
-            tc::mbar_init(&h_ready[i], MT * 4);     // one arrival per epilogue warp
-            tc::mbar_init(&acc_free[i], MT * 4);
-        }
-        for (int i = 0; i < 2 * MT; ++i) tc::mbar_init(&acc_full[i], 1);
-        tc::mbar_init(&w_full[0], 1);
-        tc::fence_barrier_init();
-        tc::prefetch_tmap(&tma_x);
-        tc::prefetch_tmap(&tma_w);
-    }
-    if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_w = tmem_base + Cfg::ACC_COLS;     // [MT][WCOLS]: tile m, 16-element k-step ks at m*WCOLS + ks*8
-
-    const bool is_epi = warp > MT;
-    const int ewarp = warp - (1 + MT);
-    const int em = ewarp >> 2;      // tile served by this epilogue warp
-    const int qt = warp & 3;        // TMEM lane quarter (the 4 warps of a tile cover all four)
-    if (is_epi) {
-        // this thread's W_hh row (tile em, row 32*qt + lane): columns C..2C-1 of the packed [W_ih | W_hh] row
-        const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)(em * 128 + qt * 32 + lane) * 2 * C + C);
-#pragma unroll 1
-        for (int cb = 0; cb < C / 32; ++cb) {
-            uint32_t r[16];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const uint4 x = __ldg(src + cb * 4 + v);
-                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
-            }
-            tc::tmem_st_32x16(tmem_w + ((uint32_t)(qt * 32) << 16) + (uint32_t)(em * Cfg::WCOLS + cb * 16), r);
-        }
-        tc::tmem_st_wait();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-
-    if (warp == 0) {
-        // ---------------- TMA producer: W_ih once, then x_t one step ahead ----------------
-        if (tc::elect_one()) {
-            tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)Cfg::WX_BYTES);
-            for (int m = 0; m < MT; ++m) {
-                for (int kb = 0; kb < KBX; ++kb) {
-                    tc::tma_load_2d(w_s + (size_t)(m * KBX + kb) * WBLK_BYTES, &tma_w, &w_full[0], kb * KBLK, m * 128);
-                }
-            }
-            for (int s = 0; s < p.T; ++s) {
-                const int t = p.reverse ? p.T - 1 - s : s;
-                const int buf = s & 1;
-                tc::mbar_wait(&z_free[buf], ((s >> 1) & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&x_full[buf], (uint32_t)(KBX * NBR * KBLK * 2));
-                for (int kb = 0; kb < KBX; ++kb) {
-                    tc::tma_load_2d(z_s + (size_t)(buf * KB + kb) * ZBLK, &tma_x, &x_full[buf], kb * KBLK, t * p.N + n0);
-                }
-            }
-        }
-    } else if (!is_epi) {
-        // ---------------- MMA issuers: warp mw owns tile mw ----------------
-        const int mw = warp - 1;
-        if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
-            const uint64_t wdesc = umma_desc_sw64(tc::smem_u32(w_s)) + (uint64_t)((mw * KBX * WBLK_BYTES) >> 4);
-            const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
-            tc::mbar_wait(&w_full[0], 0);
-            for (int s = 0; s < p.T; ++s) {
-                const int buf = s & 1;
-                const uint32_t par = (uint32_t)((s >> 1) & 1);
-                const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
-                const uint32_t d_tmem = tmem_base + (uint32_t)((buf * MT + mw) * UN);
-                tc::mbar_wait(&x_full[buf], par);
-                tc::mbar_wait(&acc_free[buf], par ^ 1);
-                tc::tc_fence_after();
-                // x half: independent of the recurrence, runs under the previous step's gate math
-#pragma unroll
-                for (int kb = 0; kb < KBX; ++kb) {
-                    const uint64_t adesc = wdesc + (uint64_t)((kb * WBLK_BYTES) >> 4);
-                    const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
-                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
-                    tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
-                }
-                const bool dbg = p.dbg && blockIdx.x == 0 && mw == 0 && s >= 64 && s < 68;
-                if (dbg) p.dbg[(s - 64) * 16 + 0] = clock64();
-                tc::mbar_wait(&h_ready[buf], par);
-                tc::tc_fence_after();
-                if (dbg) p.dbg[(s - 64) * 16 + 1] = clock64();
-#pragma unroll
-                for (int kb = 0; kb < KBX; ++kb) {
-                    const uint32_t a_t = tmem_w + (uint32_t)(mw * Cfg::WCOLS + kb * 16);
-                    const uint64_t bdesc = zd + (uint64_t)(((KBX + kb) * ZBLK) >> 4);
-                    tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, true);
-                    tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
-                }
-                tc::umma_commit(&acc_full[buf * MT + mw]);
-                tc::umma_commit(&z_free[buf]);
-                if (dbg) p.dbg[(s - 64) * 16 + 2] = clock64();
-            }
-        }
-    } else {
-        // ---------------- epilogue: gates, cell update, h_t ----------------
-        const int uk = lane >> 2, gj = lane & 3;   // unit within the warp's 8, gate type (i, f, g, o)
-        const int g0 = gj & 1, g1 = gj >> 1;
-        const float am = gj == 2 ? 2.0f : 1.0f;    // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
-        const float bias = __ldg(p.bias + em * 128 + qt * 32 + lane);
-        const bool storer = qt == 0 && lane == 0;
-        float c_reg[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) c_reg[c] = 0.0f;
-        if (lane == 0) tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0 is in place (zeroed before the CTA-wide sync)
-
-        for (int s = 0; s < p.T; ++s) {
-            const int t = p.reverse ? p.T - 1 - s : s;
-            const int buf = s & 1, nbuf = buf ^ 1;
-            const uint32_t par = (uint32_t)((s >> 1) & 1);
-            uint8_t* zh = z_s + (size_t)(nbuf * KB + KBX + em) * ZBLK;   // block of this tile's 32 units in the next operand
-            long long* d = (p.dbg && blockIdx.x == 0 && ewarp == 0 && lane == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 16 : nullptr;
-            if (d) d[4] = clock64();
-            tc::mbar_wait(&acc_full[buf * MT + em], par);
-            tc::tc_fence_after();
-            if (d) d[5] = clock64();
-            uint32_t r[NBR];
-            const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)((buf * MT + em) * UN);
-            if constexpr (NBR == 16) {
-                tc::tmem_ld_32x16(taddr, r);
-            } else if constexpr (NBR == 8) {
-                tc::tmem_ld_32x8(taddr, r);
-            } else {
-                tc::tmem_ld_32x4(taddr, r);
-            }
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            if (d) d[6] = clock64();
-            float a[NBR];
-#pragma unroll
-            for (int n = 0; n < NBR; ++n) {
-                const float v = __uint_as_float(r[n]) + bias;
-                a[n] = 1.0f - __fdividef(am, __expf(am * v) + 1.0f);
-            }
-            if (d) d[7] = clock64();
-            // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                float s0 = g0 ? a[4 * c + 0] : a[4 * c + 1];
-                float s1 = g0 ? a[4 * c + 2] : a[4 * c + 3];
-                float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-                if (g0) { a[4 * c + 0] = r0; a[4 * c + 2] = r1; } else { a[4 * c + 1] = r0; a[4 * c + 3] = r1; }
-                s0 = g1 ? a[4 * c + 0] : a[4 * c + 2];
-                s1 = g1 ? a[4 * c + 1] : a[4 * c + 3];
-                r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
-                r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
-                if (g1) { a[4 * c + 0] = r0; a[4 * c + 1] = r1; } else { a[4 * c + 2] = r0; a[4 * c + 3] = r1; }
-            }
-            if (d) d[8] = clock64();
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const float cs = a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2];
-                c_reg[c] = cs;
-                const __half h = __float2half_rn(a[4 * c + 3] * tanh_f(cs));
-                // units (uk, uk ^ 1) of chunk 4c + gj leave as one 32-bit store from the even lane
-                const uint32_t mine = (uint32_t)__half_as_ushort(h);
-                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 4);
-                if (!(uk & 1)) {
-                    *reinterpret_cast<uint32_t*>(zh + sw64_offset(4 * c + gj, qt * 8 + uk)) = mine | (other << 16);
-                }
-            }
-            if (d) d[9] = clock64();
-            tc::fence_proxy_async_smem();   // h_t -> visible to the MMAs and the TMA store (async proxy)
-            __syncwarp();
-            if (d) d[10] = clock64();
-            if (lane == 0) {
-                tc::mbar_arrive(&acc_free[buf]);
-                tc::mbar_arrive(&h_ready[nbuf]);
-            }
-            if (d) d[11] = clock64();
-            // off the chain: h_t of this tile to HBM, one TMA store of the operand block (rows = the CTA's chunks)
-            if (storer) tc::bulk_wait_group_read<0>();   // the store of the previous step has read Z[buf]'s block: it may be rewritten next step
-            named_bar_sync(1 + em, 128);
-            if (storer) {
-                tc::tma_store_2d(&tma_x, zh, em * 32, t * p.N + n0);
-                tc::bulk_commit_group();
-            }
-            if (d) d[12] = clock64();
-        }
-        if (storer) tc::bulk_wait_group<0>();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
-
-// ------------------------------------------------------------------------------------------------
 // LSTM layer for hidden sizes whose weights do not fit one SM (hac: C = 384): hoisted x-projection + cluster recurrence.
 //
 // The x_t half of the gate pre-activations does not depend on the recurrence, so it is hoisted into one large
@@ -719,6 +470,7 @@ struct LstmRecParams {
     __half* seq;          // [T][N][C] output h (in place over the layer input)
     const __half* gx;     // [T][N / 32][4C][32]
     int T, N, reverse;
+    int gather_l2;        // all-gather of h_t through L2 (TMA store + multicast TMA load) instead of bulk copies over DSMEM
     long long* dbg;       // optional clock64 timeline of CTA 0, steps 64..67 (B200_DEBUG_LSTM_TIMELINE); nullptr in production
 };
 
@@ -1172,15 +924,29 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             named_bar_sync(bar_id, 128);
             if (d) d[8] = clock64();
             if (sender) {
-                if (s + 1 < p.T) {
-#pragma unroll
-                    for (int rr = 0; rr < CL; ++rr) {
-                        tc::bulk_copy_smem_to_cluster(mapa_shared(dst_z[nbuf], (uint32_t)rr), tc::smem_u32(stage), (uint32_t)ZB,
-                                                      mapa_shared(dst_bar[nbuf], (uint32_t)rr));
+                const int yrow = t * p.N + n0 + eg * GN;
+                if (p.gather_l2) {
+                    // all-gather through L2: the block goes to HBM/L2 as the layer output anyway; once that store has
+                    // completed, ONE multicast TMA load brings it back into the operand buffer of all CL CTAs
+                    tc::tma_store_2d(&tma_y, stage, m * 32, yrow);
+                    tc::bulk_commit_group();
+                    if (s + 1 < p.T) {
+                        tc::bulk_wait_group<0>();
+                        tc::tma_load_2d_multicast(z_s + (size_t)(((eg * 2 + nbuf) * KBH + m) * ZB), &tma_y, &h_full[eg * 2 + nbuf], m * 32, yrow,
+                                                  (uint16_t)((1u << CL) - 1u));
                     }
+                } else {
+                    // all-gather over distributed shared memory: one bulk copy per destination CTA
+                    if (s + 1 < p.T) {
+#pragma unroll
+                        for (int rr = 0; rr < CL; ++rr) {
+                            tc::bulk_copy_smem_to_cluster(mapa_shared(dst_z[nbuf], (uint32_t)rr), tc::smem_u32(stage), (uint32_t)ZB,
+                                                          mapa_shared(dst_bar[nbuf], (uint32_t)rr));
+                        }
+                    }
+                    tc::tma_store_2d(&tma_y, stage, m * 32, yrow);
+                    tc::bulk_commit_group();
                 }
-                tc::tma_store_2d(&tma_y, stage, m * 32, t * p.N + n0 + eg * GN);
-                tc::bulk_commit_group();
             }
             if (d) d[9] = clock64();
         }
@@ -1218,7 +984,6 @@ public:
     std::vector<CUtensorMap> lstm_x, lstm_w;
     std::vector<LstmParams> lstm_p;
     int lstm_grid = 0, lstm_nbr = 16, lstm_groups = 3, lstm_threads = 0;
-    bool lstm_v1 = false;
     size_t lstm_smem = 0;
     void launch_lstm(int l, cudaStream_t stream) const;
     // hoisted path
@@ -1246,7 +1011,6 @@ public:
                                            size_t ws_bytes) override;
 
     b200_model_desc desc;
-    bool lstm_v1 = false;     // B200_LSTM_V1=1: first-generation single-CTA LSTM kernel (A/B comparisons)
     float* conv_w = nullptr;  // packed conv1 / conv2 weights (see Conv12Params::w)
     __half* w3 = nullptr;               // [C][K3p]
     float* b3 = nullptr;
@@ -1277,7 +1041,7 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
         // kernels are instantiated for the sizes of the reference's model zoo this engine covers
         throw Unsupported("lstm_size " + std::to_string(C) + " is not supported (96, 192 and 384 are)");
     }
-    if (const char* e = std::getenv("B200_LSTM_V1")) lstm_v1 = std::atoi(e) != 0;
+
     if (d.lstm_layers < 1 || d.lstm_layers > 8) throw std::invalid_argument("bad lstm_layers");
 
     // conv1: torch [c1][1][w] -> [c1][w]; conv2: torch [co][ci][k] -> [k][ci][co]
@@ -1333,20 +1097,6 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
                 }
         LstmLayerWeights lw;
         if ((size_t)4 * C * 2 * C * 2 <= 150 * 1024) {
-            if (!lstm_v1) {
-                // lstm_layer2_kernel: rows ordered (tile, TMEM lane quarter, unit within the quarter's 8, gate)
-                std::vector<float> w2((size_t)4 * C * 2 * C), b2((size_t)4 * C);
-                for (int m = 0; m < C / 32; ++m)
-                    for (int r = 0; r < 128; ++r) {
-                        const int g = r & 3, unit = 32 * m + 8 * (r >> 5) + ((r & 31) >> 2);
-                        const int dst = m * 128 + r, src = g * C + unit;
-                        std::memcpy(&w2[(size_t)dst * 2 * C], &wih.data[(size_t)src * C], sizeof(float) * C);
-                        std::memcpy(&w2[(size_t)dst * 2 * C + C], &whh.data[(size_t)src * C], sizeof(float) * C);
-                        b2[dst] = bih.data[src] + bhh.data[src];
-                    }
-                w.swap(w2);
-                b.swap(b2);
-            }
             lw.w = upload_f16(w);
             lw.bias = upload_f32(b);
         } else {
@@ -1501,6 +1251,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.T = T_out;
             rp.N = Np;
             rp.reverse = (l % 2 == 0) ? 1 : 0;
+            rp.gather_l2 = 1;
+            if (const char* e = std::getenv("B200_CLUSTER_GATHER")) rp.gather_l2 = std::strcmp(e, "dsmem") != 0;
             rp.dbg = nullptr;
             if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
                 B200_CUDA(cudaMalloc(&rp.dbg, 128 * sizeof(long long)));
@@ -1529,7 +1281,6 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             else throw std::invalid_argument("B200_LSTM_CHUNKS_PER_CTA must be 4, 8 or 16 and divide the padded batch");
         }
         if (C != 96) throw Unsupported("the single-CTA LSTM kernels are instantiated for lstm_size 96");
-        plan->lstm_v1 = lstm_v1;
         const int G = (MT % 6 == 0) ? 6 : (MT % 4 == 0) ? 4 : 3;
         plan->lstm_nbr = nbr;
         plan->lstm_groups = G;
@@ -1614,15 +1365,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
 
 template <int C, int NBR>
 static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    if (pl.lstm_v1) {
-        ensure_dynamic_smem(lstm_layer_kernel<C, NBR>, 227 * 1024);
-        lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
-                                                                                            pl.lstm_p[l]);
-    } else {
-        ensure_dynamic_smem(lstm_layer2_kernel<C, NBR>, (int)Lstm2Cfg<C>::SMEM);
-        lstm_layer2_kernel<C, NBR><<<pl.lstm_grid, Lstm2Cfg<C>::THREADS, Lstm2Cfg<C>::SMEM, stream>>>(pl.lstm_x[l], pl.lstm_w[l],
-                                                                                                      pl.lstm_p[l]);
-    }
+    ensure_dynamic_smem(lstm_layer_kernel<C, NBR>, 227 * 1024);
+    lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l], pl.lstm_p[l]);
 }
 
 template <int C, int CL, int UNC>

@@ -89,6 +89,15 @@ __device__ __forceinline__ void bulk_copy_smem_to_cluster(uint32_t dst_cluster_a
                  ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(dst_mbar_cluster_addr)
                  : "memory");
 }
+// TMA load multicast to the CTAs of the cluster named in cta_mask: the tile lands at the same CTA-relative shared-memory
+// offset in every destination and completes on the mbarrier at the same offset there.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+    asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+            : "memory");
+}
 // generic-proxy writes (st.shared) -> visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
