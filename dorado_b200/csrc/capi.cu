@@ -189,6 +189,17 @@ int b200_runner_accept_chunk_f32(b200_runner* r, int32_t idx, const float* sampl
     });
 }
 
+int32_t b200_runner_variable_chunk_sizes(const b200_runner* r) {
+    return r && reinterpret_cast<const b200::Runner*>(r)->variable_chunk_sizes();
+}
+
+int b200_runner_accept_chunk_var_f16(b200_runner* r, int32_t idx, const uint16_t* samples, int64_t len) {
+    return guarded([&] {
+        if (!r || !samples) throw std::invalid_argument("b200_runner_accept_chunk_var_f16: null argument");
+        reinterpret_cast<b200::Runner*>(r)->accept_chunk_var_f16(idx, samples, len);
+    });
+}
+
 uint16_t* b200_runner_input(b200_runner* r) { return r ? reinterpret_cast<b200::Runner*>(r)->input() : nullptr; }
 
 int b200_runner_call_chunks(b200_runner* r, int32_t num_chunks, b200_result* out) {

@@ -59,8 +59,8 @@ __device__ __forceinline__ float clampf(float v, float c) { return c > 0.0f ? (v
 
 template <int SL>
 __global__ void __launch_bounds__(ScanCfg<SL>::S > 256 ? ScanCfg<SL>::S : 256)
-        crf_bwd_scan_kernel(const __half* __restrict__ scores, float* __restrict__ bwd, int N, int T, float clamp_val,
-                            float blank) {
+        crf_bwd_scan_kernel(const __half* __restrict__ scores, float* __restrict__ bwd, int N, int T_pitch, float clamp_val,
+                            float blank, const int32_t* __restrict__ lens, int stride) {
     using Cfg = ScanCfg<SL>;
     constexpr int S = Cfg::S, C = Cfg::C, P4 = Cfg::P4, PITCH = Cfg::PITCH;
     constexpr int CH = S >= 256 ? 1 : 256 / S;  // chunks per CTA
@@ -72,9 +72,11 @@ __global__ void __launch_bounds__(ScanCfg<SL>::S > 256 ? ScanCfg<SL>::S : 256)
     __shared__ float st[CH][2][16 * PITCH];
     const bool active = chunk < N;
     const int chunk_c = active ? chunk : N - 1;  // idle groups shadow the last chunk (no stores)
-    const uint2* srow = reinterpret_cast<const uint2*>(scores + (size_t)chunk_c * T * C) + v;
+    // variable chunk sizes: this chunk has T of the T_pitch blocks its rows are laid out for
+    const int T = lens ? min(T_pitch, __ldg(lens + chunk_c) / stride) : T_pitch;
+    const uint2* srow = reinterpret_cast<const uint2*>(scores + (size_t)chunk_c * T_pitch * C) + v;
     constexpr int RS = C / 4;  // row stride in uint2
-    float* out = bwd + (size_t)chunk_c * (T + 1) * S;
+    float* out = bwd + (size_t)chunk_c * (T_pitch + 1) * S;
     const int q = v % P4, top = v / P4;
     const int st_row = 4 * (v & 3), st_col = v >> 2;
 
@@ -503,11 +505,13 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
                                                                           const float* __restrict__ bwd,
                                                                           uint2* __restrict__ beam,
                                                                           int N,
-                                                                          int T,
+                                                                          int T_pitch,
                                                                           float clamp_val,
                                                                           float blank,
                                                                           int W,
                                                                           float log_beam_cut,
+                                                                          const int32_t* __restrict__ lens,
+                                                                          int stride,
                                                                           long long* dbg) {
     using Cfg = ScanCfg<SL>;
     using F = FwdCfg<SL>;
@@ -531,15 +535,16 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
     __shared__ BeamSmem bsm[CH];
 
     if (chunk >= N) return;  // whole chunk groups exit together; every barrier below is per group
+    const int T = lens ? min(T_pitch, __ldg(lens + chunk) / stride) : T_pitch;  // variable chunk sizes
     const bool is_scan = tid < NT;
-    uint2* beam_out = beam + (size_t)chunk * T * kBeamW;
+    uint2* beam_out = beam + (size_t)chunk * T_pitch * kBeamW;
 
     if (is_scan) {
         // ================= scan threads =================
         const int v = tid;  // states SPT*v .. SPT*v + SPT-1
         const int wv = v >> 5;
-        const __half* srow = scores + (size_t)chunk * T * C + (size_t)v * 4 * SPT;
-        const float* brow = bwd + (size_t)chunk * (T + 1) * S + (size_t)v * SPT;
+        const __half* srow = scores + (size_t)chunk * T_pitch * C + (size_t)v * 4 * SPT;
+        const float* brow = bwd + (size_t)chunk * (T_pitch + 1) * S + (size_t)v * SPT;
         // bwd[0] for the beam initialisation, forward guide 0
 #pragma unroll
         for (int e = 0; e < SPT; ++e) {
@@ -660,7 +665,9 @@ constexpr int kTbWarps = 2;
 
 __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint2* __restrict__ beam,
                                                                       int N,
-                                                                      int T,
+                                                                      int T_pitch,
+                                                                      const int32_t* __restrict__ lens,
+                                                                      int stride,
                                                                       const b200_qtable* __restrict__ qtable,
                                                                       uint8_t* __restrict__ moves_out,
                                                                       char* __restrict__ seq_out,
@@ -675,7 +682,8 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x * kTbWarps + w;
     if (chunk >= N) return;
-    const int Tp = (T + 3) & ~3;
+    const int T = lens ? min(T_pitch, __ldg(lens + chunk) / stride) : T_pitch;  // variable chunk sizes
+    const int Tp = (T_pitch + 3) & ~3;
     // per-warp carve-up
     const size_t per_warp = (size_t)kTbTile * kBeamW * sizeof(uint2) + (size_t)Tp * (4 + 2 + 2 + 1) + 16;
     unsigned char* base = tb_smem + (size_t)w * ((per_warp + 15) & ~(size_t)15);
@@ -685,7 +693,7 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
     uint16_t* bstart = pstate + Tp;
     uint8_t* pmove = reinterpret_cast<uint8_t*>(bstart + Tp + 2);
 
-    const uint2* brow = beam + (size_t)chunk * T * kBeamW;
+    const uint2* brow = beam + (size_t)chunk * T_pitch * kBeamW;
     uint32_t ei = 0;
     for (int t_hi = T; t_hi > 0; t_hi -= kTbTile) {
         const int t_lo = t_hi - kTbTile > 0 ? t_hi - kTbTile : 0;
@@ -721,11 +729,11 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
     if (lane == 0) bstart[nb] = (uint16_t)T;
     __syncwarp();
 
-    uint8_t* mo = moves_out + (size_t)chunk * T;
-    char* so = seq_out + (size_t)chunk * T;
-    char* qo = qstr_out + (size_t)chunk * T;
-    for (int t = lane; t < T; t += 32) mo[t] = pmove[t];
-    for (int p = lane; p < T; p += 32) {
+    uint8_t* mo = moves_out + (size_t)chunk * T_pitch;
+    char* so = seq_out + (size_t)chunk * T_pitch;
+    char* qo = qstr_out + (size_t)chunk * T_pitch;
+    for (int t = lane; t < T_pitch; t += 32) mo[t] = t < T ? pmove[t] : 0;
+    for (int p = lane; p < T_pitch; p += 32) {
         char sc = 0, qc = 0;
         if (p < nb) {
             const int b0 = bstart[p], b1 = bstart[p + 1];
@@ -761,7 +769,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         constexpr int CH = S >= 256 ? 1 : 256 / S;
         const int grid = (a.N + CH - 1) / CH;
         NvtxRange r("back_guides");
-        crf_bwd_scan_kernel<SL><<<grid, S * CH, 0, stream>>>(a.scores, a.bwd, a.N, a.T, a.clamp_val, a.blank);
+        crf_bwd_scan_kernel<SL><<<grid, S * CH, 0, stream>>>(a.scores, a.bwd, a.N, a.T, a.clamp_val, a.blank, a.lens, a.stride);
         if (prof) prof->mark("crf_bwd_scan", stream);
     }
     {
@@ -769,7 +777,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         const int grid = (a.N + F::CH - 1) / F::CH;
         NvtxRange r("beam_search");  // forward scan + posteriors (the reference's "compute_posts") are fused in
         crf_fwd_beam_kernel<SL><<<grid, F::THREADS, 0, stream>>>(a.scores, a.bwd, a.beam, a.N, a.T, a.clamp_val, a.blank,
-                                                                   a.beam_width, a.log_beam_cut, a.dbg);
+                                                                   a.beam_width, a.log_beam_cut, a.lens, a.stride, a.dbg);
         if (prof) prof->mark("crf_fwd_beam", stream);
     }
     {
@@ -777,7 +785,7 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         if (smem > 48 * 1024) ensure_dynamic_smem(crf_traceback_kernel, 200 * 1024);
         const int grid = (a.N + kTbWarps - 1) / kTbWarps;
         NvtxRange r("decode");
-        crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.qtable, a.moves,
+        crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.lens, a.stride, a.qtable, a.moves,
                                                                     a.sequence, a.qstring, a.n_bases);
         if (prof) prof->mark("crf_traceback", stream);
     }
@@ -809,6 +817,7 @@ void decode_scores(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         throw std::invalid_argument("b200 decode: need 1 <= T <= 65535 and N >= 1");
     }
     if (!a.qtable) throw std::invalid_argument("b200 decode: quality table missing");
+    if (a.lens && a.stride < 1) throw std::invalid_argument("b200 decode: chunk lengths need the model stride");
     if (traceback_smem_bytes(a.T) > 200 * 1024) {
         throw std::invalid_argument("b200 decode: " + std::to_string(a.T) + " blocks per chunk exceed what the traceback kernel "
                                     "holds in shared memory (about 10 700); use a smaller chunk size");

@@ -22,6 +22,8 @@ struct DecodeArgs {
     float q_shift;
     float q_scale;
     const b200_qtable* qtable;
+    const int32_t* lens;  // optional per-chunk length in SAMPLES (variable chunk sizes); nullptr = every chunk has T blocks
+    int stride;           // samples per block (only read with lens)
     long long* dbg;  // optional clock64 timeline of chunk 0 (B200_DEBUG_BEAM_TIMELINE, test hook only); nullptr in production  // device copy of b200_qtable_build(q_scale, q_shift) (include/b200_crf_math.h)
     // scratch
     float* bwd;   // decode_scratch_bytes() -> bwd_bytes

@@ -206,6 +206,12 @@ void Runner::init() {
     B200_CUDA(cudaHostAlloc(&m_h_input, in_bytes, cudaHostAllocDefault));
     std::memset(m_h_input, 0, in_bytes);
     B200_CUDA(cudaHostAlloc(&m_h_out, m_out_bytes, cudaHostAllocDefault));
+    B200_CUDA(cudaHostAlloc(&m_h_lens, (size_t)2 * m_N * sizeof(int32_t), cudaHostAllocDefault));
+    m_h_nmoves = m_h_lens + m_N;
+    for (int i = 0; i < m_N; ++i) {
+        m_h_lens[i] = m_T_in;
+        m_h_nmoves[i] = m_T_out;
+    }
 
     size_t bwd_b = 0, beam_b = 0;
     decode_scratch_bytes(m_N, m_T_out, d.state_len, &bwd_b, &beam_b);
@@ -214,6 +220,10 @@ void Runner::init() {
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
     m_arena.reserve(al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(m_out_bytes) + 4096);
     m_d_qtable = static_cast<b200_qtable*>(m_arena.take(sizeof(b200_qtable)));  // inside the 4096 bytes of slack
+    if (engine.model().variable_chunk_sizes()) {
+        if ((size_t)m_N * sizeof(int32_t) > 2048) throw std::invalid_argument("batch_size too large for the chunk-length table");
+        m_d_lens = static_cast<int32_t*>(m_arena.take((size_t)m_N * sizeof(int32_t)));
+    }
     m_d_input = static_cast<__half*>(m_arena.take(in_bytes));
     m_d_scores = static_cast<__half*>(m_arena.take(scores_b));
     m_d_ws = m_arena.take(ws_b);
@@ -227,6 +237,11 @@ void Runner::init() {
     B200_CUDA(cudaMemsetAsync(m_d_ws, 0, ws_b, m_stream));
     B200_CUDA(cudaStreamSynchronize(m_stream));
     m_plan = engine.model().make_plan(m_N, m_T_in, m_d_input, m_d_scores, m_d_ws, ws_b);
+    if (m_d_lens) {
+        B200_CUDA(cudaMemcpyAsync(m_d_lens, m_h_lens, (size_t)m_N * sizeof(int32_t), cudaMemcpyHostToDevice, m_stream));
+        B200_CUDA(cudaStreamSynchronize(m_stream));
+        m_plan->set_chunk_lengths(m_d_lens);
+    }
     for (auto& e : m_ev) B200_CUDA(cudaEventCreate(&e));
     upload_qtable();
 }
@@ -258,6 +273,9 @@ void Runner::release() {
     m_plan.reset();
     if (m_h_input) cudaFreeHost(m_h_input);
     if (m_h_out) cudaFreeHost(m_h_out);
+    if (m_h_lens) cudaFreeHost(m_h_lens);
+    m_h_lens = nullptr;
+    m_h_nmoves = nullptr;
     if (m_h_raw) cudaFreeHost(m_h_raw);
     if (m_h_slots) cudaFreeHost(m_h_slots);
     if (m_d_raw) cudaFree(m_d_raw);
@@ -287,6 +305,24 @@ void Runner::accept_chunk_f16(int idx, const uint16_t* samples, int64_t len) {
     std::lock_guard<std::mutex> lock(m_mutex);
     clear_raw_slot(idx);
     std::memcpy(m_h_input + (size_t)idx * m_T_in, samples, (size_t)len * sizeof(uint16_t));
+    m_h_lens[idx] = m_T_in;
+    m_h_nmoves[idx] = m_T_out;
+}
+
+bool Runner::variable_chunk_sizes() const { return m_d_lens != nullptr; }
+
+void Runner::accept_chunk_var_f16(int idx, const uint16_t* samples, int64_t len) {
+    if (idx < 0 || idx >= m_N) throw std::invalid_argument("accept_chunk: chunk_idx out of range");
+    if (!m_d_lens) throw Unsupported("this model has no variable-chunk-size mode (b200_runner_variable_chunk_sizes() == 0)");
+    const int stride = m_engine.desc().stride;
+    if (len < stride || len > m_T_in || len % stride != 0) {
+        throw std::invalid_argument("accept_chunk: a variable chunk must be a positive multiple of the stride, <= chunk_size");
+    }
+    std::lock_guard<std::mutex> lock(m_mutex);
+    clear_raw_slot(idx);
+    std::memcpy(m_h_input + (size_t)idx * m_T_in, samples, (size_t)len * sizeof(uint16_t));
+    m_h_lens[idx] = (int32_t)len;
+    m_h_nmoves[idx] = (int32_t)(len / stride);
 }
 
 void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
@@ -296,6 +332,8 @@ void Runner::accept_chunk_f32(int idx, const float* samples, int64_t len) {
     clear_raw_slot(idx);
     __half* dst = reinterpret_cast<__half*>(m_h_input + (size_t)idx * m_T_in);
     for (int64_t i = 0; i < len; ++i) dst[i] = __float2half_rn(samples[i]);
+    m_h_lens[idx] = m_T_in;
+    m_h_nmoves[idx] = m_T_out;
 }
 
 uint16_t* Runner::input() {
@@ -342,11 +380,16 @@ void Runner::accept_raw_chunk(int idx, const b200_raw_chunk& c) {
     m_h_slots[idx].slice_len = slice;
     m_h_slots[idx].shift = c.shift;
     m_h_slots[idx].scale = c.scale;
+    m_h_lens[idx] = m_T_in;
+    m_h_nmoves[idx] = m_T_out;
 }
 
 // Input stage of a batch: fp16 rows by plain H2D; raw rows as staged int16 + descriptors, then one gather/scale
 // kernel writes their fp16 rows (it skips fp16 slots, so both kinds can share a batch).
 void Runner::stage_input(int n) {
+    if (m_d_lens) {
+        B200_CUDA(cudaMemcpyAsync(m_d_lens, m_h_lens, (size_t)m_N * sizeof(int32_t), cudaMemcpyHostToDevice, m_stream));
+    }
     int raw_in_n = 0;
     if (m_num_raw > 0) {
         for (int i = 0; i < n; ++i) raw_in_n += m_h_slots[i].slice_len > 0;
@@ -395,6 +438,8 @@ void Runner::run_decode(int n, ProfileSink* prof) {
     a.q_shift = m_opts.q_shift;
     a.q_scale = m_opts.q_scale;
     a.qtable = m_d_qtable;
+    a.lens = m_d_lens;
+    a.stride = d.stride;
     a.bwd = m_d_bwd;
     a.beam = m_d_beam;
     // output rows are packed for the n chunks actually called
@@ -461,6 +506,7 @@ b200_result Runner::call_chunks(int num_chunks) {
     r.n_bases = reinterpret_cast<const int32_t*>(m_h_out + nb_offset(m_N, m_T_out));
     r.t_out = m_T_out;
     r.num_chunks = num_chunks;
+    r.n_moves = m_h_nmoves;
     return r;
 }
 

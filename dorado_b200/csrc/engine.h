@@ -59,12 +59,17 @@ public:
     virtual ~ForwardPlan() = default;
     virtual void run(cudaStream_t stream, ProfileSink* prof = nullptr) = 0;
     virtual int launches() const = 0;
+    // Variable chunk sizes: device array of per-chunk lengths in samples (multiples of the stride, <= T_in), read by the
+    // kernels at run time.  Plans of models without that mode ignore it.
+    virtual void set_chunk_lengths(const int32_t* /*d_lens*/) {}
 };
 
 class Model {
 public:
     virtual ~Model() = default;
     virtual size_t workspace_bytes(int N, int T_in) const = 0;
+    // CudaCaller::variable_chunk_sizes (api/runner_creation.cpp:24-42): chunks of different lengths in one batch
+    virtual bool variable_chunk_sizes() const { return false; }
     virtual std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores,
                                                    void* workspace, size_t workspace_bytes) = 0;
 };
@@ -145,6 +150,9 @@ public:
     void set_decoder_options(const b200_decoder_options& o);
     void accept_chunk_f16(int idx, const uint16_t* samples, int64_t len);
     void accept_chunk_f32(int idx, const float* samples, int64_t len);
+    // variable chunk sizes (CudaModelRunner::accept_chunk, CudaModelRunner.cpp:21-31): len <= chunk_size, multiple of stride
+    bool variable_chunk_sizes() const;
+    void accept_chunk_var_f16(int idx, const uint16_t* samples, int64_t len);
     // raw int16 chunk: slice + scale + repeat-pad happen on the device (frontend.cu)
     void accept_raw_chunk(int idx, const b200_raw_chunk& chunk);
     void debug_read_input(int num_chunks, uint16_t* input_out);
@@ -193,6 +201,10 @@ private:
     void upload_qtable();
     unsigned char* m_d_out = nullptr;
     size_t m_out_bytes = 0;
+    // variable chunk sizes: per-slot length in samples (pinned host + device) and the blocks each result row holds
+    int32_t* m_h_lens = nullptr;
+    int32_t* m_d_lens = nullptr;
+    int32_t* m_h_nmoves = nullptr;
     cudaEvent_t m_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -39,6 +39,7 @@ struct Conv12Params {
     const float* w;   // packed: w1 [c1][w1] | b1 [16] | w2 [k][ci][co] (16x16 per tap) | b2 [16]
     int N, T, T_pad, front_pad;
     int c1, w1, w2, act1, act2;
+    const int32_t* lens;  // optional per-chunk length in samples (variable chunk sizes): the chunk is zero beyond it
 };
 
 constexpr int CONV_W_FLOATS = 16 * MAXW + 16 + MAXW * 16 * 16 + 16;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
     const int n = blockIdx.y;
     const int t0 = blockIdx.x * CONV_TT;
     const int p1 = p.w1 / 2, p2 = p.w2 / 2;
+    const int L = p.lens ? min(p.T, __ldg(p.lens + n)) : p.T;  // samples of this chunk (zero padding starts at L)
     constexpr int Y1P = CONV_TT + 2 * MAXW;  // channel-major pitch: consecutive threads -> consecutive banks
     __shared__ float xs[CONV_TT + 4 * MAXW];
     __shared__ float y1[16 * Y1P];
@@ -67,13 +69,13 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
     const int nx = CONV_TT + 2 * (p1 + p2);
     for (int i = threadIdx.x; i < nx; i += CONV_TT) {
         const int t = t0 - p1 - p2 + i;
-        xs[i] = (t >= 0 && t < p.T) ? __half2float(p.x[(size_t)n * p.T + t]) : 0.0f;
+        xs[i] = (t >= 0 && t < L) ? __half2float(p.x[(size_t)n * p.T + t]) : 0.0f;
     }
     __syncthreads();
     const int n1 = CONV_TT + 2 * p2;
     for (int i = threadIdx.x; i < n1; i += CONV_TT) {
         const int t = t0 - p2 + i;  // conv1 output position
-        const bool inside = t >= 0 && t < p.T;
+        const bool inside = t >= 0 && t < L;
         for (int c = 0; c < p.c1; ++c) {
             float acc = s_b1[c];
             for (int k = 0; k < p.w1; ++k) acc += s_w1[c * p.w1 + k] * xs[i + k];
@@ -103,6 +105,10 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
         __half2 h[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(conv_act(acc[2 * j], p.act2), conv_act(acc[2 * j + 1], p.act2));
+        if (t >= L) {  // beyond a short chunk's end: the next convolution's zero padding
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(0.0f, 0.0f);
+        }
         uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T_pad + p.front_pad + t) * 16);
         dst[0] = *reinterpret_cast<uint4*>(&h[0]);
         dst[1] = *reinterpret_cast<uint4*>(&h[4]);
@@ -470,6 +476,8 @@ struct LstmRecParams {
     __half* seq;          // [T][N][C] output h (in place over the layer input)
     const __half* gx;     // [T][N / 32][4C][32]
     int T, N, reverse;
+    const int32_t* lens;  // optional per-chunk length in samples (variable chunk sizes); stride = samples per step
+    int stride;
     int gather_l2;        // all-gather of h_t through L2 (TMA store + multicast TMA load) instead of bulk copies over DSMEM
     long long* dbg;       // optional clock64 timeline of CTA 0, steps 64..67 (B200_DEBUG_LSTM_TIMELINE); nullptr in production
 };
@@ -718,7 +726,7 @@ struct Cluster2Cfg {
     static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
     static constexpr size_t Z_BYTES = (size_t)NG * 2 * KBH * ZB;      // [group][buffer][block]
     static constexpr size_t ST_BYTES = (size_t)NG * 2 * TPC * ZB;     // [group][buffer][tile] staging
-    static constexpr size_t SMEM = 1024 + Z_BYTES + ST_BYTES + 256;
+    static constexpr size_t SMEM = 1024 + Z_BYTES + ST_BYTES + 512;
     static_assert(MT % CL == 0 && NEED <= 512, "tile split / tensor memory budget");
 };
 
@@ -737,11 +745,15 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
     uint64_t* h_full = bars;                               // [NG][2]   bytes of h landed -> MMA issuer
     uint64_t* acc_full = bars + NG * 2;                    // [NG][TPC] MMA -> epilogue
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + NG * TPC);
+    int* len_s = reinterpret_cast<int*>(tmem_holder + 2);   // [UNC] steps of every chunk of the cluster (variable chunk sizes)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x / CL;
     const int n0 = cluster_id * Cfg::UNC;
+    if (threadIdx.x < Cfg::UNC) {
+        len_s[threadIdx.x] = p.lens ? min(p.T, __ldg(p.lens + n0 + threadIdx.x) / p.stride) : p.T;
+    }
 
     for (int i = threadIdx.x; i < (int)((Cfg::Z_BYTES + Cfg::ST_BYTES) / 16); i += blockDim.x) {
         reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
@@ -792,18 +804,24 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
     cluster_wait_acquire();
 
     const uint32_t z_local = tc::smem_u32(z_s);
+    // A chunk shorter than the batch's chunk size is the sequence 0 .. len-1: outside it the state is zero (masked in the
+    // epilogue), so the cluster only walks the steps some chunk of it is alive in -- the last ones backwards, the first
+    // ones forwards -- and short chunks grouped in a cluster cost proportionally less.
+    int steps = 0;
+#pragma unroll 4
+    for (int i = 0; i < Cfg::UNC; ++i) steps = max(steps, len_s[i]);
     if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (tc::elect_one()) {
             const uint64_t zdesc0 = umma_desc_sw64(z_local);
             constexpr uint32_t idesc = tc::umma_idesc_f16(128, GN);
-            for (int s = 0; s < p.T; ++s) {
+            for (int s = 0; s < steps; ++s) {
                 const int buf = s & 1, nbuf = buf ^ 1;
                 const uint32_t par = (uint32_t)((s >> 1) & 1);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     // arm the barrier the slices of h_s will complete on (all CL CTAs x TPC tiles, this group)
-                    if (s + 1 < p.T) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
+                    if (s + 1 < steps) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
                     long long* d = (p.dbg && blockIdx.x == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + g * 4 : nullptr;
                     if (d) d[0] = clock64();
                     tc::mbar_wait(&h_full[g * 2 + buf], par);
@@ -847,8 +865,11 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             dst_z[b] = z_local + (uint32_t)(((eg * 2 + b) * KBH + m) * ZB);
             dst_bar[b] = tc::smem_u32(&h_full[eg * 2 + b]);
         }
-        for (int s = 0; s < p.T; ++s) {
-            const int t = p.reverse ? p.T - 1 - s : s;
+        int my_len[4];   // steps of the chunks this lane owns cells of
+#pragma unroll
+        for (int c = 0; c < 4; ++c) my_len[c] = len_s[eg * GN + 4 * c + gj];
+        for (int s = 0; s < steps; ++s) {
+            const int t = p.reverse ? steps - 1 - s : s;
             const int nbuf = (s & 1) ^ 1;
             const uint4* gp = reinterpret_cast<const uint4*>(gx_base + (size_t)t * gx_step);
             const uint4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
@@ -896,9 +917,10 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             float hv[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float cs = a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2];
+                const bool alive = t < my_len[c];
+                const float cs = alive ? a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2] : 0.0f;
                 c_reg[c] = cs;
-                hv[c] = a[4 * c + 3] * tanh_f(cs);
+                hv[c] = alive ? a[4 * c + 3] * tanh_f(cs) : 0.0f;
             }
             // pair the units (uk, uk ^ 1): the even lane stores chunks c = 0, 1 of both units, the odd lane c = 2, 3
             {
@@ -930,14 +952,14 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                     // completed, ONE multicast TMA load brings it back into the operand buffer of all CL CTAs
                     tc::tma_store_2d(&tma_y, stage, m * 32, yrow);
                     tc::bulk_commit_group();
-                    if (s + 1 < p.T) {
+                    if (s + 1 < steps) {
                         tc::bulk_wait_group<0>();
                         tc::tma_load_2d_multicast(z_s + (size_t)(((eg * 2 + nbuf) * KBH + m) * ZB), &tma_y, &h_full[eg * 2 + nbuf], m * 32, yrow,
                                                   (uint16_t)((1u << CL) - 1u));
                     }
                 } else {
                     // all-gather over distributed shared memory: one bulk copy per destination CTA
-                    if (s + 1 < p.T) {
+                    if (s + 1 < steps) {
 #pragma unroll
                         for (int rr = 0; rr < CL; ++rr) {
                             tc::bulk_copy_smem_to_cluster(mapa_shared(dst_z[nbuf], (uint32_t)rr), tc::smem_u32(stage), (uint32_t)ZB,
@@ -977,6 +999,11 @@ class LstmPlan final : public ForwardPlan {
 public:
     void run(cudaStream_t stream, ProfileSink* prof) override;
     int launches() const override { return 1 + 1 + num_layers * (hoisted ? 2 : 1) + num_linear; }
+    void set_chunk_lengths(const int32_t* d_lens) override {
+        if (!hoisted || rec_v1) return;  // the mode exists for the cluster recurrence (second generation) only
+        conv12.lens = d_lens;
+        for (auto& rp : rec_p) rp.lens = d_lens;
+    }
 
     Conv12Params conv12{};
     dim3 conv12_grid;
@@ -1009,6 +1036,10 @@ public:
     size_t workspace_bytes(int N, int T_in) const override;
     std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
                                            size_t ws_bytes) override;
+    bool variable_chunk_sizes() const override {
+        const char* e = std::getenv("B200_CLUSTER_V1");
+        return hoisted() && !(e && std::atoi(e) != 0);
+    }
 
     b200_model_desc desc;
     float* conv_w = nullptr;  // packed conv1 / conv2 weights (see Conv12Params::w)
@@ -1188,7 +1219,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
 
     // conv1 + conv2
     plan->conv12 = Conv12Params{signal, x2, conv_w, N, T_in, Tp, pad3(), desc.convs[0].size, desc.convs[0].winlen,
-                                desc.convs[1].winlen, desc.convs[0].activation, desc.convs[1].activation};
+                                desc.convs[1].winlen, desc.convs[0].activation, desc.convs[1].activation, nullptr};
     plan->conv12_grid = dim3((T_in + CONV_TT - 1) / CONV_TT, N, 1);
 
     // conv3: rows (n, t) read K3p contiguous halfs starting at x2[n][stride * t]
@@ -1251,8 +1282,10 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.T = T_out;
             rp.N = Np;
             rp.reverse = (l % 2 == 0) ? 1 : 0;
-            rp.gather_l2 = 1;
-            if (const char* e = std::getenv("B200_CLUSTER_GATHER")) rp.gather_l2 = std::strcmp(e, "dsmem") != 0;
+            rp.lens = nullptr;
+            rp.stride = desc.stride;
+            rp.gather_l2 = 0;  // measured on B200: 3.3 ms per layer over DSMEM, 5.7 ms through L2 (profiles/r02_b3_*)
+            if (const char* e = std::getenv("B200_CLUSTER_GATHER")) rp.gather_l2 = std::strcmp(e, "l2") == 0;
             rp.dbg = nullptr;
             if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
                 B200_CUDA(cudaMalloc(&rp.dbg, 128 * sizeof(long long)));

@@ -54,7 +54,8 @@ class DecoderOptions(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("moves", C.POINTER(C.c_uint8)), ("sequence", C.POINTER(C.c_char)), ("qstring", C.POINTER(C.c_char)),
-                ("n_bases", C.POINTER(C.c_int32)), ("t_out", C.c_int32), ("num_chunks", C.c_int32)]
+                ("n_bases", C.POINTER(C.c_int32)), ("t_out", C.c_int32), ("num_chunks", C.c_int32),
+                ("n_moves", C.POINTER(C.c_int32))]
 
 
 class RawChunk(C.Structure):
@@ -85,7 +86,8 @@ EXPORTS = [
     "b200_select_batch_size", "b200_generate_variable_chunks", "b200_engine_terminate", "b200_engine_restart",
     "b200_engine_set_low_latency", "b200_engine_is_low_latency", "b200_engine_batch_timeouts_ms",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_num_runners", "b200_pool_runner", "b200_pool_out_len",
-    "b200_pool_runner_info", "b200_pool_call_chunks",
+    "b200_pool_runner_info", "b200_pool_call_chunks", "b200_runner_variable_chunk_sizes",
+    "b200_runner_accept_chunk_var_f16",
 ]
 
 _lib = None
@@ -118,6 +120,9 @@ def load_library() -> C.CDLL:
     lib.b200_pool_runner.restype = vp
     lib.b200_pool_runner_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_int64)]
     lib.b200_pool_call_chunks.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(C.c_double)]
+    lib.b200_runner_variable_chunk_sizes.argtypes = [vp]
+    lib.b200_runner_variable_chunk_sizes.restype = i32
+    lib.b200_runner_accept_chunk_var_f16.argtypes = [vp, i32, vp, C.c_int64]
     lib.b200_engine_terminate.argtypes = [vp]
     lib.b200_engine_restart.argtypes = [vp]
     lib.b200_engine_set_low_latency.argtypes = [vp, i32]

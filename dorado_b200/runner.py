@@ -198,6 +198,12 @@ class B200ModelRunner:
             c = c.astype(np.float32, copy=False)
             L.check(self._lib.b200_runner_accept_chunk_f32(self.handle, chunk_idx, c.ctypes.data, c.size))
 
+    def accept_chunk_var(self, chunk_idx: int, chunk: np.ndarray) -> None:
+        """Variable chunk sizes (CudaModelRunner::accept_chunk, CudaModelRunner.cpp:21-31): fp16 chunk of any length that is
+        a positive multiple of the stride and <= chunk_size."""
+        c = np.ascontiguousarray(chunk, np.float16).reshape(-1)
+        L.check(self._lib.b200_runner_accept_chunk_var_f16(self.handle, chunk_idx, c.ctypes.data, c.size))
+
     def accept_raw_chunk(self, chunk_idx: int, raw: np.ndarray, input_offset: int, shift: float, scale: float) -> None:
         """One chunk of a read given as its whole RAW int16 signal: ScalerNode's (x - shift) / scale
         (ScalerNode.cpp:226-229), BasecallerNode's slice + repeat-padding (BasecallerNode.cpp:395-440) run on the
@@ -222,6 +228,7 @@ class B200ModelRunner:
         seq = np.ctypeslib.as_array(C.cast(r.sequence, C.POINTER(C.c_uint8)), shape=(self._N, T))
         qs = np.ctypeslib.as_array(C.cast(r.qstring, C.POINTER(C.c_uint8)), shape=(self._N, T))
         nb = np.ctypeslib.as_array(r.n_bases, shape=(self._N,))
+        self._n_moves = np.ctypeslib.as_array(r.n_moves, shape=(self._N,))   # == t_out unless variable chunk sizes are in use
         return moves, seq, qs, nb
 
     def call_chunks(self, num_chunks: int) -> List[DecodedChunk]:
@@ -230,7 +237,7 @@ class B200ModelRunner:
         for i in range(num_chunks):
             n = int(nb[i])
             out.append(DecodedChunk(bytes(seq[i, :n]).decode("ascii"), bytes(qs[i, :n]).decode("ascii"),
-                                    moves[i].copy()))
+                                    moves[i, :int(self._n_moves[i])].copy()))
         return out
 
     def config(self) -> BasecallModelConfig:
@@ -243,7 +250,7 @@ class B200ModelRunner:
         return self._N
 
     def variable_chunk_sizes(self) -> bool:
-        return False
+        return bool(self._lib.b200_runner_variable_chunk_sizes(self.handle))
 
     def batch_timeouts_ms(self):
         return self.caller.batch_timeouts_ms()  # CudaCaller.cpp:216-222

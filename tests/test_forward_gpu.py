@@ -231,3 +231,59 @@ def test_pool_feeds_every_runner_and_matches_a_single_runner():
             assert bytes(seq[k, :nb[k]]).decode() == c.sequence and bytes(qs[k, :nb[k]]).decode() == c.qstring
             assert (moves[k] == c.moves).all()
     pool.close()
+
+
+def test_variable_chunk_sizes_match_each_chunk_alone(crf_oracle):
+    """Variable chunk sizes (nn/AuxiliaryData.cpp, CudaModelRunner.cpp:21-31, CUDADecoder.cpp:35-62): a batch
+    of hac chunks of different lengths.  Every chunk must come out as if it were basecalled alone at its own length: scores
+    against the numpy oracle run per chunk, strings bit-identical to the C oracle decoding the engine's scores, moves of
+    len / stride blocks -- and equal to what a fixed-shape runner of exactly that chunk size returns."""
+    from oracle import nn_oracle
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir("hac"))
+    w = synthetic_weights(cfg, 42)
+    caller = B200Caller(cfg, w)
+    N, T = 64, 1998
+    runner = B200ModelRunner(caller, N, T)
+    assert runner.variable_chunk_sizes()
+    fast_runner = B200ModelRunner(B200Caller(load_model_config(model_dir("fast")), synthetic_weights(load_model_config(model_dir("fast")), 42)), 16, 1200)
+    assert not fast_runner.variable_chunk_sizes()   # lstm_size 96: the reference has no such mode either (runner_creation.cpp:27-31)
+    rng = np.random.default_rng(77)
+    lens = rng.integers(40, T // cfg.stride + 1, size=N) * cfg.stride
+    lens[0], lens[1], lens[2], lens[33] = T, cfg.stride * 40, cfg.stride, T          # full, short, one block, full
+    lens[32:40] = np.sort(lens[32:40])
+    sig = [rng.standard_normal(int(l)).astype(np.float16) for l in lens]
+    for i in range(N):
+        runner.accept_chunk_var(i, sig[i])
+    scores = runner.forward_scores(N)
+    called = runner.call_chunks(N)
+    clamp = 5.0 if cfg.clamp else 0.0
+    worst = 0.0
+    for i in range(N):
+        tn = int(lens[i]) // cfg.stride
+        assert len(called[i].moves) == tn and int(called[i].moves.sum()) == len(called[i].sequence) == len(called[i].qstring)
+        ref = crf_oracle.decode(scores[i:i + 1, :tn], clamp_val=clamp, q_shift=cfg.qbias, q_scale=cfg.qscale)
+        assert called[i].sequence == ref.sequences[0] and called[i].qstring == ref.qstrings[0]
+        assert (called[i].moves == ref.moves[0]).all()
+        if i in (0, 1, 2, 5, 33, 39, 63):   # numpy forward of the chunk alone, at its own length
+            want = nn_oracle.forward(cfg, w, sig[i][None].astype(np.float32), emulate_fp16=True)[0]
+            got = np.clip(scores[i, :tn].astype(np.float32), -5, 5) if cfg.clamp else scores[i, :tn].astype(np.float32)
+            err = np.abs(got - want)
+            scale = max(1.0, float(np.abs(want).max()))
+            assert (err > 1e-3 * scale).mean() <= 2e-3 and err.max() <= 6e-3 * scale, (i, tn, float(err.max()))
+            worst = max(worst, float(err.max()) / scale)
+    # a fixed-shape runner of exactly that chunk size gives the same call
+    for i in (1, 5):
+        alone = B200ModelRunner(caller, 32, int(lens[i]))
+        alone.accept_chunk(0, sig[i])
+        a = alone.call_chunks(1)[0]
+        assert a.sequence == called[i].sequence and a.qstring == called[i].qstring and (a.moves == called[i].moves).all()
+    print(f"\n[variable chunk sizes] {N} hac chunks of {int(lens.min())}..{int(lens.max())} samples: worst score error {worst:.2e} of max|ref|")
+    # fixed-size chunks through the same runner afterwards: the slots revert to full length
+    full = rng.standard_normal((N, runner.chunk_size())).astype(np.float16)
+    for i in range(N):
+        runner.accept_chunk(i, full[i])
+    again = runner.call_chunks(N)
+    assert all(len(c.moves) == runner.out_len() for c in again)
