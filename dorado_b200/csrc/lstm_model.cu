@@ -478,7 +478,7 @@ struct LstmRecParams {
     int T, N, reverse;
     const int32_t* lens;  // optional per-chunk length in samples (variable chunk sizes); stride = samples per step
     int stride;
-    int gather_l2;        // all-gather of h_t through L2 (TMA store + multicast TMA load) instead of bulk copies over DSMEM
+    int gather;           // all-gather of h_t: 0 bulk copies over DSMEM, 1 through L2 (TMA store + multicast load), 2 remote vector stores
     long long* dbg;       // optional clock64 timeline of CTA 0, steps 64..67 (B200_DEBUG_LSTM_TIMELINE); nullptr in production
 };
 
@@ -504,6 +504,33 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
 }
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa); release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(tc::smem_u32(bar)), "r"(parity)
+            : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("b200: cluster mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
 }
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -727,7 +754,7 @@ struct Cluster2Cfg {
     static constexpr size_t Z_BYTES = (size_t)NG * 2 * KBH * ZB;      // [group][buffer][block]
     static constexpr size_t ST_BYTES = (size_t)NG * 2 * TPC * ZB;     // [group][buffer][tile] staging
     static constexpr size_t SMEM = 1024 + Z_BYTES + ST_BYTES + 512;
-    static_assert(MT % CL == 0 && NEED <= 512, "tile split / tensor memory budget");
+    static_assert(MT % CL == 0 && NEED <= 512 && (CL * 64) % 128 == 0, "tile split / tensor memory budget / gather split");
 };
 
 template <int C, int CL, int NG>
@@ -760,7 +787,8 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
     }
     tc::fence_proxy_async_smem();
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NG * 2; ++i) tc::mbar_init(&h_full[i], 1);
+        // gather by remote vector stores: 2 warps of every (CTA, tile) arrive per destination; otherwise one armed arrival + bytes
+        for (int i = 0; i < NG * 2; ++i) tc::mbar_init(&h_full[i], p.gather == 2 ? (uint32_t)(CL * TPC * 2) : 1u);
         for (int i = 0; i < NG * TPC; ++i) tc::mbar_init(&acc_full[i], 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_y);
@@ -794,7 +822,10 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
     }
     if (threadIdx.x == 0) {
         // h_{-1} = 0 is in place: complete phase 0 of the buffer-0 barriers without bytes
-        for (int g = 0; g < NG; ++g) tc::mbar_arrive(&h_full[g * 2 + 0]);
+        for (int g = 0; g < NG; ++g) {
+            const int arrivals = p.gather == 2 ? CL * TPC * 2 : 1;
+            for (int i = 0; i < arrivals; ++i) tc::mbar_arrive(&h_full[g * 2 + 0]);
+        }
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -821,10 +852,11 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     // arm the barrier the slices of h_s will complete on (all CL CTAs x TPC tiles, this group)
-                    if (s + 1 < steps) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
+                    if (s + 1 < steps && p.gather != 2) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
                     long long* d = (p.dbg && blockIdx.x == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + g * 4 : nullptr;
                     if (d) d[0] = clock64();
-                    tc::mbar_wait(&h_full[g * 2 + buf], par);
+                    if (p.gather == 2) mbar_wait_cluster(&h_full[g * 2 + buf], par);
+                    else tc::mbar_wait(&h_full[g * 2 + buf], par);
                     tc::tc_fence_after();
                     if (d) d[1] = clock64();
                     const uint64_t zd = zdesc0 + (uint64_t)(((g * 2 + buf) * KBH * ZB) >> 4);
@@ -945,9 +977,36 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             if (d) d[7] = clock64();
             named_bar_sync(bar_id, 128);
             if (d) d[8] = clock64();
-            if (sender) {
+            if (p.gather == 2) {
+                // all-gather by remote vector stores: the tile's 128 threads copy the staged 1 KB block (64 pieces of 16 B) into
+                // the operand buffer of all CL CTAs, 3 stores each; a warp's stores go to 3 destinations (one of each CTA pair),
+                // which it then signals.  Generic-proxy writes, so the writer fences them towards the async proxy (the MMAs).
+                const int tt = (qt << 5) | lane;           // 0..127 within the tile's warps (qt runs over all four quarters)
+                if (s + 1 < steps) {
+#pragma unroll
+                    for (int q = 0; q < (CL * 64) / 128; ++q) {
+                        const int idx = tt + 128 * q;
+                        const int rr = idx >> 6, piece = idx & 63;
+                        const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * piece);
+                        st_cluster_v4(mapa_shared(dst_z[nbuf], (uint32_t)rr) + 16u * (uint32_t)piece, v);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < (CL * 64) / 128; ++q) {
+                            const int rr = ((qt << 5) + 128 * q) >> 6;
+                            mbar_arrive_cluster(mapa_shared(dst_bar[nbuf], (uint32_t)rr));
+                        }
+                    }
+                }
+                if (sender) {
+                    tc::tma_store_2d(&tma_y, stage, m * 32, t * p.N + n0 + eg * GN);
+                    tc::bulk_commit_group();
+                }
+            } else if (sender) {
                 const int yrow = t * p.N + n0 + eg * GN;
-                if (p.gather_l2) {
+                if (p.gather == 1) {
                     // all-gather through L2: the block goes to HBM/L2 as the layer output anyway; once that store has
                     // completed, ONE multicast TMA load brings it back into the operand buffer of all CL CTAs
                     tc::tma_store_2d(&tma_y, stage, m * 32, yrow);
@@ -1284,8 +1343,10 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.reverse = (l % 2 == 0) ? 1 : 0;
             rp.lens = nullptr;
             rp.stride = desc.stride;
-            rp.gather_l2 = 0;  // measured on B200: 3.3 ms per layer over DSMEM, 5.7 ms through L2 (profiles/r02_b3_*)
-            if (const char* e = std::getenv("B200_CLUSTER_GATHER")) rp.gather_l2 = std::strcmp(e, "l2") == 0;
+            rp.gather = 0;  // measured on B200: 3.3 ms per layer with bulk copies over DSMEM, 5.7 ms through L2 (profiles/r02_b3_*)
+            if (const char* e = std::getenv("B200_CLUSTER_GATHER")) {
+                rp.gather = std::strcmp(e, "l2") == 0 ? 1 : std::strcmp(e, "st") == 0 ? 2 : 0;
+            }
             rp.dbg = nullptr;
             if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
                 B200_CUDA(cudaMalloc(&rp.dbg, 128 * sizeof(long long)));

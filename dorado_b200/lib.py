@@ -14,7 +14,9 @@ import numpy as np
 from .config import BasecallModelConfig
 
 HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = HERE / "libb200call.so"
+import os as _os
+# B200CALL_LIB: load another build of the library (A/B comparisons of kernels on the GPU box)
+LIB_PATH = pathlib.Path(_os.environ["B200CALL_LIB"]) if _os.environ.get("B200CALL_LIB") else HERE / "libb200call.so"
 
 B200_OK, B200_ERR_INVALID, B200_ERR_CUDA, B200_ERR_UNSUPPORTED, B200_ERR_INTERNAL = 0, -1, -2, -3, -4
 
