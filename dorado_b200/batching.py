@@ -56,3 +56,55 @@ def determine_batch_size(caller, chunk_size: int, mem_limit_bytes: int, granular
     short_chunk = cfg.normalise_chunk_size(288 * cfg.stride)
     table = caller.benchmark_batch_sizes(short_chunk, granularity, min(cap, benchmark_limit))
     return select_batch_size(table, cap, granularity, time_penalty), table
+
+
+def gpu_name(caller) -> str:
+    buf = C.create_string_buffer(256)
+    L.check(L.load_library().b200_engine_gpu_name(caller.handle, buf, len(buf)))
+    return buf.value.decode()
+
+
+def lookup_chunk_benchmarks(gpu: str, model_name: str) -> List[Tuple[int, float]]:
+    """CudaChunkBenchmarks::get_chunk_timings (benchmarks/CudaChunkBenchmarks.cpp:24-63): [(batch size, ms per chunk)] or []."""
+    lib = L.load_library()
+    cap = 512
+    bs = (C.c_int32 * cap)()
+    ms = (C.c_float * cap)()
+    n = C.c_int32()
+    L.check(lib.b200_chunk_benchmarks_lookup(gpu.encode(), model_name.encode(), bs, ms, cap, C.byref(n)))
+    return [(int(bs[i]), float(ms[i])) for i in range(min(cap, n.value))]
+
+
+def chunk_size_buckets(cfg, chunk_size: int, overlap: int = 500, pipeline: str = "simplex") -> List[int]:
+    """The chunk sizes a caller serves (CudaCaller.cpp:379-414): the requested one and, for high-throughput simplex
+    basecalling, half of it for short reads -- each rounded down to the chunk-size granularity and kept above the overlap."""
+    gran = cfg.chunk_size_granularity()
+    min_chunk = -(-(overlap + 1) // gran) * gran
+
+    def t_out(x):
+        return max(min_chunk, (x // gran) * gran) // cfg.stride
+
+    outs = {t_out(chunk_size)}
+    if pipeline == "simplex":
+        outs.add(t_out(int(chunk_size * 0.5)))
+    return [t * cfg.stride for t in sorted(outs, reverse=True)]
+
+
+def determine_batch_dims(caller, model_name: str, chunk_size: int, mem_limit_bytes: int, time_penalty: float = 0.0,
+                         pipeline: str = "simplex", num_runners: int = 2, run_benchmarks: bool = False,
+                         benchmark_limit: int = 2048):
+    """CudaCaller::determine_batch_dims (CudaCaller.cpp:372-632): [(batch size, chunk size)] for every chunk-size bucket.
+    The timing table comes from the pre-computed ones when this GPU and model have one (unless run_benchmarks), else from
+    the live loop; the memory cap is exact per bucket."""
+    cfg = caller.cfg
+    gran = batch_size_granularity(cfg)
+    table = [] if run_benchmarks else lookup_chunk_benchmarks(gpu_name(caller), model_name)
+    source = "table" if table else "measured"
+    dims = []
+    for T in chunk_size_buckets(cfg, chunk_size, pipeline=pipeline):
+        cap = max_batch_size_for_memory(caller, T, mem_limit_bytes, gran, num_runners)
+        if not table:
+            short_chunk = cfg.normalise_chunk_size(288 * cfg.stride)
+            table = caller.benchmark_batch_sizes(short_chunk, gran, min(cap, benchmark_limit))
+        dims.append((select_batch_size(table, cap, gran, time_penalty), T))
+    return dims, source

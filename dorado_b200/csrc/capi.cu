@@ -81,6 +81,23 @@ int b200_engine_get_stats(const b200_engine* e, b200_stats* out) {
     });
 }
 
+int b200_chunk_benchmarks_lookup(const char* gpu_name, const char* model_name, int32_t* batch_sizes, float* ms_per_chunk,
+                                 int32_t capacity, int32_t* count) {
+    return guarded([&] {
+        const int n = b200::lookup_chunk_benchmarks(gpu_name, model_name, batch_sizes, ms_per_chunk, capacity);
+        if (count) *count = n;
+    });
+}
+
+int b200_engine_gpu_name(const b200_engine* e, char* buf, uint64_t buf_len) {
+    return guarded([&] {
+        if (!e || !buf || buf_len == 0) throw std::invalid_argument("b200_engine_gpu_name: null argument");
+        const std::string n = b200::device_name(reinterpret_cast<const b200::Engine*>(e)->device());
+        std::strncpy(buf, n.c_str(), buf_len - 1);
+        buf[buf_len - 1] = '\0';
+    });
+}
+
 int b200_engine_terminate(b200_engine* e) {
     return guarded([&] {
         if (!e) throw std::invalid_argument("b200_engine_terminate: null argument");

@@ -261,6 +261,10 @@ int benchmark_batch_sizes(Engine& engine, int chunk_size, int granularity, int m
 int select_batch_size(const int32_t* batch_sizes, const float* ms_per_chunk, int count, int max_batch_size, int granularity,
                       float time_penalty);
 
+// pre-computed batch-size timings (CudaChunkBenchmarks): rows found for (gpu, model), 0 if there is no table
+int lookup_chunk_benchmarks(const char* gpu_name, const char* model_name, int32_t* batch_sizes, float* ms_per_chunk, int capacity);
+std::string device_name(int device);
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per device and per function: set it once for each (device, kernel)
 // pair, from whichever thread gets there first (several runners, and in dorado several devices, share one process).
 void ensure_dynamic_smem(const void* kernel, int bytes);

@@ -27,8 +27,22 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 4;  // default ring depth
-constexpr int GEMM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int GEMM_PARTS = 4;                        // column parts of a tile, each drained by one set of 4 epilogue warps
+constexpr int GEMM_EPI_WARPS = 4 * GEMM_PARTS;       // a set = one warp per TMEM lane quarter
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+
+// 32-column chunks [cb, ce) of a tile of nch chunks that part `part` drains.  `unit` = chunks that must stay together (2 for
+// the rotary epilogue: x1 | x2 of a head).  Parts beyond the number of units get nothing.
+__host__ __device__ inline void gemm_part_range(int nch, int unit, int part, int* cb, int* ce) {
+    const int units = nch / unit;
+    const int nparts = units < GEMM_PARTS ? units : GEMM_PARTS;
+    if (part >= nparts) {
+        *cb = *ce = nch;
+        return;
+    }
+    *cb = (part * units / nparts) * unit;
+    *ce = ((part + 1) * units / nparts) * unit;
+}
 
 struct GemmKernelParams {
     int rows_per_batch, tiles_per_batch, N, num_k_blocks, bn, act;
@@ -79,8 +93,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     const int NST = p.stages;
     // staging tile of the epilogue: two column halves (one per epilogue warp set), 128 rows x bn/2 fp16 each
     uint8_t* stage_out = smem + NST * stage_bytes;
-    const uint32_t half_bytes = p.staged ? (uint32_t)(BM * (((p.bn / 32 + 1) / 2) * 32) * 2) : 0u;  // the wider half
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + 2 * half_bytes);
+    // staging tile: [128 rows][bn output columns] fp16 as sub-tiles of p.sw columns, partitioned by column range among the parts
+    const uint32_t staging_bytes = p.staged ? (uint32_t)(BM * (p.bn / (ACT == GEMM_ACT_SWIGLU ? 2 : 1)) * 2) : 0u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + staging_bytes);
     uint64_t* empty = full + kMaxStages;
     uint64_t* tmem_full = empty + kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
@@ -165,17 +180,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     } else {
         // epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
         const int lg = warp & 3;
-        const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+        const int part = (warp - 2) >> 2;  // which part of the tile's columns this warp set drains
         const int nch = p.bn / 32;
-        const int c_begin = chalf ? (nch + 1) / 2 : 0, c_end = chalf ? nch : (nch + 1) / 2;
+        int c_begin, c_end;
+        gemm_part_range(nch, ACT == GEMM_ACT_ROPE ? 2 : 1, part, &c_begin, &c_end);
         const int n_out_total = ACT == GEMM_ACT_SWIGLU ? p.N / 2 : p.N;
-        // staged epilogue: this warp set (chalf) owns one half of the staging tile; thread = tile row
+        // staged epilogue: this warp set owns the staging columns of its part; thread = tile row
         const bool staged = p.staged != 0;
         constexpr int out_div = ACT == GEMM_ACT_SWIGLU ? 2 : 1;            // output columns per accumulator column
-        uint8_t* my_stage = stage_out + (size_t)chalf * half_bytes;
+        uint8_t* my_stage = stage_out + (size_t)(c_begin * 32 / out_div) * BM * 2;
         const int trow = lg * 32 + lane;
-        const bool storer = staged && lg == 0 && lane == 0;
-        const int bar_free = 1 + 2 * chalf, bar_full = 2 + 2 * chalf;
+        const bool storer = staged && lg == 0 && lane == 0 && c_begin < c_end;
+        const int bar_free = 1 + 2 * part, bar_full = 2 + 2 * part;
         const uint32_t sub_bytes = (uint32_t)(BM * p.sw * 2);
         // 16-byte piece `piece` of output column block starting at half-relative column hc (multiple of 8) -> staging address
         auto stage_ptr = [&](int hc) -> uint4* {
@@ -196,8 +212,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             const bool valid = row < p.rows_per_batch;
             const long long g = (long long)batch * p.rows_per_batch + row;
             const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
-            if (staged) {
-                // the stores of this set's previous tile have read the staging half: it may be rewritten
+            if (staged && c_begin < c_end) {
+                // the stores of this set's previous tile have read its staging columns: they may be rewritten
                 if (storer) tc::bulk_wait_group_read<0>();
                 named_bar_sync(bar_free, 128);
             }
@@ -325,7 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                     }
                 }
             }
-            if (staged) {
+            if (staged && c_begin < c_end) {
                 tc::fence_proxy_async_smem();   // staged tile -> visible to the TMA store
                 named_bar_sync(bar_full, 128);
                 if (storer) {
@@ -420,11 +436,17 @@ static void plan_output_staging(GemmPlan& p) {
     }();
     if (direct) return;
     const int nch = p.bn / 32;
-    if (nch < 2) return;
     const int out_div = d.act == GEMM_ACT_SWIGLU ? 2 : 1;
-    const int w0 = ((nch + 1) / 2) * 32 / out_div, w1 = (nch - (nch + 1) / 2) * 32 / out_div;
-    int sw = (w0 % 64 == 0 && w1 % 64 == 0) ? 64 : (w0 % 32 == 0 && w1 % 32 == 0) ? 32 : 0;
-    if (!sw) return;
+    // every part's output width must split into sub-tiles of sw columns
+    int sw = 64;
+    for (int part = 0; part < GEMM_PARTS; ++part) {
+        int cb = 0, ce = 0;
+        gemm_part_range(nch, d.act == GEMM_ACT_ROPE ? 2 : 1, part, &cb, &ce);
+        const int w = (ce - cb) * 32 / out_div, o = cb * 32 / out_div;
+        if (w == 0) continue;
+        while (sw >= 32 && (w % sw != 0 || o % sw != 0)) sw /= 2;
+    }
+    if (sw < 32) return;
     const uint64_t ncols = (uint64_t)(d.N / out_div);
     uint64_t dims[3], strides[2];
     uint32_t box[3] = {(uint32_t)sw, (uint32_t)BM, 1};
@@ -489,7 +511,7 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
     p.grid = dim3((unsigned)(p.tiles_per_batch * d.batches), (unsigned)(d.N / p.bn), 1);
     plan_output_staging(p);
     const size_t stage_bytes = BM * BK * 2 + (size_t)p.bn * BK * 2;
-    const size_t staging = p.staged ? (size_t)2 * BM * (((p.bn / 32 + 1) / 2) * 32) * 2 : 0;
+    const size_t staging = p.staged ? (size_t)BM * (p.bn / (d.act == GEMM_ACT_SWIGLU ? 2 : 1)) * 2 : 0;
     p.stages = STAGES;
     if ((size_t)p.stages * stage_bytes + staging + 256 + 1024 > 227 * 1024) p.stages = 3;
     p.smem = (size_t)p.stages * stage_bytes + staging + 256 + 1024;

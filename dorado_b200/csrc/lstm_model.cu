@@ -478,7 +478,6 @@ struct LstmRecParams {
     int T, N, reverse;
     const int32_t* lens;  // optional per-chunk length in samples (variable chunk sizes); stride = samples per step
     int stride;
-    int stagger;          // cycles by which group g starts after group g-1 (ping-pong of the chunk groups)
     int gather;           // all-gather of h_t: 0 bulk copies over DSMEM, 1 through L2 (TMA store + multicast load), 2 remote vector stores
     long long* dbg;       // optional clock64 timeline of CTA 0, steps 64..67 (B200_DEBUG_LSTM_TIMELINE); nullptr in production
 };
@@ -838,31 +837,23 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
         if (tc::elect_one()) {
             const uint64_t zdesc0 = umma_desc_sw64(z_local);
             constexpr uint32_t idesc = tc::umma_idesc_f16(128, GN);
-            // The groups are independent recurrences: whichever has its h_{t-1} complete is issued next (no fixed order, so
-            // one group's all-gather never holds up the other's MMAs), and the second group starts half a step late so
-            // that one group's gate math and all-gather run under the other's MMAs instead of beside them.
-            int sg[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) sg[g] = 0;
-            const long long t_start = clock64();
-            bool pending = steps > 0;
-            while (pending) {
-                pending = false;
+            for (int s = 0; s < steps; ++s) {
+                const int buf = s & 1, nbuf = buf ^ 1;
+                const uint32_t par = (uint32_t)((s >> 1) & 1);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const int s = sg[g];
-                    if (s >= steps) continue;
-                    pending = true;
-                    if (g > 0 && s == 0 && p.stagger > 0 && clock64() - t_start < (long long)p.stagger * g) continue;
-                    const int buf = s & 1, nbuf = buf ^ 1;
-                    const uint32_t par = (uint32_t)((s >> 1) & 1);
-                    const bool ready = p.gather == 2 ? mbar_try_wait_cluster(&h_full[g * 2 + buf], par) : tc::mbar_try_wait(&h_full[g * 2 + buf], par);
-                    if (!ready) continue;
                     // arm the barrier the slices of h_s will complete on (all CL CTAs x TPC tiles, this group)
                     if (s + 1 < steps && p.gather != 2) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
                     long long* d = (p.dbg && blockIdx.x == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + g * 4 : nullptr;
-                    if (d) d[1] = clock64();
+                    if (d) d[0] = clock64();
+                    if (p.gather == 2) {
+                        while (!mbar_try_wait_cluster(&h_full[g * 2 + buf], par)) {
+                        }
+                    } else {
+                        tc::mbar_wait(&h_full[g * 2 + buf], par);
+                    }
                     tc::tc_fence_after();
+                    if (d) d[1] = clock64();
                     const uint64_t zd = zdesc0 + (uint64_t)(((g * 2 + buf) * KBH * ZB) >> 4);
 #pragma unroll
                     for (int i = 0; i < TPC; ++i) {
@@ -877,7 +868,6 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                         tc::umma_commit(&acc_full[g * TPC + i]);
                     }
                     if (d) d[2] = clock64();
-                    sg[g] = s + 1;
                 }
             }
         }
@@ -954,10 +944,12 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             float hv[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const bool alive = t < my_len[c];
-                const float cs = alive ? a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2] : 0.0f;
+                // outside the chunk (variable chunk sizes) the state is held at zero: a multiplicative mask, not a branch, so
+                // that the four cells' transcendentals stay interleaved
+                const float alive = t < my_len[c] ? 1.0f : 0.0f;
+                const float cs = (a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2]) * alive;
                 c_reg[c] = cs;
-                hv[c] = alive ? a[4 * c + 3] * tanh_f(cs) : 0.0f;
+                hv[c] = a[4 * c + 3] * tanh_f(cs) * alive;
             }
             // pair the units (uk, uk ^ 1): the even lane stores chunks c = 0, 1 of both units, the odd lane c = 2, 3
             {
@@ -1348,8 +1340,6 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.reverse = (l % 2 == 0) ? 1 : 0;
             rp.lens = nullptr;
             rp.stride = desc.stride;
-            rp.stagger = 1400;
-            if (const char* e = std::getenv("B200_CLUSTER_STAGGER")) rp.stagger = std::atoi(e);
             rp.gather = 0;  // measured on B200: 3.3 ms per layer with bulk copies over DSMEM, 5.7 ms through L2 (profiles/r02_b3_*)
             if (const char* e = std::getenv("B200_CLUSTER_GATHER")) {
                 rp.gather = std::strcmp(e, "l2") == 0 ? 1 : std::strcmp(e, "st") == 0 ? 2 : 0;
@@ -1577,12 +1567,12 @@ void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
         for (int s = 0; s < 4; ++s) {
             if (hoisted) {
                 const long long* e = h + s * 32;
-                const long long t0 = e[1];  // group 0 found its h complete
-                fprintf(stderr, "[cluster timeline step %d] mma g0: ready %lld..%lld issued %lld | g1: ready %lld..%lld issued %lld | epi(g0,t0): "
+                const long long t0 = e[0];
+                fprintf(stderr, "[cluster timeline step %d] mma g0: wait %lld..%lld issued %lld | g1: wait %lld..%lld issued %lld | epi(g0,t0): "
                                 "wait_acc %lld..%lld ld %lld act %lld transpose %lld cells+stage %lld fence %lld wait_read %lld bar %lld sent %lld | "
                                 "period %lld\n",
-                        64 + s, 0LL, e[1] - t0, e[2] - t0, 0LL, e[5] - t0, e[6] - t0, e[8] - t0, e[9] - t0, e[10] - t0, e[11] - t0,
-                        e[12] - t0, e[13] - t0, e[14] - t0, e[15] - t0, e[16] - t0, e[17] - t0, s > 0 ? e[1] - (e - 32)[1] : 0LL);
+                        64 + s, e[0] - t0, e[1] - t0, e[2] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[8] - t0, e[9] - t0, e[10] - t0, e[11] - t0,
+                        e[12] - t0, e[13] - t0, e[14] - t0, e[15] - t0, e[16] - t0, e[17] - t0, s > 0 ? e[0] - (e - 32)[0] : 0LL);
             } else {
                 const long long* e = h + s * 16;
                 const long long t0 = e[0];

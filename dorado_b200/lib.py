@@ -89,7 +89,7 @@ EXPORTS = [
     "b200_engine_set_low_latency", "b200_engine_is_low_latency", "b200_engine_batch_timeouts_ms",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_num_runners", "b200_pool_runner", "b200_pool_out_len",
     "b200_pool_runner_info", "b200_pool_call_chunks", "b200_runner_variable_chunk_sizes",
-    "b200_runner_accept_chunk_var_f16",
+    "b200_runner_accept_chunk_var_f16", "b200_chunk_benchmarks_lookup", "b200_engine_gpu_name",
 ]
 
 _lib = None
@@ -122,6 +122,8 @@ def load_library() -> C.CDLL:
     lib.b200_pool_runner.restype = vp
     lib.b200_pool_runner_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_int64)]
     lib.b200_pool_call_chunks.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(C.c_double)]
+    lib.b200_chunk_benchmarks_lookup.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(i32), C.POINTER(f32), i32, C.POINTER(i32)]
+    lib.b200_engine_gpu_name.argtypes = [vp, C.c_char_p, C.c_uint64]
     lib.b200_runner_variable_chunk_sizes.argtypes = [vp]
     lib.b200_runner_variable_chunk_sizes.restype = i32
     lib.b200_runner_accept_chunk_var_f16.argtypes = [vp, i32, vp, C.c_int64]

@@ -273,6 +273,17 @@ B200_API int b200_engine_benchmark_batch_sizes(b200_engine* engine,
                                                float* ms_per_chunk,
                                                int32_t capacity,
                                                int32_t* count);
+/* CudaChunkBenchmarks::get_chunk_timings (dorado/basecall/benchmarks/CudaChunkBenchmarks.cpp:24-63): the pre-computed
+ * timing table for (GPU name, model name), in ascending batch-size order; *count = 0 when there is none (the caller then
+ * runs b200_engine_benchmark_batch_sizes, as CudaCaller.cpp:506-557 does).  b200_engine_gpu_name gives the name to look up. */
+B200_API int b200_chunk_benchmarks_lookup(const char* gpu_name,
+                                          const char* model_name,
+                                          int32_t* batch_sizes,
+                                          float* ms_per_chunk,
+                                          int32_t capacity,
+                                          int32_t* count);
+B200_API int b200_engine_gpu_name(const b200_engine* engine, char* buf, uint64_t buf_len);
+
 /* The selection rule of determine_batch_dims (:487-631) on such a table (ascending batch sizes): keep the entries that
  * improve on every smaller batch size, take the first of them within (1 + time_penalty) of the best time, and return
  * the largest kept batch size up to that entry that does not exceed max_batch_size (the memory cap); `granularity` if

@@ -214,3 +214,26 @@ def test_c_abi_from_a_plain_c_client(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "abi_smoke ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_chunk_size_buckets_and_benchmark_table_lookup():
+    """CudaCaller.cpp:379-414: the requested chunk size plus half of it (simplex), normalised; CudaChunkBenchmarks lookup by
+    (GPU name, model name) with the alias list, empty for unknown pairs."""
+    from dorado_b200 import batching
+    from dorado_b200.config import load_model_config
+    from conftest import MODELS
+    hac = load_model_config(model_dir("hac"))
+    sup = load_model_config(model_dir("sup"))
+    assert batching.chunk_size_buckets(hac, 10000) == [9996, 4998]
+    assert batching.chunk_size_buckets(hac, 10000, pipeline="duplex") == [9996]
+    assert batching.chunk_size_buckets(sup, 10000) == [9984, 4992]
+    assert batching.chunk_size_buckets(hac, 600) == [600, 504]          # never below overlap + 1, rounded up to the granularity
+    assert batching.lookup_chunk_benchmarks("NVIDIA GeForce 256", MODELS["hac"]) == []
+    assert batching.lookup_chunk_benchmarks("NVIDIA B200", "no_such_model@v0") == []
+    for kind in ("fast", "hac", "sup"):
+        t = batching.lookup_chunk_benchmarks("NVIDIA B200", MODELS[kind])
+        assert t == batching.lookup_chunk_benchmarks("NVIDIA HGX B200", MODELS[kind])
+        if t:   # measured table committed: ascending batch sizes, strictly improving times
+            assert all(a[0] < b[0] and a[1] > b[1] for a, b in zip(t, t[1:]))
+            gran = batching.batch_size_granularity(load_model_config(model_dir(kind)))
+            assert all(b % gran == 0 for b, _ in t)
