@@ -218,12 +218,10 @@ void Runner::init() {
     const size_t scores_b = (size_t)m_N * m_T_out * m_C * sizeof(__half);
     const size_t ws_b = engine.model().workspace_bytes(m_N, m_T_in);
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-    m_arena.reserve(al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(m_out_bytes) + 4096);
+    const size_t lens_b = engine.model().variable_chunk_sizes() ? (size_t)m_N * sizeof(int32_t) : 0;
+    m_arena.reserve(al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(m_out_bytes) + al(lens_b) + 4096);
     m_d_qtable = static_cast<b200_qtable*>(m_arena.take(sizeof(b200_qtable)));  // inside the 4096 bytes of slack
-    if (engine.model().variable_chunk_sizes()) {
-        if ((size_t)m_N * sizeof(int32_t) > 2048) throw std::invalid_argument("batch_size too large for the chunk-length table");
-        m_d_lens = static_cast<int32_t*>(m_arena.take((size_t)m_N * sizeof(int32_t)));
-    }
+    if (lens_b) m_d_lens = static_cast<int32_t*>(m_arena.take(lens_b));
     m_d_input = static_cast<__half*>(m_arena.take(in_bytes));
     m_d_scores = static_cast<__half*>(m_arena.take(scores_b));
     m_d_ws = m_arena.take(ws_b);
@@ -645,7 +643,8 @@ size_t runner_device_bytes(Engine& engine, int batch_size, int chunk_size) {
     const size_t scores_b = (size_t)batch_size * T_out * d.outsize * sizeof(__half);
     const size_t ws_b = engine.model().workspace_bytes(batch_size, chunk_size);
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-    return al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(out_bytes) + 4096;
+    const size_t lens_b = engine.model().variable_chunk_sizes() ? (size_t)batch_size * sizeof(int32_t) : 0;
+    return al(in_bytes) + al(scores_b) + al(ws_b) + al(bwd_b) + al(beam_b) + al(out_bytes) + al(lens_b) + 4096;
 }
 
 int benchmark_batch_sizes(Engine& engine, int chunk_size, int granularity, int max_batch_size, int32_t* batch_sizes,

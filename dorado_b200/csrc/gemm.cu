@@ -61,6 +61,13 @@ struct GemmKernelParams {
     int staged;      // 0 = per-thread global stores
     int stages;      // TMA->MMA ring depth (3 when the staging tile needs the room)
     int sw;          // columns of a staging sub-tile: 64 (128-byte swizzle) or 32 (64-byte swizzle)
+    // RMSNorm folded into the epilogue (GemmDesc)
+    float* out_ss;
+    const float* a_ss;
+    const float* res_ss;
+    const float* res_gain;
+    int a_ss_parts, res_ss_parts;
+    float norm_inv_dim, norm_eps;
     int out_kind;    // coordinates of a sub-tile: 0 (col, row, batch)  1 (col, g % out_P, g / out_P)  2 (0, row, col / 32)
     int out_P;
 };
@@ -212,6 +219,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             const bool valid = row < p.rows_per_batch;
             const long long g = (long long)batch * p.rows_per_batch + row;
             const long long off = valid ? (g / p.out_m1) * p.out_s0 + (g % p.out_m1) * p.out_s1 : 0;
+            // folded RMSNorm: 1/rms of this row of A and of the residual row, from the partial sums of squares (fixed order)
+            float r_a = 1.0f, r_res = 1.0f;
+            if (p.a_ss && valid) {
+                float ss = 0.0f;
+                for (int i = 0; i < p.a_ss_parts; ++i) ss += __ldg(p.a_ss + g * p.a_ss_parts + i);
+                r_a = rsqrtf(ss * p.norm_inv_dim + p.norm_eps);
+            }
+            if (p.res_ss && valid) {
+                float ss = 0.0f;
+                for (int i = 0; i < p.res_ss_parts; ++i) ss += __ldg(p.res_ss + g * p.res_ss_parts + i);
+                r_res = rsqrtf(ss * p.norm_inv_dim + p.norm_eps);
+            }
+            float ss_out = 0.0f;  // sum of squares of what this thread stores for this tile
             if (staged && c_begin < c_end) {
                 // the stores of this set's previous tile have read its staging columns: they may be rewritten
                 if (storer) tc::bulk_wait_group_read<0>();
@@ -242,8 +262,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                         const bool rot = nc < p.rope_cols;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float a0 = __uint_as_float(r0[2 * j]), a1 = __uint_as_float(r0[2 * j + 1]);
-                            float b0 = __uint_as_float(r1[2 * j]), b1 = __uint_as_float(r1[2 * j + 1]);
+                            float a0 = __uint_as_float(r0[2 * j]) * r_a, a1 = __uint_as_float(r0[2 * j + 1]) * r_a;
+                            float b0 = __uint_as_float(r1[2 * j]) * r_a, b1 = __uint_as_float(r1[2 * j + 1]) * r_a;
                             if (rot) {
                                 const float4 cs = __ldg(tab + j);
                                 const float x0 = cs.x * a0 - cs.y * b0, y0 = cs.y * a0 + cs.x * b0;
@@ -286,7 +306,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                     const float row_bias = (p.bias && p.bias_per_row && valid) ? __ldg(p.bias + g) : 0.0f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r[j]);
+                        v[j] = __uint_as_float(r[j]) * r_a;
                         if (p.bias) v[j] += p.bias_per_row ? row_bias : __ldg(p.bias + nc + j);
                     }
                     if constexpr (ACT == GEMM_ACT_SWIGLU) {
@@ -317,8 +337,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float2 f = __half22float2(rh[j]);
-                                    v[q * 8 + 2 * j] += p.alpha * f.x;
-                                    v[q * 8 + 2 * j + 1] += p.alpha * f.y;
+                                    float ga = p.alpha * r_res, gb = ga;
+                                    if (p.res_gain) {
+                                        ga *= __ldg(p.res_gain + nc + q * 8 + 2 * j);
+                                        gb *= __ldg(p.res_gain + nc + q * 8 + 2 * j + 1);
+                                    }
+                                    v[q * 8 + 2 * j] += ga * f.x;
+                                    v[q * 8 + 2 * j + 1] += gb * f.y;
                                 }
                             }
                         }
@@ -327,6 +352,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 h[j] = __floats2half2_rn(act_apply<ACT>(v[2 * j]), act_apply<ACT>(v[2 * j + 1]));
+                            }
+                            if (p.out_ss) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const float2 f = __half22float2(h[j]);
+                                    ss_out = fmaf(f.x, f.x, ss_out);
+                                    ss_out = fmaf(f.y, f.y, ss_out);
+                                }
                             }
                             if (staged) {
                                 const int hc = (c - c_begin) * 32;
@@ -340,6 +373,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                         }
                     }
                 }
+            }
+            if (p.out_ss && valid && c_begin < c_end) {
+                // one partial per (column tile, part): consumers add them in index order
+                p.out_ss[g * (long long)(p.n_tiles * GEMM_PARTS) + nt * GEMM_PARTS + part] = ss_out;
             }
             if (staged && c_begin < c_end) {
                 tc::fence_proxy_async_smem();   // staged tile -> visible to the TMA store
@@ -435,6 +472,10 @@ static void plan_output_staging(GemmPlan& p) {
         return e && std::atoi(e) != 0;
     }();
     if (direct) return;
+    // measured on B200 (profiles/r02_b7_*): the staged epilogue wins wherever the epilogue bounds the tile (K = 512 with plain,
+    // bias, residual or rotary epilogues: 1.2-2.2x), and loses a little where the ring depth matters more than the stores
+    // (SwiGLU halves the output; K >= 1024 hides the epilogue under the main loop): those keep the per-thread stores and 4 stages
+    if (d.act == GEMM_ACT_SWIGLU || d.K >= 1024) return;
     const int nch = p.bn / 32;
     const int out_div = d.act == GEMM_ACT_SWIGLU ? 2 : 1;
     // every part's output width must split into sub-tiles of sw columns
@@ -489,6 +530,12 @@ static int pick_bn(int N) {
     return 0;
 }
 
+int gemm_out_ss_parts(int N) {
+    const int bn = pick_bn(N);
+    if (bn <= 0) throw std::invalid_argument("gemm: N must be a multiple of 32");
+    return (N / bn) * GEMM_PARTS;
+}
+
 GemmPlan make_gemm_plan(const GemmDesc& d) {
     if (d.K % BK != 0 || d.K <= 0) throw std::invalid_argument("gemm: K must be a positive multiple of 64");
     if (d.N % 32 != 0) throw std::invalid_argument("gemm: N must be a multiple of 32");
@@ -503,6 +550,15 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
         p.bn = pick_bn(d.N / 2);  // few row tiles: split N further to fill more SMs
     }
     if (p.bn == 0) throw std::invalid_argument("gemm: no valid tile width");
+    if (d.out_ss) {
+        // every part of every column tile must own columns, so that each partial slot is written
+        if (p.bn != pick_bn(d.N) || p.bn / 32 < GEMM_PARTS || d.act == GEMM_ACT_SWIGLU || d.act == GEMM_ACT_ROPE) {
+            throw std::invalid_argument("gemm: out_ss needs a plain epilogue and tiles of at least 128 columns");
+        }
+    }
+    if ((d.a_ss && (d.a_ss_parts < 1 || d.norm_dim < 1)) || (d.res_ss && (d.res_ss_parts < 1 || d.norm_dim < 1 || !d.residual))) {
+        throw std::invalid_argument("gemm: folded RMSNorm needs the partial count, the norm dimension and a residual");
+    }
     if (d.act == GEMM_ACT_SWIGLU && (p.bn % 64) != 0) throw std::invalid_argument("gemm: swiglu needs BN % 64 == 0");
     if (d.act == GEMM_ACT_ROPE && ((p.bn % 128) != 0 || !d.rope || d.rope_T <= 0)) {
         throw std::invalid_argument("gemm: rope epilogue needs BN % 128 == 0 and a table");
@@ -560,6 +616,14 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.tmem_cols = cols;
     k.n_tiles = p.d.N / p.bn;
     k.num_tiles = p.tiles_per_batch * p.d.batches * k.n_tiles;
+    k.out_ss = p.d.out_ss;
+    k.a_ss = p.d.a_ss;
+    k.res_ss = p.d.res_ss;
+    k.res_gain = p.d.res_gain;
+    k.a_ss_parts = p.d.a_ss_parts;
+    k.res_ss_parts = p.d.res_ss_parts;
+    k.norm_inv_dim = p.d.norm_dim > 0 ? 1.0f / (float)p.d.norm_dim : 0.0f;
+    k.norm_eps = p.d.norm_eps;
     k.staged = p.staged;
     k.stages = p.stages;
     k.sw = p.sw;

@@ -47,6 +47,21 @@ struct GemmDesc {
     // optional fused residual epilogue (deepnorm): v = v + alpha * residual[g][n]; requires act == NONE
     const __half* residual = nullptr;
     float alpha = 0.0f;
+    // RMSNorm folded into the GEMMs around it (no separate pass, TxModules.cpp:667,712 koi_rmsnorm_residual):
+    //   out_ss     the epilogue also writes, per output row, the sum of squares of the fp16 values it stored -- one partial
+    //              per (column tile, epilogue part), summed in a fixed order by the consumers (deterministic, no atomics);
+    //              out_ss_parts() gives how many partials a row has
+    //   a_ss       A holds UN-normalised rows u: the accumulator row is scaled by rsqrt(mean(u^2) + eps) (the gain is folded
+    //              into W's columns by the caller)
+    //   res_ss/res_gain  the residual term is alpha * rsqrt(mean(u^2) + eps) * gain[n] * u[g][n]
+    float* out_ss = nullptr;
+    const float* a_ss = nullptr;
+    int a_ss_parts = 0;
+    const float* res_ss = nullptr;
+    int res_ss_parts = 0;
+    const float* res_gain = nullptr;
+    int norm_dim = 0;
+    float norm_eps = 1e-5f;
 };
 
 struct GemmPlan {
@@ -61,6 +76,7 @@ struct GemmPlan {
 };
 
 GemmPlan make_gemm_plan(const GemmDesc& d);
+int gemm_out_ss_parts(int N);  // partial sums of squares per row a GEMM with N output columns writes (GemmDesc::out_ss)
 void run_gemm(const GemmPlan& p, cudaStream_t stream);
 
 }  // namespace b200

@@ -156,7 +156,21 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
     return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3))) << 4) + ((col & 7) << 1));
 }
 
-__device__ __forceinline__ float tanh_f(float v) { return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f); }
+// Gate activations.  sigmoid(v) = 1 - 1/(e^v + 1), tanh(v) = 1 - 2/(e^{2v} + 1): one ex2 on the SFU, and the reciprocal on
+// the FMA pipe (bit-trick seed + 3 Newton steps, relative error < 1e-7), because the recurrences are SFU-bound: 5
+// transcendentals per cell at 16 SFU lanes per clock per SM cost more than the MMAs (measured: the activation phase of a
+// step takes what the SFU needs for ex2 + rcp of all warps, profiles/r02_b2_timelines.txt).  The argument is capped at 80 so
+// that e^x + 1 stays finite for the seed.
+__device__ __forceinline__ float rcp_fma(float x) {  // x in [1, 1e35]
+    float y = __int_as_float(0x7ef311c7 - __float_as_int(x));
+    y = y * fmaf(-x, y, 2.0f);
+    y = y * fmaf(-x, y, 2.0f);
+    y = y * fmaf(-x, y, 2.0f);
+    return y;
+}
+// 1 - am / (e^{am v} + 1): am = 1 sigmoid, am = 2 tanh
+__device__ __forceinline__ float gate_act(float v, float am) { return fmaf(-am, rcp_fma(__expf(fminf(am * v, 80.0f)) + 1.0f), 1.0f); }
+__device__ __forceinline__ float tanh_f(float v) { return gate_act(v, 2.0f); }
 
 // C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).
 // NBR = chunks owned by this CTA (4, 8 or 16: small values spread a small batch over more SMs; the MMA is
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
 #pragma unroll
                 for (int n = 0; n < NBR; ++n) {
                     const float v = __uint_as_float(r[n]) + b;
-                    gs[(gate * NBR + n) * 32 + lane] = 1.0f - __fdividef(am, __expf(am * v) + 1.0f);
+                    gs[(gate * NBR + n) * 32 + lane] = gate_act(v, am);
                 }
                 float c_old[CPT];
 #pragma unroll
@@ -668,8 +682,8 @@ __global__ void __launch_bounds__(ClusterCfg<C, CL, UNC>::THREADS, 1) lstm_clust
                     for (int e = 0; e < 4; ++e) {
                         const float2 gf = __half22float2(gh[e]);
                         const float v0 = __uint_as_float(r[c8 * 8 + 2 * e]) + gf.x, v1 = __uint_as_float(r[c8 * 8 + 2 * e + 1]) + gf.y;
-                        a[2 * e] = 1.0f - __fdividef(am, __expf(am * v0) + 1.0f);
-                        a[2 * e + 1] = 1.0f - __fdividef(am, __expf(am * v1) + 1.0f);
+                        a[2 * e] = gate_act(v0, am);
+                        a[2 * e + 1] = gate_act(v1, am);
                     }
                     float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
                     dst[0] = make_float4(a[0], a[1], a[2], a[3]);
@@ -925,7 +939,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                 }
             }
 #pragma unroll
-            for (int n = 0; n < 16; ++n) a[n] = 1.0f - __fdividef(am, __expf(am * a[n]) + 1.0f);
+            for (int n = 0; n < 16; ++n) a[n] = gate_act(a[n], am);
             if (d) d[3] = clock64();
             // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
 #pragma unroll

@@ -18,6 +18,7 @@
 #include "nvtx.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -333,6 +334,7 @@ public:
     long long rows = 0;
     int N = 0, T = 0, H = 0;
     int n_launches = 0;
+    bool fold_norm = true;
 };
 
 class TxModel final : public Model {
@@ -343,6 +345,7 @@ public:
     std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
                                            size_t ws_bytes) override;
     b200_model_desc desc;
+    bool fold_norm = true;   // B200_TX_RMSNORM_PASS=1: separate RMSNorm kernel after every sub-layer (A/B comparisons)
     float* conv1_w = nullptr;
     std::vector<__half*> conv_w;  // conv 2..n  [C_out][W*C_in]
     std::vector<float*> conv_b;
@@ -376,6 +379,7 @@ TxModel::Shapes TxModel::shapes(int T_in) const {
 }
 
 TxModel::TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : desc(d) {
+    if (const char* e = std::getenv("B200_TX_RMSNORM_PASS")) fold_norm = std::atoi(e) == 0;
     if (d.d_model != 512 || d.nhead != 8) throw Unsupported("transformer path implements d_model 512, 8 heads (sup)");
     if (d.num_convs < 2 || d.convs[0].insize != 1 || d.convs[0].stride != 1 || d.convs[0].winlen > 9 || d.convs[0].size % 8) {
         throw Unsupported("transformer conv stack shape not supported");
@@ -416,11 +420,22 @@ TxModel::TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : 
         conv_b.push_back(up32(tb.data, c.size));
     }
     const int dm = d.d_model, ff = d.dim_feedforward;
+    // RMSNorm is folded into the GEMMs around it (gemm.h): x' = u * rsqrt(mean(u^2) + eps) * gain is never materialised.  The
+    // consumers of x' scale their accumulator rows by 1/rms and have the gain folded into their weight COLUMNS here.
+    auto fold = [&](const float* w, size_t rows, const float* gain) {
+        std::vector<float> out(rows * (size_t)dm);
+        for (size_t r = 0; r < rows; ++r)
+            for (int c = 0; c < dm; ++c) out[r * dm + c] = w[r * dm + c] * (gain ? gain[c] : 1.0f);
+        return out;
+    };
+    const float* prev_gain = nullptr;   // norm2 gain of the previous layer (none before layer 0: the conv output is used as is)
     for (int l = 0; l < d.depth; ++l) {
         const std::string pfx = "transformer_encoder." + std::to_string(l) + ".";
         TxLayerWeights lw;
+        const float* n1 = find_tensor(tensors, n, pfx + "norm1.weight.tensor").data;
+        const float* n2 = find_tensor(tensors, n, pfx + "norm2.weight.tensor").data;
         const auto& wqkv = find_tensor(tensors, n, pfx + "self_attn.Wqkv.weight.tensor");
-        lw.wqkv = up16(std::vector<float>(wqkv.data, wqkv.data + (size_t)3 * dm * dm));
+        lw.wqkv = up16(fold_norm ? fold(wqkv.data, (size_t)3 * dm, prev_gain) : std::vector<float>(wqkv.data, wqkv.data + (size_t)3 * dm * dm));
         const auto& wo = find_tensor(tensors, n, pfx + "self_attn.out_proj.weight.tensor");
         lw.wo = up16(std::vector<float>(wo.data, wo.data + (size_t)dm * dm));
         lw.bo = up32(find_tensor(tensors, n, pfx + "self_attn.out_proj.bias.tensor").data, dm);
@@ -431,7 +446,8 @@ TxModel::TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : 
             std::memcpy(&w1i[(size_t)(2 * j) * dm], &w1.data[(size_t)j * dm], sizeof(float) * dm);
             std::memcpy(&w1i[(size_t)(2 * j + 1) * dm], &w1.data[(size_t)(ff + j) * dm], sizeof(float) * dm);
         }
-        lw.w1 = up16(w1i);
+        lw.w1 = up16(fold_norm ? fold(w1i.data(), (size_t)2 * ff, n1) : w1i);
+        prev_gain = n2;
         const auto& w2 = find_tensor(tensors, n, pfx + "ff.fc2.weight.tensor");
         lw.w2 = up16(std::vector<float>(w2.data, w2.data + (size_t)dm * ff));
         lw.n1 = up32(find_tensor(tensors, n, pfx + "norm1.weight.tensor").data, dm);
@@ -440,7 +456,8 @@ TxModel::TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : 
     }
     {
         const auto& tw = find_tensor(tensors, n, "upsample.linear.weight.tensor");
-        wu = up16(std::vector<float>(tw.data, tw.data + (size_t)d.upsample_scale * dm * dm));
+        wu = up16(fold_norm ? fold(tw.data, (size_t)d.upsample_scale * dm, prev_gain)
+                            : std::vector<float>(tw.data, tw.data + (size_t)d.upsample_scale * dm * dm));
         bu = up32(find_tensor(tensors, n, "upsample.linear.bias.tensor").data, (size_t)d.upsample_scale * dm);
         const auto& tc_ = find_tensor(tensors, n, "crf.linear.weight.tensor");
         std::vector<float> w((size_t)d.outsize * dm);
@@ -478,6 +495,7 @@ size_t TxModel::workspace_bytes(int N, int T_in) const {
     total += al(rows * 1536 * 2);                                  // qkv
     total += al(rows * (size_t)desc.dim_feedforward * 2);          // ff hidden
     total += al(rows * (size_t)desc.upsample_scale * 512 * 2);     // upsampled
+    total += al(rows * (size_t)gemm_out_ss_parts(512) * 4) * 2;      // partial sums of squares (folded RMSNorm), two in flight
     return total + 4096;
 }
 
@@ -505,6 +523,9 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
     __half* qkv = take((size_t)rows * 1536 * 2);
     __half* hid = take((size_t)rows * desc.dim_feedforward * 2);
     __half* ups = take((size_t)rows * desc.upsample_scale * 512 * 2);
+    const int ssp = gemm_out_ss_parts(512);
+    float* ss_a = reinterpret_cast<float*>(take((size_t)rows * ssp * 4));   // of the rows in x (after fc2 / the previous layer)
+    float* ss_b = reinterpret_cast<float*>(take((size_t)rows * ssp * 4));   // of the rows in y (after out_proj)
 
     plan->conv1 = Conv1Params{signal, cbuf[0], conv1_w, N, T_in, s.t_pad[0], s.pad[0], desc.convs[0].size, desc.convs[0].winlen,
                               desc.convs[0].activation};
@@ -547,27 +568,51 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
         g.out_s1 = 0;
         g.residual = residual;
         g.alpha = alpha;
+        g.norm_dim = 512;
         if (act == GEMM_ACT_ROPE) {
             g.rope = rope;
             g.rope_T = T;
             g.rope_cols = 2 * desc.nhead * 64;
         }
-        return make_gemm_plan(g);
+        return g;
     };
     const int ff = desc.dim_feedforward;
     for (int l = 0; l < desc.depth; ++l) {
         const auto& lw = layers[l];
         TxPlan::Layer L;
-        L.qkv = dense(x, 512, lw.wqkv, 1536, nullptr, GEMM_ACT_ROPE, qkv, 1536, nullptr, 0.0f);
+        if (fold_norm) {
+            // x holds u_prev (un-normalised, ss_a) except before layer 0, y will hold u_mid (ss_b)
+            const bool first = l == 0;
+            GemmDesc q = dense(x, 512, lw.wqkv, 1536, nullptr, GEMM_ACT_ROPE, qkv, 1536, nullptr, 0.0f);
+            if (!first) { q.a_ss = ss_a; q.a_ss_parts = ssp; }
+            L.qkv = make_gemm_plan(q);
+            GemmDesc o = dense(att, 512, lw.wo, 512, lw.bo, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
+            if (!first) { o.res_ss = ss_a; o.res_ss_parts = ssp; o.res_gain = layers[l - 1].n2; }
+            o.out_ss = ss_b;
+            L.out_proj = make_gemm_plan(o);
+            GemmDesc f1 = dense(y, 512, lw.w1, 2 * ff, nullptr, GEMM_ACT_SWIGLU, hid, ff, nullptr, 0.0f);
+            f1.a_ss = ss_b; f1.a_ss_parts = ssp;
+            L.fc1 = make_gemm_plan(f1);
+            GemmDesc f2 = dense(hid, ff, lw.w2, 512, nullptr, GEMM_ACT_NONE, x, 512, y, desc.deepnorm_alpha);
+            f2.res_ss = ss_b; f2.res_ss_parts = ssp; f2.res_gain = lw.n1;
+            f2.out_ss = ss_a;
+            L.fc2 = make_gemm_plan(f2);
+        } else {
+            L.qkv = make_gemm_plan(dense(x, 512, lw.wqkv, 1536, nullptr, GEMM_ACT_ROPE, qkv, 1536, nullptr, 0.0f));
+            L.out_proj = make_gemm_plan(dense(att, 512, lw.wo, 512, lw.bo, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha));
+            L.fc1 = make_gemm_plan(dense(x, 512, lw.w1, 2 * ff, nullptr, GEMM_ACT_SWIGLU, hid, ff, nullptr, 0.0f));
+            L.fc2 = make_gemm_plan(dense(hid, ff, lw.w2, 512, nullptr, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha));
+        }
         L.attn = AttnParams{qkv, att, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
-        L.out_proj = dense(att, 512, lw.wo, 512, lw.bo, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
-        L.fc1 = dense(x, 512, lw.w1, 2 * ff, nullptr, GEMM_ACT_SWIGLU, hid, ff, nullptr, 0.0f);
-        L.fc2 = dense(hid, ff, lw.w2, 512, nullptr, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha);
         L.n1 = lw.n1;
         L.n2 = lw.n2;
         plan->layers.push_back(L);
     }
-    plan->upsample = dense(x, 512, wu, desc.upsample_scale * 512, bu, GEMM_ACT_NONE, ups, desc.upsample_scale * 512, nullptr, 0.0f);
+    {
+        GemmDesc u = dense(x, 512, wu, desc.upsample_scale * 512, bu, GEMM_ACT_NONE, ups, desc.upsample_scale * 512, nullptr, 0.0f);
+        if (fold_norm && desc.depth > 0) { u.a_ss = ss_a; u.a_ss_parts = ssp; }
+        plan->upsample = make_gemm_plan(u);
+    }
     {
         GemmDesc g{};
         g.a = ups;
@@ -590,7 +635,8 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
     plan->N = N;
     plan->T = T;
     plan->H = desc.nhead;
-    plan->n_launches = 1 + (desc.num_convs - 1) + desc.depth * 7 + 2;
+    plan->fold_norm = fold_norm;
+    plan->n_launches = 1 + (desc.num_convs - 1) + desc.depth * (fold_norm ? 5 : 7) + 2;
     return plan;
 }
 
@@ -625,7 +671,7 @@ void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
             run_gemm(L.out_proj, stream);
             if (prof) prof->mark("out_proj_gemm", stream);
         }
-        {
+        if (!fold_norm) {
             NvtxRange r("LNORM1");
             rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n1, rows);
             if (prof) prof->mark("rmsnorm", stream);
@@ -640,7 +686,7 @@ void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
             run_gemm(L.fc2, stream);
             if (prof) prof->mark("fc2_gemm", stream);
         }
-        {
+        if (!fold_norm) {
             NvtxRange r("LNORM2");
             rmsnorm512_kernel<<<norm_grid, 256, 0, stream>>>(y, x, L.n2, rows);
             if (prof) prof->mark("rmsnorm", stream);
