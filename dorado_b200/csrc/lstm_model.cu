@@ -156,20 +156,10 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
     return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3))) << 4) + ((col & 7) << 1));
 }
 
-// Gate activations.  sigmoid(v) = 1 - 1/(e^v + 1), tanh(v) = 1 - 2/(e^{2v} + 1): one ex2 on the SFU, and the reciprocal on
-// the FMA pipe (bit-trick seed + 3 Newton steps, relative error < 1e-7), because the recurrences are SFU-bound: 5
-// transcendentals per cell at 16 SFU lanes per clock per SM cost more than the MMAs (measured: the activation phase of a
-// step takes what the SFU needs for ex2 + rcp of all warps, profiles/r02_b2_timelines.txt).  The argument is capped at 80 so
-// that e^x + 1 stays finite for the seed.
-__device__ __forceinline__ float rcp_fma(float x) {  // x in [1, 1e35]
-    float y = __int_as_float(0x7ef311c7 - __float_as_int(x));
-    y = y * fmaf(-x, y, 2.0f);
-    y = y * fmaf(-x, y, 2.0f);
-    y = y * fmaf(-x, y, 2.0f);
-    return y;
-}
-// 1 - am / (e^{am v} + 1): am = 1 sigmoid, am = 2 tanh
-__device__ __forceinline__ float gate_act(float v, float am) { return fmaf(-am, rcp_fma(__expf(fminf(am * v, 80.0f)) + 1.0f), 1.0f); }
+// Gate activations: sigmoid(v) = 1 - 1/(e^v + 1), tanh(v) = 1 - 2/(e^{2v} + 1), ex2 + rcp on the SFU.  (Moving the reciprocal
+// to the FMA pipe -- seed + 3 Newton steps -- was measured SLOWER, 0.98 -> 1.03 ms per fast layer and 3.5 -> 3.85 ms per hac
+// layer: the step is bound by the latency of its dependent chain, not by SFU throughput; profiles/r02_b8_*.)
+__device__ __forceinline__ float gate_act(float v, float am) { return 1.0f - __fdividef(am, __expf(am * v) + 1.0f); }
 __device__ __forceinline__ float tanh_f(float v) { return gate_act(v, 2.0f); }
 
 // C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).

@@ -308,6 +308,231 @@ __global__ void __launch_bounds__(128) tx_attention_kernel(const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sliding-window attention on the 5th-generation tensor cores (successor of koi_masked_attention, TxModules.cpp:648;
+// window semantics TxModules.cpp:310-317).  One CTA = 128 queries of one (chunk, head); the keys they can see lie in at
+// most three aligned blocks of 128 keys, walked flash-style:
+//     S  = Q K_b^T          tcgen05.mma, 128 x 128 x 64, Q and K_b in shared memory (TMA, 128-byte swizzle), S in TMEM
+//     P  = exp2(S' - m)     one thread per query row (TMEM lane): tcgen05.ld S, running max / sum, P packed to fp16 and
+//                           written back into TENSOR MEMORY with tcgen05.st
+//     O_b = P V_b           tcgen05.mma with A = P read from TMEM and B = V_b as it lies in memory ([key][d], i.e. the
+//                           MN-major form of the B operand -- no transposed copy of V is ever made)
+//     O  = O * alpha + O_b  in registers (64 fp32 per row), so the accumulator in TMEM is never rescaled in place
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 the 128 softmax rows.  TMEM: S 128 + P 64 + O_b 64 columns =
+// 256, shared memory 80 KB, so two CTAs share an SM and one's softmax runs under the other's MMAs and loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int AT_BQ = 128, AT_BK = 128;
+constexpr int AT_TILE = 128 * 64 * 2;   // one [128 x 64] fp16 tile
+
+struct AttnTcParams {
+    __half* out;   // [N*T][H*64]
+    int N, T, H;
+    int win_upper, win_lower;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    // B operand stored [K rows][64 N-elements = 128 B]: MN-major, 128-byte swizzle, 8-row (K) groups 1024 B apart.  The tile
+    // is one swizzle atom wide in N, so only the K-direction stride matters; both offset fields carry it.
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* q_s = smem;                       // [128 q][64 d]
+    uint8_t* k_s = q_s + AT_TILE;              // [2][128 keys][64 d]
+    uint8_t* v_s = k_s + 2 * AT_TILE;          // [2][128 keys][64 d]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + 2 * AT_TILE);
+    uint64_t* q_full = bars;          // TMA -> MMA
+    uint64_t* kv_full = bars + 1;     // [2]
+    uint64_t* kv_free = bars + 3;     // [2] MMAs of a block done with K_b, V_b -> TMA
+    uint64_t* s_full = bars + 5;      // MMA -> softmax
+    uint64_t* s_free = bars + 6;      // softmax has read S -> MMA (4 warp arrivals)
+    uint64_t* p_ready = bars + 7;     // softmax wrote P -> MMA (4 warp arrivals)
+    uint64_t* o_full = bars + 8;      // MMA -> softmax
+    uint64_t* o_free = bars + 9;      // softmax has read O_b -> MMA (4 warp arrivals)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+    const int q0 = qt * AT_BQ;
+    // aligned key blocks that intersect [q0 - win_upper, q0 + 127 + win_lower] and [0, T)
+    int kb_first = (q0 - p.win_upper) / AT_BK;   // q0 >= 0, so this only goes negative through the subtraction
+    if (q0 - p.win_upper < 0) kb_first = 0;
+    int kb_last = (q0 + AT_BQ - 1 + p.win_lower) / AT_BK;
+    const int kb_max = (p.T - 1) / AT_BK;
+    if (kb_last > kb_max) kb_last = kb_max;
+    const int nblk = kb_last - kb_first + 1;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&kv_full[i], 1);
+            tc::mbar_init(&kv_free[i], 1);
+        }
+        tc::mbar_init(s_full, 1);
+        tc::mbar_init(s_free, 4);
+        tc::mbar_init(p_ready, 4);
+        tc::mbar_init(o_full, 1);
+        tc::mbar_init(o_free, 4);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tma_qkv);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tm_s = tmem_base, tm_p = tmem_base + 128, tm_o = tmem_base + 192;
+    const int row0 = n * p.T;   // first token row of this chunk in the [N*T][1536] view
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(q_full, AT_TILE);
+            tc::tma_load_2d(q_s, &tma_qkv, q_full, h * ATT_D, row0 + q0);
+            for (int b = 0; b < nblk; ++b) {
+                const int buf = b & 1;
+                tc::mbar_wait(&kv_free[buf], (uint32_t)(((b >> 1) & 1) ^ 1));
+                tc::mbar_arrive_expect_tx(&kv_full[buf], 2 * AT_TILE);
+                const int krow = row0 + (kb_first + b) * AT_BK;
+                tc::tma_load_2d(k_s + buf * AT_TILE, &tma_qkv, &kv_full[buf], (p.H + h) * ATT_D, krow);
+                tc::tma_load_2d(v_s + buf * AT_TILE, &tma_qkv, &kv_full[buf], (2 * p.H + h) * ATT_D, krow);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc_s = tc::umma_idesc_f16(128, 128);
+            constexpr uint32_t idesc_o = tc::umma_idesc_f16(128, 64) | (1u << 16);   // B operand MN-major
+            const uint64_t qdesc = tc::umma_desc_sw128(tc::smem_u32(q_s));
+            tc::mbar_wait(q_full, 0);
+            for (int b = 0; b < nblk; ++b) {
+                const int buf = b & 1;
+                const uint32_t par = (uint32_t)(b & 1);
+                tc::mbar_wait(&kv_full[buf], (uint32_t)((b >> 1) & 1));
+                tc::mbar_wait(s_free, par ^ 1);   // the rows have read S of the previous block
+                tc::tc_fence_after();
+                const uint64_t kdesc = tc::umma_desc_sw128(tc::smem_u32(k_s + buf * AT_TILE));
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k) tc::umma_f16(tm_s, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                tc::umma_commit(s_full);
+                tc::mbar_wait(p_ready, par);      // P of this block is in tensor memory
+                tc::mbar_wait(o_free, par ^ 1);   // the rows have read O of the previous block
+                tc::tc_fence_after();
+                const uint64_t vdesc = umma_desc_sw128_mn(tc::smem_u32(v_s + buf * AT_TILE));
+#pragma unroll
+                for (int k = 0; k < AT_BK / 16; ++k) {
+                    // 16 keys = 8 packed TMEM columns of P; 16 rows of V = 2048 B further on
+                    tc::umma_f16_ts(tm_o, tm_p + (uint32_t)(8 * k), vdesc + (uint64_t)((k * 2048) >> 4), idesc_o, k != 0);
+                }
+                tc::umma_commit(o_full);
+                tc::umma_commit(&kv_free[buf]);
+            }
+        }
+    } else {
+        // ---------------- softmax rows ----------------
+        const int qrt = warp & 3;                    // TMEM lane quarter
+        const int r = qrt * 32 + lane;               // query row within the tile
+        const int qi = q0 + r;
+        const uint32_t lane_sel = (uint32_t)(qrt * 32) << 16;
+        const float sc = 0.125f * 1.44269504088896341f;   // 1/sqrt(64) and the base change of exp -> exp2
+        float o[64];
+#pragma unroll
+        for (int d = 0; d < 64; ++d) o[d] = 0.0f;
+        float m_run = -1e30f, l_run = 0.0f;
+        for (int b = 0; b < nblk; ++b) {
+            const uint32_t par = (uint32_t)(b & 1);
+            const int kb = (kb_first + b) * AT_BK;
+            // keys of this block visible to this row: j in [lo, hi)
+            int lo = qi - p.win_upper - kb, hi = qi + p.win_lower + 1 - kb;
+            if (lo < 0) lo = 0;
+            if (hi > AT_BK) hi = AT_BK;
+            if (kb + hi > p.T) hi = p.T - kb;
+            if (qi >= p.T) hi = 0;
+            tc::mbar_wait(s_full, par);
+            tc::tc_fence_after();
+            // pass 1: row maximum over the visible keys (S stays in tensor memory)
+            float m_blk = -1e30f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)(32 * c), v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = 32 * c + j;
+                    if (col >= lo && col < hi) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+                }
+            }
+            const float m_new = fmaxf(m_run, m_blk * sc);
+            const float alpha = exp2f(m_run - m_new);   // 1 when nothing changed, 0 on the first visible block
+            float l_blk = 0.0f;
+            // pass 2: P = exp2(S * sc - m), packed to fp16 pairs, written to tensor memory as the A operand of P V
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32], pk[16];
+                tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)(32 * c), v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = 32 * c + 2 * j;
+                    const float p0 = (col >= lo && col < hi) ? exp2f(fmaf(__uint_as_float(v[2 * j]), sc, -m_new)) : 0.0f;
+                    const float p1 = (col + 1 >= lo && col + 1 < hi) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new)) : 0.0f;
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    const float2 back = __half22float2(hp);   // the sum runs over what the MMA will see
+                    l_blk += back.x + back.y;
+                    pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                }
+                tc::tmem_st_32x16(tm_p + lane_sel + (uint32_t)(16 * c), pk);
+            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(s_free);
+                tc::mbar_arrive(p_ready);
+            }
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+            // O = O * alpha + P V_b
+            tc::mbar_wait(o_full, par);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tm_o + lane_sel + (uint32_t)(32 * c), v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[32 * c + j] = fmaf(o[32 * c + j], alpha, __uint_as_float(v[j]));
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(o_free);
+        }
+        if (qi < p.T) {
+            const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)row0 + qi) * (size_t)(p.H * ATT_D) + (size_t)h * ATT_D);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                __half2 hh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(o[8 * q + 2 * j] * inv, o[8 * q + 2 * j + 1] * inv);
+                dst[q] = *reinterpret_cast<uint4*>(hh);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TxLayerWeights {
@@ -330,6 +555,9 @@ public:
     };
     std::vector<Layer> layers;
     GemmPlan upsample, crf;
+    bool attn_tc = true;       // tcgen05 attention (B200_ATTN_LEGACY=1: the mma.sync kernel, for A/B comparisons)
+    CUtensorMap qkv_map;       // qkv as [N*T][3*H*64], box 64 x 128 (Q, K and V tiles of the tensor-core attention)
+    AttnTcParams attn_tc_p{};
     __half *x = nullptr, *y = nullptr;
     long long rows = 0;
     int N = 0, T = 0, H = 0;
@@ -629,6 +857,9 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
         g.out_s0 = desc.outsize;
         plan->crf = make_gemm_plan(g);
     }
+    if (const char* e = std::getenv("B200_ATTN_LEGACY")) plan->attn_tc = std::atoi(e) == 0;
+    plan->qkv_map = make_tmap_2d(qkv, (uint64_t)3 * desc.nhead * ATT_D, (uint64_t)rows, (uint64_t)3 * desc.nhead * ATT_D * 2, ATT_D, 128);
+    plan->attn_tc_p = AttnTcParams{att, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
     plan->x = x;
     plan->y = y;
     plan->rows = rows;
@@ -663,7 +894,14 @@ void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
         }
         {
             NvtxRange r("MEA");
-            tx_attention_kernel<<<dim3((unsigned)((T + 63) / 64), (unsigned)H, (unsigned)N), 128, 0, stream>>>(L.attn);
+            if (attn_tc) {
+                constexpr int smem = 1024 + 5 * AT_TILE + 256;
+                ensure_dynamic_smem(tx_attention_tc_kernel, smem);
+                tx_attention_tc_kernel<<<dim3((unsigned)((T + AT_BQ - 1) / AT_BQ), (unsigned)H, (unsigned)N), 192, smem, stream>>>(qkv_map,
+                                                                                                                          attn_tc_p);
+            } else {
+                tx_attention_kernel<<<dim3((unsigned)((T + 63) / 64), (unsigned)H, (unsigned)N), 128, 0, stream>>>(L.attn);
+            }
             if (prof) prof->mark("tx_attention", stream);
         }
         {

@@ -142,21 +142,57 @@ def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_qui
         H, D = tx.nhead, tx.d_model // tx.nhead
         alpha = np.float32(tx.deepnorm_alpha)
         wc = q(w_in["crf.linear.weight.tensor"] * np.float32(tx.crf_scale))
-        for l in range(tx.depth):
-            p = f"transformer_encoder.{l}."
-            qkv = q(x @ w[p + "self_attn.Wqkv.weight.tensor"].T).reshape(N, T, 3, H, D)
-            qq, k, v = q(rope(qkv[:, :, 0], tx.theta)), q(rope(qkv[:, :, 1], tx.theta)), qkv[:, :, 2]
-            a = q(windowed_attention(qq, k, v, tx.attn_window, cpu_split_quirk).reshape(N, T, d))
-            a = q(a @ w[p + "self_attn.out_proj.weight.tensor"].T + w[p + "self_attn.out_proj.bias.tensor"] + x * alpha)
-            x = q(rmsnorm(a, w[p + "norm1.weight.tensor"]).astype(np.float32))
-            t = x @ w[p + "ff.fc1.weight.tensor"].T
-            y, gate = t[..., : tx.dim_feedforward], t[..., tx.dim_feedforward:]
-            f = q(q((gate * _sigmoid(gate)) * y) @ w[p + "ff.fc2.weight.tensor"].T + x * alpha)
-            x = q(rmsnorm(f, w[p + "norm2.weight.tensor"]).astype(np.float32))
-            if l == 0:
-                inter["layer0"] = x
-        inter["encoder"] = x
-        u = q(x @ w["upsample.linear.weight.tensor"].T + w["upsample.linear.bias.tensor"])
+        if emulate_fp16:
+            # Rounding points of the engine (tx_model.cu): RMSNorm is folded into the GEMMs around it, so the normalised
+            # x' = u * rsqrt(mean(u^2) + eps) * gain never reaches memory.  What is stored (fp16) is the un-normalised u;
+            # its consumers multiply their fp32 accumulator rows by 1/rms and carry the gain in their (fp16) weight columns;
+            # the residual term uses u, 1/rms and the gain in fp32.
+            inv_rms = lambda u_: (1.0 / np.sqrt(np.mean(u_ * u_, axis=-1, keepdims=True) + 1e-5)).astype(np.float32)
+            u_prev, r_prev, g_prev = x, None, None          # before layer 0 the conv output is used as is
+            for l in range(tx.depth):
+                p = f"transformer_encoder.{l}."
+                n1, n2 = w_in[p + "norm1.weight.tensor"], w_in[p + "norm2.weight.tensor"]
+                wq = w_in[p + "self_attn.Wqkv.weight.tensor"]
+                wq = _q16(wq * g_prev[None, :]) if g_prev is not None else _q16(wq)
+                acc = u_prev @ wq.T
+                if r_prev is not None:
+                    acc = acc * r_prev
+                qkv = acc.reshape(N, T, 3, H, D)
+                qq, k, v = q(rope(qkv[:, :, 0], tx.theta)), q(rope(qkv[:, :, 1], tx.theta)), q(qkv[:, :, 2])
+                a = q(windowed_attention(qq, k, v, tx.attn_window, cpu_split_quirk).reshape(N, T, d))
+                xn = u_prev * r_prev * g_prev if r_prev is not None else u_prev
+                u_mid = q(a @ w[p + "self_attn.out_proj.weight.tensor"].T + w[p + "self_attn.out_proj.bias.tensor"] + xn * alpha)
+                r_mid = inv_rms(u_mid)
+                t = (u_mid @ _q16(w_in[p + "ff.fc1.weight.tensor"] * n1[None, :]).T) * r_mid
+                y, gate = t[..., : tx.dim_feedforward], t[..., tx.dim_feedforward:]
+                hid = q((gate * _sigmoid(gate)) * y)
+                u_prev = q(hid @ w[p + "ff.fc2.weight.tensor"].T + (u_mid * r_mid * n1) * alpha)
+                r_prev, g_prev = inv_rms(u_prev), n2
+                if l == 0:
+                    inter["layer0"] = u_prev * r_prev * g_prev
+            inter["encoder"] = u_prev * r_prev * g_prev if r_prev is not None else u_prev
+            wu = w_in["upsample.linear.weight.tensor"]
+            wu = _q16(wu * g_prev[None, :]) if g_prev is not None else _q16(wu)
+            acc = u_prev @ wu.T
+            if r_prev is not None:
+                acc = acc * r_prev
+            u = q(acc + w["upsample.linear.bias.tensor"])
+        else:
+            for l in range(tx.depth):
+                p = f"transformer_encoder.{l}."
+                qkv = (x @ w[p + "self_attn.Wqkv.weight.tensor"].T).reshape(N, T, 3, H, D)
+                qq, k, v = rope(qkv[:, :, 0], tx.theta), rope(qkv[:, :, 1], tx.theta), qkv[:, :, 2]
+                a = windowed_attention(qq, k, v, tx.attn_window, cpu_split_quirk).reshape(N, T, d)
+                a = a @ w[p + "self_attn.out_proj.weight.tensor"].T + w[p + "self_attn.out_proj.bias.tensor"] + x * alpha
+                x = rmsnorm(a, w[p + "norm1.weight.tensor"]).astype(np.float32)
+                t = x @ w[p + "ff.fc1.weight.tensor"].T
+                y, gate = t[..., : tx.dim_feedforward], t[..., tx.dim_feedforward:]
+                f = ((gate * _sigmoid(gate)) * y) @ w[p + "ff.fc2.weight.tensor"].T + x * alpha
+                x = rmsnorm(f, w[p + "norm2.weight.tensor"]).astype(np.float32)
+                if l == 0:
+                    inter["layer0"] = x
+            inter["encoder"] = x
+            u = x @ w["upsample.linear.weight.tensor"].T + w["upsample.linear.bias.tensor"]
         u = u.reshape(N, tx.upsample_scale * T, d)
         scores = q(u @ wc.T)
         scores = scores.astype(np.float32)
