@@ -116,28 +116,33 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LSTM layer: all T steps of one layer in one persistent launch.
+// LSTM layer for a hidden size whose weights fit one SM's tensor memory (fast: C = 96): all T steps of one layer in one
+// persistent launch, no inter-CTA traffic.
 //
 // Orientation is "weights as the M operand": per step, for each tile m of 32 hidden units,
-//     D_m[128 gate rows][NB chunks] = Wp_m[128][2C] * Z_t[NB][2C]^T ,  Z_t = [x_t ; h_{t-1}]
-// where the 128 rows of Wp_m are (i | f | g | o) x 32 units, so one epilogue warp handles one gate type and
-// a CTA owns NB chunks for the whole sequence (no inter-CTA traffic).  MMA operands live in shared memory as
-// K-major tiles of 32 fp16 (64-byte swizzle): weights are TMA-loaded (resident when they fit, else streamed
-// from L2 every step through a ring), x_t arrives by TMA, h_t is written by the epilogue.
-// Accumulators are double-buffered in TMEM so the epilogue of tile m overlaps the MMAs of tile m+1.
+//     D_m[128 gate rows][16] = Wp_m[128][2C] * Z_t[16][2C]^T ,  Z_t = [x_t ; h_{t-1}]  (rows = chunks, zero-padded to 16)
+// where the 128 rows of Wp_m are (i | f | g | o) x 32 units, so one epilogue warp handles one gate type.  The permuted
+// weights (4C x 2C fp16) are written ONCE into tensor memory (tcgen05.st) and every MMA of the sequence reads its A operand
+// from there; the only shared-memory operand is the tiny Z_t: x_t arrives by TMA, h_t is written by the epilogue.
+//
+// A step is a dependent chain (MMA -> tcgen05.ld -> gates -> cell -> h_t -> MMA) of ~1000 cycles that leaves every pipe of
+// the SM idle most of the time, and a batch of 512 chunks only has 512 / NBR such chains.  So one CTA runs NG = 2 chains
+// ("groups") side by side: each group owns NBR chunks, its own Z / gate / cell buffers, barriers, accumulator columns and its
+// own 16 warps (1 TMA producer, MT MMA issuers, MT x 4 epilogue warps); the groups share nothing but the weights in tensor
+// memory, and one group's gate math runs under the other's MMAs and barrier hand-overs.
+// Accumulators are double-buffered per group so the x_t half of step s+1 (which does not depend on the recurrence) is
+// issued while the epilogue of step s still runs; only the h_{t-1} half sits on the critical path.
 // ------------------------------------------------------------------------------------------------
 constexpr int KBLK = 32;           // K elements per smem block (64 B rows, SWIZZLE_64B)
-constexpr int WBLK_BYTES = 128 * KBLK * 2;
-constexpr int UN = 16;             // UMMA N: rows of a Z block (chunks, zero-padded when a CTA owns fewer)
+constexpr int UN = 16;             // UMMA N: rows of a Z block (chunks, zero-padded when a group owns fewer)
 constexpr int ZBLK = UN * KBLK * 2;
 
 struct LstmParams {
     __half* seq;        // [T][N][C] in place
     const float* bias;  // [4C] permuted like the weight rows (b_ih + b_hh)
-    const __half* w;    // [4C][2C] permuted weights (read directly when they are kept in tensor memory)
+    const __half* w;    // [4C][2C] permuted weights
     int T, N, C, reverse;
-    int w_stages;  // 0 => weights resident on chip
-    long long* dbg;  // optional timeline (clock64 stamps of CTA 0, steps 64..67); nullptr in production
+    long long* dbg;  // optional timeline (clock64 stamps of CTA 0 / group 0, steps 64..67); nullptr in production
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -163,122 +168,100 @@ __device__ __forceinline__ float gate_act(float v, float am) { return 1.0f - __f
 __device__ __forceinline__ float tanh_f(float v) { return gate_act(v, 2.0f); }
 
 // C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).
-// NBR = chunks owned by this CTA (4, 8 or 16: small values spread a small batch over more SMs; the MMA is
-//       always N = 16 wide, padded rows are zero).
-// G   = C/32 tiles are spread over G epilogue groups of 4 warps (tile m -> group m % G) and, when the weights
-//       are resident, over G MMA-issuing warps, so the gate math and the MMA issue of the tiles of one step
-//       run concurrently.
-// Per step the x_t half of the product is issued as soon as x_t has landed (it does not depend on the
-// recurrence) and only the h_{t-1} half sits on the critical path.
-template <int C>
+// NBR = chunks owned by one group (2, 4, 8 or 16: small values spread a small batch over more SMs).
+// NG  = groups (independent recurrences) per CTA.
+template <int C, int NG>
 struct LstmCfg {
-    static constexpr int MT = C / 32;
-    static constexpr int G = (MT % 6 == 0) ? 6 : (MT % 4 == 0) ? 4 : 3;
+    static constexpr int MT = C / 32;                 // gate tiles = MMA-issuing warps = epilogue warp quartets per group
     static constexpr int KB = 2 * C / KBLK;
     static constexpr int KBX = C / KBLK;
-    static constexpr int THREADS = 32 * (1 + G) + 128 * G;
-    // weights in tensor memory: the MMA then reads only the tiny [16 x K] activation operand from shared memory
-    // instead of re-reading 4C x 2C weights every step (C = 96: 288 weight columns + 96 accumulator columns)
-    static constexpr bool WT = (MT * C + 2 * MT * UN) <= 512;
-    static constexpr int ACC_COLS = 2 * MT * UN;
-    static constexpr int NEED_COLS = ACC_COLS + (WT ? MT * C : 0);
-    static constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
-    static_assert(MT % G == 0 && 2 * MT * UN <= 512, "unsupported LSTM size");
+    static constexpr int GROUP_WARPS = 1 + MT + 4 * MT;
+    static constexpr int THREADS = 32 * GROUP_WARPS * NG;
+    static constexpr int ACC_COLS = NG * 2 * MT * UN;
+    static constexpr int NEED_COLS = ACC_COLS + MT * C;   // + the weights: tile m, k-step ks at m*C + ks*8
+    static constexpr uint32_t TMEM_COLS = NEED_COLS <= 256 ? 256 : 512;
+    static constexpr int NBAR = 8 + 2 * MT;               // mbarriers per group
+    static_assert(NEED_COLS <= 512, "weights + accumulators must fit tensor memory");
+    static_assert(GROUP_WARPS % 4 == 0, "epilogue warps must keep warp % 4 == TMEM lane quarter");
+    static_assert(THREADS <= 1024 && NG * MT + 1 <= 16, "too many warps / named barriers");
+    static constexpr size_t smem_bytes(int nbr) {
+        return 1024 + (size_t)NG * (2 * KB * ZBLK + (size_t)MT * 4 * nbr * 32 * 4 + (size_t)MT * nbr * 32 * 4 + NBAR * 8) + 64;
+    }
 };
 
-template <int C, int NBR>
-__global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(const __grid_constant__ CUtensorMap tma_x,
-                                                                           const __grid_constant__ CUtensorMap tma_w,
-                                                                           const LstmParams p) {
-    using Cfg = LstmCfg<C>;
-    constexpr int MT = Cfg::MT, G = Cfg::G, KB = Cfg::KB, KBX = Cfg::KBX;
+template <int C, int NBR, int NG>
+__global__ void __launch_bounds__(LstmCfg<C, NG>::THREADS, 1) lstm_layer_kernel(const __grid_constant__ CUtensorMap tma_x,
+                                                                               const LstmParams p) {
+    using Cfg = LstmCfg<C, NG>;
+    constexpr int MT = Cfg::MT, KB = Cfg::KB, KBX = Cfg::KBX, GW = Cfg::GROUP_WARPS, NBAR = Cfg::NBAR;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // realign by an integer offset from the __shared__ symbol so the compiler keeps the shared address space
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr bool WT = Cfg::WT;
-    const bool resident = p.w_stages == 0;
-    const int w_blocks = WT ? 0 : (resident ? MT * KB : p.w_stages);
-    uint8_t* w_s = smem;
-    uint8_t* z_s = w_s + (size_t)w_blocks * WBLK_BYTES;                   // [2][KB][ZBLK]
-    float* g_s = reinterpret_cast<float*>(z_s + (size_t)2 * KB * ZBLK);   // [G][4][NBR][32]
-    float* c_s = g_s + (size_t)G * 4 * NBR * 32;                          // [MT][NBR][32] cell state
-    uint64_t* bars = reinterpret_cast<uint64_t*>(c_s + (size_t)MT * NBR * 32);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp / GW, lw = warp % GW;   // group and role within the group
+    uint8_t* z_all = smem;                                                        // [NG][2][KB][ZBLK]
+    float* g_all = reinterpret_cast<float*>(z_all + (size_t)NG * 2 * KB * ZBLK);  // [NG][MT][4][NBR][32]
+    float* c_all = g_all + (size_t)NG * MT * 4 * NBR * 32;                        // [NG][MT][NBR][32] cell state
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(c_all + (size_t)NG * MT * NBR * 32);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars_all + NG * NBAR);
+    uint8_t* z_s = z_all + (size_t)grp * 2 * KB * ZBLK;
+    float* c_s = c_all + (size_t)grp * MT * NBR * 32;
+    uint64_t* bars = bars_all + grp * NBAR;
     uint64_t* x_full = bars;          // [2]  TMA -> MMA
-    uint64_t* z_free = bars + 2;      // [2]  MMA done with Z[buf] -> TMA
+    uint64_t* z_free = bars + 2;      // [2]  MMAs done with Z[buf] -> TMA
     uint64_t* h_ready = bars + 4;     // [2]  epilogue wrote h into Z[buf] -> MMA
     uint64_t* acc_free = bars + 6;    // [2]  epilogue done reading accumulator set -> MMA
     uint64_t* acc_full = bars + 8;    // [2][MT] MMA -> epilogue
-    uint64_t* w_full = acc_full + 2 * MT;
-    uint64_t* w_empty = w_full + (resident ? 1 : p.w_stages);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_empty + (resident ? 1 : p.w_stages));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * NBR;
-    const int mma_warps = resident ? G : 1;
+    const int n0 = (blockIdx.x * NG + grp) * NBR;
 
     // zero Z (padding rows, h_{-1}) and the cell state before anything asynchronous starts
-    for (int i = threadIdx.x; i < 2 * KB * ZBLK / 16; i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < MT * NBR * 32; i += blockDim.x) c_s[i] = 0.0f;
+    for (int i = threadIdx.x; i < NG * 2 * KB * ZBLK / 16; i += blockDim.x) reinterpret_cast<uint4*>(z_all)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NG * MT * NBR * 32; i += blockDim.x) c_all[i] = 0.0f;
     tc::fence_proxy_async_smem();
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&x_full[i], 1);
-            tc::mbar_init(&z_free[i], (uint32_t)mma_warps);
-            tc::mbar_init(&h_ready[i], G * 4);   // one arrival per epilogue warp
-            tc::mbar_init(&acc_free[i], G * 4);
-        }
-        for (int i = 0; i < 2 * MT; ++i) tc::mbar_init(&acc_full[i], 1);
-        const int nwb = resident ? 1 : p.w_stages;
-        for (int i = 0; i < nwb; ++i) {
-            tc::mbar_init(&w_full[i], 1);
-            tc::mbar_init(&w_empty[i], 1);
+        for (int gi = 0; gi < NG; ++gi) {
+            uint64_t* b = bars_all + gi * NBAR;
+            for (int i = 0; i < 2; ++i) {
+                tc::mbar_init(&b[i], 1);
+                tc::mbar_init(&b[2 + i], MT);        // one commit per MMA-issuing warp
+                tc::mbar_init(&b[4 + i], MT * 4);    // one arrival per epilogue warp
+                tc::mbar_init(&b[6 + i], MT * 4);
+            }
+            for (int i = 0; i < 2 * MT; ++i) tc::mbar_init(&b[8 + i], 1);
         }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_x);
-        tc::prefetch_tmap(&tma_w);
     }
     if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_w = tmem_base + Cfg::ACC_COLS;  // [MT][C] columns: tile m, k-step ks at m*C + ks*8
-    if constexpr (WT) {
-        if (warp > G) {
-            // epilogue warp (group = tile, quarter = warp & 3): each thread owns one weight row of its tile
-            const int ew_ = warp - (1 + G);
-            const int m = ew_ >> 2, q = warp & 3;
-            static_assert(MT == G, "weights-in-TMEM path assumes one tile per epilogue group");
-            const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)(m * 128 + q * 32 + lane) * 2 * C);
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(grp * 2 * MT * UN);
+    const uint32_t tmem_w = tmem_base + Cfg::ACC_COLS;
+    if (grp == 0 && lw > MT) {
+        // weights into tensor memory: epilogue warp (tile m, lane quarter q) of group 0, one weight row per thread
+        const int m = (lw - (1 + MT)) >> 2, q = warp & 3;
+        const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)(m * 128 + q * 32 + lane) * 2 * C);
+#pragma unroll 1
+        for (int cb = 0; cb < C / 32; ++cb) {
+            uint32_t r[32];
 #pragma unroll
-            for (int cb = 0; cb < C / 32; ++cb) {
-                uint32_t r[32];
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const uint4 x = __ldg(src + cb * 8 + v);
-                    r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
-                }
-                tc::tmem_st_32x32(tmem_w + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * C + cb * 32), r);
+            for (int v = 0; v < 8; ++v) {
+                const uint4 x = __ldg(src + cb * 8 + v);
+                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
             }
-            tc::tmem_st_wait();
+            tc::tmem_st_32x32(tmem_w + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * C + cb * 32), r);
         }
-        tc::tc_fence_before();
-        __syncthreads();
-        tc::tc_fence_after();
+        tc::tmem_st_wait();
     }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
 
-    if (warp == 0) {
+    if (lw == 0) {
         // ---------------- TMA producer ----------------
         if (tc::elect_one()) {
-            if (resident && !WT) {
-                tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)(MT * KB * WBLK_BYTES));
-                for (int m = 0; m < MT; ++m) {
-                    for (int kb = 0; kb < KB; ++kb) {
-                        tc::tma_load_2d(w_s + (size_t)(m * KB + kb) * WBLK_BYTES, &tma_w, &w_full[0], kb * KBLK, m * 128);
-                    }
-                }
-            }
-            long long wj = 0;  // streamed weight block counter
             for (int s = 0; s < p.T; ++s) {
                 const int t = p.reverse ? p.T - 1 - s : s;
                 const int buf = s & 1;
@@ -287,115 +270,55 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                 for (int kb = 0; kb < KBX; ++kb) {
                     tc::tma_load_2d(z_s + (size_t)(buf * KB + kb) * ZBLK, &tma_x, &x_full[buf], kb * KBLK, t * p.N + n0);
                 }
-                if (!resident) {
-                    // same order as the MMA issue: x blocks of every tile, then h blocks of every tile
-                    for (int half = 0; half < 2; ++half) {
-                        for (int m = 0; m < MT; ++m) {
-                            for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb, ++wj) {
-                                const int st = (int)(wj % p.w_stages);
-                                tc::mbar_wait(&w_empty[st], (uint32_t)(((wj / p.w_stages) & 1) ^ 1));
-                                tc::mbar_arrive_expect_tx(&w_full[st], WBLK_BYTES);
-                                tc::tma_load_2d(w_s + (size_t)st * WBLK_BYTES, &tma_w, &w_full[st], kb * KBLK, m * 128);
-                            }
-                        }
-                    }
-                }
             }
         }
-    } else if (warp <= G) {
-        // ---------------- MMA issuers ----------------
-        const int mw = warp - 1;
-        if (mw < mma_warps && tc::elect_one()) {
+    } else if (lw <= MT) {
+        // ---------------- MMA issuers: warp m issues the MMAs of gate tile m ----------------
+        const int m = lw - 1;
+        if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_f16(128, UN);
-            const uint64_t wdesc0 = umma_desc_sw64(tc::smem_u32(w_s));
             const uint64_t zdesc0 = umma_desc_sw64(tc::smem_u32(z_s));
-            if (resident) {
-                if constexpr (!WT) tc::mbar_wait(&w_full[0], 0);
-                // this warp owns tiles mw, mw + G, ...; descriptors are base + compile-time offsets
-                for (int s = 0; s < p.T; ++s) {
-                    const int buf = s & 1;
-                    const uint32_t par = (uint32_t)((s >> 1) & 1);
-                    const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
-                    const bool dbg = p.dbg && blockIdx.x == 0 && mw == 0 && s >= 64 && s < 68;
-                    tc::mbar_wait(&x_full[buf], par);
-                    tc::mbar_wait(&acc_free[buf], par ^ 1);
-                    tc::tc_fence_after();
+            for (int s = 0; s < p.T; ++s) {
+                const int buf = s & 1;
+                const uint32_t par = (uint32_t)((s >> 1) & 1);
+                const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
+                const uint32_t d_tmem = tmem_acc + (uint32_t)((buf * MT + m) * UN);
+                const bool dbg = p.dbg && blockIdx.x == 0 && warp == 1 && s >= 64 && s < 68;
+                tc::mbar_wait(&x_full[buf], par);
+                tc::mbar_wait(&acc_free[buf], par ^ 1);
+                tc::tc_fence_after();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (half == 1) {
-                            if (dbg) p.dbg[(s - 64) * 16 + 0] = clock64();
-                            tc::mbar_wait(&h_ready[buf], par);
-                            tc::tc_fence_after();
-                            if (dbg) p.dbg[(s - 64) * 16 + 1] = clock64();
-                        }
-#pragma unroll
-                        for (int i = 0; i < MT / G; ++i) {
-                            const int m = mw + i * G;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * MT + m) * UN);
-                            const uint64_t wd = wdesc0 + (uint64_t)((m * KB * WBLK_BYTES) >> 4);
-#pragma unroll
-                            for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb) {
-                                const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
-                                if constexpr (WT) {
-                                    const uint32_t a_t = tmem_w + (uint32_t)(m * C + kb * 16);  // 16 columns per 32-element block
-                                    tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, kb != 0);
-                                    tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
-                                } else {
-                                    const uint64_t adesc = wd + (uint64_t)((kb * WBLK_BYTES) >> 4);
-                                    tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
-                                    tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
-                                }
-                            }
-                            if (half == 1) tc::umma_commit(&acc_full[buf * MT + m]);
-                        }
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 1) {
+                        if (dbg) p.dbg[(s - 64) * 16 + 0] = clock64();
+                        tc::mbar_wait(&h_ready[buf], par);
+                        tc::tc_fence_after();
+                        if (dbg) p.dbg[(s - 64) * 16 + 1] = clock64();
                     }
-                    tc::umma_commit(&z_free[buf]);
-                    if (dbg) p.dbg[(s - 64) * 16 + 2] = clock64();
-                }
-            } else {
-                long long wj = 0;
-                for (int s = 0; s < p.T; ++s) {
-                    const int buf = s & 1;
-                    const uint32_t par = (uint32_t)((s >> 1) & 1);
-                    const uint64_t zd = zdesc0 + (uint64_t)((buf * KB * ZBLK) >> 4);
-                    tc::mbar_wait(&x_full[buf], par);
-                    tc::mbar_wait(&acc_free[buf], par ^ 1);
-                    tc::tc_fence_after();
-                    for (int half = 0; half < 2; ++half) {
-                        if (half == 1) {
-                            tc::mbar_wait(&h_ready[buf], par);
-                            tc::tc_fence_after();
-                        }
-                        for (int m = 0; m < MT; ++m) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * MT + m) * UN);
-                            for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb, ++wj) {
-                                const int st = (int)(wj % p.w_stages);
-                                tc::mbar_wait(&w_full[st], (uint32_t)((wj / p.w_stages) & 1));
-                                tc::tc_fence_after();
-                                const uint64_t adesc = wdesc0 + (uint64_t)((st * WBLK_BYTES) >> 4);
-                                const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
-                                tc::umma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
-                                tc::umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc, true);
-                                tc::umma_commit(&w_empty[st]);
-                            }
-                            if (half == 1) tc::umma_commit(&acc_full[buf * MT + m]);
-                        }
+#pragma unroll
+                    for (int kb = half * KBX; kb < (half + 1) * KBX; ++kb) {
+                        const uint64_t bdesc = zd + (uint64_t)((kb * ZBLK) >> 4);
+                        const uint32_t a_t = tmem_w + (uint32_t)(m * C + kb * 16);  // 16 columns per 32-element block
+                        tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, kb != 0);
+                        tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
                     }
-                    tc::umma_commit(&z_free[buf]);
                 }
+                tc::umma_commit(&acc_full[buf * MT + m]);
+                tc::umma_commit(&z_free[buf]);
+                if (dbg) p.dbg[(s - 64) * 16 + 2] = clock64();
             }
         }
     } else {
-        // ---------------- epilogue groups: gates, cell update, h_t ----------------
-        const int ewarp = warp - (1 + G);
-        const int g = ewarp >> 2;    // group
-        const int ew = ewarp & 3;    // warp within group -> chunks ew, ew + 4, ...
+        // ---------------- epilogue quartets: gates, cell update, h_t ----------------
+        const int ewarp = lw - (1 + MT);
+        const int m = ewarp >> 2;    // gate tile
+        const int ew = ewarp & 3;    // warp within the quartet -> chunks ew, ew + 4, ...
         const int gate = warp & 3;   // TMEM lane quarter this warp may read == gate type (i,f,g,o)
-        float* gs = g_s + (size_t)g * 4 * NBR * 32;
-        constexpr int CPT = NBR / 4;
-        float bias_r[MT / G];
-#pragma unroll
-        for (int i = 0; i < MT / G; ++i) bias_r[i] = __ldg(p.bias + (g + i * G) * 128 + gate * 32 + lane);
+        const int bar_id = 1 + grp * MT + m;
+        float* gs = g_all + ((size_t)grp * MT + m) * 4 * NBR * 32;
+        constexpr int CPT = (NBR + 3) / 4;
+        const float b = __ldg(p.bias + m * 128 + gate * 32 + lane);
+        const float am = gate == 2 ? 2.0f : 1.0f;  // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
         if (lane == 0) tc::mbar_arrive(&h_ready[0]);  // h_{-1} = 0 is in place (zeroed before the CTA-wide sync)
 
         for (int s = 0; s < p.T; ++s) {
@@ -404,41 +327,39 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
             const uint32_t par = (uint32_t)((s >> 1) & 1);
             uint8_t* zh_next = z_s + (size_t)(nbuf * KB + KBX) * ZBLK;
             __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
-            const bool dbg = p.dbg && blockIdx.x == 0 && ewarp == 0 && lane == 0 && s >= 64 && s < 68;
+            const bool dbg = p.dbg && blockIdx.x == 0 && grp == 0 && ewarp == 0 && lane == 0 && s >= 64 && s < 68;
+            if (dbg) p.dbg[(s - 64) * 16 + 4] = clock64();
+            tc::mbar_wait(&acc_full[buf * MT + m], par);
+            tc::tc_fence_after();
+            if (dbg) p.dbg[(s - 64) * 16 + 5] = clock64();
+            uint32_t r[NBR];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(gate * 32) << 16) + (uint32_t)((buf * MT + m) * UN);
+            if constexpr (NBR == 16) {
+                tc::tmem_ld_32x16(taddr, r);
+            } else if constexpr (NBR == 8) {
+                tc::tmem_ld_32x8(taddr, r);
+            } else if constexpr (NBR == 4) {
+                tc::tmem_ld_32x4(taddr, r);
+            } else {
+                tc::tmem_ld_32x2(taddr, r);
+            }
+            tc::tmem_ld_wait();
+            if (dbg) p.dbg[(s - 64) * 16 + 6] = clock64();
 #pragma unroll
-            for (int i = 0; i < MT / G; ++i) {
-                const int m = g + i * G;
-                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 4] = clock64();
-                tc::mbar_wait(&acc_full[buf * MT + m], par);
-                tc::tc_fence_after();
-                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 5] = clock64();
-                uint32_t r[NBR];
-                const uint32_t taddr = tmem_base + ((uint32_t)(gate * 32) << 16) + (uint32_t)((buf * MT + m) * UN);
-                if constexpr (NBR == 16) {
-                    tc::tmem_ld_32x16(taddr, r);
-                } else if constexpr (NBR == 8) {
-                    tc::tmem_ld_32x8(taddr, r);
-                } else {
-                    tc::tmem_ld_32x4(taddr, r);
-                }
-                tc::tmem_ld_wait();
-                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 6] = clock64();
-                const float b = bias_r[i];
-                const float am = gate == 2 ? 2.0f : 1.0f;  // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
+            for (int n = 0; n < NBR; ++n) gs[(gate * NBR + n) * 32 + lane] = gate_act(__uint_as_float(r[n]) + b, am);
+            float c_old[CPT];
 #pragma unroll
-                for (int n = 0; n < NBR; ++n) {
-                    const float v = __uint_as_float(r[n]) + b;
-                    gs[(gate * NBR + n) * 32 + lane] = gate_act(v, am);
-                }
-                float c_old[CPT];
+            for (int j = 0; j < CPT; ++j) {
+                const int n = ew + 4 * j;
+                c_old[j] = n < NBR ? c_s[((size_t)m * NBR + n) * 32 + lane] : 0.0f;
+            }
+            if (dbg) p.dbg[(s - 64) * 16 + 7] = clock64();
+            named_bar_sync(bar_id, 128);
+            if (dbg) p.dbg[(s - 64) * 16 + 8] = clock64();
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) c_old[j] = c_s[((size_t)m * NBR + ew + 4 * j) * 32 + lane];
-                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 7] = clock64();
-                named_bar_sync(1 + g, 128);
-                if (dbg && i == 0) p.dbg[(s - 64) * 16 + 8] = clock64();
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    const int n = ew + 4 * j;
+            for (int j = 0; j < CPT; ++j) {
+                const int n = ew + 4 * j;
+                if (n < NBR) {
                     const float ig = gs[(0 * NBR + n) * 32 + lane];
                     const float fg = gs[(1 * NBR + n) * 32 + lane];
                     const float gg = gs[(2 * NBR + n) * 32 + lane];
@@ -449,7 +370,6 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                     *reinterpret_cast<__half*>(zh_next + (size_t)m * ZBLK + sw64_offset(n, lane)) = h;
                     y_t[(size_t)n * C + m * 32 + lane] = h;
                 }
-                if (i + 1 < MT / G) named_bar_sync(1 + g, 128);  // gs reuse within the step
             }
             if (dbg) p.dbg[(s - 64) * 16 + 9] = clock64();
             tc::tc_fence_before();
@@ -460,7 +380,7 @@ __global__ void __launch_bounds__(LstmCfg<C>::THREADS, 1) lstm_layer_kernel(cons
                 tc::mbar_arrive(&h_ready[nbuf]);
             }
             if (dbg) p.dbg[(s - 64) * 16 + 10] = clock64();
-            named_bar_sync(1 + g, 128);  // gs reuse across steps
+            named_bar_sync(bar_id, 128);  // gs reuse across steps
         }
     }
     tc::tc_fence_before();
@@ -1068,9 +988,9 @@ public:
     Conv12Params conv12{};
     dim3 conv12_grid;
     GemmPlan conv3;
-    std::vector<CUtensorMap> lstm_x, lstm_w;
+    std::vector<CUtensorMap> lstm_x;
     std::vector<LstmParams> lstm_p;
-    int lstm_grid = 0, lstm_nbr = 16, lstm_groups = 3, lstm_threads = 0;
+    int lstm_grid = 0, lstm_nbr = 16, lstm_ng = 2;
     size_t lstm_smem = 0;
     void launch_lstm(int l, cudaStream_t stream) const;
     // hoisted path
@@ -1358,38 +1278,31 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         }
     } else {
         plan->num_layers = desc.lstm_layers;
-        const int MT = C / 32;
-        const size_t w_bytes = (size_t)4 * C * 2 * C * 2;
-        const bool resident = w_bytes <= 150 * 1024;
-        // chunks per CTA: spread small batches over more SMs when the weights are resident; when they are
-        // streamed from L2 every step, fewer and fatter CTAs keep that traffic down
-        int nbr = 16;
-        if (resident) {
-            if (Np / 16 < 100 && Np % 8 == 0) nbr = 8;
-            if (Np / 8 < 100 && Np % 4 == 0) nbr = 4;
+        if (C != 96) throw Unsupported("the single-CTA LSTM kernel is instantiated for lstm_size 96");
+        // Two independent recurrences (groups) per CTA hide each other's step latency; chunks per group: the smallest that
+        // still fills the machine's 148 SMs with one CTA each (a step costs the same for 2 or 16 chunks).
+        int ng = 2, nbr = 16;
+        if (const char* e = std::getenv("B200_LSTM_GROUPS")) ng = std::atoi(e) == 1 ? 1 : 2;   // A/B comparisons
+        for (int v = 2; v <= 16; v *= 2) {
+            if (Np % (v * ng) == 0 && (Np / (v * ng) <= 148 || v == 16)) {
+                nbr = v;
+                break;
+            }
         }
+        if (Np % (nbr * ng) != 0) ng = 1;   // Np is a multiple of 16
         // tuning override: with several runners in flight, fatter CTAs (fewer SMs per kernel) let the recurrences of
-        // different batches run side by side instead of queueing for the same SMs (tools/exp_inflight.sh)
+        // different batches run side by side instead of queueing for the same SMs
         if (const char* e = std::getenv("B200_LSTM_CHUNKS_PER_CTA")) {
             const int v = std::atoi(e);
-            if ((v == 4 || v == 8 || v == 16) && Np % v == 0) nbr = v;
-            else throw std::invalid_argument("B200_LSTM_CHUNKS_PER_CTA must be 4, 8 or 16 and divide the padded batch");
+            if ((v == 2 || v == 4 || v == 8 || v == 16) && Np % (v * ng) == 0) nbr = v;
+            else throw std::invalid_argument("B200_LSTM_CHUNKS_PER_CTA must be 2, 4, 8 or 16 and divide the padded batch");
         }
-        if (C != 96) throw Unsupported("the single-CTA LSTM kernels are instantiated for lstm_size 96");
-        const int G = (MT % 6 == 0) ? 6 : (MT % 4 == 0) ? 4 : 3;
         plan->lstm_nbr = nbr;
-        plan->lstm_groups = G;
-        plan->lstm_threads = 64 + 128 * G;
-        plan->lstm_grid = Np / nbr;
-        const int KB = 2 * C / KBLK;
-        const int w_stages = resident ? 0 : 12;
-        const bool w_in_tmem = (C / 32) * C + 2 * (C / 32) * UN <= 512;
-        const size_t wsm = w_in_tmem ? 0 : (resident ? w_bytes : (size_t)w_stages * WBLK_BYTES);
-        plan->lstm_smem = 1024 + wsm + (size_t)2 * KB * ZBLK + (size_t)G * 4 * nbr * 32 * 4 + (size_t)MT * nbr * 32 * 4 +
-                          8 * (8 + 2 * MT + 2 * 16) + 64;
+        plan->lstm_ng = ng;
+        plan->lstm_grid = Np / (nbr * ng);
+        plan->lstm_smem = ng == 2 ? LstmCfg<96, 2>::smem_bytes(nbr) : LstmCfg<96, 1>::smem_bytes(nbr);
         for (int l = 0; l < desc.lstm_layers; ++l) {
             plan->lstm_x.push_back(make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, KBLK, nbr));
-            plan->lstm_w.push_back(make_tmap_2d(layers[l].w, (uint64_t)2 * C, (uint64_t)4 * C, (uint64_t)2 * C * 2, KBLK, 128));
             LstmParams lp{};
             lp.seq = seq;
             lp.bias = layers[l].bias;
@@ -1398,7 +1311,6 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             lp.N = Np;
             lp.C = C;
             lp.reverse = (l % 2 == 0) ? 1 : 0;  // reverse_first = true (CRFModel.cpp:40, LSTMStack.cpp:31-41)
-            lp.w_stages = w_stages;
             lp.dbg = nullptr;
             if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
                 B200_CUDA(cudaMalloc(&lp.dbg, 64 * sizeof(long long)));
@@ -1458,10 +1370,10 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     return plan;
 }
 
-template <int C, int NBR>
+template <int C, int NBR, int NG>
 static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    ensure_dynamic_smem(lstm_layer_kernel<C, NBR>, 227 * 1024);
-    lstm_layer_kernel<C, NBR><<<pl.lstm_grid, LstmCfg<C>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_w[l], pl.lstm_p[l]);
+    ensure_dynamic_smem(lstm_layer_kernel<C, NBR, NG>, (int)LstmCfg<C, NG>::smem_bytes(NBR));
+    lstm_layer_kernel<C, NBR, NG><<<pl.lstm_grid, LstmCfg<C, NG>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_p[l]);
 }
 
 template <int C, int CL, int UNC>
@@ -1522,10 +1434,20 @@ void LstmPlan::launch_rec(int l, cudaStream_t stream) const {
 
 template <int C>
 static void launch_lstm_c(const LstmPlan& pl, int l, cudaStream_t stream) {
-    switch (pl.lstm_nbr) {
-        case 4: launch_lstm_t<C, 4>(pl, l, stream); break;
-        case 8: launch_lstm_t<C, 8>(pl, l, stream); break;
-        default: launch_lstm_t<C, 16>(pl, l, stream); break;
+    if (pl.lstm_ng == 2) {
+        switch (pl.lstm_nbr) {
+            case 2: launch_lstm_t<C, 2, 2>(pl, l, stream); break;
+            case 4: launch_lstm_t<C, 4, 2>(pl, l, stream); break;
+            case 8: launch_lstm_t<C, 8, 2>(pl, l, stream); break;
+            default: launch_lstm_t<C, 16, 2>(pl, l, stream); break;
+        }
+    } else {
+        switch (pl.lstm_nbr) {
+            case 2: launch_lstm_t<C, 2, 1>(pl, l, stream); break;
+            case 4: launch_lstm_t<C, 4, 1>(pl, l, stream); break;
+            case 8: launch_lstm_t<C, 8, 1>(pl, l, stream); break;
+            default: launch_lstm_t<C, 16, 1>(pl, l, stream); break;
+        }
     }
 }
 

@@ -147,6 +147,9 @@ __device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors

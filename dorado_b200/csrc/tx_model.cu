@@ -2,7 +2,7 @@
 //
 // Replaces the CUDA path of dorado/basecall/model/TxModel.cpp:20-41 and dorado/nn/TxModules.cpp:
 //   conv stack (torch conv1d on the reference's CUDA path)   ConvStack.cpp:146-163    -> conv1 kernel + gemm.cu
-//   koi_qkv_rotary / koi_masked_attention                    TxModules.cpp:642-648    -> gemm.cu + tx_attention_kernel
+//   koi_qkv_rotary / koi_masked_attention                    TxModules.cpp:642-648    -> gemm.cu + tx_attention_tc_kernel
 //   koi_linear (out_proj, fc2) + koi_rmsnorm_residual        TxModules.cpp:653-712    -> gemm.cu (fused residual) + rmsnorm
 //   koi_mm_swiglu                                            TxModules.cpp:683        -> gemm.cu (SwiGLU epilogue)
 //   LinearUpsample, LinearScaledCRF                          LinearUpsample.cpp:17-23, TxModules.cpp:1010-1016 -> gemm.cu
@@ -108,208 +108,12 @@ __global__ void __launch_bounds__(256) rmsnorm512_kernel(const __half* __restric
     dst[1] = *reinterpret_cast<uint4*>(&o2[4]);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Sliding-window attention with rotary embedding, head_dim 64.
-// One CTA = 64 queries of one (chunk, head); 4 warps x 16 query rows; keys in blocks of 64.
-// qkv: [N*T][3][H][64] fp16 (output of the Wqkv GEMM); out: [N*T][H*64] fp16.
-// ------------------------------------------------------------------------------------------------
-constexpr int ATT_D = 64;
-constexpr int ATT_PITCH = 72;  // halfs per smem row (padding kills the 128-byte-stride bank conflicts)
-
-__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    asm volatile(
-            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-struct AttnParams {
-    const __half* qkv;  // [N*T][3][H][64], q and k already rotated (QKV GEMM epilogue)
-    __half* out;        // [N*T][H*64]
-    int N, T, H;
-    int win_upper, win_lower;  // keys j with -win_upper <= j - i <= win_lower
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t* r, const void* p) {
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* p) {
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
-}
-
-// copy 64 token rows x 64 dims (which = 0 q, 1 k, 2 v) for tokens [t0, t0+64) into smem [64][PITCH]; rows outside
-// [0, T) are zero-filled
-__device__ __forceinline__ void load_tile_async(const AttnParams& p, int n, int h, int which, int t0, __half* dst) {
-    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-        const int r = i >> 3, j = i & 7;
-        const int t = t0 + r;
-        const bool ok = t >= 0 && t < p.T;
-        const __half* src = p.qkv + (((size_t)n * p.T + (ok ? t : 0)) * 3 + which) * p.H * ATT_D + (size_t)h * ATT_D + 8 * j;
-        cp_async16(dst + r * ATT_PITCH + 8 * j, src, ok);
-    }
-}
-
-__global__ void __launch_bounds__(128) tx_attention_kernel(const AttnParams p) {
-    __shared__ __align__(16) __half q_s[64 * ATT_PITCH];
-    __shared__ __align__(16) __half k_s[2][64 * ATT_PITCH];
-    __shared__ __align__(16) __half v_s[2][64 * ATT_PITCH];
-    const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-    const int q0 = qt * 64;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, tig = lane & 3;
-
-    int kstart = q0 - p.win_upper;
-    if (kstart < 0) kstart = 0;
-    kstart &= ~63;
-    int kend = q0 + 63 + p.win_lower + 1;
-    if (kend > p.T) kend = p.T;
-    const int nblk = (kend - kstart + 63) / 64;
-
-    load_tile_async(p, n, h, 0, q0, q_s);
-    load_tile_async(p, n, h, 1, kstart, k_s[0]);
-    load_tile_async(p, n, h, 2, kstart, v_s[0]);
-    cp_async_commit();
-
-    float o[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[i][j] = 0.0f;
-    float row_max[2] = {-INFINITY, -INFINITY}, row_sum[2] = {0.0f, 0.0f};
-    const int qi[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
-    uint32_t qa[4][4];
-    // ldmatrix address patterns (lane -> row/col of the 8x8 tiles)
-    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;  // A operand / V: rows 0-15
-    const int lm_col = (lane >> 4) * 8;                     // second pair of tiles: +8 columns
-
-    for (int ib = 0; ib < nblk; ++ib) {
-        const int kb = kstart + ib * 64;
-        const int cur = ib & 1;
-        if (ib + 1 < nblk) {
-            load_tile_async(p, n, h, 1, kb + 64, k_s[cur ^ 1]);
-            load_tile_async(p, n, h, 2, kb + 64, v_s[cur ^ 1]);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (ib == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qa[ks], q_s + (warp * 16 + lm_row) * ATT_PITCH + ks * 16 + lm_col);
-        }
-        const __half* kt = k_s[cur];
-        const __half* vt = v_s[cur];
-
-        // S = Q K^T : 8 key tiles of 8.  B fragments of two key tiles per ldmatrix.x4:
-        //   matrices: (keys nt*8.., d ks*16..+7), (same keys, d +8), (keys +8, d ..+7), (keys +8, d +8)
-        float s[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t b[4];
-                const int krow = np * 16 + (lane & 7) + (lane >> 4) * 8;
-                const int kcol = ks * 16 + ((lane >> 3) & 1) * 8;
-                ldmatrix_x4(b, kt + krow * ATT_PITCH + kcol);
-                mma_16816(s[2 * np], qa[ks], b[0], b[1]);
-                mma_16816(s[2 * np + 1], qa[ks], b[2], b[3]);
-            }
-        }
-        // scale, mask, online softmax
-        float blk_max[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = e >> 1;
-                const int j = kb + nt * 8 + 2 * tig + (e & 1);
-                const int d = j - qi[r];
-                const bool ok = j < p.T && d >= -p.win_upper && d <= p.win_lower && qi[r] < p.T;
-                s[nt][e] = ok ? s[nt][e] * 0.125f : -INFINITY;
-                blk_max[r] = fmaxf(blk_max[r], s[nt][e]);
-            }
-        }
-        float scale_old[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            blk_max[r] = fmaxf(blk_max[r], __shfl_xor_sync(0xffffffffu, blk_max[r], 1));
-            blk_max[r] = fmaxf(blk_max[r], __shfl_xor_sync(0xffffffffu, blk_max[r], 2));
-            const float nm = fmaxf(row_max[r], blk_max[r]);
-            scale_old[r] = nm == -INFINITY ? 1.0f : __expf(row_max[r] - nm);
-            row_max[r] = nm;
-            row_sum[r] *= scale_old[r];
-        }
-        uint32_t pa[4][4];  // P as A fragments: 4 k-steps of 16 keys
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            float pv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = e >> 1;
-                pv[e] = row_max[r] == -INFINITY ? 0.0f : __expf(s[nt][e] - row_max[r]);
-                row_sum[r] += pv[e];
-            }
-            const __half2 lo = __floats2half2_rn(pv[0], pv[1]), hi = __floats2half2_rn(pv[2], pv[3]);
-            pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&lo);
-            pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
-        }
-        // O = O * scale + P V.  B[k = key][n = d] from row-major V via ldmatrix.trans:
-        //   matrices: (keys ks*16..+7, d dp*16..+7), (keys +8, d ..+7), (keys ..+7, d +8), (keys +8, d +8)
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-            o[dt][0] *= scale_old[0];
-            o[dt][1] *= scale_old[0];
-            o[dt][2] *= scale_old[1];
-            o[dt][3] *= scale_old[1];
-        }
-#pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t b[4];
-                ldmatrix_x4_trans(b, vt + (ks * 16 + lm_row) * ATT_PITCH + dp * 16 + lm_col);
-                mma_16816(o[2 * dp], pa[ks], b[0], b[1]);
-                mma_16816(o[2 * dp + 1], pa[ks], b[2], b[3]);
-            }
-        }
-        __syncthreads();  // all warps done with k_s/v_s[cur] before it is refilled
-    }
-    // finalise: divide by the row sums (quad-reduced) and store
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        row_sum[r] += __shfl_xor_sync(0xffffffffu, row_sum[r], 1);
-        row_sum[r] += __shfl_xor_sync(0xffffffffu, row_sum[r], 2);
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        if (qi[r] < p.T) {
-            const float inv = row_sum[r] > 0.0f ? 1.0f / row_sum[r] : 0.0f;
-            __half* dst = p.out + ((size_t)n * p.T + qi[r]) * p.H * ATT_D + (size_t)h * ATT_D;
-#pragma unroll
-            for (int dt = 0; dt < 8; ++dt) {
-                *reinterpret_cast<__half2*>(dst + dt * 8 + 2 * tig) = __floats2half2_rn(o[dt][2 * r] * inv, o[dt][2 * r + 1] * inv);
-            }
-        }
-    }
-}
+constexpr int ATT_D = 64;   // head dimension
 
 // ------------------------------------------------------------------------------------------------
 // Sliding-window attention on the 5th-generation tensor cores (successor of koi_masked_attention, TxModules.cpp:648;
-// window semantics TxModules.cpp:310-317).  One CTA = 128 queries of one (chunk, head); the keys they can see lie in at
+// window semantics TxModules.cpp:310-317: keys j with -win_upper <= j - i <= win_lower).
+// qkv: [N*T][3][H][64] fp16 (output of the Wqkv GEMM, q and k already rotated); out: [N*T][H*64] fp16.  One CTA = 128 queries of one (chunk, head); the keys they can see lie in at
 // most three aligned blocks of 128 keys, walked flash-style:
 //     S  = Q K_b^T          tcgen05.mma, 128 x 128 x 64, Q and K_b in shared memory (TMA, 128-byte swizzle), S in TMEM
 //     P  = exp2(S' - m)     one thread per query row (TMEM lane): tcgen05.ld S, running max / sum, P packed to fp16 and
@@ -328,6 +132,12 @@ struct AttnTcParams {
     int N, T, H;
     int win_upper, win_lower;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
     // B operand stored [K rows][64 N-elements = 128 B]: MN-major, 128-byte swizzle, 8-row (K) groups 1024 B apart.  The tile
@@ -455,39 +265,67 @@ __global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_co
             if (hi > AT_BK) hi = AT_BK;
             if (kb + hi > p.T) hi = p.T - kb;
             if (qi >= p.T) hi = 0;
+            // The window is a band, so per warp (32 consecutive rows) a 32-key column chunk is either invisible to every row
+            // (skipped: no tensor-memory load, no exponentials, P = 0), visible to every row (no per-element masking) or --
+            // for at most two of the twelve chunks a warp meets -- cut by the band's edge.
+            const int wlo_min = __reduce_min_sync(0xffffffffu, lo), wlo_max = __reduce_max_sync(0xffffffffu, lo);
+            const int whi_min = __reduce_min_sync(0xffffffffu, hi), whi_max = __reduce_max_sync(0xffffffffu, hi);
             tc::mbar_wait(s_full, par);
             tc::tc_fence_after();
             // pass 1: row maximum over the visible keys (S stays in tensor memory)
             float m_blk = -1e30f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
+                const int c0 = 32 * c;
+                if (c0 + 32 <= wlo_min || c0 >= whi_max) continue;
                 uint32_t v[32];
-                tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)(32 * c), v);
+                tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
+                if (c0 >= wlo_max && c0 + 32 <= whi_min) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = 32 * c + j;
-                    if (col >= lo && col < hi) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (c0 + j >= lo && c0 + j < hi) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
+                    }
                 }
             }
             const float m_new = fmaxf(m_run, m_blk * sc);
-            const float alpha = exp2f(m_run - m_new);   // 1 when nothing changed, 0 on the first visible block
+            const float alpha = ex2_approx(m_run - m_new);   // 1 when nothing changed, 0 on the first visible block
             float l_blk = 0.0f;
             // pass 2: P = exp2(S * sc - m), packed to fp16 pairs, written to tensor memory as the A operand of P V
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-                uint32_t v[32], pk[16];
-                tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)(32 * c), v);
-                tc::tmem_ld_wait();
+                const int c0 = 32 * c;
+                uint32_t pk[16];
+                if (c0 + 32 <= wlo_min || c0 >= whi_max) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = 32 * c + 2 * j;
-                    const float p0 = (col >= lo && col < hi) ? exp2f(fmaf(__uint_as_float(v[2 * j]), sc, -m_new)) : 0.0f;
-                    const float p1 = (col + 1 >= lo && col + 1 < hi) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new)) : 0.0f;
-                    const __half2 hp = __floats2half2_rn(p0, p1);
-                    const float2 back = __half22float2(hp);   // the sum runs over what the MMA will see
-                    l_blk += back.x + back.y;
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                } else {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)c0, v);
+                    tc::tmem_ld_wait();
+                    if (c0 >= wlo_max && c0 + 32 <= whi_min) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m_new));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new));
+                            l_blk += p0 + p1;
+                            const __half2 hp = __floats2half2_rn(p0, p1);
+                            pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = c0 + 2 * j;
+                            const float p0 = (col >= lo && col < hi) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m_new)) : 0.0f;
+                            const float p1 = (col + 1 >= lo && col + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new)) : 0.0f;
+                            l_blk += p0 + p1;
+                            const __half2 hp = __floats2half2_rn(p0, p1);
+                            pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                        }
+                    }
                 }
                 tc::tmem_st_32x16(tm_p + lane_sel + (uint32_t)(16 * c), pk);
             }
@@ -550,12 +388,10 @@ public:
     std::vector<GemmPlan> convs;  // conv 2..n
     struct Layer {
         GemmPlan qkv, out_proj, fc1, fc2;
-        AttnParams attn;
         const float *n1, *n2;
     };
     std::vector<Layer> layers;
     GemmPlan upsample, crf;
-    bool attn_tc = true;       // tcgen05 attention (B200_ATTN_LEGACY=1: the mma.sync kernel, for A/B comparisons)
     CUtensorMap qkv_map;       // qkv as [N*T][3*H*64], box 64 x 128 (Q, K and V tiles of the tensor-core attention)
     AttnTcParams attn_tc_p{};
     __half *x = nullptr, *y = nullptr;
@@ -831,7 +667,6 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
             L.fc1 = make_gemm_plan(dense(x, 512, lw.w1, 2 * ff, nullptr, GEMM_ACT_SWIGLU, hid, ff, nullptr, 0.0f));
             L.fc2 = make_gemm_plan(dense(hid, ff, lw.w2, 512, nullptr, GEMM_ACT_NONE, y, 512, x, desc.deepnorm_alpha));
         }
-        L.attn = AttnParams{qkv, att, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
         L.n1 = lw.n1;
         L.n2 = lw.n2;
         plan->layers.push_back(L);
@@ -857,7 +692,6 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
         g.out_s0 = desc.outsize;
         plan->crf = make_gemm_plan(g);
     }
-    if (const char* e = std::getenv("B200_ATTN_LEGACY")) plan->attn_tc = std::atoi(e) == 0;
     plan->qkv_map = make_tmap_2d(qkv, (uint64_t)3 * desc.nhead * ATT_D, (uint64_t)rows, (uint64_t)3 * desc.nhead * ATT_D * 2, ATT_D, 128);
     plan->attn_tc_p = AttnTcParams{att, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
     plan->x = x;
@@ -894,14 +728,9 @@ void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
         }
         {
             NvtxRange r("MEA");
-            if (attn_tc) {
-                constexpr int smem = 1024 + 5 * AT_TILE + 256;
-                ensure_dynamic_smem(tx_attention_tc_kernel, smem);
-                tx_attention_tc_kernel<<<dim3((unsigned)((T + AT_BQ - 1) / AT_BQ), (unsigned)H, (unsigned)N), 192, smem, stream>>>(qkv_map,
-                                                                                                                          attn_tc_p);
-            } else {
-                tx_attention_kernel<<<dim3((unsigned)((T + 63) / 64), (unsigned)H, (unsigned)N), 128, 0, stream>>>(L.attn);
-            }
+            constexpr int smem = 1024 + 5 * AT_TILE + 256;
+            ensure_dynamic_smem(tx_attention_tc_kernel, smem);
+            tx_attention_tc_kernel<<<dim3((unsigned)((T + AT_BQ - 1) / AT_BQ), (unsigned)H, (unsigned)N), 192, smem, stream>>>(qkv_map, attn_tc_p);
             if (prof) prof->mark("tx_attention", stream);
         }
         {
