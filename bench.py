@@ -288,7 +288,7 @@ def bench_b200(kind, batch, chunksize, steps, warmup, R, rank, local_rank, world
     from dorado_b200.weights import synthetic_weights
     cfg = load_model_config(model_dir(kind))
     T = cfg.normalise_chunk_size(chunksize)
-    caller = B200Caller(cfg, synthetic_weights(cfg, 42), device=local_rank)
+    caller = B200Caller(cfg, synthetic_weights(cfg, 42), device=local_rank, num_runners=R)
     runners = [B200ModelRunner(caller, batch, chunksize) for _ in range(R)]
     runner = runners[0]
     rng = np.random.default_rng(1234 + rank)

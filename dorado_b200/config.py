@@ -53,6 +53,7 @@ class BasecallModelConfig:
     num_features: int = 1
     lstm_size: int = -1
     lstm_layers: int = 0
+    lstm_inner_dim: "int | None" = None   # FLSTM models: rank of the factorised gate matrices (is_flstm_model)
     clamp: bool = False
     bias: bool = False
     out_features: Optional[int] = None
@@ -65,6 +66,11 @@ class BasecallModelConfig:
     @property
     def is_tx_model(self) -> bool:
         return self.tx is not None
+
+    @property
+    def is_flstm_model(self) -> bool:
+        """BasecallModelConfig::is_flstm_model (BasecallModelConfig.h:145)."""
+        return self.tx is None and self.lstm_inner_dim is not None
 
     @property
     def num_states(self) -> int:
@@ -144,6 +150,7 @@ def load_model_config(path) -> BasecallModelConfig:
         state_len=toml["global_norm"]["state_len"], outsize=0,
         num_features=toml["input"]["features"], lstm_size=convs[-1].size,
         clamp=any(s["type"] == "clamp" for s in subs), qscale=qscale, qbias=qbias)
+    flstm_layers = 0
     for s in subs:
         if s["type"] == "linear":
             cfg.out_features = s["out_features"]
@@ -154,6 +161,15 @@ def load_model_config(path) -> BasecallModelConfig:
         elif s["type"] == "lstm":
             cfg.lstm_layers += 1
         elif s["type"] == "flstm":
-            raise NotImplementedError("FLSTM models are outside the round-1 hot path")
+            # factorised LSTM (BasecallModelConfig.cpp:257-279): all layers share one inner dimension, no mixing with LSTM
+            inner = int(s["inner_dim"])
+            if cfg.lstm_inner_dim is not None and cfg.lstm_inner_dim != inner:
+                raise ValueError(f"Mismatch in inner dimension of FLSTM, found  {cfg.lstm_inner_dim} and {inner}")
+            cfg.lstm_inner_dim = inner
+            flstm_layers += 1
+    if flstm_layers > 0:
+        if cfg.lstm_layers > 0:
+            raise ValueError(f"Cannot mix LSTM and FLSTM layers, found {cfg.lstm_layers} and {flstm_layers}")
+        cfg.lstm_layers = flstm_layers
     cfg.outsize = 4 ** (cfg.state_len + 1)
     return cfg

@@ -119,6 +119,15 @@ int b200_engine_set_low_latency(b200_engine* e, int32_t on) {
     });
 }
 
+int b200_engine_set_num_runners(b200_engine* e, int32_t num_runners) {
+    return guarded([&] {
+        if (!e || num_runners < 1) throw std::invalid_argument("b200_engine_set_num_runners: null engine or num_runners < 1");
+        reinterpret_cast<b200::Engine*>(e)->set_num_runners(num_runners);
+    });
+}
+
+int32_t b200_engine_num_runners(const b200_engine* e) { return e ? reinterpret_cast<const b200::Engine*>(e)->num_runners() : 0; }
+
 int32_t b200_engine_is_low_latency(const b200_engine* e) { return e && reinterpret_cast<const b200::Engine*>(e)->low_latency(); }
 
 int b200_engine_batch_timeouts_ms(const b200_engine* e, int32_t* first_chunk_ms, int32_t* last_chunk_ms) {

@@ -70,6 +70,10 @@ public:
     virtual size_t workspace_bytes(int N, int T_in) const = 0;
     // CudaCaller::variable_chunk_sizes (api/runner_creation.cpp:24-42): chunks of different lengths in one batch
     virtual bool variable_chunk_sizes() const { return false; }
+    // How many runners (batches in flight) the engine expects to serve concurrently (Engine::set_num_runners).  Plans of
+    // latency-bound kernels use it to size their grids: with R batches in flight a recurrence is better run on ~1/R of the
+    // SMs with more chunks per CTA, side by side with the other batches' kernels, than spread thin over the whole GPU.
+    int num_runners_hint = 2;
     virtual std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores,
                                                    void* workspace, size_t workspace_bytes) = 0;
 };
@@ -104,6 +108,10 @@ public:
     // gives them a task queue of their own (CudaCaller.cpp:204-214) -- their runners get CUDA streams of the highest
     // priority, so their kernels are scheduled ahead of the throughput runners sharing the GPU.  Set before creating runners.
     void set_low_latency(bool on) { m_low_latency.store(on); }
+    // num_runners of api::create_basecall_runners (api/runner_creation.cpp:46-130; dorado's default is 2 per device): the
+    // number of runners this engine is going to serve.  Set before creating runners; it only shapes launch plans.
+    void set_num_runners(int n) { m_model->num_runners_hint = n < 1 ? 1 : (n > 16 ? 16 : n); }
+    int num_runners() const { return m_model->num_runners_hint; }
     bool low_latency() const { return m_low_latency.load(); }
     void batch_timeouts_ms(int* first_chunk_ms, int* last_chunk_ms) const;
     struct CallGuard {  // brackets one call_chunks

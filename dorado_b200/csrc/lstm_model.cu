@@ -1018,7 +1018,8 @@ public:
                                            size_t ws_bytes) override;
     bool variable_chunk_sizes() const override {
         const char* e = std::getenv("B200_CLUSTER_V1");
-        return hoisted() && !(e && std::atoi(e) != 0);
+        // FLSTM models never run variable chunk sizes (api/runner_creation.cpp:28)
+        return hoisted() && desc.lstm_inner_dim == 0 && !(e && std::atoi(e) != 0);
     }
 
     b200_model_desc desc;
@@ -1092,10 +1093,44 @@ LstmModel::LstmModel(const b200_model_desc& d, const b200_tensor* tensors, int n
     // LSTM layers: permute gate rows into tiles of (i|f|g|o) x 32 units, concatenate [W_ih | W_hh]
     for (int l = 0; l < d.lstm_layers; ++l) {
         const std::string pfx = std::to_string(d.num_convs + l + 1) + ".rnn.";
-        const auto& wih = find_tensor(tensors, n, pfx + "weight_ih_l0.tensor");
-        const auto& whh = find_tensor(tensors, n, pfx + "weight_hh_l0.tensor");
-        const auto& bih = find_tensor(tensors, n, pfx + "bias_ih_l0.tensor");
-        const auto& bhh = find_tensor(tensors, n, pfx + "bias_hh_l0.tensor");
+        // plain LSTM: the tensors as they are.  FLSTM (nn/FLSTMStack.cpp:18-25,108-124): gates = up_ih (dn_ih x_t) +
+        // up_hh (dn_hh h_{t-1}) + bias, folded once into W = up x dn (double accumulation, rounded to fp32) so that the
+        // recurrence kernels -- and their weights-in-tensor-memory residency -- serve both model kinds.
+        struct View { const float* data; };
+        std::vector<float> folded_ih, folded_hh;
+        View wih{}, whh{}, bih{}, bhh{};
+        if (d.lstm_inner_dim > 0) {
+            const int K = d.lstm_inner_dim;
+            auto fold = [&](const char* up_name, const char* dn_name, std::vector<float>& out) {
+                const auto& up = find_tensor(tensors, n, pfx + up_name);
+                const auto& dn = find_tensor(tensors, n, pfx + dn_name);
+                if (up.ndim != 2 || dn.ndim != 2 || up.dims[0] != 4 * C || up.dims[1] != K || dn.dims[0] != K || dn.dims[1] != C) {
+                    throw std::invalid_argument("FLSTM tensor " + pfx + up_name + " / " + dn_name + " has the wrong shape");
+                }
+                out.assign((size_t)4 * C * C, 0.0f);
+                std::vector<double> acc((size_t)C);
+                for (int r = 0; r < 4 * C; ++r) {
+                    std::fill(acc.begin(), acc.end(), 0.0);
+                    for (int k = 0; k < K; ++k) {
+                        const double u = up.data[(size_t)r * K + k];
+                        const float* drow = dn.data + (size_t)k * C;
+                        for (int c2 = 0; c2 < C; ++c2) acc[c2] += u * (double)drow[c2];
+                    }
+                    for (int c2 = 0; c2 < C; ++c2) out[(size_t)r * C + c2] = (float)acc[c2];
+                }
+            };
+            fold("up_weight_ih.tensor", "dn_weight_ih.tensor", folded_ih);
+            fold("up_weight_hh.tensor", "dn_weight_hh.tensor", folded_hh);
+            wih.data = folded_ih.data();
+            whh.data = folded_hh.data();
+            bih.data = find_tensor(tensors, n, pfx + "up_bias_ih.tensor").data;
+            bhh.data = find_tensor(tensors, n, pfx + "up_bias_hh.tensor").data;
+        } else {
+            wih.data = find_tensor(tensors, n, pfx + "weight_ih_l0.tensor").data;
+            whh.data = find_tensor(tensors, n, pfx + "weight_hh_l0.tensor").data;
+            bih.data = find_tensor(tensors, n, pfx + "bias_ih_l0.tensor").data;
+            bhh.data = find_tensor(tensors, n, pfx + "bias_hh_l0.tensor").data;
+        }
         std::vector<float> w((size_t)4 * C * 2 * C), b((size_t)4 * C);
         for (int m = 0; m < C / 32; ++m)
             for (int g = 0; g < 4; ++g)

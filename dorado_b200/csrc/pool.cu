@@ -74,7 +74,10 @@ Pool::Pool(const b200_model_desc& desc, const b200_tensor* tensors, int num_tens
            int runners_per_device, int batch_size, int chunk_size)
         : m_batch(batch_size), m_chunk(chunk_size) {
     if (num_devices < 1 || runners_per_device < 1 || !devices) throw std::invalid_argument("pool: need >= 1 device and runner");
-    for (int d = 0; d < num_devices; ++d) m_engines.emplace_back(new Engine(desc, tensors, num_tensors, devices[d]));
+    for (int d = 0; d < num_devices; ++d) {
+        m_engines.emplace_back(new Engine(desc, tensors, num_tensors, devices[d]));
+        m_engines.back()->set_num_runners(runners_per_device);
+    }
     m_t_out = chunk_size / desc.stride;
     for (int d = 0; d < num_devices; ++d) {
         for (int r = 0; r < runners_per_device; ++r) {

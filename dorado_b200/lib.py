@@ -42,6 +42,7 @@ class ModelDesc(C.Structure):
         ("attn_window_upper", C.c_int32), ("attn_window_lower", C.c_int32),
         ("upsample_scale", C.c_int32), ("max_seq_len", C.c_int32),
         ("deepnorm_alpha", C.c_float), ("theta", C.c_float), ("tx_crf_scale", C.c_float),
+        ("lstm_inner_dim", C.c_int32),
     ]
 
 
@@ -87,6 +88,7 @@ EXPORTS = [
     "b200_runner_debug_read_input", "b200_engine_runner_bytes", "b200_engine_benchmark_batch_sizes",
     "b200_select_batch_size", "b200_generate_variable_chunks", "b200_engine_terminate", "b200_engine_restart",
     "b200_engine_set_low_latency", "b200_engine_is_low_latency", "b200_engine_batch_timeouts_ms",
+    "b200_engine_set_num_runners", "b200_engine_num_runners",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_num_runners", "b200_pool_runner", "b200_pool_out_len",
     "b200_pool_runner_info", "b200_pool_call_chunks", "b200_runner_variable_chunk_sizes",
     "b200_runner_accept_chunk_var_f16", "b200_chunk_benchmarks_lookup", "b200_engine_gpu_name",
@@ -130,6 +132,9 @@ def load_library() -> C.CDLL:
     lib.b200_engine_terminate.argtypes = [vp]
     lib.b200_engine_restart.argtypes = [vp]
     lib.b200_engine_set_low_latency.argtypes = [vp, i32]
+    lib.b200_engine_set_num_runners.argtypes = [vp, i32]
+    lib.b200_engine_num_runners.argtypes = [vp]
+    lib.b200_engine_num_runners.restype = i32
     lib.b200_engine_is_low_latency.argtypes = [vp]
     lib.b200_engine_is_low_latency.restype = i32
     lib.b200_engine_batch_timeouts_ms.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
@@ -182,6 +187,7 @@ def model_desc_from_config(cfg: BasecallModelConfig) -> ModelDesc:
     d.state_len, d.outsize, d.stride, d.clamp = cfg.state_len, cfg.outsize, cfg.stride, int(cfg.clamp)
     d.qscale, d.qbias = cfg.qscale, cfg.qbias
     d.lstm_size, d.lstm_layers = cfg.lstm_size, cfg.lstm_layers
+    d.lstm_inner_dim = cfg.lstm_inner_dim or 0
     d.linear_bias, d.out_features, d.crf_scale = int(cfg.bias), cfg.out_features or 0, cfg.scale
     if cfg.tx:
         t = cfg.tx

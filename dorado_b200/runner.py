@@ -35,7 +35,8 @@ class DecodedChunk:
 class B200Caller:
     """One model replica on one GPU (CudaCaller, dorado/basecall/CudaCaller.cpp:149-202)."""
 
-    def __init__(self, cfg: BasecallModelConfig, weights: dict, device: int = 0, low_latency: bool = False):
+    def __init__(self, cfg: BasecallModelConfig, weights: dict, device: int = 0, low_latency: bool = False,
+                 num_runners: int = 2):
         self.cfg = cfg
         self.device = device
         lib = L.load_library()
@@ -54,6 +55,8 @@ class B200Caller:
         L.check(lib.b200_engine_create(C.byref(desc), arr, len(weights), device, C.byref(self.handle)))
         self._keep = None  # the engine copied everything to the device
         L.check(lib.b200_engine_set_low_latency(self.handle, int(low_latency)))
+        # api::create_basecall_runners' num_runners (api/runner_creation.cpp:46-130): shapes launch plans only
+        L.check(lib.b200_engine_set_num_runners(self.handle, int(num_runners)))
 
     def terminate(self) -> None:
         """CudaCaller::terminate (CudaCaller.cpp:273-280): refuse new batches, wait for the ones in flight."""

@@ -50,6 +50,15 @@ def tensor_specs(cfg: BasecallModelConfig) -> "OrderedDict[str, tuple]":
     C = cfg.lstm_size
     for l in range(cfg.lstm_layers):
         layer = len(cfg.convs) + l + 1  # the reference skips one index for the fused permute layer
+        if cfg.is_flstm_model:  # crf_utils.cpp:36-41, shapes of FLSTMLayerImpl (nn/FLSTMStack.cpp:18-25)
+            K = cfg.lstm_inner_dim
+            specs[f"{layer}.rnn.dn_weight_ih.tensor"] = (K, C)
+            specs[f"{layer}.rnn.dn_weight_hh.tensor"] = (K, C)
+            specs[f"{layer}.rnn.up_weight_ih.tensor"] = (4 * C, K)
+            specs[f"{layer}.rnn.up_weight_hh.tensor"] = (4 * C, K)
+            specs[f"{layer}.rnn.up_bias_ih.tensor"] = (4 * C,)
+            specs[f"{layer}.rnn.up_bias_hh.tensor"] = (4 * C,)
+            continue
         specs[f"{layer}.rnn.weight_ih_l0.tensor"] = (4 * C, C)
         specs[f"{layer}.rnn.weight_hh_l0.tensor"] = (4 * C, C)
         specs[f"{layer}.rnn.bias_ih_l0.tensor"] = (4 * C,)
@@ -74,7 +83,7 @@ def synthetic_weights(cfg: BasecallModelConfig, seed: int = 42, crf_gain: float 
     for name, shape in tensor_specs(cfg).items():
         if "norm" in name:
             w = np.ones(shape, np.float32) + 0.05 * rng.standard_normal(shape).astype(np.float32)
-        elif name.endswith("bias_hh_l0.tensor"):
+        elif name.endswith("bias_hh_l0.tensor") or name.endswith("up_bias_hh.tensor"):
             w = np.zeros(shape, np.float32)
         elif len(shape) == 1:
             w = (0.1 * rng.uniform(-1, 1, shape)).astype(np.float32)
@@ -88,6 +97,12 @@ def synthetic_weights(cfg: BasecallModelConfig, seed: int = 42, crf_gain: float 
                 gain = 6.0  # lively gates ...
             if "rnn.weight_hh" in name:
                 gain = 1.5  # ... but a contractive recurrence: a chaotic LSTM would amplify fp16 rounding
+            if "rnn.dn_weight" in name:
+                gain = 2.0
+            if "rnn.up_weight_ih" in name:
+                gain = 3.0  # up @ dn then has about the spread of weight_ih above
+            if "rnn.up_weight_hh" in name:
+                gain = 0.75
             if name.endswith("linear.weight.tensor") and not cfg.is_tx_model and "upsample" not in name:
                 gain = crf_gain if crf_gain is not None else 12.0
             if name == "crf.linear.weight.tensor" and crf_gain is not None:
@@ -124,4 +139,24 @@ def load_b2w(path) -> "OrderedDict[str, np.ndarray]":
             dims = struct.unpack(f"<{nd}I", f.read(4 * nd))
             cnt = int(np.prod(dims)) if nd else 1
             out[name] = np.frombuffer(f.read(4 * cnt), dtype=np.float32).reshape(dims).copy()
+    return out
+
+
+def fold_flstm_weights(cfg: BasecallModelConfig, tensors: Dict[str, np.ndarray]) -> "OrderedDict[str, np.ndarray]":
+    """The LSTM tensors an FLSTM model is equivalent to: gates = up_ih (dn_ih x_t) + up_hh (dn_hh h_{t-1}) + bias
+    (nn/FLSTMStack.cpp:108-124) = (up_ih dn_ih) x_t + (up_hh dn_hh) h_{t-1} + bias.  The engine folds the same way (fp32
+    products, lstm_model.cu), so an FLSTM model and its folded LSTM model produce identical scores."""
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for name, w in tensors.items():
+        if ".rnn.dn_weight_ih." in name:
+            p = name[: name.index("dn_weight_ih")]
+            f32 = lambda k: np.asarray(tensors[p + k + ".tensor"], np.float32)
+            out[p + "weight_ih_l0.tensor"] = (f32("up_weight_ih").astype(np.float64) @ f32("dn_weight_ih").astype(np.float64)).astype(np.float32)
+            out[p + "weight_hh_l0.tensor"] = (f32("up_weight_hh").astype(np.float64) @ f32("dn_weight_hh").astype(np.float64)).astype(np.float32)
+            out[p + "bias_ih_l0.tensor"] = f32("up_bias_ih")
+            out[p + "bias_hh_l0.tensor"] = f32("up_bias_hh")
+        elif ".rnn.dn_weight_hh." in name or ".rnn.up_" in name:
+            continue
+        else:
+            out[name] = w
     return out

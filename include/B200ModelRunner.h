@@ -33,7 +33,8 @@ namespace dorado::basecall {
 class B200Caller {
 public:
     // low_latency: params.pipeline_type == PipelineType::simplex_low_latency (CudaCaller.cpp:149-152)
-    B200Caller(const config::BasecallModelConfig& model_config, int device_index, bool low_latency = false)
+    // num_runners: how many runners create_basecall_runners is going to build on this caller (api/runner_creation.cpp:91-123)
+    B200Caller(const config::BasecallModelConfig& model_config, int device_index, bool low_latency = false, int num_runners = 2)
             : m_config(model_config), m_device(device_index) {
         b200_model_desc d{};
         d.model_type = model_config.is_tx_model() ? B200_MODEL_TX : B200_MODEL_LSTM;
@@ -50,6 +51,7 @@ public:
         d.qbias = model_config.qbias;
         d.lstm_size = model_config.lstm_size;
         d.lstm_layers = model_config.lstm_layers;
+        d.lstm_inner_dim = model_config.lstm_inner_dim.value_or(0);
         d.linear_bias = model_config.bias ? 1 : 0;
         d.out_features = model_config.is_tx_model() ? 0 : model_config.out_features.value_or(0);
         d.crf_scale = model_config.scale;
@@ -87,6 +89,7 @@ public:
         }
         check(b200_engine_create(&d, bt.data(), static_cast<int32_t>(bt.size()), device_index, &m_engine));
         check(b200_engine_set_low_latency(m_engine, low_latency ? 1 : 0));
+        check(b200_engine_set_num_runners(m_engine, num_runners));
     }
     ~B200Caller() { b200_engine_destroy(m_engine); }
     B200Caller(const B200Caller&) = delete;
@@ -129,6 +132,13 @@ public:
         }
         for (int l = 0; l < cfg.lstm_layers; ++l) {
             const std::string p = std::to_string(cfg.convs.size() + l + 1) + ".rnn.";
+            if (cfg.is_flstm_model()) {  // crf_utils.cpp:36-41
+                for (const char* s : {"dn_weight_ih.tensor", "dn_weight_hh.tensor", "up_weight_ih.tensor", "up_weight_hh.tensor",
+                                      "up_bias_ih.tensor", "up_bias_hh.tensor"}) {
+                    n.push_back(p + s);
+                }
+                continue;
+            }
             for (const char* s : {"weight_ih_l0.tensor", "weight_hh_l0.tensor", "bias_ih_l0.tensor", "bias_hh_l0.tensor"}) {
                 n.push_back(p + s);
             }

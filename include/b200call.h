@@ -64,6 +64,10 @@ typedef struct b200_model_desc {
     int32_t attn_window_upper, attn_window_lower;
     int32_t upsample_scale, max_seq_len;
     float deepnorm_alpha, theta, tx_crf_scale;
+    /* FLSTM models (config.lstm_inner_dim, BasecallModelConfig.h:145; dorado/nn/FLSTMStack.cpp): > 0 = every LSTM layer comes
+     * as dn_weight_ih/hh [K, C], up_weight_ih/hh [4C, K], up_bias_ih/hh [4C]; the engine folds up x dn into the [4C, C] gate
+     * matrices once at load time and runs the LSTM kernels unchanged. */
+    int32_t lstm_inner_dim;
 } b200_model_desc;
 
 /* Host fp32 tensors, named and ordered as the reference's *.tensor files
@@ -139,6 +143,12 @@ B200_API int b200_engine_restart(b200_engine* engine);
 B200_API int b200_engine_set_low_latency(b200_engine* engine, int32_t on);
 B200_API int32_t b200_engine_is_low_latency(const b200_engine* engine);
 B200_API int b200_engine_batch_timeouts_ms(const b200_engine* engine, int32_t* first_chunk_ms, int32_t* last_chunk_ms);
+/* num_runners of api::create_basecall_runners (api/runner_creation.cpp:46-130, default 2 per device): how many runners
+ * (batches in flight) the caller is going to create on this engine.  Runners created afterwards size the grids of their
+ * latency-bound kernels for that much concurrency (more chunks per CTA on fewer SMs, side by side with the other batches'
+ * kernels).  Results do not depend on it.  Default 2. */
+B200_API int b200_engine_set_num_runners(b200_engine* engine, int32_t num_runners);
+B200_API int32_t b200_engine_num_runners(const b200_engine* engine);
 
 /* CudaModelRunner::CudaModelRunner (CudaModelRunner.cpp:13-19) + CudaCaller::create_input/output_tensor
  * (CudaCaller.cpp:289-314): pinned fp16 input [batch, 1, chunk_size], pinned output, device arena. */

@@ -207,8 +207,18 @@ def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_qui
     nconv = len(cfg.convs)
     for l in range(cfg.lstm_layers):
         p = f"{nconv + l + 1}.rnn."
-        x = lstm_layer(x, w[p + "weight_ih_l0.tensor"], w[p + "weight_hh_l0.tensor"], w[p + "bias_ih_l0.tensor"],
-                       w[p + "bias_hh_l0.tensor"], reverse=(l % 2 == 0), quant=q)
+        if getattr(cfg, "lstm_inner_dim", None):
+            # FLSTM (nn/FLSTMStack.cpp:108-124; the reference has no CPU forward for it): gates = up_ih (dn_ih x_t) +
+            # up_hh (dn_hh h_{t-1}) + bias = an LSTM whose gate matrices are the products up @ dn
+            f64 = lambda k: np.asarray(w_in[p + k + ".tensor"], np.float64)
+            w_ih = (f64("up_weight_ih") @ f64("dn_weight_ih")).astype(np.float32)
+            w_hh = (f64("up_weight_hh") @ f64("dn_weight_hh")).astype(np.float32)
+            if emulate_fp16:
+                w_ih, w_hh = _q16(w_ih), _q16(w_hh)
+            x = lstm_layer(x, w_ih, w_hh, w[p + "up_bias_ih.tensor"], w[p + "up_bias_hh.tensor"], reverse=(l % 2 == 0), quant=q)
+        else:
+            x = lstm_layer(x, w[p + "weight_ih_l0.tensor"], w[p + "weight_hh_l0.tensor"], w[p + "bias_ih_l0.tensor"],
+                           w[p + "bias_hh_l0.tensor"], reverse=(l % 2 == 0), quant=q)
         inter[f"lstm{l}"] = x
     layer = nconv + cfg.lstm_layers + 1
     scores = x @ w[f"{layer}.linear.weight.tensor"].T

@@ -13,6 +13,7 @@ MODELS = {
     "fast": "dna_r10.4.1_e8.2_400bps_fast@v5.0.0",
     "hac": "dna_r10.4.1_e8.2_400bps_hac@v5.0.0",
     "sup": "dna_r10.4.1_e8.2_400bps_sup@v5.0.0",
+    "flstm": "synthetic_fast_flstm@v0",   # fast topology with factorised LSTM layers (nn/FLSTMStack.cpp)
 }
 
 

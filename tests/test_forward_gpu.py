@@ -60,6 +60,39 @@ def test_lstm_model_scores(kind, N, T):
     _check_scores(got, ref16, ref32, cfg.clamp)
 
 
+def test_flstm_model_reuses_the_lstm_kernels():
+    """FLSTM (nn/FLSTMStack.cpp:108-124): the factorised gate matrices are folded at load time, so an
+    FLSTM model and the LSTM model with the products up @ dn as its weights give bit-identical scores and calls; the
+    scores also sit on the numpy oracle's (the reference has no CPU forward for FLSTM to pin against)."""
+    from oracle import nn_oracle
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import fold_flstm_weights, synthetic_weights
+    N, T = 32, 3000
+    cfg_f = load_model_config(model_dir("flstm"))
+    cfg_l = load_model_config(model_dir("fast"))
+    assert cfg_f.is_flstm_model and cfg_f.lstm_inner_dim == 32 and cfg_f.lstm_layers == cfg_l.lstm_layers
+    w_f = synthetic_weights(cfg_f, 11)
+    w_l = fold_flstm_weights(cfg_f, w_f)
+    assert list(w_l) == list(synthetic_weights(cfg_l, 11))          # same tensor names as a plain LSTM model
+    sig = np.random.default_rng(5).standard_normal((N, cfg_f.normalise_chunk_size(T))).astype(np.float16)
+    out = []
+    for cfg, w in ((cfg_f, w_f), (cfg_l, w_l)):
+        caller = B200Caller(cfg, w)
+        runner = B200ModelRunner(caller, N, T)
+        assert not runner.variable_chunk_sizes()                    # api/runner_creation.cpp:28
+        for i in range(N):
+            runner.accept_chunk(i, sig[i])
+        out.append((runner.forward_scores(N).copy(), [np.array(a) for a in runner.call_chunks_raw(N)]))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        np.testing.assert_array_equal(a, b)
+    assert int(out[0][1][3].sum()) > N * 20                        # real calls, not empty strings
+    ref32 = nn_oracle.forward(cfg_f, w_f, sig.astype(np.float32))
+    ref16 = nn_oracle.forward(cfg_f, w_f, sig.astype(np.float32), emulate_fp16=True)
+    _check_scores(out[0][0], ref16, ref32, cfg_f.clamp)
+
+
 @pytest.mark.parametrize("N,T", [(2, 1920), (3, 3264)])
 def test_tx_model_scores(N, T):
     """sup topology: conv x5 -> 18 transformer layers -> upsample -> scaled CRF linear.  The oracle uses the true

@@ -237,3 +237,29 @@ def test_chunk_size_buckets_and_benchmark_table_lookup():
             assert all(a[0] < b[0] and a[1] > b[1] for a, b in zip(t, t[1:]))
             gran = batching.batch_size_granularity(load_model_config(model_dir(kind)))
             assert all(b % gran == 0 for b, _ in t)
+
+
+def test_flstm_config_and_weight_folding():
+    """FLSTM models (BasecallModelConfig.cpp:257-279, nn/FLSTMStack.cpp): config parsing, tensor list (crf_utils.cpp:36-41) and
+    the fold up @ dn that lets the LSTM kernels serve them: the oracle's FLSTM forward equals its LSTM forward on the folded
+    tensors."""
+    from conftest import model_dir
+    from dorado_b200.config import load_model_config
+    from dorado_b200.weights import fold_flstm_weights, synthetic_weights, tensor_specs
+    from oracle import nn_oracle
+    cfg = load_model_config(model_dir("flstm"))
+    plain = load_model_config(model_dir("fast"))
+    assert cfg.is_flstm_model and not plain.is_flstm_model
+    assert cfg.lstm_inner_dim == 32 and cfg.lstm_layers == 5 and cfg.lstm_size == 96
+    names = list(tensor_specs(cfg))
+    assert names[6:12] == [f"4.rnn.{k}.tensor" for k in ("dn_weight_ih", "dn_weight_hh", "up_weight_ih", "up_weight_hh",
+                                                         "up_bias_ih", "up_bias_hh")]
+    w = synthetic_weights(cfg, 3)
+    folded = fold_flstm_weights(cfg, w)
+    assert list(folded) == list(tensor_specs(plain))
+    assert folded["4.rnn.weight_ih_l0.tensor"].shape == (384, 96)
+    sig = np.random.default_rng(0).standard_normal((2, cfg.normalise_chunk_size(1200))).astype(np.float32)
+    a = nn_oracle.forward(cfg, w, sig)
+    b = nn_oracle.forward(plain, folded, sig)
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
+    assert np.abs(a).max() > 1.0
