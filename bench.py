@@ -49,6 +49,8 @@ MODELS = {
 # algorithmic FLOP per input sample
 FLOP_PER_SAMPLE = {"fast": 0.1435e6, "hac": 2.139e6, "sup": 14.35e6}
 SUB_MODELS = {"hac": dict(batch=512, steps=8), "sup": dict(batch=128, steps=6)}
+NUM_SMS = 148
+DEFAULT_RUNNERS = {"fast": 4, "hac": 2, "sup": 2}   # batches in flight per GPU (dorado's --num-runners; see --runners)
 METRIC = "basecalled samples/s"
 
 
@@ -392,6 +394,22 @@ def bench_b200(kind, batch, chunksize, steps, warmup, R, rank, local_rank, world
                 "frac": round(ach / pkv, 4)}
 
     roof["per_kernel"] = {k: entry(k) for k in agg if k in work}
+    # Kernels that are deliberately launched on a share of the SMs (several runners' latency-bound kernels side by side,
+    # b200_engine_set_num_runners): `frac` above stays launch work / launch time / whole-GPU peak; `frac_of_sms_used` scales
+    # the peak to the SMs the launch occupies (one CTA per SM), which is the efficiency of the SM-time it consumes.
+    plan = runner.plan_info()
+    for k, e in roof["per_kernel"].items():
+        ctas = plan.get(k + ".ctas")
+        if ctas and ctas < NUM_SMS:
+            e["ctas"] = ctas
+            e["frac_of_sms_used"] = round(e["frac"] * NUM_SMS / ctas, 4)
+    if dom in roof["per_kernel"] and "ctas" in roof["per_kernel"][dom]:
+        roof["ctas"] = roof["per_kernel"][dom]["ctas"]
+        roof["frac_of_sms_used"] = roof["frac"] * NUM_SMS / roof["ctas"]
+        roof["note"] = (f"{dom} runs on {roof['ctas']} of {NUM_SMS} SMs by design ({R} batches in flight share the GPU); frac = "
+                        f"launch work / launch time / whole-GPU peak, frac_of_sms_used = the same against the peak of the SMs used")
+    if plan:
+        roof["plan"] = plan
     dec_kernels = [k for k in ("crf_bwd_scan", "crf_fwd_beam", "crf_traceback") if k in agg]
     dec_total_ms = sum(agg[k][0] * agg[k][1] for k in dec_kernels)
     dec_alg = (2.0 * C + 3.0) * T_out * N
@@ -435,8 +453,10 @@ def main():
     ap.add_argument("--model", default="fast", choices=list(MODELS))
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--chunksize", type=int, default=10000)
-    ap.add_argument("--runners", type=int, default=2,
-                    help="runners (batches in flight) per GPU; dorado's default is 2 per device (api/runner_creation.cpp)")
+    ap.add_argument("--runners", type=int, default=None,
+                    help="runners (batches in flight) per GPU = dorado's --num-runners (default there 2 per device, "
+                         "api/runner_creation.cpp:91-123).  Default here: 4 for fast (its recurrence and beam search are latency "
+                         "chains; four batches side by side fill the SMs, profiles/r02_b11_*), 2 for hac and sup")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference leg (batch sweeps)")
     ap.add_argument("--no-sub-models", action="store_true", help="skip the hac@512 / sup@128 sub-results of the default run")
     args = ap.parse_args()
@@ -452,7 +472,7 @@ def main():
     config = {"workload": f"{MODELS[kind]} topology (synthetic weights), batch {args.batch} per GPU, chunksize "
                           f"{args.chunksize} -> {T} samples/chunk, synthetic N(0,1) fp16 signal",
               "model": kind, "batch_per_gpu": args.batch, "chunk_samples": T, "parallelism": f"replica x{args.gpus}",
-              "runners_per_gpu": args.runners,
+              "runners_per_gpu": args.runners if args.runners is not None else DEFAULT_RUNNERS[kind],
               "l2": "per-step working set (conv activations + scores > 400 MB) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
@@ -472,14 +492,15 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)  # let nvidia-smi reach its sampling loop
-    R = max(1, args.runners)
+    R = max(1, args.runners if args.runners is not None else DEFAULT_RUNNERS[kind])
+    config["runners_per_gpu"] = R
     main_res = bench_b200(kind, args.batch, args.chunksize, args.steps, args.warmup, R, rank, local_rank, world, sampler=sampler,
                           want_cpu=(world == 1 and not args.no_cpu_baseline))
     subs = {}
     default_run = kind == "fast" and args.batch == 512 and not args.no_sub_models
     if default_run:
         for sk, sc in SUB_MODELS.items():
-            res = bench_b200(sk, sc["batch"], args.chunksize, sc["steps"], 3, R, rank, local_rank, world)
+            res = bench_b200(sk, sc["batch"], args.chunksize, sc["steps"], 3, DEFAULT_RUNNERS[sk], rank, local_rank, world)
             if rank == 0:
                 keep = ("value", "ms_per_step", "steps", "e2e", "forward_ms_per_step", "decode_ms_per_step", "batch_per_gpu",
                         "chunk_samples", "runners_per_gpu", "gpu_launches", "bases_called_last_step")

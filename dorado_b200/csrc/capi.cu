@@ -339,6 +339,15 @@ int b200_runner_profile(b200_runner* r, int32_t num_chunks, char* buf, uint64_t 
     });
 }
 
+int b200_runner_plan_info(const b200_runner* r, char* buf, uint64_t buf_len) {
+    return guarded([&] {
+        if (!r || !buf || buf_len == 0) throw std::invalid_argument("b200_runner_plan_info: null argument");
+        const std::string s = reinterpret_cast<const b200::Runner*>(r)->plan_info();
+        std::strncpy(buf, s.c_str(), buf_len - 1);
+        buf[buf_len - 1] = 0;
+    });
+}
+
 int b200_runner_debug_read_workspace(b200_runner* r, uint64_t offset, uint64_t bytes, void* dst) {
     return guarded([&] {
         if (!r || !dst) throw std::invalid_argument("debug_read_workspace: null argument");

@@ -62,6 +62,9 @@ public:
     // Variable chunk sizes: device array of per-chunk lengths in samples (multiples of the stride, <= T_in), read by the
     // kernels at run time.  Plans of models without that mode ignore it.
     virtual void set_chunk_lengths(const int32_t* /*d_lens*/) {}
+    // "key=value;..." facts about the launch plan that measurements need (grid sizes of kernels that deliberately occupy
+    // only part of the GPU); empty when every kernel spans the machine
+    virtual std::string info() const { return std::string(); }
 };
 
 class Model {
@@ -172,6 +175,7 @@ public:
     void debug_read_workspace(uint64_t offset, uint64_t bytes, void* dst);
     // one forward+decode pass with an event after every launch; returns "name=ms;name=ms;..."
     std::string profile(int num_chunks);
+    std::string plan_info() const { return m_plan ? m_plan->info() : std::string(); }
 
 private:
     void init();     // everything the constructor allocates; may throw

@@ -979,6 +979,11 @@ class LstmPlan final : public ForwardPlan {
 public:
     void run(cudaStream_t stream, ProfileSink* prof) override;
     int launches() const override { return 1 + 1 + num_layers * (hoisted ? 2 : 1) + num_linear; }
+    std::string info() const override {
+        if (hoisted) return "lstm_rec.ctas=" + std::to_string(lstm_grid);
+        return "lstm_layer.ctas=" + std::to_string(lstm_grid) + ";lstm_layer.groups=" + std::to_string(lstm_ng) +
+               ";lstm_layer.chunks_per_group=" + std::to_string(lstm_nbr);
+    }
     void set_chunk_lengths(const int32_t* d_lens) override {
         if (!hoisted || rec_v1) return;  // the mode exists for the cluster recurrence (second generation) only
         conv12.lens = d_lens;
@@ -1314,12 +1319,20 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     } else {
         plan->num_layers = desc.lstm_layers;
         if (C != 96) throw Unsupported("the single-CTA LSTM kernel is instantiated for lstm_size 96");
-        // Two independent recurrences (groups) per CTA hide each other's step latency; chunks per group: the smallest that
-        // still fills the machine's 148 SMs with one CTA each (a step costs the same for 2 or 16 chunks).
-        int ng = 2, nbr = 16;
+        // Grid shape.  A step costs a dependent chain of ~1000-2200 cycles whether a group holds 2 or 8 chunks, so SM-time per
+        // chunk falls with chunks per CTA while the latency of one launch rises.  With R runners (batches) in flight the
+        // recurrence is therefore sized for ~1/R of the SMs, two groups per CTA, and runs side by side with the other
+        // batches' recurrences and decodes (measured at batch 512, profiles/r02_b10_*, r02_b11_*: 4 runners x 32 CTAs x
+        // 2 x 8 chunks 5.76 ms/step; 2 runners x 64 CTAs x 2 x 4 chunks 7.27; 2 runners x 128 CTAs x 1 x 4 chunks 8.0-8.9).  A lone
+        // runner has nothing to overlap with: one group of 4 chunks on every SM is fastest (0.98 vs 1.17 ms per layer).
+        const int hint = num_runners_hint < 1 ? 1 : num_runners_hint;
+        int ng = hint == 1 ? 1 : 2, nbr = 16;
         if (const char* e = std::getenv("B200_LSTM_GROUPS")) ng = std::atoi(e) == 1 ? 1 : 2;   // A/B comparisons
-        for (int v = 2; v <= 16; v *= 2) {
-            if (Np % (v * ng) == 0 && (Np / (v * ng) <= 148 || v == 16)) {
+        if (Np % (2 * ng) != 0) ng = 1;
+        const int target = 148 / hint > 0 ? 148 / hint : 1;
+        const int min_nbr = ng == 1 ? 4 : 2;
+        for (int v = min_nbr; v <= 16; v *= 2) {
+            if (Np % (v * ng) == 0 && (Np / (v * ng) <= target || v == 16)) {
                 nbr = v;
                 break;
             }

@@ -83,7 +83,7 @@ EXPORTS = [
     "b200_engine_destroy", "b200_engine_get_stats", "b200_runner_create", "b200_runner_destroy",
     "b200_runner_set_decoder_options", "b200_runner_batch_size", "b200_runner_chunk_size", "b200_runner_out_len",
     "b200_runner_accept_chunk_f16", "b200_runner_accept_chunk_f32", "b200_runner_input", "b200_runner_call_chunks",
-    "b200_runner_upload", "b200_runner_step_device", "b200_runners_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_debug_read_workspace", "b200_decode_scores",
+    "b200_runner_upload", "b200_runner_step_device", "b200_runners_step_device", "b200_runner_forward_scores", "b200_runner_profile", "b200_runner_plan_info", "b200_runner_debug_read_workspace", "b200_decode_scores",
     "b200_test_gemm", "b200_generate_chunks", "b200_stitch_chunks", "b200_runner_accept_raw_chunk",
     "b200_runner_debug_read_input", "b200_engine_runner_bytes", "b200_engine_benchmark_batch_sizes",
     "b200_select_batch_size", "b200_generate_variable_chunks", "b200_engine_terminate", "b200_engine_restart",
@@ -158,6 +158,7 @@ def load_library() -> C.CDLL:
     lib.b200_runner_forward_scores.argtypes = [vp, i32, vp]
     lib.b200_decode_scores.argtypes = [i32, vp, i32, i32, i32, f32, C.POINTER(DecoderOptions), vp, vp, vp, vp]
     lib.b200_runner_profile.argtypes = [vp, i32, C.c_char_p, C.c_uint64]
+    lib.b200_runner_plan_info.argtypes = [vp, C.c_char_p, C.c_uint64]
     lib.b200_runner_debug_read_workspace.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     lib.b200_test_gemm.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, vp]
     u64 = C.c_uint64

@@ -296,6 +296,12 @@ class B200ModelRunner:
                 out.append((k, float(v)))
         return out
 
+    def plan_info(self) -> dict:
+        """Launch-plan facts (grid sizes of kernels sized for a share of the SMs): {"lstm_layer.ctas": 32, ...}."""
+        buf = C.create_string_buffer(1024)
+        L.check(self._lib.b200_runner_plan_info(self.handle, buf, len(buf)))
+        return {k: int(v) for k, v in (item.split("=") for item in buf.value.decode().split(";") if item)}
+
     def debug_read_workspace(self, offset: int, nbytes: int) -> np.ndarray:
         out = np.empty(nbytes, np.uint8)
         L.check(self._lib.b200_runner_debug_read_workspace(self.handle, offset, nbytes, out.ctypes.data))

@@ -360,6 +360,11 @@ B200_API int b200_decode_scores(int32_t device,
  * device milliseconds) into buf. */
 B200_API int b200_runner_profile(b200_runner* runner, int32_t num_chunks, char* buf, uint64_t buf_len);
 
+/* Facts about the runner's launch plan as "key=value;...": the grid (CTAs) of kernels that are deliberately sized for a share
+ * of the SMs so that several runners' kernels run side by side (b200_engine_set_num_runners), e.g.
+ * "lstm_layer.ctas=32;lstm_layer.groups=2;lstm_layer.chunks_per_group=8".  Empty when every kernel spans the GPU. */
+B200_API int b200_runner_plan_info(const b200_runner* runner, char* buf, uint64_t buf_len);
+
 /* Debug: copy `bytes` of the runner's forward workspace (device) starting at `offset` to `dst` (host). */
 B200_API int b200_runner_debug_read_workspace(b200_runner* runner, uint64_t offset, uint64_t bytes, void* dst);
 
