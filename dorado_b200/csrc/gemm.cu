@@ -53,12 +53,13 @@ struct GemmKernelParams {
     long long out_col_m1, out_col_s0;
     int bias_per_row;
     const float* rope;
-    int rope_T, rope_cols;
+    int rope_T, rope_cols, rope_stride;
     const __half* residual;
     float alpha;
     uint32_t tmem_cols;
     // staged epilogue: the fp16 tile goes through swizzled shared memory and leaves as TMA stores (tma_o)
     int staged;      // 0 = per-thread global stores
+    int res_tma;     // staged only: the residual tile is TMA-loaded into the staging tile before the epilogue reads it
     int stages;      // TMA->MMA ring depth (3 when the staging tile needs the room)
     int sw;          // columns of a staging sub-tile: 64 (128-byte swizzle) or 32 (64-byte swizzle)
     // RMSNorm folded into the epilogue (GemmDesc)
@@ -89,6 +90,7 @@ template <int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                            const __grid_constant__ CUtensorMap tma_w,
                                                                            const __grid_constant__ CUtensorMap tma_o,
+                                                                           const __grid_constant__ CUtensorMap tma_r,
                                                                            const GemmKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages x (A 16 KB | W bn*128 B), then barriers
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     uint64_t* empty = full + kMaxStages;
     uint64_t* tmem_full = empty + kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_full = tmem_empty + 2;    // [GEMM_PARTS] residual tile landed in the part's staging columns
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + GEMM_PARTS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -120,10 +123,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             tc::mbar_init(&tmem_full[i], 1);
             tc::mbar_init(&tmem_empty[i], 32 * GEMM_EPI_WARPS);
         }
+        for (int i = 0; i < GEMM_PARTS; ++i) tc::mbar_init(&res_full[i], 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_a);
         tc::prefetch_tmap(&tma_w);
         if (p.staged) tc::prefetch_tmap(&tma_o);
+        if (p.res_tma) tc::prefetch_tmap(&tma_r);
     }
     if (warp == 1) tc::tmem_alloc(tmem_holder, p.tmem_cols);
     tc::tc_fence_before();
@@ -234,11 +239,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             float ss_out = 0.0f;  // sum of squares of what this thread stores for this tile
             if (staged && c_begin < c_end) {
                 // the stores of this set's previous tile have read its staging columns: they may be rewritten
-                if (storer) tc::bulk_wait_group_read<0>();
+                if (storer) {
+                    tc::bulk_wait_group_read<0>();
+                    if (p.res_tma) {
+                        // The residual tile of this set's columns comes in by TMA, into the very staging bytes the output will
+                        // overwrite (same swizzle, so thread (row) x 16-byte piece reads and writes its own address): issued
+                        // here, it lands while the main loop of this tile still runs, and the epilogue never does the
+                        // row-per-thread global loads (32 cache lines per warp request) it would otherwise need.
+                        const int oc0 = c_begin * 32, oc1 = c_end * 32;
+                        const int nsub = (oc1 - oc0) / p.sw;
+                        tc::mbar_arrive_expect_tx(&res_full[part], (uint32_t)nsub * sub_bytes);
+                        for (int k = 0; k < nsub; ++k) {
+                            tc::tma_load_3d(my_stage + (size_t)k * sub_bytes, &tma_r, &res_full[part], n0 + oc0 + k * p.sw, r0, batch);
+                        }
+                    }
+                }
                 named_bar_sync(bar_free, 128);
             }
             tc::mbar_wait(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
             tc::tc_fence_after();
+            if (p.res_tma && c_begin < c_end) tc::mbar_wait(&res_full[part], (uint32_t)(ti & 1));
             if (c_begin == c_end) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(&tmem_empty[ab]);
@@ -246,7 +266,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             if constexpr (ACT == GEMM_ACT_ROPE) {
                 // head_dim 64 = two 32-column chunks (x1 | x2): out1 = cos*x1 - sin*x2, out2 = sin*x1 + cos*x2
                 const int tpos = (int)(g % p.rope_T);
-                const float4* tab = reinterpret_cast<const float4*>(p.rope) + (size_t)tpos * 16;  // (cos,sin) x 2 dims
+                const float4* tab = reinterpret_cast<const float4*>(p.rope) + tpos;  // [j][position]: (cos,sin) x 2 dims
                 for (int c = c_begin; c < c_end; c += 2) {
                     uint32_t r0[32], r1[32];
                     tc::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ab * p.bn + c * 32), r0);
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                             float a0 = __uint_as_float(r0[2 * j]) * r_a, a1 = __uint_as_float(r0[2 * j + 1]) * r_a;
                             float b0 = __uint_as_float(r1[2 * j]) * r_a, b1 = __uint_as_float(r1[2 * j + 1]) * r_a;
                             if (rot) {
-                                const float4 cs = __ldg(tab + j);
+                                const float4 cs = __ldg(tab + (size_t)j * p.rope_stride);
                                 const float x0 = cs.x * a0 - cs.y * b0, y0 = cs.y * a0 + cs.x * b0;
                                 const float x1 = cs.z * a1 - cs.w * b1, y1 = cs.w * a1 + cs.z * b1;
                                 a0 = x0; b0 = y0; a1 = x1; b1 = y1;
@@ -305,9 +325,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                     float v[32];
                     const float row_bias = (p.bias && p.bias_per_row && valid) ? __ldg(p.bias + g) : 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r[j]) * r_a;
-                        if (p.bias) v[j] += p.bias_per_row ? row_bias : __ldg(p.bias + nc + j);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * r_a;
+                    if (p.bias) {
+                        if (p.bias_per_row) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += row_bias;
+                        } else {
+                            // the column vector is the same for every lane: 8 broadcast 16-byte loads, not 32 scalar ones
+                            const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = __ldg(bp + q);
+                                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+                            }
+                        }
                     }
                     if constexpr (ACT == GEMM_ACT_SWIGLU) {
                         if (valid || staged) {
@@ -328,22 +359,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                             }
                         }
                     } else {
-                        if (p.residual && valid) {
+                        if (p.residual && (valid || p.res_tma)) {
                             const uint4* res = reinterpret_cast<const uint4*>(p.residual + g * (long long)n_out_total + nc);
+                            const float ar = p.alpha * r_res;
+                            const int hc_res = (c - c_begin) * 32;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const uint4 rv = __ldg(res + q);
+                                const uint4 rv = p.res_tma ? *stage_ptr(hc_res + 8 * q) : __ldg(res + q);
                                 const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                                float gq[8];
+                                if (p.res_gain) {
+                                    const float4* gp4 = reinterpret_cast<const float4*>(p.res_gain + nc + q * 8);
+                                    const float4 ga = __ldg(gp4), gb = __ldg(gp4 + 1);
+                                    gq[0] = ga.x; gq[1] = ga.y; gq[2] = ga.z; gq[3] = ga.w;
+                                    gq[4] = gb.x; gq[5] = gb.y; gq[6] = gb.z; gq[7] = gb.w;
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) gq[j] = 1.0f;
+                                }
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float2 f = __half22float2(rh[j]);
-                                    float ga = p.alpha * r_res, gb = ga;
-                                    if (p.res_gain) {
-                                        ga *= __ldg(p.res_gain + nc + q * 8 + 2 * j);
-                                        gb *= __ldg(p.res_gain + nc + q * 8 + 2 * j + 1);
-                                    }
-                                    v[q * 8 + 2 * j] += ga * f.x;
-                                    v[q * 8 + 2 * j + 1] += gb * f.y;
+                                    v[q * 8 + 2 * j] += (ar * gq[2 * j]) * f.x;
+                                    v[q * 8 + 2 * j + 1] += (ar * gq[2 * j + 1]) * f.y;
                                 }
                             }
                         }
@@ -475,7 +513,11 @@ static void plan_output_staging(GemmPlan& p) {
     // measured on B200 (profiles/r02_b7_*): the staged epilogue wins wherever the epilogue bounds the tile (K = 512 with plain,
     // bias, residual or rotary epilogues: 1.2-2.2x), and loses a little where the ring depth matters more than the stores
     // (SwiGLU halves the output; K >= 1024 hides the epilogue under the main loop): those keep the per-thread stores and 4 stages
-    if (d.act == GEMM_ACT_SWIGLU || d.K >= 1024) return;
+    static const bool stage_all = [] {
+        const char* e = std::getenv("B200_GEMM_STAGE_ALL");  // A/B switch: stage K >= 1024 GEMMs too (3-stage ring)
+        return e && std::atoi(e) != 0;
+    }();
+    if (d.act == GEMM_ACT_SWIGLU || (d.K >= 1024 && !stage_all)) return;
     const int nch = p.bn / 32;
     const int out_div = d.act == GEMM_ACT_SWIGLU ? 2 : 1;
     // every part's output width must split into sub-tiles of sw columns
@@ -520,6 +562,17 @@ static void plan_output_staging(GemmPlan& p) {
     p.tma_o = encode(d.out, 3, dims, strides, box, sw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     p.sw = sw;
     p.staged = 1;
+    // the residual is dense [batches * rows][N]; per batch so that a tile's rows beyond the batch are clipped (zero-filled)
+    static const bool res_ldg = [] {
+        const char* e = std::getenv("B200_GEMM_RES_LDG");  // A/B switch: residual by per-thread global loads
+        return e && std::atoi(e) != 0;
+    }();
+    if (d.residual && out_div == 1 && !res_ldg && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 && (ncols * 2) % 16 == 0) {
+        const uint64_t rdims[3] = {ncols, (uint64_t)d.rows_per_batch, (uint64_t)d.batches};
+        const uint64_t rstrides[2] = {ncols * 2, ncols * 2 * (uint64_t)d.rows_per_batch};
+        p.tma_r = encode(d.residual, 3, rdims, rstrides, box, sw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+        p.res_tma = 1;
+    }
 }
 
 static int pick_bn(int N) {
@@ -585,9 +638,9 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
 
 template <int ACT>
 static void launch_gemm(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& o,
-                        const GemmKernelParams& k) {
+                        const CUtensorMap& r, const GemmKernelParams& k) {
     ensure_dynamic_smem(gemm_f16_tcgen05_kernel<ACT>, 227 * 1024);
-    gemm_f16_tcgen05_kernel<ACT><<<grid, GEMM_THREADS, smem, stream>>>(a, w, o, k);
+    gemm_f16_tcgen05_kernel<ACT><<<grid, GEMM_THREADS, smem, stream>>>(a, w, o, r, k);
 }
 
 void run_gemm(const GemmPlan& p, cudaStream_t stream) {
@@ -609,6 +662,7 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.rope = p.d.rope;
     k.rope_T = p.d.rope_T;
     k.rope_cols = p.d.rope_cols;
+    k.rope_stride = p.d.rope_stride;
     k.residual = p.d.residual;
     k.alpha = p.d.alpha;
     uint32_t cols = 32;
@@ -629,16 +683,23 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.sw = p.sw;
     k.out_kind = p.out_kind;
     k.out_P = p.out_P > 0 ? p.out_P : 1;
-    const int grid = k.num_tiles < kNumSMs ? k.num_tiles : kNumSMs;
+    static const int max_ctas = [] {
+        const char* e = std::getenv("B200_GEMM_MAX_CTAS");  // experiment: leave SMs to other runners' latency-bound kernels
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 && v < kNumSMs ? v : kNumSMs;
+    }();
+    const int grid = k.num_tiles < max_ctas ? k.num_tiles : max_ctas;
     const CUtensorMap& tmo = p.staged ? p.tma_o : p.tma_a;
+    const CUtensorMap& tmr = p.staged && p.res_tma ? p.tma_r : p.tma_a;
+    k.res_tma = p.staged && p.res_tma;
     switch (p.d.act) {
-        case GEMM_ACT_NONE: launch_gemm<GEMM_ACT_NONE>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
-        case GEMM_ACT_SWISH: launch_gemm<GEMM_ACT_SWISH>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
-        case GEMM_ACT_SWISH_CLAMP: launch_gemm<GEMM_ACT_SWISH_CLAMP>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
-        case GEMM_ACT_TANH: launch_gemm<GEMM_ACT_TANH>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
-        case GEMM_ACT_TANH_X5: launch_gemm<GEMM_ACT_TANH_X5>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
-        case GEMM_ACT_SWIGLU: launch_gemm<GEMM_ACT_SWIGLU>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
-        case GEMM_ACT_ROPE: launch_gemm<GEMM_ACT_ROPE>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, k); break;
+        case GEMM_ACT_NONE: launch_gemm<GEMM_ACT_NONE>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
+        case GEMM_ACT_SWISH: launch_gemm<GEMM_ACT_SWISH>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
+        case GEMM_ACT_SWISH_CLAMP: launch_gemm<GEMM_ACT_SWISH_CLAMP>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
+        case GEMM_ACT_TANH: launch_gemm<GEMM_ACT_TANH>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
+        case GEMM_ACT_TANH_X5: launch_gemm<GEMM_ACT_TANH_X5>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
+        case GEMM_ACT_SWIGLU: launch_gemm<GEMM_ACT_SWIGLU>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
+        case GEMM_ACT_ROPE: launch_gemm<GEMM_ACT_ROPE>(grid, p.smem, stream, p.tma_a, p.tma_w, tmo, tmr, k); break;
         default: throw std::invalid_argument("gemm: unknown activation");
     }
     B200_CUDA(cudaGetLastError());

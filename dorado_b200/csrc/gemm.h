@@ -44,6 +44,7 @@ struct GemmDesc {
     const float* rope = nullptr;
     int rope_T = 0;
     int rope_cols = 0;
+    int rope_stride = 0;   // positions per table row: the table is [16 dim pairs][rope_stride positions] float4 (cos, sin, cos, sin)
     // optional fused residual epilogue (deepnorm): v = v + alpha * residual[g][n]; requires act == NONE
     const __half* residual = nullptr;
     float alpha = 0.0f;
@@ -67,12 +68,13 @@ struct GemmDesc {
 struct GemmPlan {
     CUtensorMap tma_a, tma_w;
     CUtensorMap tma_o;   // output, when the epilogue leaves through shared memory + TMA stores (staged)
+    CUtensorMap tma_r;   // residual [batches][rows][N], TMA-loaded into the staging tile ahead of the epilogue (res_tma)
     GemmDesc d;
     int bn = 128;
     int tiles_per_batch = 0;
     dim3 grid;
     size_t smem = 0;
-    int staged = 0, stages = 4, sw = 64, out_kind = 0, out_P = 1;
+    int staged = 0, stages = 4, sw = 64, out_kind = 0, out_P = 1, res_tma = 0;
 };
 
 GemmPlan make_gemm_plan(const GemmDesc& d);

@@ -161,10 +161,16 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
     return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3))) << 4) + ((col & 7) << 1));
 }
 
-// Gate activations: sigmoid(v) = 1 - 1/(e^v + 1), tanh(v) = 1 - 2/(e^{2v} + 1), ex2 + rcp on the SFU.  (Moving the reciprocal
-// to the FMA pipe -- seed + 3 Newton steps -- was measured SLOWER, 0.98 -> 1.03 ms per fast layer and 3.5 -> 3.85 ms per hac
-// layer: the step is bound by the latency of its dependent chain, not by SFU throughput; profiles/r02_b8_*.)
-__device__ __forceinline__ float gate_act(float v, float am) { return 1.0f - __fdividef(am, __expf(am * v) + 1.0f); }
+// Gate activations: sigmoid(v) = 1 - 1/(e^v + 1), tanh(v) = 1 - 2/(e^{2v} + 1): one ex2 and one rcp on the SFU, 5 instructions
+// (FMUL by am*log2(e), MUFU.EX2, FADD, MUFU.RCP, FFMA).  e^x = inf gives 1, e^x = 0 gives 1 - am.  (Moving the reciprocal to
+// the FMA pipe -- seed + 3 Newton steps -- was measured SLOWER, 0.98 -> 1.03 ms per fast layer and 3.5 -> 3.85 ms per hac
+// layer; profiles/r02_b8_*.)
+__device__ __forceinline__ float gate_act(float v, float am) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * (am * 1.4426950408889634f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-am, r, 1.0f);
+}
 __device__ __forceinline__ float tanh_f(float v) { return gate_act(v, 2.0f); }
 
 // C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).
@@ -392,9 +398,32 @@ __global__ void __launch_bounds__(LstmCfg<C, NG>::THREADS, 1) lstm_layer_kernel(
 // LSTM layer for hidden sizes whose weights do not fit one SM (hac: C = 384): hoisted x-projection + cluster recurrence.
 //
 // The x_t half of the gate pre-activations does not depend on the recurrence, so it is hoisted into one large
-// tcgen05 GEMM per layer (gemm.cu) that writes gx[t][chunk block][gate row][chunk] (fp16, bias included).  Gate rows
-// are permuted so that a warp's 32 TMEM lanes hold (8 units x 4 gates); the 4 gates of a unit meet through a
-// per-warp shared-memory exchange (no block barrier).
+// tcgen05 GEMM per layer (gemm.cu) that writes gx[t][chunk block of 32][gate row][chunk] (fp16, bias included).  Gate rows
+// are permuted so that a warp's 32 TMEM lanes hold (8 units x 4 gates).
+//
+// Recurrence: W_hh (4C x C fp16 = 1.18 MB for C = 384) is split by gate tile across the CL = 6 CTAs of a thread-block
+// cluster and stays in their TENSOR MEMORY for the whole sequence (A operand of tcgen05.mma read from TMEM, written once with
+// tcgen05.st).  Every step each CTA computes the gates of its own 32 * TPC hidden units from the full h_{t-1} (its private
+// copy in shared memory) and all-gathers its slice of h_t into every CTA's copy.  The kernel is built around what bounds a
+// step -- the latency of that exchange and of the gate math -- not around barriers:
+//   * the cluster's chunks form NG = 2 independent groups of GN = 16 or 32; the MMA issuer ping-pongs between them, so group
+//     A's gate math and all-gather run under group B's MMAs (a single group has nothing to overlap with);
+//   * h_t travels as BULK ASYNC COPIES (cp.async.bulk shared::cta -> shared::cluster): an epilogue tile stages its
+//     32 units x GN chunks in the swizzled operand layout in local shared memory and one thread sends the block to
+//     every CTA of the cluster; the bytes complete on the destination's mbarrier, which is what its MMA issuer waits on.
+//     No cluster barrier, no remote scalar stores, and the operand is written and read by the async proxy (no
+//     generic->async fence on the receiving side).  Measured alternatives, both slower (3.3 -> 5.7 ms per layer,
+//     profiles/r02_b3_*, r02_b5_*): the exchange through L2 (TMA store + multicast TMA load) and remote 16-byte stores with
+//     remote mbarrier arrivals;
+//   * the same staged block leaves for HBM as one TMA store (no per-thread global stores);
+//   * the four gates of a cell meet by quad transposes in registers (shuffles) instead of a shared-memory exchange.
+// A step's cost hardly depends on GN (it is latency, ~12 small copies per CTA and group), so GN = 32 -- 64 chunks per
+// cluster, 8 clusters = 48 SMs for a batch of 512 -- does the same work in fewer SM-cycles and leaves room for the
+// recurrences of two more batches next to it; GN = 16 is the lower-latency shape for a lone runner.
+// Safety of buffer reuse without extra barriers (Z and staging are double-buffered): a CTA starts step s+2 for a group
+// only after every CTA's slice of h_{s+1} has landed, which those CTAs sent only after their step-(s+1) MMAs completed,
+// which needed every slice of h_s to have landed everywhere -- so by then nobody reads Z[(s) & 1] of step s or the
+// staging block sent at step s any more.
 // ------------------------------------------------------------------------------------------------
 struct LstmRecParams {
     __half* seq;          // [T][N][C] output h (in place over the layer input)
@@ -402,20 +431,9 @@ struct LstmRecParams {
     int T, N, reverse;
     const int32_t* lens;  // optional per-chunk length in samples (variable chunk sizes); stride = samples per step
     int stride;
-    int gather;           // all-gather of h_t: 0 bulk copies over DSMEM, 1 through L2 (TMA store + multicast load), 2 remote vector stores
     long long* dbg;       // optional clock64 timeline of CTA 0, steps 64..67 (B200_DEBUG_LSTM_TIMELINE); nullptr in production
 };
 
-// ------------------------------------------------------------------------------------------------
-// Weights-stationary LSTM recurrence over a thread-block cluster (hac: C = 384, cluster of 6 CTAs).
-//
-// W_hh (4C x C fp16 = 1.18 MB for C = 384) is split by gate tile across the CL CTAs of a cluster and stays in
-// their TENSOR MEMORY for the whole sequence (A operand of tcgen05.mma read from TMEM, written once with
-// tcgen05.st); the cluster owns UNC = 16 or 32 chunks.  Every step each CTA computes the gates of its own 32*TPC
-// hidden units from the full h_{t-1} (its private copy in shared memory), and all-gathers its slice of h_t into
-// every CTA's copy through distributed shared memory (st.shared::cluster), followed by one cluster barrier.  No
-// weight traffic after the prologue; the x_t half comes from the hoisted gx GEMM.
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -426,258 +444,37 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// arrive on an mbarrier of another CTA of the cluster (address from mapa); release at cluster scope
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(tc::smem_u32(bar)), "r"(parity)
-            : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-template <int C, int CL, int UNC>
+template <int C, int CL, int NG, int GN>
 struct ClusterCfg {
-    static constexpr int MT = C / 32;
-    static constexpr int TPC = MT / CL;           // tiles per CTA
-    static constexpr int KBH = C / KBLK;
-    static constexpr int EW = 4 * TPC;            // epilogue warps
-    static constexpr int THREADS = 64 + 32 * EW;
-    static constexpr int ZB = UNC * KBLK * 2;     // bytes of one operand block (UNC chunk rows x 32 fp16)
-    static constexpr int WCOLS = C / 2;           // TMEM columns of one weight tile (two fp16 per column)
-    static constexpr int ACC0 = TPC * WCOLS;      // accumulators start behind the weights
-    static constexpr int NEED = ACC0 + 2 * TPC * UNC;
-    static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
-    static constexpr size_t Z_BYTES = (size_t)2 * KBH * ZB;
-    static constexpr size_t SMEM = 1024 + Z_BYTES + (size_t)EW * 1024 + 256;
-    static_assert(MT % CL == 0, "cluster size must divide the tile count");
-    static_assert(NEED <= 512, "weights + accumulators must fit tensor memory");
-};
-
-// UNC = chunks per cluster (16 or 32).  W_hh tiles live in TENSOR MEMORY (A operand from TMEM): 2 tiles x C/2
-// columns for C = 384 plus 2 * TPC * UNC accumulator columns = 448 / 512 of the 512 columns.
-template <int C, int CL, int UNC>
-__global__ void __launch_bounds__(ClusterCfg<C, CL, UNC>::THREADS, 1) lstm_cluster_kernel(const __half* __restrict__ w_hh,
-                                                                                          const LstmRecParams p) {
-    using Cfg = ClusterCfg<C, CL, UNC>;
-    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH, ZB = Cfg::ZB;
-    constexpr int GB = 32;  // chunk block of the gx layout
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* z_s = smem;                                           // [2][KBH][ZB]  full h, this CTA's copy
-    float* xs = reinterpret_cast<float*>(z_s + Cfg::Z_BYTES);      // [EW][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + Cfg::EW * 256);
-    uint64_t* acc_full = bars;  // [TPC]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + TPC);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int cluster_id = blockIdx.x / CL;
-    const int n0 = cluster_id * UNC;
-
-    for (int i = threadIdx.x; i < (int)(Cfg::Z_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
-    tc::fence_proxy_async_smem();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < TPC; ++i) tc::mbar_init(&acc_full[i], 1);
-        tc::fence_barrier_init();
-    }
-    if (warp == 1) tc::tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-
-    const bool is_mma = warp == 1;
-    const bool is_epi = warp >= 2;
-    const int ewarp = warp - 2;
-    const int ti = ewarp >> 2;       // which of this CTA's tiles the warp serves
-    const int qt = warp & 3;         // TMEM lane quarter
-    if (is_epi) {
-        // this thread's weight row (tile rank*TPC + ti, row 32*qt + lane) -> tensor memory, once
-        const int m = (int)rank * TPC + ti;
-        const uint4* src = reinterpret_cast<const uint4*>(w_hh + (size_t)(m * 128 + qt * 32 + lane) * C);
-#pragma unroll 1
-        for (int cb = 0; cb < C / 64; ++cb) {
-            uint32_t r[32];
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const uint4 x = __ldg(src + cb * 8 + v);
-                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
-            }
-            tc::tmem_st_32x32(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(ti * Cfg::WCOLS + cb * 32), r);
-        }
-        tc::tmem_st_wait();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    // everybody in the cluster has zeroed its Z copy before any remote h store may land
-    cluster_arrive_release();
-    cluster_wait_acquire();
-
-    const int uk = lane >> 2, gj = lane & 3;   // activation role: unit within the warp's 8, gate type
-    const int up = lane >> 3, cc = lane & 7;   // cell-update role: unit pair (2up, 2up+1), column cc of each 8-column chunk
-    float* xw = xs + (is_epi ? ewarp : 0) * 256;
-    const float am = gj == 2 ? 2.0f : 1.0f;
-    float c_reg[UNC / 4];  // [chunk of 8 columns][unit of the pair]
-#pragma unroll
-    for (int k = 0; k < UNC / 4; ++k) c_reg[k] = 0.0f;
-    const uint32_t z_local = tc::smem_u32(z_s);
-    const uint64_t zdesc0 = umma_desc_sw64(z_local);
-    constexpr uint32_t idesc = tc::umma_idesc_f16(128, UNC);
-
-    for (int s = 0; s < p.T; ++s) {
-        const int t = p.reverse ? p.T - 1 - s : s;
-        const int buf = s & 1, nbuf = buf ^ 1;
-        if (is_mma) {
-            if (tc::elect_one()) {
-                tc::tc_fence_after();  // (the writers of h issued fence.proxy.async before the cluster barrier)
-                const uint64_t zd = zdesc0 + (uint64_t)((buf * KBH * ZB) >> 4);
-                // 2 * TPC independent accumulation chains (tile x K-parity), interleaved; the epilogue adds the halves
-#pragma unroll
-                for (int kb = 0; kb < KBH; ++kb) {
-#pragma unroll
-                    for (int i = 0; i < TPC; ++i) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(Cfg::ACC0 + (2 * i + (kb & 1)) * UNC);
-                        const uint32_t a_t = tmem_base + (uint32_t)(i * Cfg::WCOLS + kb * 16);
-                        const uint64_t bdesc = zd + (uint64_t)((kb * ZB) >> 4);
-                        tc::umma_f16_ts(d_tmem, a_t, bdesc, idesc, kb >= 2);
-                        tc::umma_f16_ts(d_tmem, a_t + 8, bdesc + 2, idesc, true);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < TPC; ++i) tc::umma_commit(&acc_full[i]);
-            }
-            __syncwarp();
-        } else if (is_epi) {
-            const int m = (int)rank * TPC + ti;
-            const __half* gx_row = p.gx + ((size_t)t * (p.N / GB) + (n0 / GB)) * (size_t)(4 * C) * GB + (n0 % GB) +
-                                   (size_t)(m * 128 + qt * 32 + lane) * GB;
-            uint4 gxv[UNC / 8];
-#pragma unroll
-            for (int k = 0; k < UNC / 8; ++k) gxv[k] = __ldg(reinterpret_cast<const uint4*>(gx_row + 8 * k));
-            __half* y_t = p.seq + ((size_t)t * p.N + n0) * C;
-            tc::mbar_wait(&acc_full[ti], (uint32_t)(s & 1));
-            tc::tc_fence_after();
-#pragma unroll
-            for (int c16 = 0; c16 < UNC / 16; ++c16) {
-                uint32_t r[16], r2[16];
-                tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(Cfg::ACC0 + (2 * ti) * UNC + c16 * 16), r);
-                tc::tmem_ld_32x16(tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(Cfg::ACC0 + (2 * ti + 1) * UNC + c16 * 16), r2);
-                tc::tmem_ld_wait();
-                if (c16 == UNC / 16 - 1) tc::tc_fence_before();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
-#pragma unroll
-                for (int c8 = 0; c8 < 2; ++c8) {
-                    const int ch = c16 * 2 + c8;  // 8-column chunk index
-                    const uint4 gcur = gxv[ch];
-                    const __half2* gh = reinterpret_cast<const __half2*>(&gcur);
-                    float a[8];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 gf = __half22float2(gh[e]);
-                        const float v0 = __uint_as_float(r[c8 * 8 + 2 * e]) + gf.x, v1 = __uint_as_float(r[c8 * 8 + 2 * e + 1]) + gf.y;
-                        a[2 * e] = gate_act(v0, am);
-                        a[2 * e + 1] = gate_act(v1, am);
-                    }
-                    float4* dst = reinterpret_cast<float4*>(xw + (gj * 8 + uk) * 8);
-                    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
-                    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
-                    __syncwarp();
-                    float ig[2], fg[2], gg[2], og[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        ig[e] = xw[(0 * 8 + 2 * up + e) * 8 + cc];
-                        fg[e] = xw[(1 * 8 + 2 * up + e) * 8 + cc];
-                        gg[e] = xw[(2 * 8 + 2 * up + e) * 8 + cc];
-                        og[e] = xw[(3 * 8 + 2 * up + e) * 8 + cc];
-                    }
-                    __syncwarp();
-                    const float c0 = fg[0] * c_reg[2 * ch] + ig[0] * gg[0];
-                    const float c1 = fg[1] * c_reg[2 * ch + 1] + ig[1] * gg[1];
-                    c_reg[2 * ch] = c0;
-                    c_reg[2 * ch + 1] = c1;
-                    const __half2 hh = __floats2half2_rn(og[0] * tanh_f(c0), og[1] * tanh_f(c1));
-                    const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hh);
-                    const int u = qt * 8 + 2 * up;   // even unit within the tile
-                    const int nA = ch * 8 + cc;      // chunk (row of the operand block)
-                    // all-gather: units (u, u+1) of chunk nA go into block m of every CTA's Z[nbuf] as one 32-bit store
-                    const uint32_t off0 = (uint32_t)((nbuf * KBH + m) * ZB) + sw64_offset(nA, u);
-#pragma unroll
-                    for (int rr = 0; rr < CL; ++rr) st_cluster_u32(mapa_shared(z_local, (uint32_t)rr) + off0, hbits);
-                    *reinterpret_cast<uint32_t*>(y_t + (size_t)nA * C + m * 32 + u) = hbits;
-                }
-            }
-            asm volatile("fence.proxy.async;" ::: "memory");  // generic writes -> async-proxy readers
-        }
-        // h_t complete everywhere (and every accumulator drained) before the next step starts
-        cluster_arrive_release();
-        cluster_wait_acquire();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Cluster recurrence, second generation (the default): same weights-stationary decomposition, restructured around
-// what bounds a step -- the tensor pipe (2 * TPC tiles of 128 x 16 x C per group) and the SFU (5 transcendentals per
-// cell) -- instead of around barriers:
-//   * the cluster's chunks form NG = 2 independent groups of 16; the MMA issuer ping-pongs between them, so group A's
-//     gate math and all-gather run under group B's MMAs (a single group has nothing to overlap with);
-//   * h_t travels as BULK ASYNC COPIES (cp.async.bulk shared::cta -> shared::cluster): an epilogue tile stages its
-//     32 units x 16 chunks in the swizzled operand layout in local shared memory and one thread sends the 1 KB block to
-//     every CTA of the cluster; the bytes complete on the destination's mbarrier, which is what its MMA issuer waits on.
-//     No cluster barrier, no remote scalar stores, and the operand is written and read by the async proxy (no
-//     generic->async fence on the receiving side);
-//   * the same staged block leaves for HBM as one TMA store (no per-thread global stores);
-//   * the four gates of a cell meet by quad transposes in registers (shuffles) instead of a shared-memory exchange.
-// Safety of buffer reuse without extra barriers (Z and staging are double-buffered): a CTA starts step s+2 for a group
-// only after every CTA's slice of h_{s+1} has landed, which those CTAs sent only after their step-(s+1) MMAs completed,
-// which needed every slice of h_s to have landed everywhere -- so by then nobody reads Z[(s) & 1] of step s or the
-// staging block sent at step s any more.
-// ------------------------------------------------------------------------------------------------
-template <int C, int CL, int NG>
-struct Cluster2Cfg {
     static constexpr int MT = C / 32;
     static constexpr int TPC = MT / CL;            // gate tiles per CTA
     static constexpr int KBH = C / KBLK;           // operand blocks (32 hidden units each)
-    static constexpr int GN = 16;                  // chunks per group = UMMA N
     static constexpr int UNC = NG * GN;            // chunks per cluster
+    static constexpr int NQ = GN / 4;              // chunk quads per group: a lane owns the cells (unit, chunk 4c + gate lane)
     static constexpr int EW = 4 * TPC * NG;        // epilogue warps: (group, tile, TMEM lane quarter)
     static constexpr int THREADS = 64 + 32 * EW;
-    static constexpr int ZB = GN * KBLK * 2;       // bytes of one operand block (16 chunk rows x 32 fp16)
+    static constexpr int ZB = GN * KBLK * 2;       // bytes of one operand block (GN chunk rows x 32 fp16)
     static constexpr int WCOLS = C / 2;            // TMEM columns of one weight tile
     static constexpr int ACC0 = TPC * WCOLS;       // accumulators start behind the weights
     static constexpr int NEED = ACC0 + NG * TPC * GN;
     static constexpr uint32_t TMEM_COLS = NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
     static constexpr size_t Z_BYTES = (size_t)NG * 2 * KBH * ZB;      // [group][buffer][block]
     static constexpr size_t ST_BYTES = (size_t)NG * 2 * TPC * ZB;     // [group][buffer][tile] staging
-    static constexpr size_t SMEM = 1024 + Z_BYTES + ST_BYTES + 512;
-    static_assert(MT % CL == 0 && NEED <= 512 && (CL * 64) % 128 == 0, "tile split / tensor memory budget / gather split");
+    static constexpr size_t SMEM = 1024 + Z_BYTES + ST_BYTES + 1024;
+    static_assert(MT % CL == 0 && NEED <= 512, "tile split / tensor memory budget");
+    static_assert(GN == 16 || GN == 32, "a group is 16 or 32 chunks (UMMA N, tcgen05.ld shape, gx block)");
+    static_assert(UNC <= 64, "chunk-length table");
 };
 
-template <int C, int CL, int NG>
-__global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_cluster2_kernel(const __grid_constant__ CUtensorMap tma_y,
-                                                                                          const __half* __restrict__ w_hh,
-                                                                                          const LstmRecParams p) {
-    using Cfg = Cluster2Cfg<C, CL, NG>;
-    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH, ZB = Cfg::ZB, GN = Cfg::GN;
+template <int C, int CL, int NG, int GN>
+__global__ void __launch_bounds__(ClusterCfg<C, CL, NG, GN>::THREADS, 1) lstm_cluster_kernel(const __grid_constant__ CUtensorMap tma_y,
+                                                                                            const __half* __restrict__ w_hh,
+                                                                                            const LstmRecParams p) {
+    using Cfg = ClusterCfg<C, CL, NG, GN>;
+    constexpr int TPC = Cfg::TPC, KBH = Cfg::KBH, ZB = Cfg::ZB, NQ = Cfg::NQ;
     constexpr int GB = 32;  // chunk block of the gx layout
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -702,8 +499,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
     }
     tc::fence_proxy_async_smem();
     if (threadIdx.x == 0) {
-        // gather by remote vector stores: 2 warps of every (CTA, tile) arrive per destination; otherwise one armed arrival + bytes
-        for (int i = 0; i < NG * 2; ++i) tc::mbar_init(&h_full[i], p.gather == 2 ? (uint32_t)(CL * TPC * 2) : 1u);
+        for (int i = 0; i < NG * 2; ++i) tc::mbar_init(&h_full[i], 1);   // one armed arrival + the bytes of all slices
         for (int i = 0; i < NG * TPC; ++i) tc::mbar_init(&acc_full[i], 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_y);
@@ -737,10 +533,7 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
     }
     if (threadIdx.x == 0) {
         // h_{-1} = 0 is in place: complete phase 0 of the buffer-0 barriers without bytes
-        for (int g = 0; g < NG; ++g) {
-            const int arrivals = p.gather == 2 ? CL * TPC * 2 : 1;
-            for (int i = 0; i < arrivals; ++i) tc::mbar_arrive(&h_full[g * 2 + 0]);
-        }
+        for (int g = 0; g < NG; ++g) tc::mbar_arrive(&h_full[g * 2 + 0]);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -767,15 +560,10 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     // arm the barrier the slices of h_s will complete on (all CL CTAs x TPC tiles, this group)
-                    if (s + 1 < steps && p.gather != 2) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
+                    if (s + 1 < steps) tc::mbar_arrive_expect_tx(&h_full[g * 2 + nbuf], (uint32_t)(CL * TPC * ZB));
                     long long* d = (p.dbg && blockIdx.x == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + g * 4 : nullptr;
                     if (d) d[0] = clock64();
-                    if (p.gather == 2) {
-                        while (!mbar_try_wait_cluster(&h_full[g * 2 + buf], par)) {
-                        }
-                    } else {
-                        tc::mbar_wait(&h_full[g * 2 + buf], par);
-                    }
+                    tc::mbar_wait(&h_full[g * 2 + buf], par);
                     tc::tc_fence_after();
                     if (d) d[1] = clock64();
                     const uint64_t zd = zdesc0 + (uint64_t)(((g * 2 + buf) * KBH * ZB) >> 4);
@@ -804,11 +592,13 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
         const float am = gj == 2 ? 2.0f : 1.0f;    // tanh(v) = 1 - 2/(e^{2v}+1), sigmoid(v) = 1 - 1/(e^{v}+1)
         const bool sender = qt == 0 && lane == 0;
         const int bar_id = 1 + eg * TPC + ti;
-        float c_reg[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // cells (unit uk, chunk 4c + gj)
+        float c_reg[NQ];                           // cells (unit uk, chunk 4c + gj)
+#pragma unroll
+        for (int c = 0; c < NQ; ++c) c_reg[c] = 0.0f;
         const uint32_t taddr = tmem_base + ((uint32_t)(qt * 32) << 16) + (uint32_t)(Cfg::ACC0 + (eg * TPC + ti) * GN);
-        const size_t gx_row_off = (size_t)(m * 128 + qt * 32 + lane) * GB + (size_t)(n0 % GB) + (size_t)eg * GN;
+        const int nc0 = n0 + eg * GN;              // first chunk of this group
         const size_t gx_step = (size_t)(p.N / GB) * (size_t)(4 * C) * GB;
-        const __half* gx_base = p.gx + (size_t)(n0 / GB) * (size_t)(4 * C) * GB + gx_row_off;
+        const __half* gx_base = p.gx + (size_t)(nc0 / GB) * (size_t)(4 * C) * GB + (size_t)(m * 128 + qt * 32 + lane) * GB + (size_t)(nc0 % GB);
         // remote addresses of this tile's operand block and of the barrier it completes on, per buffer
         uint32_t dst_z[2], dst_bar[2];
 #pragma unroll
@@ -816,44 +606,46 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             dst_z[b] = z_local + (uint32_t)(((eg * 2 + b) * KBH + m) * ZB);
             dst_bar[b] = tc::smem_u32(&h_full[eg * 2 + b]);
         }
-        int my_len[4];   // steps of the chunks this lane owns cells of
+        int my_len[NQ];   // steps of the chunks this lane owns cells of
 #pragma unroll
-        for (int c = 0; c < 4; ++c) my_len[c] = len_s[eg * GN + 4 * c + gj];
+        for (int c = 0; c < NQ; ++c) my_len[c] = len_s[eg * GN + 4 * c + gj];
         for (int s = 0; s < steps; ++s) {
             const int t = p.reverse ? steps - 1 - s : s;
             const int nbuf = (s & 1) ^ 1;
             const uint4* gp = reinterpret_cast<const uint4*>(gx_base + (size_t)t * gx_step);
-            const uint4 gx0 = __ldg(gp), gx1 = __ldg(gp + 1);
+            uint4 gxv[GN / 8];
+#pragma unroll
+            for (int e = 0; e < GN / 8; ++e) gxv[e] = __ldg(gp + e);
             uint8_t* stage = st_s + (size_t)((eg * 2 + (s & 1)) * TPC + ti) * ZB;
             long long* d = (p.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && s >= 64 && s < 68) ? p.dbg + (s - 64) * 32 + 8 : nullptr;
             if (d) d[0] = clock64();
             tc::mbar_wait(&acc_full[eg * TPC + ti], (uint32_t)(s & 1));
             tc::tc_fence_after();
             if (d) d[1] = clock64();
-            uint32_t r[16];
-            tc::tmem_ld_32x16(taddr, r);
+            uint32_t r[GN];
+            if constexpr (GN == 32) {
+                tc::tmem_ld_32x32(taddr, r);
+            } else {
+                tc::tmem_ld_32x16(taddr, r);
+            }
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             if (d) d[2] = clock64();
-            float a[16];
-            {
-                const __half2* h0 = reinterpret_cast<const __half2*>(&gx0);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&gx1);
+            float a[GN];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f0 = __half22float2(h0[e]), f1 = __half22float2(h1[e]);
-                    a[2 * e] = __uint_as_float(r[2 * e]) + f0.x;
-                    a[2 * e + 1] = __uint_as_float(r[2 * e + 1]) + f0.y;
-                    a[8 + 2 * e] = __uint_as_float(r[8 + 2 * e]) + f1.x;
-                    a[8 + 2 * e + 1] = __uint_as_float(r[8 + 2 * e + 1]) + f1.y;
+            for (int e = 0; e < GN / 8; ++e) {
+                const __half2* hx = reinterpret_cast<const __half2*>(&gxv[e]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(hx[j]);
+                    a[8 * e + 2 * j] = gate_act(__uint_as_float(r[8 * e + 2 * j]) + f.x, am);
+                    a[8 * e + 2 * j + 1] = gate_act(__uint_as_float(r[8 * e + 2 * j + 1]) + f.y, am);
                 }
             }
-#pragma unroll
-            for (int n = 0; n < 16; ++n) a[n] = gate_act(a[n], am);
             if (d) d[3] = clock64();
             // 4x4 transposes inside the quad: afterwards a[4c + k] = gate k of (unit uk, chunk 4c + gj)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NQ; ++c) {
                 float s0 = g0 ? a[4 * c + 0] : a[4 * c + 1];
                 float s1 = g0 ? a[4 * c + 2] : a[4 * c + 3];
                 float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -865,31 +657,37 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
                 if (g1) { a[4 * c + 0] = r0; a[4 * c + 1] = r1; } else { a[4 * c + 2] = r0; a[4 * c + 3] = r1; }
             }
             if (d) d[4] = clock64();
-            float hv[4];
+            float hv[NQ];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NQ; ++c) {
                 // outside the chunk (variable chunk sizes) the state is held at zero: a multiplicative mask, not a branch, so
-                // that the four cells' transcendentals stay interleaved
+                // that the cells' transcendentals stay interleaved
                 const float alive = t < my_len[c] ? 1.0f : 0.0f;
                 const float cs = (a[4 * c + 1] * c_reg[c] + a[4 * c + 0] * a[4 * c + 2]) * alive;
                 c_reg[c] = cs;
                 hv[c] = a[4 * c + 3] * tanh_f(cs) * alive;
             }
-            // pair the units (uk, uk ^ 1): the even lane stores chunks c = 0, 1 of both units, the odd lane c = 2, 3
+            // Pair the units (uk, uk ^ 1): of the NQ / 2 chunk-quad pairs the even unit's lane stores the first half for both
+            // units and the odd unit's lane the second half, as 32-bit words (two adjacent units of one chunk row).
             {
-                const __half2 mine_lo = __floats2half2_rn(hv[0], hv[1]), mine_hi = __floats2half2_rn(hv[2], hv[3]);
                 const bool odd = uk & 1;
-                const uint32_t send = odd ? *reinterpret_cast<const uint32_t*>(&mine_lo) : *reinterpret_cast<const uint32_t*>(&mine_hi);
-                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 4);
-                const uint32_t keep = odd ? *reinterpret_cast<const uint32_t*>(&mine_hi) : *reinterpret_cast<const uint32_t*>(&mine_lo);
-                // keep = my h for chunks (cb, cb+1), got = the partner unit's h for the same chunks; cb = odd ? 2 : 0
-                const uint32_t even_unit = odd ? got : keep, odd_unit = odd ? keep : got;
-                const int cb = odd ? 2 : 0;
                 const int ucol = qt * 8 + (uk & ~1);
-                const uint32_t w0 = (even_unit & 0xffffu) | (odd_unit << 16);          // chunk 4*cb + gj
-                const uint32_t w1 = (even_unit >> 16) | (odd_unit & 0xffff0000u);      // chunk 4*(cb+1) + gj
-                *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * cb + gj, ucol)) = w0;
-                *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * (cb + 1) + gj, ucol)) = w1;
+                constexpr int NP = NQ / 2;        // half2 pairs of chunk quads per lane: (hv[2i], hv[2i+1])
+#pragma unroll
+                for (int i = 0; i < NP / 2; ++i) {
+                    const __half2 first = __floats2half2_rn(hv[2 * i], hv[2 * i + 1]);
+                    const __half2 second = __floats2half2_rn(hv[2 * (NP / 2 + i)], hv[2 * (NP / 2 + i) + 1]);
+                    const uint32_t fu = *reinterpret_cast<const uint32_t*>(&first), su = *reinterpret_cast<const uint32_t*>(&second);
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? fu : su, 4);
+                    const uint32_t keep = odd ? su : fu;
+                    // keep = my h for quads (q0, q0+1), got = the partner unit's h for the same quads
+                    const uint32_t even_unit = odd ? got : keep, odd_unit = odd ? keep : got;
+                    const int q0 = 2 * (odd ? NP / 2 + i : i);
+                    const uint32_t w0 = (even_unit & 0xffffu) | (odd_unit << 16);          // chunk 4*q0 + gj
+                    const uint32_t w1 = (even_unit >> 16) | (odd_unit & 0xffff0000u);      // chunk 4*(q0+1) + gj
+                    *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * q0 + gj, ucol)) = w0;
+                    *reinterpret_cast<uint32_t*>(stage + sw64_offset(4 * (q0 + 1) + gj, ucol)) = w1;
+                }
             }
             if (d) d[5] = clock64();
             tc::fence_proxy_async_smem();            // staged block -> visible to the bulk copy / TMA store
@@ -898,57 +696,17 @@ __global__ void __launch_bounds__(Cluster2Cfg<C, CL, NG>::THREADS, 1) lstm_clust
             if (d) d[7] = clock64();
             named_bar_sync(bar_id, 128);
             if (d) d[8] = clock64();
-            if (p.gather == 2) {
-                // all-gather by remote vector stores: the tile's 128 threads copy the staged 1 KB block (64 pieces of 16 B) into
-                // the operand buffer of all CL CTAs, 3 stores each; a warp's stores go to 3 destinations (one of each CTA pair),
-                // which it then signals.  Generic-proxy writes, so the writer fences them towards the async proxy (the MMAs).
-                const int tt = (qt << 5) | lane;           // 0..127 within the tile's warps (qt runs over all four quarters)
+            if (sender) {
+                // all-gather over distributed shared memory: one bulk copy per destination CTA
                 if (s + 1 < steps) {
 #pragma unroll
-                    for (int q = 0; q < (CL * 64) / 128; ++q) {
-                        const int idx = tt + 128 * q;
-                        const int rr = idx >> 6, piece = idx & 63;
-                        const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * piece);
-                        st_cluster_v4(mapa_shared(dst_z[nbuf], (uint32_t)rr) + 16u * (uint32_t)piece, v);
-                    }
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-#pragma unroll
-                        for (int q = 0; q < (CL * 64) / 128; ++q) {
-                            const int rr = ((qt << 5) + 128 * q) >> 6;
-                            mbar_arrive_cluster(mapa_shared(dst_bar[nbuf], (uint32_t)rr));
-                        }
+                    for (int rr = 0; rr < CL; ++rr) {
+                        tc::bulk_copy_smem_to_cluster(mapa_shared(dst_z[nbuf], (uint32_t)rr), tc::smem_u32(stage), (uint32_t)ZB,
+                                                      mapa_shared(dst_bar[nbuf], (uint32_t)rr));
                     }
                 }
-                if (sender) {
-                    tc::tma_store_2d(&tma_y, stage, m * 32, t * p.N + n0 + eg * GN);
-                    tc::bulk_commit_group();
-                }
-            } else if (sender) {
-                const int yrow = t * p.N + n0 + eg * GN;
-                if (p.gather == 1) {
-                    // all-gather through L2: the block goes to HBM/L2 as the layer output anyway; once that store has
-                    // completed, ONE multicast TMA load brings it back into the operand buffer of all CL CTAs
-                    tc::tma_store_2d(&tma_y, stage, m * 32, yrow);
-                    tc::bulk_commit_group();
-                    if (s + 1 < steps) {
-                        tc::bulk_wait_group<0>();
-                        tc::tma_load_2d_multicast(z_s + (size_t)(((eg * 2 + nbuf) * KBH + m) * ZB), &tma_y, &h_full[eg * 2 + nbuf], m * 32, yrow,
-                                                  (uint16_t)((1u << CL) - 1u));
-                    }
-                } else {
-                    // all-gather over distributed shared memory: one bulk copy per destination CTA
-                    if (s + 1 < steps) {
-#pragma unroll
-                        for (int rr = 0; rr < CL; ++rr) {
-                            tc::bulk_copy_smem_to_cluster(mapa_shared(dst_z[nbuf], (uint32_t)rr), tc::smem_u32(stage), (uint32_t)ZB,
-                                                          mapa_shared(dst_bar[nbuf], (uint32_t)rr));
-                        }
-                    }
-                    tc::tma_store_2d(&tma_y, stage, m * 32, yrow);
-                    tc::bulk_commit_group();
-                }
+                tc::tma_store_2d(&tma_y, stage, m * 32, t * p.N + nc0);
+                tc::bulk_commit_group();
             }
             if (d) d[9] = clock64();
         }
@@ -980,12 +738,12 @@ public:
     void run(cudaStream_t stream, ProfileSink* prof) override;
     int launches() const override { return 1 + 1 + num_layers * (hoisted ? 2 : 1) + num_linear; }
     std::string info() const override {
-        if (hoisted) return "lstm_rec.ctas=" + std::to_string(lstm_grid);
+        if (hoisted) return "lstm_rec.ctas=" + std::to_string(lstm_grid) + ";lstm_rec.chunks_per_cluster=" + std::to_string(rec_un);
         return "lstm_layer.ctas=" + std::to_string(lstm_grid) + ";lstm_layer.groups=" + std::to_string(lstm_ng) +
                ";lstm_layer.chunks_per_group=" + std::to_string(lstm_nbr);
     }
     void set_chunk_lengths(const int32_t* d_lens) override {
-        if (!hoisted || rec_v1) return;  // the mode exists for the cluster recurrence (second generation) only
+        if (!hoisted) return;  // the mode exists for the cluster recurrence only
         conv12.lens = d_lens;
         for (auto& rp : rec_p) rp.lens = d_lens;
     }
@@ -1002,12 +760,11 @@ public:
     long long* dbg_timeline = nullptr;
     int debug_layers = -1;  // >= 0: stop after that many LSTM layers (B200_DEBUG_LSTM_LAYERS, read once at plan creation)
     bool hoisted = false;
-    int rec_un = 16;
+    int rec_un = 32;       // chunks per cluster: 16 (one group of 16), 32 (two groups of 16) or 64 (two groups of 32)
     std::vector<GemmPlan> gx_gemm;
     std::vector<const __half*> rec_whh;
     std::vector<LstmRecParams> rec_p;
-    bool rec_v1 = false;   // B200_CLUSTER_V1=1: the first-generation cluster kernel (A/B comparisons)
-    CUtensorMap rec_y_map; // seq as [T_out * Np][C], box 32 units x 16 chunks: the TMA store of h_t
+    CUtensorMap rec_y_map; // seq as [T_out * Np][C], box 32 units x (chunks of a group): the TMA store of h_t
     void launch_rec(int l, cudaStream_t stream) const;
     GemmPlan linear1, linear2;
     int num_layers = 0, num_linear = 1;
@@ -1022,9 +779,8 @@ public:
     std::unique_ptr<ForwardPlan> make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
                                            size_t ws_bytes) override;
     bool variable_chunk_sizes() const override {
-        const char* e = std::getenv("B200_CLUSTER_V1");
         // FLSTM models never run variable chunk sizes (api/runner_creation.cpp:28)
-        return hoisted() && desc.lstm_inner_dim == 0 && !(e && std::atoi(e) != 0);
+        return hoisted() && desc.lstm_inner_dim == 0;
     }
 
     b200_model_desc desc;
@@ -1267,13 +1023,21 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         plan->num_layers = desc.lstm_layers;
         plan->hoisted = true;
         if (C != 192 && C != 384) throw Unsupported("hoisted LSTM path is instantiated for lstm_size 192 and 384");
-        // weights-stationary cluster kernel (6 CTAs): 16 chunks per cluster, 32 once 16 would need more clusters than
-        // are co-resident (ncu: launch__cluster_max_active = 22 on B200)
+        // Weights-stationary cluster kernel (6 CTAs per cluster).  Chunks per cluster: a step costs about the same for 16, 32 or
+        // 64 chunks, so fewer and fatter clusters do the same work in fewer SM-cycles at a higher latency per launch.  With R
+        // runners in flight the recurrence takes ~1/R of the SMs (64 chunks per cluster: 8 clusters = 48 SMs at batch 512,
+        // three batches' recurrences side by side); a lone runner spreads out (32 per cluster = 96 SMs, 16 for small batches).
+        const int hint = num_runners_hint < 1 ? 1 : num_runners_hint;
         int un = Np > 256 ? 32 : 16;
+        if (hint >= 2 && Np % 64 == 0 && (Np / 32) * 6 > 148 / hint) un = 64;
+        if (const char* e = std::getenv("B200_CLUSTER_CHUNKS")) {   // tuning / A-B override
+            const int v = std::atoi(e);
+            if ((v == 16 || v == 32 || v == 64) && Np % v == 0) un = v;
+            else throw std::invalid_argument("B200_CLUSTER_CHUNKS must be 16, 32 or 64 and divide the padded batch");
+        }
         while (Np % un != 0) un /= 2;
         plan->rec_un = un;
-        if (const char* e = std::getenv("B200_CLUSTER_V1")) plan->rec_v1 = std::atoi(e) != 0;
-        plan->rec_y_map = make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, 32, 16);
+        plan->rec_y_map = make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, 32, un == 64 ? 32 : 16);
         const int GB = 32;  // chunk block of the gx layout (n_pad = 32 on this path)
         plan->lstm_grid = (Np / un) * 6;
         for (int l = 0; l < desc.lstm_layers; ++l) {
@@ -1304,10 +1068,6 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             rp.reverse = (l % 2 == 0) ? 1 : 0;
             rp.lens = nullptr;
             rp.stride = desc.stride;
-            rp.gather = 0;  // measured on B200: 3.3 ms per layer with bulk copies over DSMEM, 5.7 ms through L2 (profiles/r02_b3_*)
-            if (const char* e = std::getenv("B200_CLUSTER_GATHER")) {
-                rp.gather = std::strcmp(e, "l2") == 0 ? 1 : std::strcmp(e, "st") == 0 ? 2 : 0;
-            }
             rp.dbg = nullptr;
             if (l == 0 && getenv("B200_DEBUG_LSTM_TIMELINE")) {
                 B200_CUDA(cudaMalloc(&rp.dbg, 128 * sizeof(long long)));
@@ -1424,10 +1184,10 @@ static void launch_lstm_t(const LstmPlan& pl, int l, cudaStream_t stream) {
     lstm_layer_kernel<C, NBR, NG><<<pl.lstm_grid, LstmCfg<C, NG>::THREADS, pl.lstm_smem, stream>>>(pl.lstm_x[l], pl.lstm_p[l]);
 }
 
-template <int C, int CL, int UNC>
+template <int C, int CL, int NG, int GN>
 static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    using Cfg = ClusterCfg<C, CL, UNC>;
-    ensure_dynamic_smem(lstm_cluster_kernel<C, CL, UNC>, (int)Cfg::SMEM);
+    using Cfg = ClusterCfg<C, CL, NG, GN>;
+    ensure_dynamic_smem(lstm_cluster_kernel<C, CL, NG, GN>, (int)Cfg::SMEM);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)pl.lstm_grid, 1, 1);
     cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
@@ -1440,36 +1200,15 @@ static void launch_cluster_t(const LstmPlan& pl, int l, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<C, CL, UNC>, pl.rec_whh[l], pl.rec_p[l]));
-}
-
-template <int C, int CL, int NG>
-static void launch_cluster2_t(const LstmPlan& pl, int l, cudaStream_t stream) {
-    using Cfg = Cluster2Cfg<C, CL, NG>;
-    ensure_dynamic_smem(lstm_cluster2_kernel<C, CL, NG>, (int)Cfg::SMEM);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)pl.lstm_grid, 1, 1);
-    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster2_kernel<C, CL, NG>, pl.rec_y_map, pl.rec_whh[l], pl.rec_p[l]));
+    B200_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<C, CL, NG, GN>, pl.rec_y_map, pl.rec_whh[l], pl.rec_p[l]));
 }
 
 template <int C>
 static void launch_cluster_c(const LstmPlan& pl, int l, cudaStream_t stream) {
-    if (pl.rec_v1) {
-        if (pl.rec_un == 32) launch_cluster_t<C, 6, 32>(pl, l, stream);
-        else launch_cluster_t<C, 6, 16>(pl, l, stream);
-    } else {
-        if (pl.rec_un == 32) launch_cluster2_t<C, 6, 2>(pl, l, stream);
-        else launch_cluster2_t<C, 6, 1>(pl, l, stream);
+    switch (pl.rec_un) {
+        case 64: launch_cluster_t<C, 6, 2, 32>(pl, l, stream); break;
+        case 32: launch_cluster_t<C, 6, 2, 16>(pl, l, stream); break;
+        default: launch_cluster_t<C, 6, 1, 16>(pl, l, stream); break;
     }
 }
 

@@ -537,8 +537,11 @@ TxModel::TxModel(const b200_model_desc& d, const b200_tensor* tensors, int n) : 
             const float inv = (float)(1.0 / std::pow((double)d.theta, (double)fi));
             for (int t = 0; t < tmax; ++t) {
                 const float ang = (float)t * inv;
-                tab[((size_t)t * half + i) * 2] = std::cos(ang);
-                tab[((size_t)t * half + i) * 2 + 1] = std::sin(ang);
+                // position-minor layout [pair of dims j = i / 2][t][(cos, sin) of dim 2j, (cos, sin) of dim 2j + 1]: the GEMM
+                // epilogue's 32 lanes hold 32 consecutive positions, so their 16-byte reads of one j are contiguous
+                const size_t at = (((size_t)(i >> 1) * tmax + t) * 2 + (i & 1)) * 2;
+                tab[at] = std::cos(ang);
+                tab[at + 1] = std::sin(ang);
             }
         }
         rope = up32(tab.data(), tab.size());
@@ -636,6 +639,7 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
         if (act == GEMM_ACT_ROPE) {
             g.rope = rope;
             g.rope_T = T;
+            g.rope_stride = desc.max_seq_len > 0 ? desc.max_seq_len : 2048;
             g.rope_cols = 2 * desc.nhead * 64;
         }
         return g;

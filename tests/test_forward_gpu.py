@@ -266,6 +266,47 @@ def test_pool_feeds_every_runner_and_matches_a_single_runner():
     pool.close()
 
 
+def test_cluster_shapes_agree():
+    """The hac recurrence runs 16, 32 or 64 chunks per cluster (one or two groups of 16 or 32; chosen from the batch size and
+    the engine's num_runners): the result must not depend on that choice -- bit for bit, fixed and variable chunk sizes --
+    and the 16-chunk shape is the one the other tests pin against the oracle."""
+    import os
+    from dorado_b200.config import load_model_config
+    from dorado_b200.runner import B200Caller, B200ModelRunner
+    from dorado_b200.weights import synthetic_weights
+    cfg = load_model_config(model_dir("hac"))
+    caller = B200Caller(cfg, synthetic_weights(cfg, 42))
+    N, T = 128, 1200
+    rng = np.random.default_rng(3)
+    sig = rng.standard_normal((N, cfg.normalise_chunk_size(T))).astype(np.float16)
+    lens = rng.integers(10, sig.shape[1] // cfg.stride + 1, size=N) * cfg.stride
+    got = {}
+    try:
+        for un in (16, 32, 64):
+            os.environ["B200_CLUSTER_CHUNKS"] = str(un)
+            runner = B200ModelRunner(caller, N, T)
+            assert runner.plan_info()["lstm_rec.chunks_per_cluster"] == un and runner.plan_info()["lstm_rec.ctas"] == N // un * 6
+            for i in range(N):
+                runner.accept_chunk(i, sig[i])
+            fixed = runner.forward_scores(N).copy()
+            for i in range(N):
+                runner.accept_chunk_var(i, sig[i, :lens[i]])
+            got[un] = (fixed, runner.forward_scores(N).copy(), [np.array(a) for a in runner.call_chunks_raw(N)])
+            runner.close()
+    finally:
+        os.environ.pop("B200_CLUSTER_CHUNKS", None)
+    for un in (32, 64):
+        np.testing.assert_array_equal(got[un][0], got[16][0])
+        for i in range(N):   # beyond a chunk's own length the score rows are unspecified
+            tn = int(lens[i]) // cfg.stride
+            np.testing.assert_array_equal(got[un][1][i, :tn], got[16][1][i, :tn])
+        (mv, sq, qs, nb), (mv0, sq0, qs0, nb0) = got[un][2], got[16][2]
+        np.testing.assert_array_equal(nb, nb0)
+        for i in range(N):
+            tn = int(lens[i]) // cfg.stride
+            assert (mv[i, :tn] == mv0[i, :tn]).all() and (sq[i, :nb[i]] == sq0[i, :nb[i]]).all() and (qs[i, :nb[i]] == qs0[i, :nb[i]]).all()
+
+
 def test_variable_chunk_sizes_match_each_chunk_alone(crf_oracle):
     """Variable chunk sizes (nn/AuxiliaryData.cpp, CudaModelRunner.cpp:21-31, CUDADecoder.cpp:35-62): a batch
     of hac chunks of different lengths.  Every chunk must come out as if it were basecalled alone at its own length: scores
