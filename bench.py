@@ -8,12 +8,15 @@ Multi-GPU: one process per GPU (torchrun), each with its own engine replica and 
 embarrassingly; no collective on the data path) -> weak scaling; time = max over ranks of the device time.
 
   value  whole-job samples/s with the batches already resident in HBM (CUDA events bracketing the runners' streams);
-         `--runners` batches are in flight per GPU (default 2, dorado's num_runners per device), so one batch's decode
-         overlaps the next batch's network -- every step is still a full forward + decode of one batch
+         `--runners` batches are in flight per GPU (dorado's --num-runners; default here 4 for fast / hac, 2 for sup): the
+         recurrences and the beam search are latency chains, so each runner's kernels are sized for a share of the SMs and
+         several batches run side by side -- every step is still a full forward + decode of one batch
   e2e    same metric through the C ABI call the adapter makes (b200_runner_call_chunks via
          B200ModelRunner.call_chunks_raw) from pinned host buffers, one host thread per runner:
          H2D of the fp16 batch and D2H of moves/sequence/qstring inside the timed region
-  roofline      dominant kernel of the step, timed live per launch with CUDA events; per-kernel table beside it
+  roofline      dominant kernel of the step, timed live per launch with CUDA events (one runner alone, its launch plan
+                unchanged); per-kernel table beside it.  A kernel sized for a share of the SMs reports `frac` against the
+                whole-GPU peak as the contract defines it, and `frac_of_sms_used` against the peak of the SMs it occupies
                 (each decode kernel is charged the bytes of its own interface; `decode` is the three together against the
                 algorithmic 2C+3 bytes per chunk-block of SURVEY.md 8d)
   cpu_baseline  the reference's own CPU runner (dorado::basecall::ModelRunner::call_chunks, compiled from the reference
@@ -50,7 +53,7 @@ MODELS = {
 FLOP_PER_SAMPLE = {"fast": 0.1435e6, "hac": 2.139e6, "sup": 14.35e6}
 SUB_MODELS = {"hac": dict(batch=512, steps=8), "sup": dict(batch=128, steps=6)}
 NUM_SMS = 148
-DEFAULT_RUNNERS = {"fast": 4, "hac": 2, "sup": 2}   # batches in flight per GPU (dorado's --num-runners; see --runners)
+DEFAULT_RUNNERS = {"fast": 4, "hac": 4, "sup": 2}   # batches in flight per GPU (dorado's --num-runners; see --runners)
 METRIC = "basecalled samples/s"
 
 
@@ -416,14 +419,20 @@ def bench_b200(kind, batch, chunksize, steps, warmup, R, rank, local_rank, world
     roof["decode"] = {"bound": "hbm", "algorithmic_bytes": dec_alg, "ms": round(dec_total_ms, 4),
                       "achieved": round(dec_alg / (dec_total_ms * 1e-3) / 1e9, 2),
                       "frac": round(dec_alg / (dec_total_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
-    # DRAM bytes per launch of the dominant kernel from this round's `ncu --set full` capture of the same workload
-    # (profiles/r02_traffic.json, written by tools/ncu_summary.py); null when that kernel was not captured
+    # DRAM bytes per launch from this round's `ncu --set full` captures of the same workload (profiles/r02_traffic.json,
+    # written by tools/ncu_summary.py): for the dominant kernel as roofline.traffic, and per kernel; null when not captured
     try:
-        tr = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())[f"{kind}_n{N}_{dom}"]
+        tr_all = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
+    except (OSError, ValueError):
+        tr_all = {}
+    for k, e in roof["per_kernel"].items():
+        tr = tr_all.get(f"{kind}_n{N}_{k}")
+        if tr:
+            e["traffic"] = tr["dram_bytes"]
+    tr = tr_all.get(f"{kind}_n{N}_{dom}")
+    if tr:
         roof["traffic"] = tr["dram_bytes"]
-        roof["traffic_source"] = f"profiles/{tr['file']} ({tr['kernel']})"
-    except (OSError, KeyError, ValueError):
-        pass
+        roof["traffic_source"] = f"profiles/{tr['file']} launch {tr['launch']} ({tr['kernel']})"
     roof["peak_source"] = pk["source"]
     roof["ms_per_launch"] = dom_ms
     roof["launches_per_step"] = dom_cnt

@@ -683,11 +683,12 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
     k.sw = p.sw;
     k.out_kind = p.out_kind;
     k.out_P = p.out_P > 0 ? p.out_P : 1;
-    static const int max_ctas = [] {
-        const char* e = std::getenv("B200_GEMM_MAX_CTAS");  // experiment: leave SMs to other runners' latency-bound kernels
+    static const int env_ctas = [] {
+        const char* e = std::getenv("B200_GEMM_MAX_CTAS");  // experiments: overrides every plan's cap
         const int v = e ? std::atoi(e) : 0;
-        return v > 0 && v < kNumSMs ? v : kNumSMs;
+        return v > 0 && v < kNumSMs ? v : 0;
     }();
+    int max_ctas = env_ctas > 0 ? env_ctas : (p.d.max_ctas > 0 && p.d.max_ctas < kNumSMs ? p.d.max_ctas : kNumSMs);
     const int grid = k.num_tiles < max_ctas ? k.num_tiles : max_ctas;
     const CUtensorMap& tmo = p.staged ? p.tma_o : p.tma_a;
     const CUtensorMap& tmr = p.staged && p.res_tma ? p.tma_r : p.tma_a;

@@ -44,6 +44,7 @@ struct GemmDesc {
     const float* rope = nullptr;
     int rope_T = 0;
     int rope_cols = 0;
+    int max_ctas = 0;      // > 0: persistent grid of at most this many CTAs (leave SMs to other runners' latency-bound kernels)
     int rope_stride = 0;   // positions per table row: the table is [16 dim pairs][rope_stride positions] float4 (cos, sin, cos, sin)
     // optional fused residual epilogue (deepnorm): v = v + alpha * residual[g][n]; requires act == NONE
     const __half* residual = nullptr;

@@ -1039,6 +1039,10 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         plan->rec_un = un;
         plan->rec_y_map = make_tmap_2d(seq, (uint64_t)C, (uint64_t)T_out * Np, (uint64_t)C * 2, 32, un == 64 ? 32 : 16);
         const int GB = 32;  // chunk block of the gx layout (n_pad = 32 on this path)
+        // With three or more batches in flight the x-projection GEMMs keep off 32 SMs, so that another batch's recurrence
+        // (48 SMs, several milliseconds of latency chain) can start beside them instead of queueing behind a GEMM that owns every SM
+        // (measured at batch 512, 4 runners: 26.4 -> 24.0 ms per step, profiles/r02_b13_hac_cap*).
+        const int gemm_cap = hint >= 3 ? 116 : 0;
         plan->lstm_grid = (Np / un) * 6;
         for (int l = 0; l < desc.lstm_layers; ++l) {
             GemmDesc g{};
@@ -1058,6 +1062,7 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
             g.out_s0 = GB;
             g.out_col_m1 = GB;
             g.out_col_s0 = (int64_t)4 * C * GB;
+            g.max_ctas = gemm_cap;
             plan->gx_gemm.push_back(make_gemm_plan(g));
             plan->rec_whh.push_back(layers[l].w_hh);
             LstmRecParams rp{};
