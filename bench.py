@@ -517,6 +517,25 @@ def main():
                 r = res["roofline"]
                 subs[sk]["roofline"] = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step",
                                                           "per_kernel", "decode", "forward_tflops", "traffic")}
+        # BASELINE.json configs[2], [3]: the same models at the batch size the engine picks itself -- the counterpart of
+        # CudaCaller::determine_batch_dims (pre-computed "NVIDIA B200" table + exact memory cap at 80 % of the free HBM)
+        from dorado_b200 import batching
+        from dorado_b200.config import load_model_config as _lc
+        from dorado_b200.runner import B200Caller
+        from dorado_b200.weights import synthetic_weights
+        for sk, sc in SUB_MODELS.items():
+            cfg_s = _lc(model_dir(sk))
+            probe = B200Caller(cfg_s, synthetic_weights(cfg_s, 42), device=local_rank, num_runners=DEFAULT_RUNNERS[sk])
+            free_b, _tot = torch.cuda.mem_get_info(local_rank)
+            dims, source = batching.determine_batch_dims(probe, MODELS[sk], args.chunksize, int(0.8 * free_b),
+                                                         num_runners=DEFAULT_RUNNERS[sk])
+            probe.close()
+            auto_batch = int(dims[0][0])
+            res = bench_b200(sk, auto_batch, args.chunksize, max(3, sc["steps"] // 2), 3, DEFAULT_RUNNERS[sk], rank, local_rank, world)
+            if rank == 0:
+                subs[sk + "_auto_batch"] = {k: res[k] for k in ("value", "ms_per_step", "steps", "e2e", "batch_per_gpu",
+                                                               "chunk_samples", "runners_per_gpu", "gpu_launches")}
+                subs[sk + "_auto_batch"]["batch_source"] = f"determine_batch_dims: {source}, chunk-size buckets {dims}"
     if rank != 0:
         return 0
     line = {"metric": METRIC, "value": main_res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,

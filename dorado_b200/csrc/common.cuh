@@ -31,6 +31,22 @@ __device__ __forceinline__ float warp_max(float v) {
     return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
 }
 
+// Activations on the SFU: one ex2 and one rcp each (MUFU.EX2 / MUFU.RCP, ~1 ulp), no IEEE division sequences.  Finite inputs
+// only: e^x = inf gives the correct limit, x = -inf itself would give swish = NaN.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float swish_fast(float v) { return v * sigmoid_fast(v); }
+__device__ __forceinline__ float tanh_fast(float v) { return fmaf(-2.0f, rcp_approx(ex2_approx(2.885390081777927f * v) + 1.0f), 1.0f); }
+
 __device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

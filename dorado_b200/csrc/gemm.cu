@@ -79,10 +79,10 @@ constexpr int kMaxStages = 4;
 // compiler if-converts it and every element pays for every variant's ex2 / rcp (measured: 2.7x on the plain-store GEMMs).
 template <int ACT>
 __device__ __forceinline__ float act_apply(float v) {
-    if constexpr (ACT == GEMM_ACT_SWISH) return v / (1.0f + __expf(-v));
-    else if constexpr (ACT == GEMM_ACT_SWISH_CLAMP) return fminf(v / (1.0f + __expf(-v)), 3.5f);
-    else if constexpr (ACT == GEMM_ACT_TANH) return 1.0f - 2.0f / (__expf(2.0f * v) + 1.0f);
-    else if constexpr (ACT == GEMM_ACT_TANH_X5) return 5.0f * (1.0f - 2.0f / (__expf(2.0f * v) + 1.0f));
+    if constexpr (ACT == GEMM_ACT_SWISH) return swish_fast(v);
+    else if constexpr (ACT == GEMM_ACT_SWISH_CLAMP) return fminf(swish_fast(v), 3.5f);
+    else if constexpr (ACT == GEMM_ACT_TANH) return tanh_fast(v);
+    else if constexpr (ACT == GEMM_ACT_TANH_X5) return 5.0f * tanh_fast(v);
     else return v;
 }
 
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float y0 = v[4 * j], g0 = v[4 * j + 1], y1 = v[4 * j + 2], g1 = v[4 * j + 3];
-                                h[j] = __floats2half2_rn(y0 * (g0 / (1.0f + __expf(-g0))), y1 * (g1 / (1.0f + __expf(-g1))));
+                                h[j] = __floats2half2_rn(y0 * swish_fast(g0), y1 * swish_fast(g1));
                             }
                             if (staged) {
                                 const int hc = (c - c_begin) * 16;

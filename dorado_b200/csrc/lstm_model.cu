@@ -44,15 +44,27 @@ struct Conv12Params {
 
 constexpr int CONV_W_FLOATS = 16 * MAXW + 16 + MAXW * 16 * 16 + 16;
 
-__device__ __forceinline__ float conv_act(float v, int act) {
-    switch (act) {
-        case B200_ACT_SWISH: return v / (1.0f + __expf(-v));
-        case B200_ACT_SWISH_CLAMP: return fminf(v / (1.0f + __expf(-v)), 3.5f);
-        default: return 1.0f - 2.0f / (__expf(2.0f * v) + 1.0f);
-    }
+// swish(v) = v / (1 + e^-v), optionally capped at 3.5, or tanh(v) = 1 - 2 / (e^{2v} + 1): one branch-free path (ex2, rcp, select,
+// fma, min) whose constants are picked once per thread -- a switch on the run-time activation would be if-converted and every
+// element would pay for every variant's transcendentals
+struct ConvAct {
+    float k, cap;
+    bool is_tanh;
+};
+__device__ __forceinline__ ConvAct conv_act_coef(int act) {
+    ConvAct c;
+    c.is_tanh = act != B200_ACT_SWISH && act != B200_ACT_SWISH_CLAMP;
+    c.k = c.is_tanh ? 2.885390081777927f : -1.4426950408889634f;
+    c.cap = act == B200_ACT_SWISH_CLAMP ? 3.5f : __int_as_float(0x7f800000);
+    return c;
+}
+__device__ __forceinline__ float conv_act(float v, const ConvAct& c) {
+    const float r = rcp_approx(1.0f + ex2_approx(c.k * v));
+    return fminf(c.is_tanh ? fmaf(-2.0f, r, 1.0f) : v * r, c.cap);
 }
 
 __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
+    const ConvAct a1 = conv_act_coef(p.act1), a2 = conv_act_coef(p.act2);
     const int n = blockIdx.y;
     const int t0 = blockIdx.x * CONV_TT;
     const int p1 = p.w1 / 2, p2 = p.w2 / 2;
@@ -79,7 +91,7 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
         for (int c = 0; c < p.c1; ++c) {
             float acc = s_b1[c];
             for (int k = 0; k < p.w1; ++k) acc += s_w1[c * p.w1 + k] * xs[i + k];
-            y1[c * Y1P + i] = inside ? conv_act(acc, p.act1) : 0.0f;  // conv2 zero-pads conv1's *output*
+            y1[c * Y1P + i] = inside ? conv_act(acc, a1) : 0.0f;  // conv2 zero-pads conv1's *output*
         }
     }
     __syncthreads();
@@ -104,7 +116,7 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
         }
         __half2 h[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(conv_act(acc[2 * j], p.act2), conv_act(acc[2 * j + 1], p.act2));
+        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(conv_act(acc[2 * j], a2), conv_act(acc[2 * j + 1], a2));
         if (t >= L) {  // beyond a short chunk's end: the next convolution's zero padding
 #pragma unroll
             for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(0.0f, 0.0f);

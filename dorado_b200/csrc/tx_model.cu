@@ -26,7 +26,7 @@ namespace b200 {
 
 namespace {
 
-__device__ __forceinline__ float swish_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float swish_f(float v) { return swish_fast(v); }
 
 // ------------------------------------------------------------------------------------------------
 // conv1: 1 -> C1 channels, stride 1.  out[n][pad_out + t][c] = swish(b[c] + sum_k w[c][k] x[n][t + k - W/2])
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) tx_conv1_kernel(const Conv1Params p) {
             const int c = cg * 8 + 2 * j + e;
             float acc = __ldg(p.w + p.C1 * p.W + c);
             for (int k = 0; k < p.W; ++k) acc += __ldg(p.w + c * p.W + k) * xs[k];
-            v[e] = p.act == B200_ACT_TANH ? (1.0f - 2.0f / (__expf(2.0f * acc) + 1.0f))
+            v[e] = p.act == B200_ACT_TANH ? tanh_fast(acc)
                                           : (p.act == B200_ACT_SWISH_CLAMP ? fminf(swish_f(acc), 3.5f) : swish_f(acc));
         }
         h[j] = __floats2half2_rn(v[0], v[1]);
@@ -113,31 +113,33 @@ constexpr int ATT_D = 64;   // head dimension
 // ------------------------------------------------------------------------------------------------
 // Sliding-window attention on the 5th-generation tensor cores (successor of koi_masked_attention, TxModules.cpp:648;
 // window semantics TxModules.cpp:310-317: keys j with -win_upper <= j - i <= win_lower).
-// qkv: [N*T][3][H][64] fp16 (output of the Wqkv GEMM, q and k already rotated); out: [N*T][H*64] fp16.  One CTA = 128 queries of one (chunk, head); the keys they can see lie in at
-// most three aligned blocks of 128 keys, walked flash-style:
-//     S  = Q K_b^T          tcgen05.mma, 128 x 128 x 64, Q and K_b in shared memory (TMA, 128-byte swizzle), S in TMEM
-//     P  = exp2(S' - m)     one thread per query row (TMEM lane): tcgen05.ld S, running max / sum, P packed to fp16 and
-//                           written back into TENSOR MEMORY with tcgen05.st
-//     O_b = P V_b           tcgen05.mma with A = P read from TMEM and B = V_b as it lies in memory ([key][d], i.e. the
+// qkv: [N*T][3][H][64] fp16 (output of the Wqkv GEMM, q and k already rotated); out: [N*T][H*64] fp16.
+// One CTA = 128 queries of one (chunk, head); the keys they can see lie in at most three aligned blocks of 128 keys (the
+// kernel requires win_upper + win_lower + 128 <= 3 * 128), walked flash-style:
+//     S_b = Q K_b^T         tcgen05.mma, 128 x 128 x 64, Q and K_b in shared memory (TMA, 128-byte swizzle), S_b in TMEM
+//     P_b = exp2(S_b' - m)  one thread per query row (TMEM lane): tcgen05.ld S, running max / sum, P packed to fp16 and
+//                           written back into TENSOR MEMORY with tcgen05.st -- over the S columns it has consumed
+//     O_b = P_b V_b         tcgen05.mma with A = P read from TMEM and B = V_b as it lies in memory ([key][d], i.e. the
 //                           MN-major form of the B operand -- no transposed copy of V is ever made)
-//     O  = O * alpha + O_b  in registers (64 fp32 per row), so the accumulator in TMEM is never rescaled in place
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 the 128 softmax rows.  TMEM: S 128 + P 64 + O_b 64 columns =
-// 256, shared memory 80 KB, so two CTAs share an SM and one's softmax runs under the other's MMAs and loads.
+//     O   = O * alpha + O_b in registers (64 fp32 per row), so the accumulator in TMEM is never rescaled in place
+// Tensor memory holds two 128-column buffers; buffer b & 1 carries S_b, then P_b in its columns 0-63 and O_b in its columns
+// 64-127.  That lets the issuer run ahead: S_1 is computed while the rows are still in the softmax of block 0, P_0 V_0 runs
+// under the softmax of block 1, and the rows fold O_b in one block late -- the dependent chain S -> softmax -> PV of a block
+// is off the critical path except at the ends.  All three K/V blocks are loaded up front (V in three buffers, K_2 reuses K_0's
+// buffer once S_0 has completed).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 the 128 softmax rows.  TMEM 256 columns, shared memory 97 KB:
+// two CTAs share an SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int AT_BQ = 128, AT_BK = 128;
 constexpr int AT_TILE = 128 * 64 * 2;   // one [128 x 64] fp16 tile
+constexpr int AT_MAXBLK = 3;
+constexpr int AT_SMEM = 1024 + (1 + 2 + AT_MAXBLK) * AT_TILE + 256;
 
 struct AttnTcParams {
     __half* out;   // [N*T][H*64]
     int N, T, H;
     int win_upper, win_lower;
 };
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
     // B operand stored [K rows][64 N-elements = 128 B]: MN-major, 128-byte swizzle, 8-row (K) groups 1024 B apart.  The tile
@@ -155,18 +157,17 @@ __global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_co
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* q_s = smem;                       // [128 q][64 d]
-    uint8_t* k_s = q_s + AT_TILE;              // [2][128 keys][64 d]
-    uint8_t* v_s = k_s + 2 * AT_TILE;          // [2][128 keys][64 d]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + 2 * AT_TILE);
+    uint8_t* k_s = q_s + AT_TILE;              // [2][128 keys][64 d]   block b in buffer b & 1
+    uint8_t* v_s = k_s + 2 * AT_TILE;          // [3][128 keys][64 d]   block b in buffer b
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + AT_MAXBLK * AT_TILE);
     uint64_t* q_full = bars;          // TMA -> MMA
-    uint64_t* kv_full = bars + 1;     // [2]
-    uint64_t* kv_free = bars + 3;     // [2] MMAs of a block done with K_b, V_b -> TMA
-    uint64_t* s_full = bars + 5;      // MMA -> softmax
-    uint64_t* s_free = bars + 6;      // softmax has read S -> MMA (4 warp arrivals)
-    uint64_t* p_ready = bars + 7;     // softmax wrote P -> MMA (4 warp arrivals)
-    uint64_t* o_full = bars + 8;      // MMA -> softmax
-    uint64_t* o_free = bars + 9;      // softmax has read O_b -> MMA (4 warp arrivals)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* kv_full = bars + 1;     // [3] TMA -> MMA
+    uint64_t* k_free = bars + 4;      // S_0 has completed: K buffer 0 may take block 2
+    uint64_t* s_full = bars + 5;      // [2] MMA -> softmax
+    uint64_t* p_ready = bars + 7;     // [2] softmax wrote P -> MMA (4 warp arrivals)
+    uint64_t* o_full = bars + 9;      // [2] MMA -> softmax
+    uint64_t* buf_free = bars + 11;   // [2] softmax has read O_b: the TMEM buffer may take S of block b + 2 (4 warp arrivals)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -177,19 +178,18 @@ __global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_co
     int kb_last = (q0 + AT_BQ - 1 + p.win_lower) / AT_BK;
     const int kb_max = (p.T - 1) / AT_BK;
     if (kb_last > kb_max) kb_last = kb_max;
-    const int nblk = kb_last - kb_first + 1;
+    const int nblk = kb_last - kb_first + 1;     // 1..3 (checked on the host)
 
     if (threadIdx.x == 0) {
         tc::mbar_init(q_full, 1);
+        for (int i = 0; i < AT_MAXBLK; ++i) tc::mbar_init(&kv_full[i], 1);
+        tc::mbar_init(k_free, 1);
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&kv_full[i], 1);
-            tc::mbar_init(&kv_free[i], 1);
+            tc::mbar_init(&s_full[i], 1);
+            tc::mbar_init(&p_ready[i], 4);
+            tc::mbar_init(&o_full[i], 1);
+            tc::mbar_init(&buf_free[i], 4);
         }
-        tc::mbar_init(s_full, 1);
-        tc::mbar_init(s_free, 4);
-        tc::mbar_init(p_ready, 4);
-        tc::mbar_init(o_full, 1);
-        tc::mbar_init(o_free, 4);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_qkv);
     }
@@ -198,21 +198,19 @@ __global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_co
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tm_s = tmem_base, tm_p = tmem_base + 128, tm_o = tmem_base + 192;
     const int row0 = n * p.T;   // first token row of this chunk in the [N*T][1536] view
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
+        // ---------------- TMA producer: everything up front ----------------
         if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(q_full, AT_TILE);
             tc::tma_load_2d(q_s, &tma_qkv, q_full, h * ATT_D, row0 + q0);
             for (int b = 0; b < nblk; ++b) {
-                const int buf = b & 1;
-                tc::mbar_wait(&kv_free[buf], (uint32_t)(((b >> 1) & 1) ^ 1));
-                tc::mbar_arrive_expect_tx(&kv_full[buf], 2 * AT_TILE);
+                if (b == 2) tc::mbar_wait(k_free, 0);
+                tc::mbar_arrive_expect_tx(&kv_full[b], 2 * AT_TILE);
                 const int krow = row0 + (kb_first + b) * AT_BK;
-                tc::tma_load_2d(k_s + buf * AT_TILE, &tma_qkv, &kv_full[buf], (p.H + h) * ATT_D, krow);
-                tc::tma_load_2d(v_s + buf * AT_TILE, &tma_qkv, &kv_full[buf], (2 * p.H + h) * ATT_D, krow);
+                tc::tma_load_2d(k_s + (b & 1) * AT_TILE, &tma_qkv, &kv_full[b], (p.H + h) * ATT_D, krow);
+                tc::tma_load_2d(v_s + b * AT_TILE, &tma_qkv, &kv_full[b], (2 * p.H + h) * ATT_D, krow);
             }
         }
     } else if (warp == 1) {
@@ -221,28 +219,34 @@ __global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_co
             constexpr uint32_t idesc_s = tc::umma_idesc_f16(128, 128);
             constexpr uint32_t idesc_o = tc::umma_idesc_f16(128, 64) | (1u << 16);   // B operand MN-major
             const uint64_t qdesc = tc::umma_desc_sw128(tc::smem_u32(q_s));
-            tc::mbar_wait(q_full, 0);
-            for (int b = 0; b < nblk; ++b) {
-                const int buf = b & 1;
-                const uint32_t par = (uint32_t)(b & 1);
-                tc::mbar_wait(&kv_full[buf], (uint32_t)((b >> 1) & 1));
-                tc::mbar_wait(s_free, par ^ 1);   // the rows have read S of the previous block
+            auto issue_s = [&](int b) {
+                tc::mbar_wait(&kv_full[b], 0);
                 tc::tc_fence_after();
-                const uint64_t kdesc = tc::umma_desc_sw128(tc::smem_u32(k_s + buf * AT_TILE));
+                const uint64_t kdesc = tc::umma_desc_sw128(tc::smem_u32(k_s + (b & 1) * AT_TILE));
+                const uint32_t tm_s = tmem_base + (uint32_t)((b & 1) * 128);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k) tc::umma_f16(tm_s, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
-                tc::umma_commit(s_full);
-                tc::mbar_wait(p_ready, par);      // P of this block is in tensor memory
-                tc::mbar_wait(o_free, par ^ 1);   // the rows have read O of the previous block
+                tc::umma_commit(&s_full[b & 1]);
+            };
+            tc::mbar_wait(q_full, 0);
+            issue_s(0);
+            if (nblk > 2) tc::umma_commit(k_free);   // S_0 done -> K buffer 0 is free for block 2
+            if (nblk > 1) issue_s(1);
+            for (int b = 0; b < nblk; ++b) {
+                const uint32_t tm = tmem_base + (uint32_t)((b & 1) * 128);
+                tc::mbar_wait(&p_ready[b & 1], (uint32_t)((b >> 1) & 1));      // P_b is in tensor memory
                 tc::tc_fence_after();
-                const uint64_t vdesc = umma_desc_sw128_mn(tc::smem_u32(v_s + buf * AT_TILE));
+                const uint64_t vdesc = umma_desc_sw128_mn(tc::smem_u32(v_s + b * AT_TILE));
 #pragma unroll
                 for (int k = 0; k < AT_BK / 16; ++k) {
                     // 16 keys = 8 packed TMEM columns of P; 16 rows of V = 2048 B further on
-                    tc::umma_f16_ts(tm_o, tm_p + (uint32_t)(8 * k), vdesc + (uint64_t)((k * 2048) >> 4), idesc_o, k != 0);
+                    tc::umma_f16_ts(tm + 64u, tm + (uint32_t)(8 * k), vdesc + (uint64_t)((k * 2048) >> 4), idesc_o, k != 0);
                 }
-                tc::umma_commit(o_full);
-                tc::umma_commit(&kv_free[buf]);
+                tc::umma_commit(&o_full[b & 1]);
+                if (b + 2 < nblk) {
+                    tc::mbar_wait(&buf_free[b & 1], (uint32_t)((b >> 1) & 1));   // the rows have folded O_b in
+                    issue_s(b + 2);
+                }
             }
         }
     } else {
@@ -255,103 +259,110 @@ __global__ void __launch_bounds__(192, 2) tx_attention_tc_kernel(const __grid_co
         float o[64];
 #pragma unroll
         for (int d = 0; d < 64; ++d) o[d] = 0.0f;
-        float m_run = -1e30f, l_run = 0.0f;
-        for (int b = 0; b < nblk; ++b) {
-            const uint32_t par = (uint32_t)(b & 1);
-            const int kb = (kb_first + b) * AT_BK;
-            // keys of this block visible to this row: j in [lo, hi)
-            int lo = qi - p.win_upper - kb, hi = qi + p.win_lower + 1 - kb;
-            if (lo < 0) lo = 0;
-            if (hi > AT_BK) hi = AT_BK;
-            if (kb + hi > p.T) hi = p.T - kb;
-            if (qi >= p.T) hi = 0;
-            // The window is a band, so per warp (32 consecutive rows) a 32-key column chunk is either invisible to every row
-            // (skipped: no tensor-memory load, no exponentials, P = 0), visible to every row (no per-element masking) or --
-            // for at most two of the twelve chunks a warp meets -- cut by the band's edge.
-            const int wlo_min = __reduce_min_sync(0xffffffffu, lo), wlo_max = __reduce_max_sync(0xffffffffu, lo);
-            const int whi_min = __reduce_min_sync(0xffffffffu, hi), whi_max = __reduce_max_sync(0xffffffffu, hi);
-            tc::mbar_wait(s_full, par);
-            tc::tc_fence_after();
-            // pass 1: row maximum over the visible keys (S stays in tensor memory)
-            float m_blk = -1e30f;
+        float m_run = -1e30f, l_run = 0.0f, alpha_prev = 0.0f;
+        for (int it = 0; it <= nblk; ++it) {
+            float alpha = 0.0f;
+            if (it < nblk) {
+                const int b = it;
+                const uint32_t tm = tmem_base + (uint32_t)((b & 1) * 128);
+                const int kb = (kb_first + b) * AT_BK;
+                // keys of this block visible to this row: j in [lo, hi)
+                int lo = qi - p.win_upper - kb, hi = qi + p.win_lower + 1 - kb;
+                if (lo < 0) lo = 0;
+                if (hi > AT_BK) hi = AT_BK;
+                if (kb + hi > p.T) hi = p.T - kb;
+                if (qi >= p.T) hi = 0;
+                // The window is a band, so per warp (32 consecutive rows) a 32-key column chunk is either invisible to every
+                // row (skipped: no tensor-memory load, no exponentials, P = 0), visible to every row (no per-element masking)
+                // or -- for at most two of the twelve chunks a warp meets -- cut by the band's edge.
+                const int wlo_min = __reduce_min_sync(0xffffffffu, lo), wlo_max = __reduce_max_sync(0xffffffffu, lo);
+                const int whi_min = __reduce_min_sync(0xffffffffu, hi), whi_max = __reduce_max_sync(0xffffffffu, hi);
+                tc::mbar_wait(&s_full[b & 1], (uint32_t)((b >> 1) & 1));
+                tc::tc_fence_after();
+                // pass 1: row maximum over the visible keys (S stays in tensor memory)
+                float m_blk = -1e30f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int c0 = 32 * c;
-                if (c0 + 32 <= wlo_min || c0 >= whi_max) continue;
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)c0, v);
-                tc::tmem_ld_wait();
-                if (c0 >= wlo_max && c0 + 32 <= whi_min) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (c0 + j >= lo && c0 + j < hi) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
-                    }
-                }
-            }
-            const float m_new = fmaxf(m_run, m_blk * sc);
-            const float alpha = ex2_approx(m_run - m_new);   // 1 when nothing changed, 0 on the first visible block
-            float l_blk = 0.0f;
-            // pass 2: P = exp2(S * sc - m), packed to fp16 pairs, written to tensor memory as the A operand of P V
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int c0 = 32 * c;
-                uint32_t pk[16];
-                if (c0 + 32 <= wlo_min || c0 >= whi_max) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
-                } else {
+                for (int c = 0; c < 4; ++c) {
+                    const int c0 = 32 * c;
+                    if (c0 + 32 <= wlo_min || c0 >= whi_max) continue;
                     uint32_t v[32];
-                    tc::tmem_ld_32x32(tm_s + lane_sel + (uint32_t)c0, v);
+                    tc::tmem_ld_32x32(tm + lane_sel + (uint32_t)c0, v);
                     tc::tmem_ld_wait();
                     if (c0 >= wlo_max && c0 + 32 <= whi_min) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m_new));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new));
-                            l_blk += p0 + p1;
-                            const __half2 hp = __floats2half2_rn(p0, p1);
-                            pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
-                        }
+                        for (int j = 0; j < 32; ++j) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int col = c0 + 2 * j;
-                            const float p0 = (col >= lo && col < hi) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m_new)) : 0.0f;
-                            const float p1 = (col + 1 >= lo && col + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new)) : 0.0f;
-                            l_blk += p0 + p1;
-                            const __half2 hp = __floats2half2_rn(p0, p1);
-                            pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j >= lo && c0 + j < hi) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
                         }
                     }
                 }
-                tc::tmem_st_32x16(tm_p + lane_sel + (uint32_t)(16 * c), pk);
-            }
-            tc::tmem_st_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                tc::mbar_arrive(s_free);
-                tc::mbar_arrive(p_ready);
-            }
-            l_run = l_run * alpha + l_blk;
-            m_run = m_new;
-            // O = O * alpha + P V_b
-            tc::mbar_wait(o_full, par);
-            tc::tc_fence_after();
+                const float m_new = fmaxf(m_run, m_blk * sc);
+                alpha = ex2_approx(m_run - m_new);   // 1 when nothing changed, 0 on the first visible block
+                float l_blk = 0.0f;
+                // pass 2: P = exp2(S * sc - m), packed to fp16 pairs, written over the consumed S columns as the A operand of P V
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int c0 = 32 * c;
+                    uint32_t pk[16];
+                    if (c0 + 32 <= wlo_min || c0 >= whi_max) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tm_o + lane_sel + (uint32_t)(32 * c), v);
-                tc::tmem_ld_wait();
+                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    } else {
+                        uint32_t v[32];
+                        tc::tmem_ld_32x32(tm + lane_sel + (uint32_t)c0, v);
+                        tc::tmem_ld_wait();
+                        if (c0 >= wlo_max && c0 + 32 <= whi_min) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[32 * c + j] = fmaf(o[32 * c + j], alpha, __uint_as_float(v[j]));
+                            for (int j = 0; j < 16; ++j) {
+                                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m_new));
+                                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new));
+                                l_blk += p0 + p1;
+                                const __half2 hp = __floats2half2_rn(p0, p1);
+                                pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int col = c0 + 2 * j;
+                                const float p0 = (col >= lo && col < hi) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m_new)) : 0.0f;
+                                const float p1 = (col + 1 >= lo && col + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m_new)) : 0.0f;
+                                l_blk += p0 + p1;
+                                const __half2 hp = __floats2half2_rn(p0, p1);
+                                pk[j] = *reinterpret_cast<const uint32_t*>(&hp);
+                            }
+                        }
+                    }
+                    // chunk c of S (columns 32c .. 32c+31) has been read; its P lands in columns 16c .. 16c+15, all consumed
+                    tc::tmem_st_32x16(tm + lane_sel + (uint32_t)(16 * c), pk);
+                }
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&p_ready[b & 1]);
+                l_run = l_run * alpha + l_blk;
+                m_run = m_new;
             }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(o_free);
+            if (it >= 1) {
+                // O = O * alpha_b + P_b V_b for the previous block b = it - 1 (its MMAs ran under this block's softmax)
+                const int b = it - 1;
+                const uint32_t tm = tmem_base + (uint32_t)((b & 1) * 128) + 64u;
+                tc::mbar_wait(&o_full[b & 1], (uint32_t)((b >> 1) & 1));
+                tc::tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(tm + lane_sel + (uint32_t)(32 * c), v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[32 * c + j] = fmaf(o[32 * c + j], alpha_prev, __uint_as_float(v[j]));
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&buf_free[b & 1]);
+            }
+            alpha_prev = alpha;
         }
         if (qi < p.T) {
             const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
@@ -697,6 +708,9 @@ std::unique_ptr<ForwardPlan> TxModel::make_plan(int N, int T_in, const __half* s
         plan->crf = make_gemm_plan(g);
     }
     plan->qkv_map = make_tmap_2d(qkv, (uint64_t)3 * desc.nhead * ATT_D, (uint64_t)rows, (uint64_t)3 * desc.nhead * ATT_D * 2, ATT_D, 128);
+    if (desc.attn_window_upper > AT_BK || desc.attn_window_lower > AT_BK || desc.attn_window_upper < 0 || desc.attn_window_lower < 0) {
+        throw Unsupported("attention window must lie within [-128, +128] (three key blocks per query tile)");
+    }
     plan->attn_tc_p = AttnTcParams{att, N, T, desc.nhead, desc.attn_window_upper, desc.attn_window_lower};
     plan->x = x;
     plan->y = y;
@@ -732,7 +746,7 @@ void TxPlan::run(cudaStream_t stream, ProfileSink* prof) {
         }
         {
             NvtxRange r("MEA");
-            constexpr int smem = 1024 + 5 * AT_TILE + 256;
+            constexpr int smem = AT_SMEM;
             ensure_dynamic_smem(tx_attention_tc_kernel, smem);
             tx_attention_tc_kernel<<<dim3((unsigned)((T + AT_BQ - 1) / AT_BQ), (unsigned)H, (unsigned)N), 192, smem, stream>>>(qkv_map, attn_tc_p);
             if (prof) prof->mark("tx_attention", stream);
