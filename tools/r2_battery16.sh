@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, battery 16 (re-entry): full GPU suite of the committed tree, default bench line, then the ncu evidence of tools/r2_profile_all.sh
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+( time timeout 1200 python -m pytest tests -m gpu -q -s -p no:cacheprovider ) > gpurun_out/b16_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/b16_tests.log
+( time timeout 900 python bench.py ) > gpurun_out/b16_bench_default.json 2> gpurun_out/b16_bench_default.err
+timeout 1500 bash tools/r2_profile_all.sh > gpurun_out/b16_profile.log 2>&1
+echo done > gpurun_out/b16_done
