@@ -281,7 +281,7 @@ def kernel_work(cfg, kind, N, T, T_out):
     # decode: every kernel is charged the bytes of its own interface (what it must read and write once)
     work["crf_bwd_scan"] = ("hbm", (2.0 * C + 4.0 * S) * T_out * N)               # scores in, fp32 guides out
     work["crf_fwd_beam"] = ("hbm", (2.0 * C + 4.0 * S + 8.0 * 32) * T_out * N)    # scores + guides in, beam records out
-    work["crf_traceback"] = ("hbm", (8.0 * 32 + 3.0) * T_out * N)                 # beam records in, moves/seq/qstring out
+    work["crf_traceback"] = ("hbm", (4.0 * 32 + 32.0 + 3.0) * T_out * N)          # meta plane + one 32 B sector of the prob plane per block in, moves/seq/qstring out
     return work
 
 

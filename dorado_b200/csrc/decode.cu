@@ -13,7 +13,9 @@
 // Data layout in HBM (per batch of N chunks, T blocks, S = 4^state_len states, C = 4S):
 //   scores  fp16  [N][T][C]        read twice (once per scan direction), coalesced 32 B per thread
 //   bwd     fp32  [N][T+1][S]      written by kernel 1, read once by kernel 2
-//   beam    8 B   [N][T][32]       {state:16, prev:8, stay:8, posterior:f32 (before the ^0.4 of the qscore)} per kept element
+//   beam    2 x 4 B [N][T][32]     two planes per kept element: meta {state:16, prev:8, stay:8} (all the traceback's pointer
+//                                  chase reads) and the block probability f32 (before the ^0.4 of the qscore; read along the
+//                                  chosen path only)
 //   out     u8    moves/seq/qstr [N][T], n_bases i32 [N]
 // Thread mapping: one thread per state in both scans (two states per thread for S = 1024 in the forward
 // kernel); the forward kernel adds one beam-search warp per chunk that runs one block behind the scan.
@@ -161,13 +163,16 @@ __device__ __forceinline__ uint32_t crc2_inv(uint32_t crc, uint32_t nb) {
     return crc;
 }
 
+constexpr int kHashSlots = 1024;  // lane-id table over the low hash bits (stay/step merge lookup)
+
 struct BeamSmem {
-    float cand_score[5 * kBeamW];
-    uint32_t cand_hash[5 * kBeamW];
+    __align__(16) float cand_score[5 * kBeamW];   // [prev][base] step candidates; stays at 4 * width + prev (replay path only)
+    uint32_t cand_hash[5 * kBeamW];               // replay path only
     float new_score[kBeamW];
     uint32_t new_hash[kBeamW];
     uint32_t new_meta[kBeamW];  // state | prev << 16 | stay << 24
     __align__(16) uint32_t prev_hash[kBeamW];
+    uint8_t slot_lane[kHashSlots];  // never cleared: an entry is only trusted after comparing the hash it points to
 };
 
 struct BeamLane {
@@ -231,8 +236,48 @@ __device__ int beam_init(const float* bw_row, BeamSmem& bs, BeamLane& me, int W,
     return width;
 }
 
+// Block probability of a kept element's kmer (beam_search.cpp:459-503, before the pow(p, 0.4) that the traceback kernel
+// applies along the chosen path only): the posterior of the state plus those of its distinct shift neighbours, added in the
+// reference's order L0, R0, L1, R1, ... (L_b = state >> 2 | b << (2k-2), R_b = (state << 2 | b) mod S).  The L's are mutually
+// distinct and so are the R's, so a neighbour is skipped iff it equals the state or an earlier neighbour of the OTHER kind.
+template <int SL>
+__device__ __forceinline__ float kmer_block_prob(const float* post_row, int state) {
+    constexpr int S = Dims<SL>::S;
+    float prob = post_row[state];
+    const int l = state >> 2;
+    const int r = (state << 2) & (S - 1);
+    constexpr int msb = S >> 2;
+    // R_b' == L_b  <=>  r + b' == l + msb * b; with d = l - r:  b' - msb * b == d
+    const int d = l - r;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int L = l + msb * b, R = r + b;
+        // L_b against the state and R_0 .. R_{b-1}
+        bool keepL = L != state;
+#pragma unroll
+        for (int bb = 0; bb < b; ++bb) keepL = keepL && (bb - msb * b != d);
+        if (keepL) prob = B200_ADD(prob, post_row[L]);
+        // R_b against the state and L_0 .. L_b
+        bool keepR = R != state;
+#pragma unroll
+        for (int bb = 0; bb <= b; ++bb) keepR = keepR && (b - msb * bb != d);
+        if (keepR) prob = B200_ADD(prob, post_row[R]);
+    }
+    return prob < 0.0f ? 0.0f : (prob > 1.0f ? 1.0f : prob);
+}
+
 // One block of the beam search for one chunk, executed by one warp (lane = beam element).
-// Returns the new beam width; writes the kept elements (and their block probabilities) to beam_row.
+// Returns the new beam width; writes the kept elements (meta plane) and their block probabilities (prob plane).
+//
+// Measured on the B200 (profiles/r02_b17_*): the decode kernels are bound by instruction issue -- the backward scan runs at
+// ~0.5 instructions per cycle and scheduler on the SMs it occupies, and the beam warp's block time is its instruction count
+// times ~3 cycles -- so the step is written for few instructions: an in-kernel experiment that evaluated three levels of the
+// beam-cut bisection at once (7 cutoffs per round) shortened the dependent chain and made the kernel SLOWER.
+//   * stay/step merge: a stay i can only merge with the step (j, b_i) whose previous hash is crc2_inv(hash_i, b_i); that j is
+//     found through a 1024-entry lane-id table over the low hash bits (one byte store, one byte load, one compare) instead of
+//     comparing against all 32 hashes.  Lanes whose table entry was overwritten by another lane (a slot shared by two
+//     hashes) are broadcast and compared directly, which also detects equal hashes -- the one case that needs the
+//     reference's sequential order (replay path).
 template <int SL>
 __device__ int beam_step(const __half* sc_row,
                          const float* bw_row,
@@ -244,7 +289,8 @@ __device__ int beam_step(const __half* sc_row,
                          float log_beam_cut,
                          float blank,
                          bool last_block,
-                         uint2* beam_row,
+                         uint32_t* meta_row,
+                         float* prob_row,
                          int lane,
                          long long* dbg) {
     constexpr int S = Dims<SL>::S;
@@ -253,91 +299,93 @@ __device__ int beam_step(const __half* sc_row,
     constexpr uint32_t mask = S - 1;
     const bool valid = lane < width;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t vmask = width >= 32 ? 0xffffffffu : ((1u << width) - 1u);
 
     // --- candidates (beam_search.cpp:225-262) ---
     uint32_t ns[4], hs[4];
     float s[5];
     float lmax = B200_FLT_LOWEST;
+    const uint32_t latest = me.state & 3u;
+    const uint32_t target = crc2_inv(me.hash, latest);   // the hash a step's parent must have to merge with this stay
+    const uint32_t own_slot = me.hash & (kHashSlots - 1);
     if (valid) {
         const uint32_t shifted = me.state << 2;
         const uint32_t dropped = shifted >> SB;
+        const uint32_t nb = shifted & mask;
+        const float4 bw4 = *reinterpret_cast<const float4*>(bw_row + nb);   // bwd of the four successor states
+        const float bws = bw_row[me.state];
+        const float bwv[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
+        bs.slot_lane[own_slot] = (uint8_t)lane;
+        bs.prev_hash[lane] = me.hash;
 #pragma unroll
         for (uint32_t b = 0; b < 4; ++b) {
-            ns[b] = (shifted & mask) | b;
+            ns[b] = nb | b;
             const uint32_t move_idx = ((ns[b] << 2) + dropped) & 0xffffu;
-            s[b] = B200_ADD(B200_ADD(me.score, __half2float(sc_row[move_idx])), bw_row[ns[b]]);
+            s[b] = B200_ADD(B200_ADD(me.score, __half2float(sc_row[move_idx])), bwv[b]);
             hs[b] = crc2(me.hash, b);
             lmax = b200_fmaxf(lmax, s[b]);
         }
-        s[4] = B200_ADD(B200_ADD(me.score, blank), bw_row[me.state]);
+        s[4] = B200_ADD(B200_ADD(me.score, blank), bws);
         lmax = b200_fmaxf(lmax, s[4]);
+        *reinterpret_cast<float4*>(&bs.cand_score[lane * 4]) = make_float4(s[0], s[1], s[2], s[3]);
     }
     float max_score = warp_max(lmax);
+    __syncwarp();
     if (dbg && lane == 0) dbg[1] = clock64();
 
     // --- merge stays with equal-hash steps (beam_search.cpp:264-305) ---
-    // stay i matches step (j, b_i) iff hash_j == crc2_inv(hash_i, b_i): one lookup of the 32 previous hashes
-    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    int jm = -1;
     bool dup = false;
-    if (valid) dup = __popc(__match_any_sync(vmask, me.hash)) > 1;
-    bs.prev_hash[lane] = valid ? me.hash : 0u;
-    if (valid) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) bs.cand_score[lane * 4 + b] = s[b];
+    {
+        const uint32_t rb = valid ? bs.slot_lane[own_slot] : (uint32_t)lane;
+        const uint32_t c = bs.slot_lane[target & (kHashSlots - 1)] & 31u;
+        uint32_t ov = __ballot_sync(0xffffffffu, valid && rb != (uint32_t)lane);
+        if (valid && ((vmask >> c) & 1u) && bs.prev_hash[c] == target) jm = (int)c;
+        while (ov) {  // lanes not reachable through the table (warp-uniform loop, usually zero or one trip)
+            const int j = __ffs(ov) - 1;
+            ov &= ov - 1;
+            const uint32_t hj = __shfl_sync(0xffffffffu, me.hash, j);
+            if (valid && lane != j && me.hash == hj) dup = true;
+            if (valid && target == hj) jm = j;
+        }
     }
-    __syncwarp();
     if (!__any_sync(0xffffffffu, dup)) {
         float folded = B200_FLT_LOWEST;
-        if (valid) {
-            const uint32_t latest = me.state & 3u;
-            const uint32_t target = crc2_inv(me.hash, latest);
-            uint32_t hit = 0u;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const uint4 h = *reinterpret_cast<const uint4*>(&bs.prev_hash[4 * j4]);
-                hit |= (h.x == target ? 1u : 0u) << (4 * j4);
-                hit |= (h.y == target ? 1u : 0u) << (4 * j4 + 1);
-                hit |= (h.z == target ? 1u : 0u) << (4 * j4 + 2);
-                hit |= (h.w == target ? 1u : 0u) << (4 * j4 + 3);
-            }
-            hit &= vmask;
-            if (hit) {
-                const int jm = __ffs(hit) - 1;  // hashes are distinct: at most one bit
-                const int pi = jm * 4 + (int)latest;
-                const float st = s[4], sp = bs.cand_score[pi];
-                folded = b200_log_sum_exp(st, sp);
-                if (st > sp) {
-                    s[4] = folded;
-                    bs.cand_score[pi] = B200_FLT_LOWEST;
-                } else {
-                    bs.cand_score[pi] = folded;
-                    s[4] = B200_FLT_LOWEST;
-                }
+        if (jm >= 0) {  // hashes are distinct: at most one parent matches
+            const int pi = jm * 4 + (int)latest;
+            const float st = s[4], sp = bs.cand_score[pi];
+            folded = b200_log_sum_exp(st, sp);
+            if (st > sp) {
+                s[4] = folded;
+                bs.cand_score[pi] = B200_FLT_LOWEST;
+            } else {
+                bs.cand_score[pi] = folded;
+                s[4] = B200_FLT_LOWEST;
             }
         }
         max_score = b200_fmaxf(max_score, warp_max(folded));
         __syncwarp();
         if (valid) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) s[b] = bs.cand_score[lane * 4 + b];
+            const float4 r = *reinterpret_cast<const float4*>(&bs.cand_score[lane * 4]);
+            s[0] = r.x; s[1] = r.y; s[2] = r.z; s[3] = r.w;
         }
     } else {
-        // hash collision between beam elements (rare): replay the reference's sequential order
+        // equal hashes among the beam elements (rare): replay the reference's sequential order
         if (valid) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) bs.cand_hash[lane * 4 + b] = hs[b];
             bs.cand_score[4 * width + lane] = s[4];
             bs.cand_hash[4 * width + lane] = me.hash;
         }
-        bs.new_meta[lane] = valid ? (me.state & 3u) : 0u;
+        bs.new_meta[lane] = valid ? latest : 0u;
         __syncwarp();
         float m2 = max_score;
         if (lane == 0) {
             for (int i = 0; i < width; ++i) {
                 const int si = 4 * width + i;
-                const int latest = (int)bs.new_meta[i];
+                const int lt = (int)bs.new_meta[i];
                 for (int j = 0; j < width; ++j) {
-                    const int pi = j * 4 + latest;
+                    const int pi = j * 4 + lt;
                     if (bs.cand_hash[si] == bs.cand_hash[pi]) {
                         const float st = bs.cand_score[si], sp = bs.cand_score[pi];
                         const float folded = b200_log_sum_exp(st, sp);
@@ -360,20 +408,21 @@ __device__ int beam_step(const __half* sc_row,
             for (int b = 0; b < 4; ++b) s[b] = bs.cand_score[lane * 4 + b];
             s[4] = bs.cand_score[4 * width + lane];
         }
+        __syncwarp();
     }
 
     if (dbg && lane == 0) dbg[2] = clock64();
     // --- cutoff (beam_search.cpp:310-396) ---
-    float cutoff = B200_SUB(max_score, log_beam_cut);
-    auto count_ge = [&](float c) {
+    auto count_part = [&](float c) {  // this lane's share of count_ge(c)
         int n = 0;
         if (valid) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) n += (s[k] >= c);
         }
-        return warp_sum_int(n);
+        return n;
     };
-    int cnt = count_ge(cutoff);
+    float cutoff = B200_SUB(max_score, log_beam_cut);
+    int cnt = warp_sum_int(count_part(cutoff));
     if (cnt > W) {
         const int min_w = (W * 8) / 10;
         float lo = cutoff, hi = max_score;
@@ -381,17 +430,17 @@ __device__ int beam_step(const __half* sc_row,
         while ((cnt > W || cnt < min_w) && guesses < 10) {
             if (cnt > W) {
                 lo = cutoff;
-                cutoff = B200_DIV(B200_ADD(cutoff, hi), 2.0f);
+                cutoff = B200_MUL(B200_ADD(cutoff, hi), 0.5f);  // == (cutoff + hi) / 2.0f bit for bit
             } else {
                 hi = cutoff;
-                cutoff = B200_DIV(B200_ADD(cutoff, lo), 2.0f);
+                cutoff = B200_MUL(B200_ADD(cutoff, lo), 0.5f);
             }
-            cnt = count_ge(cutoff);
+            cnt = warp_sum_int(count_part(cutoff));
             ++guesses;
         }
         if (guesses == 10) {
             cutoff = hi;
-            cnt = count_ge(cutoff);
+            cnt = warp_sum_int(count_part(cutoff));
         }
         if (cnt > W) cnt = W;
     }
@@ -453,33 +502,12 @@ __device__ int beam_step(const __half* sc_row,
         meta = m2;
         me.state = meta & 0xffffu;
     }
-
     if (nvalid) {
         me.score = B200_SUB(me.score, bw_row[me.state]);
-        // block probability of this element's kmer (beam_search.cpp:459-503)
-        const int state = (int)me.state;
-        float prob = post_row[state];
-        int sh[8];
-        const int l = state >> 2;
-        const int r = (state << 2) & (S - 1);
-        const int msb = S >> 2;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            sh[2 * b] = l + msb * b;
-            sh[2 * b + 1] = r + b;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            bool count = sh[k] != state;
-#pragma unroll
-            for (int j = 0; j < k; ++j) count = count && (sh[j] != sh[k]);
-            if (count) prob = B200_ADD(prob, post_row[sh[k]]);
-        }
-        prob = prob < 0.0f ? 0.0f : (prob > 1.0f ? 1.0f : prob);
-        // the pow(p, 0.4) of beam_search.cpp:503 is applied by the traceback kernel, only along the chosen path
-        beam_row[lane] = make_uint2(meta, __float_as_uint(prob));
+        meta_row[lane] = meta;
+        prob_row[lane] = kmer_block_prob<SL>(post_row, (int)me.state);
     }
-    __syncwarp();
+    __syncwarp();  // the next step's shared-memory writes come after every lane's reads of this one
     if (dbg && lane == 0) {
         dbg[5] = clock64();
         dbg[6] = cnt;
@@ -487,8 +515,10 @@ __device__ int beam_step(const __half* sc_row,
     return cnt;
 }
 
+// bar.arrive orders the arriving thread's earlier shared-memory accesses before the barrier completes (the PTX
+// producer / consumer pattern: st.shared; bar.arrive  ||  bar.sync; ld.shared), so no membar is issued here -- the
+// __threadfence_block() this used to carry cost a MEMBAR.CTA per block on both sides of the hand-over.
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-    __threadfence_block();  // publish this thread's shared-memory writes before signalling the consumer
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
@@ -524,7 +554,8 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
     const int tid = threadIdx.x % GT;
     const int lane = threadIdx.x & 31;
     const int chunk = blockIdx.x * CH + g;
-    // barrier ids of this chunk group
+    // barrier ids of this chunk group.  SCAN: the scan threads among themselves (+ the beam warp for the two start-up
+    // syncs); FULL[slot]: scan threads arrive, beam warp waits; EMPTY[slot]: beam warp arrives, scan threads wait.
     const int BAR_SCAN = 1 + 5 * g, BAR_FULL = 2 + 5 * g, BAR_EMPTY = 4 + 5 * g;
 
     __shared__ __align__(16) float fa[CH][2][S];
@@ -536,10 +567,11 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
 
     if (chunk >= N) return;  // whole chunk groups exit together; every barrier below is per group
     const int T = lens ? min(T_pitch, __ldg(lens + chunk) / stride) : T_pitch;  // variable chunk sizes
-    const bool is_scan = tid < NT;
-    uint2* beam_out = beam + (size_t)chunk * T_pitch * kBeamW;
+    // beam history: two planes of [N][T][32] 4-byte words, meta = (state, prev, stay) and the block probability
+    uint32_t* meta_out = reinterpret_cast<uint32_t*>(beam) + (size_t)chunk * T_pitch * kBeamW;
+    float* prob_out = reinterpret_cast<float*>(beam) + ((size_t)N + chunk) * T_pitch * kBeamW;
 
-    if (is_scan) {
+    if (tid < NT) {
         // ================= scan threads =================
         const int v = tid;  // states SPT*v .. SPT*v + SPT-1
         const int wv = v >> 5;
@@ -610,11 +642,13 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
                         lmax = b200_fmaxf(lmax, vsum[e]);
                     }
                     float mx = warp_max(lmax);
-                    if (lane == 0) red[g][0][wv] = mx;
-                    named_bar_sync(BAR_SCAN, NT);
-                    mx = red[g][0][0];
+                    if constexpr (NW > 1) {
+                        if (lane == 0) red[g][0][wv] = mx;
+                        named_bar_sync(BAR_SCAN, NT);
+                        mx = red[g][0][0];
 #pragma unroll
-                    for (int w = 1; w < NW; ++w) mx = b200_fmaxf(mx, red[g][0][w]);
+                        for (int w = 1; w < NW; ++w) mx = b200_fmaxf(mx, red[g][0][w]);
+                    }
                     // posterior normaliser in the contract's order: per-thread left-to-right, per-warp xor butterfly,
                     // warps left to right (oracle/crf_oracle.c posts_row)
                     float ex[SPT];
@@ -626,11 +660,14 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
                     }
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) part = B200_ADD(part, __shfl_xor_sync(0xffffffffu, part, o));
-                    if (lane == 0) red[g][1][wv] = part;
-                    named_bar_sync(BAR_SCAN, NT);
-                    float z = red[g][1][0];
+                    float z = part;
+                    if constexpr (NW > 1) {
+                        if (lane == 0) red[g][1][wv] = part;
+                        named_bar_sync(BAR_SCAN, NT);
+                        z = red[g][1][0];
 #pragma unroll
-                    for (int w = 1; w < NW; ++w) z = B200_ADD(z, red[g][1][w]);
+                        for (int w = 1; w < NW; ++w) z = B200_ADD(z, red[g][1][w]);
+                    }
 #pragma unroll
                     for (int e = 0; e < SPT; ++e) post_row[g][slot][SPT * v + e] = B200_DIV(ex[e], z);
                     named_bar_arrive(BAR_FULL + slot, GT);  // slot t is complete
@@ -650,8 +687,8 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
             long long* d = (dbg && chunk == 0 && t >= 100 && t < 108) ? dbg + (t - 100) * 16 : nullptr;
             if (d && lane == 0) d[7] = clock64();
             named_bar_sync(BAR_FULL + slot, GT);
-            width = beam_step<SL>(sc_row[g][slot], bw_row[g][slot], post_row[g][slot], bsm[g], me, width, W, log_beam_cut,
-                                  blank, t == T - 1, beam_out + (size_t)t * kBeamW, lane, d);
+            width = beam_step<SL>(sc_row[g][slot], bw_row[g][slot], post_row[g][slot], bsm[g], me, width, W, log_beam_cut, blank,
+                                  t == T - 1, meta_out + (size_t)t * kBeamW, prob_out + (size_t)t * kBeamW, lane, d);
             if (t + 2 < T) named_bar_arrive(BAR_EMPTY + slot, GT);
         }
     }
@@ -659,11 +696,20 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 3: traceback + sequence / qstring generation (beam_search.cpp:447-455, :54-102).
+// One warp per chunk.  The pointer chase only needs the 4-byte (state, prev, stay) words, so the beam history is two planes
+// (meta, prob) and the chase streams the meta plane alone, in tiles of 32 blocks: while lane 0 walks one tile in shared
+// memory the next tile's 32 rows are already in flight (one register per row and lane).  The block probabilities are then
+// gathered along the chosen path only (one 4-byte load per block, all independent).
 // ------------------------------------------------------------------------------------------------
 constexpr int kTbTile = 32;
 constexpr int kTbWarps = 2;
 
-__global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint2* __restrict__ beam,
+__host__ __device__ constexpr size_t traceback_warp_bytes(int T) {
+    return ((size_t)kTbTile * kBeamW * 4 + (size_t)((T + 3) & ~3) * (4 + 4 + 2) + 16 + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint32_t* __restrict__ beam_meta,
+                                                                      const float* __restrict__ beam_prob,
                                                                       int N,
                                                                       int T_pitch,
                                                                       const int32_t* __restrict__ lens,
@@ -685,43 +731,55 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
     const int T = lens ? min(T_pitch, __ldg(lens + chunk) / stride) : T_pitch;  // variable chunk sizes
     const int Tp = (T_pitch + 3) & ~3;
     // per-warp carve-up
-    const size_t per_warp = (size_t)kTbTile * kBeamW * sizeof(uint2) + (size_t)Tp * (4 + 2 + 2 + 1) + 16;
-    unsigned char* base = tb_smem + (size_t)w * ((per_warp + 15) & ~(size_t)15);
-    uint2* tile = reinterpret_cast<uint2*>(base);
-    float* pprob = reinterpret_cast<float*>(base + (size_t)kTbTile * kBeamW * sizeof(uint2));
-    uint16_t* pstate = reinterpret_cast<uint16_t*>(pprob + Tp);
-    uint16_t* bstart = pstate + Tp;
-    uint8_t* pmove = reinterpret_cast<uint8_t*>(bstart + Tp + 2);
+    unsigned char* base = tb_smem + (size_t)w * traceback_warp_bytes(T_pitch);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(base);                         // [32 blocks][32 elements]
+    uint32_t* path = tile + kTbTile * kBeamW;                                   // state | move << 16 | element << 24
+    float* pprob = reinterpret_cast<float*>(path + Tp);
+    uint16_t* bstart = reinterpret_cast<uint16_t*>(pprob + Tp);
 
-    const uint2* brow = beam + (size_t)chunk * T_pitch * kBeamW;
+    const uint32_t* mrow = beam_meta + (size_t)chunk * T_pitch * kBeamW + lane;
+    uint32_t nxt[kTbTile];
+    auto load_tile = [&](int t_hi) {  // rows t_hi-32 .. t_hi-1 (those >= 0), row r of the tile in nxt[r]
+        const int t_lo = t_hi - kTbTile;
+#pragma unroll
+        for (int r = 0; r < kTbTile; ++r) {
+            const int t = t_lo + r;
+            nxt[r] = t >= 0 ? __ldg(mrow + (size_t)t * kBeamW) : 0u;
+        }
+    };
+    if (T > 0) load_tile(T);
     uint32_t ei = 0;
     for (int t_hi = T; t_hi > 0; t_hi -= kTbTile) {
-        const int t_lo = t_hi - kTbTile > 0 ? t_hi - kTbTile : 0;
-        const int rows = t_hi - t_lo;
-        for (int r = 0; r < rows; ++r) tile[r * kBeamW + lane] = brow[(size_t)(t_lo + r) * kBeamW + lane];
+#pragma unroll
+        for (int r = 0; r < kTbTile; ++r) tile[r * kBeamW + lane] = nxt[r];
         __syncwarp();
+        if (t_hi - kTbTile > 0) load_tile(t_hi - kTbTile);  // in flight during the walk below
         if (lane == 0) {
-            for (int r = rows - 1; r >= 0; --r) {
-                const uint2 e = tile[r * kBeamW + ei];
-                const int t = t_lo + r;
-                pstate[t] = (uint16_t)(e.x & 0xffffu);
-                pmove[t] = ((e.x >> 24) & 1u) ? 0 : 1;
-                pprob[t] = __uint_as_float(e.y);
-                ei = (e.x >> 16) & 0xffu;
+            const int t_lo = t_hi - kTbTile;
+            const int r_lo = t_lo < 0 ? -t_lo : 0;
+            for (int r = kTbTile - 1; r >= r_lo; --r) {
+                const uint32_t e = tile[r * kBeamW + ei];
+                path[t_lo + r] = (e & 0xffffu) | ((((e >> 24) & 1u) ^ 1u) << 16) | (ei << 24);
+                ei = (e >> 16) & 0xffu;
             }
         }
         __syncwarp();
     }
-    if (lane == 0) pmove[0] = 1;  // always step in the first block
+    if (lane == 0 && T > 0) path[0] |= 1u << 16;  // always step in the first block
     __syncwarp();
-    for (int t = lane; t < T; t += 32) pprob[t] = b200_pow0p4f(pprob[t]);  // "power fudge factor", beam_search.cpp:503
+    {
+        const float* prow = beam_prob + (size_t)chunk * T_pitch * kBeamW;
+        for (int t = lane; t < T; t += 32) {  // "power fudge factor", beam_search.cpp:503
+            pprob[t] = b200_pow0p4f(__ldg(prow + (size_t)t * kBeamW + (path[t] >> 24)));
+        }
+    }
     __syncwarp();
 
     // base start blocks
     int nb = 0;
     for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
-        const bool m = t < T && pmove[t];
+        const bool m = t < T && ((path[t] >> 16) & 1u);
         const uint32_t bal = __ballot_sync(0xffffffffu, m);
         if (m) bstart[nb + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
         nb += __popc(bal);
@@ -732,7 +790,7 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
     uint8_t* mo = moves_out + (size_t)chunk * T_pitch;
     char* so = seq_out + (size_t)chunk * T_pitch;
     char* qo = qstr_out + (size_t)chunk * T_pitch;
-    for (int t = lane; t < T_pitch; t += 32) mo[t] = t < T ? pmove[t] : 0;
+    for (int t = lane; t < T_pitch; t += 32) mo[t] = t < T ? (uint8_t)((path[t] >> 16) & 1u) : 0;
     for (int p = lane; p < T_pitch; p += 32) {
         char sc = 0, qc = 0;
         if (p < nb) {
@@ -740,14 +798,14 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
             float bp = 0.0f, tp = 0.0f;
             int base = 0;
             for (int blk = b0; blk < b1; ++blk) {
-                base = pstate[blk] & 3;
+                base = path[blk] & 3;
                 const float prob = pprob[blk];
                 const float wrong = B200_DIV(B200_SUB(1.0f, prob), 3.0f);
                 bp = B200_ADD(bp, prob);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) tp = B200_ADD(tp, k == base ? prob : wrong);
             }
-            sc = "ACGT"[pstate[b0] & 3];
+            sc = "ACGT"[path[b0] & 3];
             qc = b200_qtable_lookup(&qt, bp, tp);
         }
         so[p] = sc;
@@ -756,11 +814,7 @@ __global__ void __launch_bounds__(kTbWarps * 32) crf_traceback_kernel(const uint
     if (lane == 0) n_bases_out[chunk] = nb;
 }
 
-size_t traceback_smem_bytes(int T) {
-    const int Tp = (T + 3) & ~3;
-    const size_t per_warp = (size_t)kTbTile * kBeamW * sizeof(uint2) + (size_t)Tp * (4 + 2 + 2 + 1) + 16;
-    return kTbWarps * ((per_warp + 15) & ~(size_t)15);
-}
+size_t traceback_smem_bytes(int T) { return kTbWarps * traceback_warp_bytes(T); }
 
 template <int SL>
 void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) {
@@ -785,7 +839,9 @@ void launch_decode(const DecodeArgs& a, cudaStream_t stream, ProfileSink* prof) 
         if (smem > 48 * 1024) ensure_dynamic_smem(crf_traceback_kernel, 200 * 1024);
         const int grid = (a.N + kTbWarps - 1) / kTbWarps;
         NvtxRange r("decode");
-        crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(a.beam, a.N, a.T, a.lens, a.stride, a.qtable, a.moves,
+        const uint32_t* meta = reinterpret_cast<const uint32_t*>(a.beam);
+        const float* prob = reinterpret_cast<const float*>(a.beam) + (size_t)a.N * a.T * kBeamW;
+        crf_traceback_kernel<<<grid, kTbWarps * 32, smem, stream>>>(meta, prob, a.N, a.T, a.lens, a.stride, a.qtable, a.moves,
                                                                     a.sequence, a.qstring, a.n_bases);
         if (prof) prof->mark("crf_traceback", stream);
     }

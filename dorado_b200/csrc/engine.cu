@@ -749,6 +749,17 @@ void decode_host_scores(int device, const uint16_t* scores, int N, int T, int C,
             a.dbg = d_dbg;
         }
         decode_scores(a, s);
+        if (std::getenv("B200_DEBUG_DECODE_TIMES")) {  // test hook only: per-kernel times of three more passes on the same scores
+            for (int rep = 0; rep < 3; ++rep) {
+                ProfileSink sink;
+                sink.begin(s);
+                decode_scores(a, s, &sink);
+                B200_CUDA(cudaStreamSynchronize(s));
+                std::string line = "[decode times]";
+                for (auto& kv : sink.report()) line += " " + kv.first + "=" + std::to_string(kv.second);
+                fprintf(stderr, "%s ms\n", line.c_str());
+            }
+        }
         if (d_dbg) {
             long long h[128];
             B200_CUDA(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, s));

@@ -18,6 +18,7 @@
 #include "nvtx.h"
 #include "tc.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,6 +41,7 @@ struct Conv12Params {
     int N, T, T_pad, front_pad;
     int c1, w1, w2, act1, act2;
     const int32_t* lens;  // optional per-chunk length in samples (variable chunk sizes): the chunk is zero beyond it
+    int* tile_counter;    // conv12_tc_kernel: next tile to hand out (zeroed on the stream before every launch)
 };
 
 constexpr int CONV_W_FLOATS = 16 * MAXW + 16 + MAXW * 16 * 16 + 16;
@@ -128,6 +130,172 @@ __global__ void __launch_bounds__(CONV_TT) conv12_kernel(const Conv12Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv1 + conv2 with conv2 on the tensor cores (the v5 shape: conv1 1 -> 16, conv2 16 -> 16 with 5 taps).
+//
+// conv2 is 1280 of the 1360 multiply-adds per sample; on the FMA pipe (conv12_kernel above) that is 1.4e10 FLOP per batch of
+// 512 x 9996 samples and the kernel sat at 4 % of the HBM roofline it should be bound by (2 B in, 32 B out per sample).  Here a
+// tile of 128 output samples is one M = 128, N = 16, K = 80 contraction on tcgen05:
+//   * conv1 (+ activation) runs on the FMA pipe, one thread per conv1 position, and its 16 channels are rounded to fp16
+//     (every activation tensor between layers is fp16, as in the reference's CUDA path);
+//   * the A operand is conv2's im2col tile built directly in shared memory in the 128-byte-swizzled K-major layout:
+//     K index = tap * 16 + channel, so the 32 bytes of conv1 position j go to row j - tap, 16-byte chunks 2 tap and 2 tap + 1
+//     (five 2 x 16 B stores per thread; the XOR swizzle keeps the eight rows of a phase on distinct banks);
+//   * B = the conv2 weights [16][80] fp16 in the same layout, written once per CTA; the accumulator is 16 TMEM columns;
+//   * four warps read the accumulator back (thread = output sample), add the bias, apply the activation and store the
+//     sample's 16 fp16 channels as one 32-byte row: a warp writes 1 KB contiguous.
+// The phases of a tile are separated by CTA barriers; five CTAs fit an SM (37 KB shared memory, 32 TMEM columns, 12288
+// registers each) and hide each other's barrier and MMA latency.  The grid is persistent and takes tiles from a counter.
+// ------------------------------------------------------------------------------------------------
+constexpr int C12_TILE = 128;
+// warps 0-3: conv1 producers and epilogue (TMEM lane quarter = warp); warp 4: tail positions + MMA issue; warp 5 only pads the
+// CTA to 192 threads x 64 registers = 12288 registers: more than the recurrence kernels leave free on their SMs (fast: 8192,
+// hac: 10240).  Those kernels hold all 512 tensor-memory columns for a whole layer, and a CTA of this kernel placed beside one
+// would sit in tcgen05.alloc until that layer ends.  Tiles are also handed out dynamically (atomic counter), so a CTA that
+// does get stuck holds no work.
+constexpr int C12_THREADS = 192;
+constexpr int C12_SMEM = 2 * 16384 + 2 * 2048 + 1024;  // A (2 k-blocks of 128 rows x 128 B), B (2 k-blocks of 16 rows), alignment slack
+
+__global__ void __launch_bounds__(C12_THREADS, 5) conv12_tc_kernel(const Conv12Params p, int tiles_per_chunk, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t c12_smem_raw[];
+    uint8_t* smem = c12_smem_raw + ((1024u - (tc::smem_u32(c12_smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_tile = smem;               // [2][128 rows][128 B]
+    uint8_t* b_tile = smem + 2 * 16384;   // [2][16 rows][128 B]
+    __shared__ float xs[C12_TILE + 4 + 2 * MAXW];
+    __shared__ float s_w1[16 * MAXW], s_b1[16], s_b2[16];
+    __shared__ uint64_t mma_done;
+    __shared__ uint32_t tmem_holder;
+    __shared__ int s_tile;
+    const ConvAct a1 = conv_act_coef(p.act1), a2 = conv_act_coef(p.act2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int p1 = p.w1 / 2;
+    constexpr int p2 = 2;
+
+    // ---- once per CTA: conv1 weights / biases, conv2 weights as the fp16 B operand, barrier, tensor memory
+    for (int i = tid; i < 16 * MAXW; i += C12_THREADS) s_w1[i] = __ldg(p.w + i);
+    if (tid < 16) {
+        s_b1[tid] = __ldg(p.w + 16 * MAXW + tid);
+        s_b2[tid] = __ldg(p.w + 16 * MAXW + 16 + MAXW * 16 * 16 + tid);
+    }
+    for (int i = tid; i < 2 * 2048 / 16; i += C12_THREADS) reinterpret_cast<uint4*>(b_tile)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    {
+        const float* w2 = p.w + 16 * MAXW + 16;  // [tap][ci][co]
+        for (int i = tid; i < 5 * 16 * 16; i += C12_THREADS) {
+            const int co = i & 15, ci = (i >> 4) & 15, tap = i >> 8;
+            const int c = (tap * 2 + (ci >> 3)) & 7, kb = tap >> 2;
+            *reinterpret_cast<__half*>(b_tile + kb * 2048 + tc::sw128_offset(co, c) + (ci & 7) * 2) =
+                    __float2half_rn(__ldg(w2 + (tap * 16 + ci) * 16 + co));
+        }
+    }
+    if (tid == 0) {
+        tc::mbar_init(&mma_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 4) tc::tmem_alloc(&tmem_holder, 32);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_acc = tmem_holder;
+    const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(a_tile));
+    const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(b_tile));
+    constexpr uint32_t idesc = tc::umma_idesc_f16(128, 16);
+
+    uint32_t parity = 0;
+    for (;;) {
+        __syncthreads();  // the previous tile's accumulator has been read and its MMAs have read A: both may be overwritten
+        if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= num_tiles) break;
+        const int n = tile / tiles_per_chunk;
+        const int t0 = (tile - n * tiles_per_chunk) * C12_TILE;
+        const int L = p.lens ? min(p.T, __ldg(p.lens + n)) : p.T;  // samples of this chunk (zero padding starts at L)
+        // ---- signal window: xs[i] <-> sample t0 - p2 - p1 + i
+        if (tid < C12_TILE + 2 * (p1 + p2)) {
+            const int t = t0 - p2 - p1 + tid;
+            xs[tid] = (t >= 0 && t < L) ? __half2float(p.x[(size_t)n * p.T + t]) : 0.0f;
+        }
+        __syncthreads();
+        // ---- conv1 at position j <-> sample t0 - p2 + j, scattered into the im2col rows j - tap
+        if (tid < C12_TILE + 2 * p2) {
+            const int j = tid;
+            const int t = t0 - p2 + j;
+            const bool inside = t >= 0 && t < L;  // conv2 zero-pads conv1's *output*
+            float xv[MAXW];
+#pragma unroll
+            for (int k = 0; k < MAXW; ++k) xv[k] = k < p.w1 ? xs[j + k] : 0.0f;
+            __half2 h[8];
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+                float acc0 = s_b1[2 * c2], acc1 = s_b1[2 * c2 + 1];
+#pragma unroll
+                for (int k = 0; k < MAXW; ++k) {
+                    if (k < p.w1) {
+                        acc0 = fmaf(s_w1[(2 * c2) * p.w1 + k], xv[k], acc0);
+                        acc1 = fmaf(s_w1[(2 * c2 + 1) * p.w1 + k], xv[k], acc1);
+                    }
+                }
+                h[c2] = inside ? __floats2half2_rn(conv_act(acc0, a1), conv_act(acc1, a1)) : __floats2half2_rn(0.0f, 0.0f);
+            }
+            const uint4 lo = *reinterpret_cast<const uint4*>(&h[0]), hi = *reinterpret_cast<const uint4*>(&h[4]);
+#pragma unroll
+            for (int tap = 0; tap < 5; ++tap) {
+                const int i = j - tap;
+                if (i >= 0 && i < C12_TILE) {
+                    uint8_t* base = a_tile + (tap >> 2) * 16384;
+                    const int c = (tap * 2) & 7;
+                    *reinterpret_cast<uint4*>(base + tc::sw128_offset(i, c)) = lo;
+                    *reinterpret_cast<uint4*>(base + tc::sw128_offset(i, c + 1)) = hi;
+                }
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        // ---- conv2: five K = 16 steps (one per tap), issued by one thread
+        if (tid == 128) {
+            tc::tc_fence_after();
+#pragma unroll
+            for (int tap = 0; tap < 5; ++tap) {
+                const uint64_t off = (uint64_t)(((tap >> 2) * 16384) >> 4) + (uint64_t)(2 * (tap & 3));
+                const uint64_t boff = (uint64_t)(((tap >> 2) * 2048) >> 4) + (uint64_t)(2 * (tap & 3));
+                tc::umma_f16(tmem_acc, adesc0 + off, bdesc0 + boff, idesc, tap != 0);
+            }
+            tc::umma_commit(&mma_done);
+        }
+        // ---- epilogue: thread = output sample
+        if (warp < 4) {
+            tc::mbar_wait(&mma_done, parity);
+            tc::tc_fence_after();
+            uint32_t r[16];
+            tc::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
+            tc::tmem_ld_wait();
+            const int t = t0 + tid;
+            if (t < p.T) {
+                __half2 o[8];
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) {
+                    o[c2] = __floats2half2_rn(conv_act(__uint_as_float(r[2 * c2]) + s_b2[2 * c2], a2),
+                                              conv_act(__uint_as_float(r[2 * c2 + 1]) + s_b2[2 * c2 + 1], a2));
+                }
+                if (t >= L) {  // beyond a short chunk's end: the next convolution's zero padding
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) o[c2] = __floats2half2_rn(0.0f, 0.0f);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)n * p.T_pad + p.front_pad + t) * 16);
+                dst[0] = *reinterpret_cast<uint4*>(&o[0]);
+                dst[1] = *reinterpret_cast<uint4*>(&o[4]);
+            }
+            tc::tc_fence_before();
+        }
+        parity ^= 1u;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem_acc, 32);
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSTM layer for a hidden size whose weights fit one SM's tensor memory (fast: C = 96): all T steps of one layer in one
 // persistent launch, no inter-CTA traffic.
 //
@@ -177,12 +345,23 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
 // (FMUL by am*log2(e), MUFU.EX2, FADD, MUFU.RCP, FFMA).  e^x = inf gives 1, e^x = 0 gives 1 - am.  (Moving the reciprocal to
 // the FMA pipe -- seed + 3 Newton steps -- was measured SLOWER, 0.98 -> 1.03 ms per fast layer and 3.5 -> 3.85 ms per hac
 // layer; profiles/r02_b8_*.)
+#ifdef B200_LSTM_TANH_APPROX
+// Experiment (build with EXTRA=-DB200_LSTM_TANH_APPROX): one MUFU.TANH per activation instead of MUFU.EX2 + MUFU.RCP
+// (sigmoid(v) = 0.5 tanh(0.5 v) + 0.5); tanh.approx.f32 is good to ~2^-11 relative, the ex2 / rcp form to ~2^-22.
+__device__ __forceinline__ float gate_act(float v, float am) {
+    const float s = 0.5f * am;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v * s));
+    return fmaf(t, s, 1.0f - s);
+}
+#else
 __device__ __forceinline__ float gate_act(float v, float am) {
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * (am * 1.4426950408889634f)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return fmaf(-am, r, 1.0f);
 }
+#endif
 __device__ __forceinline__ float tanh_f(float v) { return gate_act(v, 2.0f); }
 
 // C   = hidden size (compile time so the MMA issue loops unroll into immediate-offset descriptors).
@@ -762,6 +941,8 @@ public:
 
     Conv12Params conv12{};
     dim3 conv12_grid;
+    bool conv12_tc = false;  // conv2 on tcgen05 (conv12_tc_kernel)
+    int conv12_tiles_per_chunk = 0, conv12_tc_grid = 0;
     GemmPlan conv3;
     std::vector<CUtensorMap> lstm_x;
     std::vector<LstmParams> lstm_p;
@@ -976,7 +1157,7 @@ size_t LstmModel::workspace_bytes(int N, int T_in) const {
     const size_t seq = (size_t)(T_out + 1) * n_pad(N) * desc.lstm_size * 2 + 4096;
     const size_t mid = desc.out_features > 0 ? (size_t)T_out * n_pad(N) * desc.out_features * 2 + 4096 : 0;
     const size_t gx = hoisted() ? (size_t)T_out * n_pad(N) * 4 * desc.lstm_size * 2 + 4096 : 0;
-    return x2 + seq + mid + gx;
+    return x2 + seq + mid + gx + 4096;  // + the tile counter of conv12_tc_kernel
 }
 
 std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half* signal, __half* scores, void* ws,
@@ -1004,11 +1185,20 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
     __half* seq = reinterpret_cast<__half*>(take((size_t)(T_out + 1) * Np * C * 2));
     __half* mid = desc.out_features > 0 ? reinterpret_cast<__half*>(take((size_t)T_out * Np * desc.out_features * 2)) : nullptr;
     __half* gxbuf = hoisted() ? reinterpret_cast<__half*>(take((size_t)T_out * Np * 4 * C * 2)) : nullptr;
+    int* tile_counter = reinterpret_cast<int*>(take(256));
 
     // conv1 + conv2
     plan->conv12 = Conv12Params{signal, x2, conv_w, N, T_in, Tp, pad3(), desc.convs[0].size, desc.convs[0].winlen,
-                                desc.convs[1].winlen, desc.convs[0].activation, desc.convs[1].activation, nullptr};
+                                desc.convs[1].winlen, desc.convs[0].activation, desc.convs[1].activation, nullptr, tile_counter};
     plan->conv12_grid = dim3((T_in + CONV_TT - 1) / CONV_TT, N, 1);
+    // the v5 shape runs conv2 on the tensor cores (conv12_tc_kernel); anything else keeps the FMA-pipe kernel
+    plan->conv12_tc = desc.convs[0].size == 16 && desc.convs[1].winlen == 5 && !std::getenv("B200_CONV12_FMA");
+    plan->conv12_tiles_per_chunk = (T_in + C12_TILE - 1) / C12_TILE;
+    {
+        const long long tiles = (long long)plan->conv12_tiles_per_chunk * N;
+        plan->conv12_tc_grid = (int)std::min<long long>(tiles, 5LL * kNumSMs);
+        if (plan->conv12_tc) ensure_dynamic_smem(conv12_tc_kernel, C12_SMEM);
+    }
 
     // conv3: rows (n, t) read K3p contiguous halfs starting at x2[n][stride * t]
     {
@@ -1265,7 +1455,13 @@ void LstmPlan::launch_lstm(int l, cudaStream_t stream) const {
 void LstmPlan::run(cudaStream_t stream, ProfileSink* prof) {
     {
         NvtxRange r("conv");
-        conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
+        if (conv12_tc) {
+            B200_CUDA(cudaMemsetAsync(conv12.tile_counter, 0, sizeof(int), stream));
+            conv12_tc_kernel<<<conv12_tc_grid, C12_THREADS, C12_SMEM, stream>>>(conv12, conv12_tiles_per_chunk,
+                                                                                 conv12_tiles_per_chunk * conv12.N);
+        } else {
+            conv12_kernel<<<conv12_grid, CONV_TT, 0, stream>>>(conv12);
+        }
         if (prof) prof->mark("conv12", stream);
         run_gemm(conv3, stream);
         if (prof) prof->mark("conv3_gemm", stream);

@@ -54,19 +54,16 @@ static inline float b200_u2f_(uint32_t u) {
 
 B200_MATH_FN float b200_fmaxf(float a, float b) { return a > b ? a : b; }
 
-/* exp(x) for any finite x <= ~88; returns 0 below -86 (results there would be subnormal). */
+/* exp(x) for any finite x <= ~88; returns 0 below -86 (results there would be subnormal).
+ * Written without control flow (clamp, evaluate, select): the scans evaluate five of these per state and block, and with an
+ * early return the GPU compiler kept five branch regions that ran one after the other instead of interleaving. */
 B200_MATH_FN float b200_expf(float x) {
-    if (x < -86.0f) {
-        return 0.0f;
-    }
-    if (x > 88.0f) {
-        x = 88.0f;
-    }
+    const float xc = x < -86.0f ? -86.0f : (x > 88.0f ? 88.0f : x);
     /* n = round-to-nearest-even(x / ln2) via the 1.5*2^23 trick */
-    const float t = B200_MUL(x, 1.44269504088896341f);
+    const float t = B200_MUL(xc, 1.44269504088896341f);
     const float big = 12582912.0f;
     const float n = B200_SUB(B200_ADD(t, big), big);
-    float r = B200_FMA(n, -0.693359375f, x);
+    float r = B200_FMA(n, -0.693359375f, xc);
     r = B200_FMA(n, 2.12194440e-4f, r);
     float p = 1.9875691500e-4f;
     p = B200_FMA(p, r, 1.3981999507e-3f);
@@ -79,7 +76,8 @@ B200_MATH_FN float b200_expf(float x) {
     p = B200_ADD(p, 1.0f);
     const int32_t ni = (int32_t)n;
     const float scale = B200_U2F((uint32_t)(ni + 127) << 23);
-    return B200_MUL(p, scale);
+    const float y = B200_MUL(p, scale);
+    return x < -86.0f ? 0.0f : y;
 }
 
 /* log(x) for normal x > 0. */

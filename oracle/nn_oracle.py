@@ -126,9 +126,12 @@ def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_qui
     inter = {}
     q = _q16 if emulate_fp16 else (lambda a: a)
     w_in = w
+    # LSTM models whose conv2 runs on the tensor cores (conv12_tc_kernel: conv1 -> 16 channels, conv2 with 5 taps): conv1's
+    # output and conv2's weights are fp16 operands there; other shapes keep both in fp32 inside the fused FMA kernel
+    conv2_tc = (not cfg.is_tx_model) and len(cfg.convs) == 3 and cfg.convs[0].size == 16 and cfg.convs[1].winlen == 5
     if emulate_fp16:
-        w = {k: (_q16(v) if v.ndim >= 2 and not (k.startswith("0.conv") or k.startswith("1.conv")) else v)
-             for k, v in w.items()}
+        keep32 = ("0.conv",) if conv2_tc else ("0.conv", "1.conv")
+        w = {k: (_q16(v) if v.ndim >= 2 and not k.startswith(keep32) else v) for k, v in w.items()}
     if cfg.is_tx_model:
         tx = cfg.tx
         if emulate_fp16:
@@ -200,8 +203,8 @@ def forward(cfg: BasecallModelConfig, w: dict, signal: np.ndarray, cpu_split_qui
 
     for i, c in enumerate(cfg.convs):
         x = conv1d(x, w[f"{i}.conv.weight.tensor"], w[f"{i}.conv.bias.tensor"], c.stride, c.activation)
-        if i >= 1:
-            x = q(x)  # conv1 output stays on chip (fused conv1+conv2 kernel)
+        if i >= 1 or conv2_tc:
+            x = q(x)  # conv1's output stays on chip (fused conv1+conv2 kernel); as the tensor-core operand it is fp16
         inter[f"conv{i}"] = x
     x = np.ascontiguousarray(x.transpose(0, 2, 1))
     nconv = len(cfg.convs)

@@ -361,3 +361,39 @@ def test_variable_chunk_sizes_match_each_chunk_alone(crf_oracle):
         runner.accept_chunk(i, full[i])
     again = runner.call_chunks(N)
     assert all(len(c.moves) == runner.out_len() for c in again)
+
+
+def test_conv12_tensor_core_kernel_matches_the_fma_kernel_and_the_oracle(monkeypatch):
+    """conv1 + conv2 of the v5 LSTM models: the tcgen05 kernel (conv2 as a 128 x 16 x 80 contraction per tile of 128 samples,
+    conv1's output as its fp16 operand) against the fp32 FMA-pipe kernel (B200_CONV12_FMA=1) and against nn_oracle's conv2
+    output with the same rounding points.  The conv2 output buffer x2 [N][T + 2 * pad + 8][16] is the first workspace block;
+    its padding rows must stay zero.  Ragged T (not a multiple of the 128-sample tile) and several tiles per chunk."""
+    from oracle import nn_oracle
+    from dorado_b200.runner import B200ModelRunner
+    N, T = 32, 1998
+    cfg, w, caller, runner, sig = _setup("fast", N, T)
+    T = runner.chunk_size()
+    pad = cfg.convs[2].winlen // 2
+    Tp = T + 2 * pad + 8
+
+    def x2_of(r):
+        r.forward_scores(N)
+        return r.debug_read_workspace(0, N * Tp * 16 * 2).view(np.float16).reshape(N, Tp, 16).astype(np.float32)
+
+    tc_out = x2_of(runner)
+    monkeypatch.setenv("B200_CONV12_FMA", "1")
+    fma_runner = B200ModelRunner(caller, N, T)
+    monkeypatch.delenv("B200_CONV12_FMA")
+    for i in range(N):
+        fma_runner.accept_chunk(i, sig[i])
+    fma_out = x2_of(fma_runner)
+    _, inter = nn_oracle.forward(cfg, w, sig.astype(np.float32), return_intermediates=True, emulate_fp16=True)
+    ref = inter["conv1"].transpose(0, 2, 1)  # conv index 1 = conv2's output, [N][T][16]
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(tc_out[:, :pad]).max() == 0 and np.abs(tc_out[:, pad + T:]).max() == 0, "padding rows must stay zero"
+    err_ref = np.abs(tc_out[:, pad:pad + T] - ref)
+    err_fma = np.abs(tc_out - fma_out)
+    print(f"\n[conv12 tensor-core kernel] vs oracle: max {err_ref.max():.2e} mean {err_ref.mean():.2e}; "
+          f"vs fp32 FMA kernel: max {err_fma.max():.2e} mean {err_fma.mean():.2e} (scale {scale:.2f})")
+    assert err_ref.max() <= 2e-3 * scale    # one fp16 rounding of the output + accumulation order
+    assert err_fma.max() <= 6e-3 * scale    # the FMA kernel keeps conv1's output and conv2's weights in fp32

@@ -43,15 +43,25 @@ def main():
            f"taken by tools/r2_profile_all.sh from `python bench.py --steps 1 --warmup 1`; regenerate with tools/ncu_summary.py.",
            "# Durations here are cold-cache, serialised replays: the bench line's live CUDA-event times are the ones that count.", ""]
     traffic = {}
-    for rep in sorted((ROOT / "profiles").glob(f"{prefix}_*.ncu-rep")):
-        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a capture is either the .ncu-rep itself or its `ncu -i ... --page raw --csv` export made on the GPU box (the box returns
+    # at most 64 MiB per call, so not every .ncu-rep travels; tools/r2_profile_all.sh)
+    prof = ROOT / "profiles"
+    stems = sorted({f.name[:-len(".ncu-rep")] for f in prof.glob(f"{prefix}_*.ncu-rep")} |
+                   {f.name[:-len(".raw.csv")] for f in prof.glob(f"{prefix}_*.raw.csv")})
+    for full_stem in stems:
+        csv_file, rep = prof / f"{full_stem}.raw.csv", prof / f"{full_stem}.ncu-rep"
+        if csv_file.exists():
+            raw = csv_file.read_text()
+            rep = csv_file
+        else:
+            raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         if len(rows) < 3:
             out.append(f"== {rep.name}: unreadable")
             continue
         head, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(head)}
-        stem = rep.stem[len(prefix) + 1:]
+        stem = full_stem[len(prefix) + 1:]
         workload, names = CAPTURES.get(stem, (None, []))
         for li, vals in enumerate(rows[2:]):
             kname = vals[col["Kernel Name"]] if "Kernel Name" in col else "?"
