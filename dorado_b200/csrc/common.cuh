@@ -33,6 +33,11 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // Activations on the SFU: one ex2 and one rcp each (MUFU.EX2 / MUFU.RCP, ~1 ulp), no IEEE division sequences.  Finite inputs
 // only: e^x = inf gives the correct limit, x = -inf itself would give swish = NaN.
+// tanh_mufu is MUFU.TANH (tanh.approx.f32, relative error ~2^-11).  It serves the LSTM gates (lstm_model.cu: the recurrences
+// are SFU- and issue-bound and the score error is unchanged).  Swish through it -- h + h tanh(h), h = v / 2 -- was measured
+// and REJECTED (battery 20): conv1+conv2 0.277 -> 0.271 ms and the SwiGLU GEMM 0.423 -> 0.436 ms, i.e. no gain, while the
+// fraction of fast / hac scores further than 1e-3 of the score range from the fp16-storage oracle rose from 2e-4 to 7e-3 (the
+// convolution outputs are the recurrence's inputs and the approximation error is systematic, not rounding noise).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -41,6 +46,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float v) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }

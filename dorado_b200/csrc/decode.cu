@@ -57,7 +57,12 @@ struct ScanCfg {
     static constexpr int PITCH = P4 + 2;                // 4 * PITCH == 8 (mod 32): conflict-free staging
 };
 
-__device__ __forceinline__ float clampf(float v, float c) { return c > 0.0f ? (v < -c ? -c : (v > c ? c : v)) : v; }
+// Score clamp (Decoder.cpp:19): c <= 0 means no clamp.  min / max (two ALU-pipe instructions) instead of two compare + select
+// pairs on the FMA pipe; identical for every non-NaN score.
+__device__ __forceinline__ float clampf(float v, float c) {
+    const float ce = c > 0.0f ? c : __int_as_float(0x7f800000);
+    return fminf(fmaxf(v, -ce), ce);
+}
 
 template <int SL>
 __global__ void __launch_bounds__(ScanCfg<SL>::S > 256 ? ScanCfg<SL>::S : 256)
@@ -655,7 +660,7 @@ __global__ void __launch_bounds__(FwdCfg<SL>::THREADS) crf_fwd_beam_kernel(const
                     float part = 0.0f;
 #pragma unroll
                     for (int e = 0; e < SPT; ++e) {
-                        ex[e] = b200_expf(B200_SUB(vsum[e], mx));
+                        ex[e] = b200_expf_nonpos(B200_SUB(vsum[e], mx));
                         part = e == 0 ? ex[0] : B200_ADD(part, ex[e]);
                     }
 #pragma unroll

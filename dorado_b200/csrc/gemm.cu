@@ -71,7 +71,42 @@ struct GemmKernelParams {
     float norm_inv_dim, norm_eps;
     int out_kind;    // coordinates of a sub-tile: 0 (col, row, batch)  1 (col, g % out_P, g / out_P)  2 (0, row, col / 32)
     int out_P;
+    // operand-stationary schedules.  wstat = 1: CTA b owns column tile b % n_tiles for its whole life, keeps that slice of W (all
+    // num_k_blocks K blocks) resident in shared memory and walks the row tiles b / n_tiles, + gridDim.x / n_tiles, ...
+    // wstat = 2: the same with the roles swapped -- row tile b % m_tiles of A resident, column tiles streamed.
+    int wstat;
+    int m_tiles;     // row tiles (all batches)
+    int mfast;       // default schedule: row tile index runs fastest (fewer row tiles than column tiles)
 };
+
+// i-th tile of this CTA: row tile mt, column tile nt; false when the CTA has run out of tiles.  All three roles walk the same
+// sequence.
+__device__ __forceinline__ bool gemm_tile_at(const GemmKernelParams& p, int i, int* mt, int* nt) {
+    if (p.wstat == 1) {
+        *nt = (int)blockIdx.x % p.n_tiles;
+        *mt = (int)blockIdx.x / p.n_tiles + i * ((int)gridDim.x / p.n_tiles);
+        return *mt < p.m_tiles;
+    }
+    if (p.wstat == 2) {
+        *mt = (int)blockIdx.x % p.m_tiles;
+        *nt = (int)blockIdx.x / p.m_tiles + i * ((int)gridDim.x / p.m_tiles);
+        return *nt < p.n_tiles;
+    }
+    // default schedule: CTAs take consecutive tiles, and the SHORTER dimension runs fastest, so that the CTAs working at any
+    // moment share their tiles of the long operand (read from HBM once, then served by L2) and sweep the long operand once.
+    // With the column tile always fastest, the hac x-projection (12 row tiles of W_ih against 3332 column tiles of
+    // activations) swept the 655 MB of activations once per row tile: 7.9 GB of DRAM reads per launch, 81 % of the HBM
+    // peak (profiles/r02_gx_gemm_hac_n512.raw.csv).
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    if (p.mfast) {
+        *mt = tile % p.m_tiles;
+        *nt = tile / p.m_tiles;
+    } else {
+        *mt = tile / p.n_tiles;
+        *nt = tile % p.n_tiles;
+    }
+    return tile < p.num_tiles;
+}
 
 constexpr int kMaxStages = 4;
 
@@ -98,10 +133,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_bytes = BM * BK * 2;
     const uint32_t w_bytes = (uint32_t)p.bn * BK * 2;
-    const uint32_t stage_bytes = a_bytes + w_bytes;
+    // ring stage: A | W, or only the streamed operand when the other one is resident (its K blocks sit in front of the ring)
+    const uint32_t res_kb_bytes = p.wstat == 1 ? w_bytes : a_bytes;   // one K block of the resident operand
+    const uint32_t stage_bytes = p.wstat == 0 ? a_bytes + w_bytes : (p.wstat == 1 ? a_bytes : w_bytes);
     const int NST = p.stages;
+    uint8_t* w_res = smem;
+    uint8_t* ring = smem + (p.wstat ? (uint32_t)p.num_k_blocks * res_kb_bytes : 0u);
     // staging tile of the epilogue: two column halves (one per epilogue warp set), 128 rows x bn/2 fp16 each
-    uint8_t* stage_out = smem + NST * stage_bytes;
+    uint8_t* stage_out = ring + NST * stage_bytes;
     // staging tile: [128 rows][bn output columns] fp16 as sub-tiles of p.sw columns, partitioned by column range among the parts
     const uint32_t staging_bytes = p.staged ? (uint32_t)(BM * (p.bn / (ACT == GEMM_ACT_SWIGLU ? 2 : 1)) * 2) : 0u;
     uint64_t* full = reinterpret_cast<uint64_t*>(stage_out + staging_bytes);
@@ -109,7 +148,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
     uint64_t* tmem_full = empty + kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
     uint64_t* res_full = tmem_empty + 2;    // [GEMM_PARTS] residual tile landed in the part's staging columns
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + GEMM_PARTS);
+    uint64_t* w_full = res_full + GEMM_PARTS;   // weight-stationary: the resident W slice has landed
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -124,6 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             tc::mbar_init(&tmem_empty[i], 32 * GEMM_EPI_WARPS);
         }
         for (int i = 0; i < GEMM_PARTS; ++i) tc::mbar_init(&res_full[i], 1);
+        tc::mbar_init(w_full, 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tma_a);
         tc::prefetch_tmap(&tma_w);
@@ -140,17 +181,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
         if (tc::elect_one()) {
             int s = 0;            // ring slot and its phase, advanced incrementally (the ring depth is a run-time value)
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            int mt, nt;
+            if (p.wstat && gemm_tile_at(p, 0, &mt, &nt)) {
+                tc::mbar_arrive_expect_tx(w_full, (uint32_t)p.num_k_blocks * res_kb_bytes);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    if (p.wstat == 1) {
+                        tc::tma_load_2d(w_res + (size_t)kb * res_kb_bytes, &tma_w, w_full, kb * BK, nt * p.bn);
+                    } else {
+                        tc::tma_load_3d(w_res + (size_t)kb * res_kb_bytes, &tma_a, w_full, kb * BK, (mt % p.tiles_per_batch) * BM,
+                                        mt / p.tiles_per_batch);
+                    }
+                }
+            }
+            for (int i = 0; gemm_tile_at(p, i, &mt, &nt); ++i) {
                 const int batch = mt / p.tiles_per_batch;
                 const int r0 = (mt % p.tiles_per_batch) * BM;
                 const int n0 = nt * p.bn;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
-                    uint8_t* a_s = smem + s * stage_bytes;
-                    tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
-                    tc::tma_load_2d(a_s + a_bytes, &tma_w, &full[s], kb * BK, n0);
+                    uint8_t* a_s = ring + s * stage_bytes;
+                    if (p.wstat != 2) tc::tma_load_3d(a_s, &tma_a, &full[s], kb * BK, r0, batch);
+                    if (p.wstat != 1) tc::tma_load_2d(a_s + (p.wstat == 2 ? 0u : a_bytes), &tma_w, &full[s], kb * BK, n0);
                     if (++s == NST) {
                         s = 0;
                         ph ^= 1;
@@ -163,8 +215,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             const uint32_t idesc = tc::umma_idesc_f16(BM, p.bn);
             int s = 0;
             uint32_t ph = 0;
-            int ti = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+            int mt, nt;
+            if (p.wstat && gemm_tile_at(p, 0, &mt, &nt)) {
+                tc::mbar_wait(w_full, 0);
+                tc::tc_fence_after();
+            }
+            for (int ti = 0; gemm_tile_at(p, ti, &mt, &nt); ++ti) {
                 const int ab = ti & 1;
                 tc::mbar_wait(&tmem_empty[ab], (uint32_t)(((ti >> 1) & 1) ^ 1));
                 tc::tc_fence_after();
@@ -172,9 +228,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     tc::mbar_wait(&full[s], ph);
                     tc::tc_fence_after();
-                    const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
-                    const uint64_t adesc = tc::umma_desc_sw128(a_addr);
-                    const uint64_t bdesc = tc::umma_desc_sw128(a_addr + a_bytes);
+                    const uint32_t st_addr = tc::smem_u32(ring + s * stage_bytes);
+                    const uint32_t rs_addr = tc::smem_u32(w_res + (size_t)kb * res_kb_bytes);
+                    const uint64_t adesc = tc::umma_desc_sw128(p.wstat == 2 ? rs_addr : st_addr);
+                    const uint64_t bdesc = tc::umma_desc_sw128(p.wstat == 1 ? rs_addr : (p.wstat == 2 ? st_addr : st_addr + a_bytes));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
@@ -213,10 +270,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f16_tcgen05_kernel(const
             return reinterpret_cast<uint4*>(my_stage + (size_t)sub * sub_bytes + (size_t)trow * (p.sw * 2) +
                                             (((uint32_t)piece ^ sw_xor) << 4));
         };
-        int ti = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+        int mt, nt;
+        for (int ti = 0; gemm_tile_at(p, ti, &mt, &nt); ++ti) {
             const int ab = ti & 1;
-            const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
             const int batch = mt / p.tiles_per_batch;
             const int r0 = (mt % p.tiles_per_batch) * BM;
             const int n0 = nt * p.bn;
@@ -617,18 +673,42 @@ GemmPlan make_gemm_plan(const GemmDesc& d) {
         throw std::invalid_argument("gemm: rope epilogue needs BN % 128 == 0 and a table");
     }
     p.tiles_per_batch = (d.rows_per_batch + BM - 1) / BM;
+    // Operand-stationary schedules (1: W resident, 2: A resident): 128-column tiles, the CTA's slice of the small operand
+    // (K / 64 blocks of 16 KB) resident in front of a ring that then carries the other operand alone.  Built on the theory
+    // that the K <= 512 GEMMs are bound by L2 -> SM operand traffic; measured and REJECTED (battery 22, parity green): the
+    // hac x-projection 1.75 -> 1.99 ms, sup QKV+RoPE 0.27 -> 0.48 ms, FC1+SwiGLU 0.46 -> 0.61 ms.  The 128-column tile halves
+    // the work per epilogue hand-over (and leaves two of the four epilogue warp sets idle in the rotary epilogue), and that,
+    // not operand traffic, is what these GEMMs are short of; the x-projection's real problem was its tile order (above).
+    // The schedule stays in the kernel as an experiment switch: B200_GEMM_WSTAT=1 (W resident) or 2 (A resident) applies it to
+    // every GEMM whose shape qualifies.
+    static const int wstat_mode = [] {
+        const char* e = std::getenv("B200_GEMM_WSTAT");
+        const int v = e ? std::atoi(e) : 0;
+        return v == 1 || v == 2 ? v : 0;
+    }();
+    const long long m_tiles = (long long)p.tiles_per_batch * d.batches;
+    if (wstat_mode && !d.out_ss && d.N % 128 == 0 && d.K / BK <= 8) {
+        const long long fixed = wstat_mode == 1 ? d.N / 128 : m_tiles;      // tiles along the resident operand
+        const long long walked = wstat_mode == 1 ? m_tiles : d.N / 128;
+        if (fixed <= kNumSMs / 2 && walked >= 4 * (kNumSMs / fixed)) {
+            p.bn = 128;
+            p.wstat = wstat_mode;
+        }
+    }
     p.grid = dim3((unsigned)(p.tiles_per_batch * d.batches), (unsigned)(d.N / p.bn), 1);
     plan_output_staging(p);
-    const size_t stage_bytes = BM * BK * 2 + (size_t)p.bn * BK * 2;
+    const size_t w_res_bytes = p.wstat ? (size_t)(d.K / BK) * (p.wstat == 1 ? p.bn : BM) * BK * 2 : 0;
+    const size_t stage_bytes = (p.wstat == 2 ? 0 : (size_t)BM * BK * 2) + (p.wstat == 1 ? 0 : (size_t)p.bn * BK * 2);
     const size_t staging = p.staged ? (size_t)BM * (p.bn / (d.act == GEMM_ACT_SWIGLU ? 2 : 1)) * 2 : 0;
     p.stages = STAGES;
-    if ((size_t)p.stages * stage_bytes + staging + 256 + 1024 > 227 * 1024) p.stages = 3;
-    p.smem = (size_t)p.stages * stage_bytes + staging + 256 + 1024;
+    if (w_res_bytes + (size_t)p.stages * stage_bytes + staging + 256 + 1024 > 227 * 1024) p.stages = 3;
+    p.smem = w_res_bytes + (size_t)p.stages * stage_bytes + staging + 256 + 1024;
     if (p.smem > 227 * 1024) {
         p.staged = 0;
         p.stages = STAGES;
-        p.smem = (size_t)p.stages * stage_bytes + 256 + 1024;
+        p.smem = w_res_bytes + (size_t)p.stages * stage_bytes + 256 + 1024;
     }
+    if (p.smem > 227 * 1024) throw std::logic_error("gemm: shared-memory plan does not fit");
     const uint64_t batch_stride = d.batches > 1 ? (uint64_t)d.a_batch_stride * 2 : (uint64_t)d.a_row_stride * 2 * d.rows_per_batch;
     p.tma_a = make_tmap_3d(d.a, (uint64_t)(d.a_inner > 0 ? d.a_inner : d.K), (uint64_t)d.rows_per_batch, (uint64_t)d.batches, (uint64_t)d.a_row_stride * 2,
                            batch_stride, BK, BM, 1);
@@ -689,7 +769,20 @@ void run_gemm(const GemmPlan& p, cudaStream_t stream) {
         return v > 0 && v < kNumSMs ? v : 0;
     }();
     int max_ctas = env_ctas > 0 ? env_ctas : (p.d.max_ctas > 0 && p.d.max_ctas < kNumSMs ? p.d.max_ctas : kNumSMs);
-    const int grid = k.num_tiles < max_ctas ? k.num_tiles : max_ctas;
+    int grid = k.num_tiles < max_ctas ? k.num_tiles : max_ctas;
+    k.wstat = p.wstat;
+    k.m_tiles = p.tiles_per_batch * p.d.batches;
+    static const bool no_mfast = [] {
+        const char* e = std::getenv("B200_GEMM_NFAST");  // A/B switch: column tile always fastest (the old order)
+        return e && std::atoi(e) != 0;
+    }();
+    k.mfast = (k.m_tiles < k.n_tiles && !no_mfast) ? 1 : 0;
+    if (p.wstat) {
+        // every CTA owns one tile of the resident operand: the grid is a multiple of the number of those tiles
+        const int fixed = p.wstat == 1 ? k.n_tiles : k.m_tiles;
+        grid = (max_ctas / fixed) * fixed;
+        if (grid < fixed) grid = fixed;
+    }
     const CUtensorMap& tmo = p.staged ? p.tma_o : p.tma_a;
     const CUtensorMap& tmr = p.staged && p.res_tma ? p.tma_r : p.tma_a;
     k.res_tma = p.staged && p.res_tma;

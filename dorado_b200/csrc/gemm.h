@@ -76,6 +76,7 @@ struct GemmPlan {
     dim3 grid;
     size_t smem = 0;
     int staged = 0, stages = 4, sw = 64, out_kind = 0, out_P = 1, res_tma = 0;
+    int wstat = 0;   // operand-stationary schedule in effect (experiment switch B200_GEMM_WSTAT, gemm.cu): 1 = W resident, 2 = A
 };
 
 GemmPlan make_gemm_plan(const GemmDesc& d);

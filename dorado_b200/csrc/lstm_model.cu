@@ -341,18 +341,17 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int col) {
     return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3))) << 4) + ((col & 7) << 1));
 }
 
-// Gate activations: sigmoid(v) = 1 - 1/(e^v + 1), tanh(v) = 1 - 2/(e^{2v} + 1): one ex2 and one rcp on the SFU, 5 instructions
-// (FMUL by am*log2(e), MUFU.EX2, FADD, MUFU.RCP, FFMA).  e^x = inf gives 1, e^x = 0 gives 1 - am.  (Moving the reciprocal to
-// the FMA pipe -- seed + 3 Newton steps -- was measured SLOWER, 0.98 -> 1.03 ms per fast layer and 3.5 -> 3.85 ms per hac
-// layer; profiles/r02_b8_*.)
-#ifdef B200_LSTM_TANH_APPROX
-// Experiment (build with EXTRA=-DB200_LSTM_TANH_APPROX): one MUFU.TANH per activation instead of MUFU.EX2 + MUFU.RCP
-// (sigmoid(v) = 0.5 tanh(0.5 v) + 0.5); tanh.approx.f32 is good to ~2^-11 relative, the ex2 / rcp form to ~2^-22.
+// Gate activations on one MUFU.TANH each: sigmoid(v) = 0.5 tanh(0.5 v) + 0.5 (am = 1), tanh(v) (am = 2); FMUL, MUFU.TANH, FFMA.
+// A step of the recurrence applies 5 C activations per chunk, and with ex2 + rcp (two MUFU operations each, ~2^-22) the SFU
+// was the busiest unit of the fast kernel (44 % at 2 x 8 chunks per CTA) and capped how many chunks a CTA could carry:
+// 1.83 -> 1.60 ms per fast layer, 4.6 -> 4.1 ms per hac layer (profiles/r02_b19_*).  tanh.approx.f32 is good to ~2^-11 -- the
+// rounding h_t gets anyway when it is stored as fp16; score errors against both oracles are unchanged
+// (profiles/r02_b19_err_*.txt: the gates saturate and contract the error).  The same substitution in the swish of the
+// convolutions was rejected, see common.cuh.  -DB200_LSTM_EX2_RCP restores the two-MUFU form.
+#ifndef B200_LSTM_EX2_RCP
 __device__ __forceinline__ float gate_act(float v, float am) {
     const float s = 0.5f * am;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v * s));
-    return fmaf(t, s, 1.0f - s);
+    return fmaf(tanh_mufu(v * s), s, 1.0f - s);
 }
 #else
 __device__ __forceinline__ float gate_act(float v, float am) {

@@ -59,10 +59,11 @@ B200_MATH_FN float b200_fmaxf(float a, float b) { return a > b ? a : b; }
  * early return the GPU compiler kept five branch regions that ran one after the other instead of interleaving. */
 B200_MATH_FN float b200_expf(float x) {
     const float xc = x < -86.0f ? -86.0f : (x > 88.0f ? 88.0f : x);
-    /* n = round-to-nearest-even(x / ln2) via the 1.5*2^23 trick */
+    /* n = round-to-nearest-even(x / ln2) via the 1.5*2^23 trick: the integer sits in the low mantissa bits of t + big */
     const float t = B200_MUL(xc, 1.44269504088896341f);
     const float big = 12582912.0f;
-    const float n = B200_SUB(B200_ADD(t, big), big);
+    const float tb = B200_ADD(t, big);
+    const float n = B200_SUB(tb, big);
     float r = B200_FMA(n, -0.693359375f, xc);
     r = B200_FMA(n, 2.12194440e-4f, r);
     float p = 1.9875691500e-4f;
@@ -74,8 +75,32 @@ B200_MATH_FN float b200_expf(float x) {
     const float r2 = B200_MUL(r, r);
     p = B200_FMA(p, r2, r);
     p = B200_ADD(p, 1.0f);
-    const int32_t ni = (int32_t)n;
-    const float scale = B200_U2F((uint32_t)(ni + 127) << 23);
+    /* 2^n: bits(t + big) = 0x4B400000 + n for |n| < 2^22, and 0x4B400000 << 23 == 0 (mod 2^32), so the exponent field is
+     * (bits << 23) + bias -- one integer instruction, no float -> int conversion */
+    const float scale = B200_U2F((B200_F2U(tb) << 23) + 0x3f800000u);
+    const float y = B200_MUL(p, scale);
+    return x < -86.0f ? 0.0f : y;
+}
+
+/* exp(x) for x <= 0 (the arguments of a max-shifted sum): b200_expf without the upper clamp, bit-identical there. */
+B200_MATH_FN float b200_expf_nonpos(float x) {
+    const float xc = x < -86.0f ? -86.0f : x;
+    const float t = B200_MUL(xc, 1.44269504088896341f);
+    const float big = 12582912.0f;
+    const float tb = B200_ADD(t, big);
+    const float n = B200_SUB(tb, big);
+    float r = B200_FMA(n, -0.693359375f, xc);
+    r = B200_FMA(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = B200_FMA(p, r, 1.3981999507e-3f);
+    p = B200_FMA(p, r, 8.3334519073e-3f);
+    p = B200_FMA(p, r, 4.1665795894e-2f);
+    p = B200_FMA(p, r, 1.6666665459e-1f);
+    p = B200_FMA(p, r, 5.0000001201e-1f);
+    const float r2 = B200_MUL(r, r);
+    p = B200_FMA(p, r2, r);
+    p = B200_ADD(p, 1.0f);
+    const float scale = B200_U2F((B200_F2U(tb) << 23) + 0x3f800000u);
     const float y = B200_MUL(p, scale);
     return x < -86.0f ? 0.0f : y;
 }
@@ -134,11 +159,12 @@ B200_MATH_FN float b200_lse5(float v_stay, float v0, float v1, float v2, float v
     m = b200_fmaxf(m, v1);
     m = b200_fmaxf(m, v2);
     m = b200_fmaxf(m, v3);
-    float s = b200_expf(B200_SUB(v_stay, m));
-    s = B200_ADD(s, b200_expf(B200_SUB(v0, m)));
-    s = B200_ADD(s, b200_expf(B200_SUB(v1, m)));
-    s = B200_ADD(s, b200_expf(B200_SUB(v2, m)));
-    s = B200_ADD(s, b200_expf(B200_SUB(v3, m)));
+    /* every argument is <= 0 (m is the maximum) */
+    float s = b200_expf_nonpos(B200_SUB(v_stay, m));
+    s = B200_ADD(s, b200_expf_nonpos(B200_SUB(v0, m)));
+    s = B200_ADD(s, b200_expf_nonpos(B200_SUB(v1, m)));
+    s = B200_ADD(s, b200_expf_nonpos(B200_SUB(v2, m)));
+    s = B200_ADD(s, b200_expf_nonpos(B200_SUB(v3, m)));
     return B200_ADD(m, b200_logf(s));
 }
 

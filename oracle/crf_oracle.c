@@ -117,7 +117,7 @@ static void posts_row(const float* f, const float* b, int S, float* out) {
     const int SPT = S > 512 ? S / 512 : 1;
     const int P = S / SPT;
     for (int q = 0; q < P; ++q) {
-        for (int j = 0; j < SPT; ++j) e[SPT * q + j] = b200_expf(B200_SUB(v[SPT * q + j], mx));
+        for (int j = 0; j < SPT; ++j) e[SPT * q + j] = b200_expf_nonpos(B200_SUB(v[SPT * q + j], mx));
         part[q] = e[SPT * q];
         for (int j = 1; j < SPT; ++j) part[q] = B200_ADD(part[q], e[SPT * q + j]);
     }

@@ -11,7 +11,7 @@ import collections, re, subprocess, sys, pathlib
 lib = sys.argv[1] if len(sys.argv) > 1 else "dorado_b200/libb200call.so"
 prefix = sys.argv[2] if len(sys.argv) > 2 else "profiles/r02_sass"
 FULL = ["crf_fwd_beam_kernel<3>", "crf_bwd_scan_kernel<3>", "crf_traceback_kernel", "tx_attention_tc_kernel",
-        "lstm_layer_kernel<96, 8, 2>", "conv12_kernel"]
+        "lstm_layer_kernel<96, 8, 2>", "conv12_tc_kernel", "lstm_cluster_kernel<384, 6, 2, 32>"]
 KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "HMMA", "IMMA", "MUFU",
         "REDUX", "MATCH", "SHFL", "BAR", "MEMBAR", "LDS", "STS", "LDG", "STG", "FFMA", "FADD", "FMUL", "DFMA"]
 
