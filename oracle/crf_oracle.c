@@ -525,6 +525,31 @@ int crf_decode_f32(const float* scores,
 
 /* scalar entry points so the tests can probe the numerics contract directly */
 float crf_math_expf(float x) { return b200_expf(x); }
+float crf_math_expf_nonpos(float x) { return b200_expf_nonpos(x); }
+/* number of the n arguments (bit patterns, walked with the given stride from start) on which b200_expf_nonpos and b200_expf
+ * differ, and on which the 2^n scale built by the bit trick differs from the (int) conversion form it replaced */
+long crf_expf_audit(uint32_t start, uint32_t stride, long n, long* scale_mismatch) {
+    long bad = 0, sbad = 0;
+    uint32_t u = start;
+    for (long i = 0; i < n; ++i, u += stride) {
+        float x;
+        memcpy(&x, &u, 4);
+        if (!(x <= 0.0f)) continue; /* also skips NaN */
+        const float a = b200_expf(x), b = b200_expf_nonpos(x);
+        if (memcmp(&a, &b, 4) != 0) ++bad;
+        const float xc = x < -86.0f ? -86.0f : x;
+        const float t = xc * 1.44269504088896341f;
+        const float tb = t + 12582912.0f;
+        const float nn = tb - 12582912.0f;
+        uint32_t bits;
+        memcpy(&bits, &tb, 4);
+        const uint32_t trick = (bits << 23) + 0x3f800000u;
+        const uint32_t conv = (uint32_t)((int32_t)nn + 127) << 23;
+        if (trick != conv) ++sbad;
+    }
+    *scale_mismatch = sbad;
+    return bad;
+}
 float crf_math_logf(float x) { return b200_logf(x); }
 float crf_math_log1pf(float x) { return b200_log1pf(x); }
 float crf_math_pow0p4f(float x) { return b200_pow0p4f(x); }

@@ -61,7 +61,7 @@ class CrfOracle:
         lib.crf_beam_search.restype = C.c_float
         lib.crf_generate_sequence.argtypes = [_u8p, _i32p, _f32p, C.c_int, C.c_float, C.c_float, _u8p, _u8p]
         lib.crf_generate_sequence.restype = C.c_int
-        for fn in ("crf_math_expf", "crf_math_logf", "crf_math_log1pf", "crf_math_pow0p4f"):
+        for fn in ("crf_math_expf", "crf_math_expf_nonpos", "crf_math_logf", "crf_math_log1pf", "crf_math_pow0p4f"):
             getattr(lib, fn).argtypes = [C.c_float]
             getattr(lib, fn).restype = C.c_float
         lib.crf_math_lse2.argtypes = [C.c_float, C.c_float]

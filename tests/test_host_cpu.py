@@ -107,6 +107,22 @@ def test_numerics_contract_accuracy(crf_oracle):
     np.testing.assert_array_equal(conv.view(np.uint32), halfs.view(np.float16).astype(np.float32).view(np.uint32))
 
 
+def test_expf_variants_are_bit_identical(crf_oracle):
+    """b200_expf_nonpos (what the max-shifted sums of the scans call: no upper clamp) equals b200_expf bit for bit on every
+    sampled x <= 0 (all of [-0, -inf) in steps of 4099 bit patterns, plus a dense window around the -86 cut-off), and the
+    integer form of the 2^n scale equals the float -> int conversion it replaced."""
+    import ctypes as C
+    lib = crf_oracle.lib
+    lib.crf_expf_audit.restype = C.c_long
+    lib.crf_expf_audit.argtypes = [C.c_uint32, C.c_uint32, C.c_long, C.POINTER(C.c_long)]
+    sb = C.c_long()
+    n = (0xff800000 - 0x80000000) // 4099 + 1
+    assert lib.crf_expf_audit(0x80000000, 4099, n, C.byref(sb)) == 0 and sb.value == 0
+    cut = int(np.float32(-86.0).view(np.uint32))
+    assert lib.crf_expf_audit(cut - 200000, 1, 400000, C.byref(sb)) == 0 and sb.value == 0
+    assert lib.crf_math_expf_nonpos(0.0) == 1.0 and lib.crf_math_expf_nonpos(-87.0) == 0.0
+
+
 def test_pow0p4_against_libm(crf_oracle):
     """The contract's pow(p, 0.4f) (binary64 exp(0.4f * log p), one rounding) is the correctly rounded powf on every
     sampled argument; the host libm's powf is within 1 ulp of it and differs on < 0.2 % of the arguments."""
