@@ -1,7 +1,8 @@
 // Conv -> LSTM -> linear CRF forward (fast / hac models) for sm_100a.
 //
 // Replaces, for the CUDA path of dorado/basecall/model/CRFModel.cpp:69-115:
-//   ConvStack layers 1,2   host_convolution_f16              dorado/nn/ConvStack.cpp:216-232
+//   ConvStack layers 1,2   host_convolution_f16              dorado/nn/ConvStack.cpp:216-232  -> conv12_tc_kernel (conv2 on
+//                                                                                         tcgen05; v5 shapes), conv12_kernel (FMA pipe)
 //   ConvStack layer 3      host_linear "cutlass conv"        dorado/nn/ConvStack.cpp:236-275  -> gemm.cu
 //   LSTMStack              host_cutlass_lstm/host_small_lstm dorado/nn/LSTMStack.cpp:127-238 -> lstm_layer_kernel (C = 96),
 //                                                                                         gx GEMM + lstm_cluster_kernel (C = 192, 384)
