@@ -1,4 +1,4 @@
-"""CPU models of two pieces of integer logic inside dorado_b200/csrc/decode.cu, checked against the straightforward form the
+"""CPU models of pieces of integer logic inside dorado_b200/csrc/decode.cu and gemm.cu, checked against the straightforward form the
 reference uses.  The kernels themselves are pinned bit for bit against the C oracle on the GPU (tests/test_decode_gpu.py,
 tests/test_full_size_gpu.py); these tests pin the *reasoning* behind the two rewrites, including the rare paths real data
 seldom reaches (equal hashes inside a beam, hash-table slots shared by several lanes, a table full of stale entries).
@@ -126,3 +126,39 @@ def test_kmer_neighbour_deduplication():
                 if R != state and all(b - msb * bb != d for bb in range(b + 1)):
                     got.append(2 * b + 1)
             assert got == ref, (state_len, state)
+
+
+def test_gemm_tile_schedules_cover_every_tile_once():
+    """gemm.cu gemm_tile_at + the grid rule of run_gemm: the default order (shorter dimension fastest) and the two
+    operand-stationary experiment schedules each visit every (row tile, column tile) exactly once."""
+    def tiles_of(cta, grid, m_tiles, n_tiles, wstat, mfast):
+        i = 0
+        while True:
+            if wstat == 1:
+                nt, mt = cta % n_tiles, cta // n_tiles + i * (grid // n_tiles)
+                if mt >= m_tiles:
+                    return
+            elif wstat == 2:
+                mt, nt = cta % m_tiles, cta // m_tiles + i * (grid // m_tiles)
+                if nt >= n_tiles:
+                    return
+            else:
+                tile = cta + i * grid
+                if tile >= m_tiles * n_tiles:
+                    return
+                mt, nt = (tile % m_tiles, tile // m_tiles) if mfast else (tile // n_tiles, tile % n_tiles)
+            yield mt, nt
+            i += 1
+
+    for m_tiles, n_tiles in [(12, 3332), (832, 12), (832, 32), (7, 6), (1, 5), (300, 1)]:
+        for max_ctas in (148, 116, 37):
+            for wstat in (0, 1, 2):
+                fixed = {0: 1, 1: n_tiles, 2: m_tiles}[wstat]
+                if wstat and fixed > 74:
+                    continue  # make_gemm_plan does not pick a stationary schedule for such shapes
+                grid = min(m_tiles * n_tiles, max_ctas) if wstat == 0 else max(fixed, (max_ctas // fixed) * fixed)
+                seen = {}
+                for cta in range(grid):
+                    for t in tiles_of(cta, grid, m_tiles, n_tiles, wstat, m_tiles < n_tiles):
+                        seen[t] = seen.get(t, 0) + 1
+                assert len(seen) == m_tiles * n_tiles and set(seen.values()) == {1}, (m_tiles, n_tiles, max_ctas, wstat)
