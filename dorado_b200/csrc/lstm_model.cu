@@ -1243,7 +1243,8 @@ std::unique_ptr<ForwardPlan> LstmModel::make_plan(int N, int T_in, const __half*
         const int GB = 32;  // chunk block of the gx layout (n_pad = 32 on this path)
         // With three or more batches in flight the x-projection GEMMs keep off 32 SMs, so that another batch's recurrence
         // (48 SMs, several milliseconds of latency chain) can start beside them instead of queueing behind a GEMM that owns every SM
-        // (measured at batch 512, 4 runners: 26.4 -> 24.0 ms per step, profiles/r02_b13_hac_cap*).
+        // (measured at batch 512, 4 runners: 26.4 -> 24.0 ms per step in battery 13, whose files were lost; after the tile-order change
+        // caps of 100-148 are within the run-to-run spread, profiles/r02_b26_bench_hac_cap*).
         const int gemm_cap = hint >= 3 ? 116 : 0;
         plan->lstm_grid = (Np / un) * 6;
         for (int l = 0; l < desc.lstm_layers; ++l) {
